@@ -1,0 +1,139 @@
+/*
+ * kmc.h — C ABI of libkmc.so, the B200 (sm_100a) k-mer counting engine.
+ *
+ * The reference (jaxonwang/k-mer-count) has no plugin / operator / FFI interface: its only boundary
+ * is the process (k-mer-count/src/main.rs:43-44 in, :88-90 out).  This header is the thin C ABI the
+ * task's north_star asks for between host code and the CUDA kernels, following the proposal in
+ * SURVEY.md §8b.  Every entry point cites the reference lines whose work it replaces.  Plain C
+ * types only — no torch / C++ types cross this boundary — so a Rust `-sys` crate, cgo or ctypes can
+ * bind it unchanged (INTEGRATION.md shows the bindings).
+ *
+ * Call chain (one ctx per GPU, one host thread per ctx; a ctx is not thread-safe):
+ *     kmc_create → { kmc_staging → fill → kmc_submit }*  → kmc_finish → kmc_read* → kmc_destroy
+ * or, with inputs already resident in HBM:
+ *     kmc_create → kmc_submit_device* → kmc_finish → kmc_table_device / kmc_read
+ * Multi-GPU (one process per GPU; the exchange itself is done by the host with NCCL):
+ *     kmc_submit* → kmc_route(n_parts) → [all-to-all of the routed keys] → kmc_ingest_keys* → kmc_finish
+ *
+ * There is no CPU fallback anywhere behind this ABI: without a CUDA device kmc_create fails with
+ * KMC_E_NO_DEVICE.
+ */
+#ifndef KMC_H
+#define KMC_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMC_ABI_VERSION 1
+
+/* ---- error codes (all entry points return 0 or one of these; nothing throws or aborts) ------- */
+enum {
+  KMC_OK = 0,
+  KMC_E_ARG = -1,            /* bad argument / bad call order                                      */
+  KMC_E_NO_DEVICE = -2,      /* no CUDA device / wrong architecture                                */
+  KMC_E_CUDA = -3,           /* a CUDA runtime call failed; kmc_last_error has the text            */
+  KMC_E_NOMEM = -4,          /* host or device allocation failed                                   */
+  KMC_E_BADBASE = -5,        /* lr-gapped mode: a byte other than A,C,G,T inside an emitted chunk:
+                                main.rs:23 panic!("Unexpected charactor ..") → exit 101            */
+  KMC_E_EMPTY = -6,          /* lr-gapped mode: no chunk at all: main.rs:35 source[0] panics       */
+  KMC_E_COUNT_OVERFLOW = -7, /* a multiplicity does not fit the table's 32-bit count               */
+  KMC_E_CAPACITY = -8,       /* more input than the ctx was sized for and it could not grow        */
+  KMC_E_BADBASE_OFFSET0 = -9 /* lr-gapped mode: non-ACGT byte only at chunk offset 0, which
+                                main.rs:36 never inspects and would print verbatim; a 2-bit key
+                                cannot hold it, so this build refuses (documented divergence)      */
+};
+
+/* ---- configuration ---------------------------------------------------------------------------- */
+enum { KMC_MODE_CONTIGUOUS = 0, /* ordinary k-mers, k <= 32 → 64-bit keys, k <= 64 → 128-bit keys   */
+       KMC_MODE_LR_GAPPED = 1 };/* the reference: L‖R gapped pairs, main.rs:48-49,63-80            */
+enum { KMC_STRATEGY_AUTO = 0, KMC_STRATEGY_HASH = 1, KMC_STRATEGY_SORT = 2,
+       KMC_STRATEGY_SORT_BASELINE = 3 /* plain extract → LSD radix sort → run-length encode        */ };
+
+typedef struct {
+  uint32_t abi_version;    /* KMC_ABI_VERSION                                                     */
+  uint32_t mode;           /* KMC_MODE_*                                                          */
+  uint32_t k;              /* contiguous: 1..64; ignored in lr-gapped mode                        */
+  uint32_t canonical;      /* contiguous: key = min(k-mer, reverse complement); must be 0 for lr  */
+  uint32_t strategy;       /* KMC_STRATEGY_*                                                      */
+  int32_t  device;         /* CUDA ordinal, -1 = current device                                   */
+  uint32_t l_len, r_len;   /* lr-gapped: 0,0 → 27,27  (main.rs:48-49); each 1..32                 */
+  uint32_t d_min, d_max;   /* lr-gapped: chunk sizes, 0,0 → 80,140 (main.rs:63 `80..141`)         */
+  uint64_t expected_bases; /* sizing hint for device buffers; 0 = grow on demand                  */
+  uint32_t reserved[8];    /* must be zero                                                        */
+} kmc_config;
+
+typedef struct kmc_ctx kmc_ctx; /* opaque; owns all device memory, streams and events             */
+
+/* Replaces main.rs:43-50 (process set-up: open input, allocate `lr_chunk`).                        */
+int kmc_create(kmc_ctx **out, const kmc_config *cfg);
+void kmc_destroy(kmc_ctx *ctx);
+/* Text of the last failure on this ctx (or of the last failed kmc_create when ctx is NULL);
+ * library-owned, valid until the next call.  Replaces the panic message on stderr.                */
+const char *kmc_last_error(const kmc_ctx *ctx);
+const char *kmc_strerror(int code);
+
+/* Optional: run everything on the caller's CUDA stream (a cudaStream_t / CUstream as void*).      */
+int kmc_set_stream(kmc_ctx *ctx, void *cuda_stream);
+/* Forget submitted input and results but keep device buffers (next job on the same ctx).          */
+int kmc_reset(kmc_ctx *ctx);
+
+/* ---- input: what main.rs:58-62 + :73 (`reader.read`, `record.seq()`) hand to the hot loop ------
+ * Sequence bytes are raw ASCII, records concatenated; rec_off has n_recs+1 entries, rec_off[0]=0,
+ * rec_off[n_recs]=n_bases (offsets relative to THIS submit).  Windows never span records.  The N /
+ * lower-case policy lives in the kernels, not in the parser.                                      */
+
+/* Library-owned PINNED host buffers for the host to fill (double-buffered: the pointers change
+ * between calls; a call may block until the previous copy out of the returned buffer finished).   */
+int kmc_staging(kmc_ctx *ctx, size_t want_bases, size_t want_recs, uint8_t **bases, uint64_t **rec_off,
+                size_t *cap_bases, size_t *cap_recs);
+/* Asynchronous H2D of the last staging buffer + append to the device-resident input.              */
+int kmc_submit(kmc_ctx *ctx, size_t n_bases, size_t n_recs);
+/* Same, from caller-owned HOST memory (pageable or pinned); copies synchronously if pageable.     */
+int kmc_submit_host(kmc_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, size_t n_bases, size_t n_recs);
+/* Same, but the input is already in HBM (device pointers, `bases` 16-byte aligned).  The buffers
+ * are referenced, not copied, and must stay valid and unchanged until kmc_finish returns.         */
+int kmc_submit_device(kmc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, size_t n_bases, size_t n_recs);
+
+/* ---- the hot path: main.rs:63-81 (window extraction) + :84-87 (ordering / grouping) ------------
+ * Extract every key, count, and leave the table — distinct keys ascending by (key_hi,key_lo), with
+ * multiplicities — resident in HBM.  n_total = number of key occurrences (lines the reference would
+ * print), n_distinct = rows.                                                                       */
+int kmc_finish(kmc_ctx *ctx, uint64_t *n_distinct, uint64_t *n_total);
+
+/* ---- output: what main.rs:88-90 prints, as arrays --------------------------------------------
+ * Rows [first, first+n) into caller-owned HOST arrays (any of them may be NULL).  key_hi is zero for
+ * keys of <= 64 bits.  Key encoding: A=0,C=1,G=2,T=3, first base most significant, so ascending
+ * integer order is the bytewise String order of main.rs:87.                                        */
+int kmc_read(kmc_ctx *ctx, uint64_t first, uint64_t n, uint64_t *key_lo, uint64_t *key_hi, uint64_t *count);
+/* Device pointers of the table (valid until reset/destroy).  d_key_hi is NULL for 64-bit keys.    */
+int kmc_table_device(kmc_ctx *ctx, const uint64_t **d_key_lo, const uint64_t **d_key_hi, const uint32_t **d_count);
+/* Order-independent 64-bit digest of the table, computed on the device:
+ * sum over rows of mix(key_hi,key_lo,count) mod 2^64 (SURVEY.md §8d full-scale parity check).     */
+int kmc_digest(kmc_ctx *ctx, uint64_t *digest);
+/* Number of bases per key: k, or l_len+r_len in lr-gapped mode.                                   */
+uint32_t kmc_key_bases(const kmc_ctx *ctx);
+
+/* ---- multi-GPU: hash-prefix routing -------------------------------------------
+ * kmc_route: extract this rank's keys from the submitted input and group them by owner
+ * part = (mix64(key) * n_parts) >> 64 into one device buffer; part p's keys are
+ * [part_off[p], part_off[p+1]) (part_off: caller-owned host array of n_parts+1 entries).
+ * Keys are 8 bytes (k<=32) or 16 bytes (lo,hi) each; key_bytes tells which.                       */
+int kmc_route(kmc_ctx *ctx, uint32_t n_parts, uint64_t *part_off, const void **d_keys, uint32_t *key_bytes);
+/* Hand the ctx keys it owns (device pointer, same layout as kmc_route's output; referenced until
+ * kmc_finish).  kmc_finish then counts the ingested keys instead of extracting from the input.    */
+int kmc_ingest_keys(kmc_ctx *ctx, const void *d_keys, uint64_t n_keys);
+/* owner part of a key, host-side (the same function the device uses).                            */
+uint32_t kmc_owner_of(uint64_t key_hi, uint64_t key_lo, uint32_t n_parts);
+
+/* ---- introspection ------------------------------------------------------------------------------
+ * JSON object: per-phase device times (CUDA events on the ctx stream), kernel-launch count, chosen
+ * strategy, sizes.  Returns bytes needed (incl. NUL); writes at most cap.                          */
+size_t kmc_stats_json(kmc_ctx *ctx, char *buf, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMC_H */

@@ -1,0 +1,672 @@
+// kmc_api.cu — the C ABI of include/kmc.h: context, staging, pipeline orchestration.
+// All device work is hand-written CUDA for sm_100a (kmc_extract.cuh, kmc_sort.cuh, kmc_fast.cuh,
+// kmc_hash.cuh).  There is no CPU fallback: every path below launches kernels or fails.
+#include "../../include/kmc.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kmc_common.cuh"
+#include "kmc_extract.cuh"
+#include "kmc_sort.cuh"
+
+using namespace kmc;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct Segment {            // one submit's worth of input, resident in HBM
+  DevBuf own_bases, own_off, brk;
+  const uint8_t *bases = nullptr;   // points into own_bases or at caller memory (submit_device)
+  const uint64_t *rec_off = nullptr;
+  uint64_t n_bases = 0, n_recs = 0;
+};
+
+struct Phase {
+  std::string name;
+  cudaEvent_t a = nullptr, b = nullptr;
+  float ms = 0.f;
+};
+
+} // namespace
+
+struct kmc_ctx {
+  kmc_config cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint32_t key_bits = 0, key_bases = 0;
+  bool wide = false; // 128-bit keys
+
+  // pinned staging, double-buffered
+  uint8_t *h_bases[2] = {nullptr, nullptr};
+  uint64_t *h_off[2] = {nullptr, nullptr};
+  size_t cap_bases = 0, cap_recs = 0;
+  int cur = 0;
+  bool staged = false;
+  cudaEvent_t copy_done[2] = {nullptr, nullptr};
+  bool copy_pending[2] = {false, false};
+
+  // input
+  std::vector<Segment> segs;
+  size_t n_segs = 0; // live segments (segs beyond are pooled buffers)
+  uint64_t total_bases = 0, total_recs = 0;
+
+  // ingested keys (multi-GPU)
+  std::vector<std::pair<const void *, uint64_t>> ingested;
+
+  // work buffers (grow-only, reused across kmc_reset)
+  DevBuf keys_a, keys_b, block_hist, offsets, sums, scalars, route_keys;
+  DevBuf gap_l, gap_r, gap_f;
+  DevBuf t_lo, t_hi, t_cnt;
+
+  // results
+  bool finished = false;
+  uint64_t n_total = 0, n_distinct = 0;
+  uint32_t strategy_used = 0;
+
+  // stats
+  std::vector<Phase> phases;
+  std::vector<cudaEvent_t> event_pool;
+  size_t events_used = 0;
+  uint64_t launches = 0, launches_total = 0;
+  uint64_t h2d_bytes = 0;
+  std::string stats;
+};
+
+namespace {
+
+int fail(kmc_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(c, e_ == cudaErrorMemoryAllocation ? KMC_E_NOMEM : KMC_E_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                           \
+  } while (0)
+
+#define LAUNCH(kern, grid, block, smem, ...)                                                             \
+  do {                                                                                                   \
+    kern<<<(grid), (block), (smem), c->stream>>>(__VA_ARGS__);                                           \
+    c->launches++;                                                                                       \
+    CK(cudaGetLastError());                                                                              \
+  } while (0)
+
+int ensure(kmc_ctx *c, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return KMC_OK;
+  if (b.p) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+  size_t want = std::max<size_t>(bytes, 256);
+  want = (want + 255) & ~size_t(255);
+  CK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return KMC_OK;
+}
+void release(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.cap = 0;
+}
+
+int phase_begin(kmc_ctx *c, const char *name) {
+  Phase ph;
+  ph.name = name;
+  for (cudaEvent_t *e : {&ph.a, &ph.b}) {
+    if (c->events_used == c->event_pool.size()) {
+      cudaEvent_t ev;
+      CK(cudaEventCreate(&ev));
+      c->event_pool.push_back(ev);
+    }
+    *e = c->event_pool[c->events_used++];
+  }
+  CK(cudaEventRecord(ph.a, c->stream));
+  c->phases.push_back(ph);
+  return KMC_OK;
+}
+int phase_end(kmc_ctx *c) {
+  CK(cudaEventRecord(c->phases.back().b, c->stream));
+  return KMC_OK;
+}
+#define PHASE_BEGIN(name) do { int r_ = phase_begin(c, name); if (r_) return r_; } while (0)
+#define PHASE_END() do { int r_ = phase_end(c); if (r_) return r_; } while (0)
+#define TRY(x) do { int r_ = (x); if (r_) return r_; } while (0)
+
+inline uint32_t grid_for(uint64_t n, uint32_t per_block) { return (uint32_t)std::max<uint64_t>(1, (n + per_block - 1) / per_block); }
+
+// scalars buffer layout (device): [0] cursor u64, [1] digest u64, [2] err flags u32 (in a u64 slot), [3] spare
+unsigned long long *d_cursor(kmc_ctx *c) { return (unsigned long long *)c->scalars.p; }
+unsigned long long *d_digest(kmc_ctx *c) { return (unsigned long long *)c->scalars.p + 1; }
+uint32_t *d_err(kmc_ctx *c) { return (uint32_t *)((unsigned long long *)c->scalars.p + 2); }
+
+int zero_scalars(kmc_ctx *c) {
+  TRY(ensure(c, c->scalars, 64));
+  CK(cudaMemsetAsync(c->scalars.p, 0, 64, c->stream));
+  return KMC_OK;
+}
+int read_scalars(kmc_ctx *c, uint64_t *cursor, uint32_t *err) {
+  unsigned long long h[4];
+  CK(cudaMemcpyAsync(h, c->scalars.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (cursor) *cursor = h[0];
+  if (err) *err = (uint32_t)h[2];
+  return KMC_OK;
+}
+
+// ---- input segments ------------------------------------------------------------------------------------
+int new_segment(kmc_ctx *c, Segment **out) {
+  if (c->n_segs == c->segs.size()) c->segs.emplace_back();
+  Segment &s = c->segs[c->n_segs++];
+  s.bases = nullptr; s.rec_off = nullptr; s.n_bases = s.n_recs = 0;
+  *out = &s;
+  return KMC_OK;
+}
+
+// after bases / rec_off are in place (device): build the record-start mask
+int segment_mark(kmc_ctx *c, Segment &s) {
+  size_t words = (s.n_bases + 31) / 32 + 4;
+  TRY(ensure(c, s.brk, words * 4));
+  CK(cudaMemsetAsync(s.brk.p, 0, words * 4, c->stream));
+  if (s.n_recs)
+    LAUNCH(mark_breaks_kernel, grid_for(s.n_recs, 256), 256, 0, s.rec_off, s.n_recs, 0ull, (uint32_t *)s.brk.p);
+  return KMC_OK;
+}
+
+int submit_from_host(kmc_ctx *c, const uint8_t *bases, const uint64_t *rec_off, size_t n_bases, size_t n_recs,
+                     cudaEvent_t done) {
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_submit after kmc_finish (call kmc_reset first)");
+  Segment *s;
+  TRY(new_segment(c, &s));
+  TRY(ensure(c, s->own_bases, n_bases + 64));
+  TRY(ensure(c, s->own_off, (n_recs + 1) * 8));
+  PHASE_BEGIN("h2d");
+  if (n_bases) CK(cudaMemcpyAsync(s->own_bases.p, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(s->own_off.p, rec_off, (n_recs + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  if (done) CK(cudaEventRecord(done, c->stream));
+  PHASE_END();
+  c->h2d_bytes += n_bases + (n_recs + 1) * 8;
+  s->bases = (const uint8_t *)s->own_bases.p;
+  s->rec_off = (const uint64_t *)s->own_off.p;
+  s->n_bases = n_bases; s->n_recs = n_recs;
+  c->total_bases += n_bases; c->total_recs += n_recs;
+  PHASE_BEGIN("mark");
+  TRY(segment_mark(c, *s));
+  PHASE_END();
+  return KMC_OK;
+}
+
+// ---- generic radix sort + RLE ---------------------------------------------------------------------------
+// sorts n keys in buffer `a` (scratch `b`) on bits [0,bits); *sorted receives the buffer with the result
+template <typename KeyT>
+int radix_sort(kmc_ctx *c, KeyT *a, KeyT *b, uint64_t n, uint32_t bits, KeyT **sorted) {
+  *sorted = a;
+  if (n <= 1 || bits == 0) return KMC_OK;
+  uint32_t n_blocks = grid_for(n, kRsTile);
+  uint64_t m = (uint64_t)n_blocks * kRadix;
+  TRY(ensure(c, c->block_hist, m * 4));
+  TRY(ensure(c, c->offsets, m * 8));
+  uint32_t scan_blocks = grid_for(m, kScanTile);
+  TRY(ensure(c, c->sums, (size_t)std::max<uint64_t>(scan_blocks, grid_for(n, kRleTile)) * 8 + 64));
+  KeyT *src = a, *dst = b;
+  for (uint32_t shift = 0; shift < bits; shift += 8) {
+    uint32_t nb = std::min<uint32_t>(8, bits - shift);
+    LAUNCH(rs_hist_kernel<KeyT>, n_blocks, kRsThreads, 0, src, n, shift, nb, (uint32_t *)c->block_hist.p, n_blocks);
+    LAUNCH(scan_reduce_kernel, scan_blocks, kScanThreads, 0, (const uint32_t *)c->block_hist.p, m, (uint64_t *)c->sums.p);
+    LAUNCH(scan_spine_kernel, 1, 1024, 0, (uint64_t *)c->sums.p, (uint64_t)scan_blocks);
+    LAUNCH(scan_apply_kernel, scan_blocks, kScanThreads, 0, (const uint32_t *)c->block_hist.p, m,
+           (const uint64_t *)c->sums.p, (uint64_t *)c->offsets.p);
+    LAUNCH(rs_scatter_kernel<KeyT>, n_blocks, kRsThreads, 0, src, dst, n, shift, nb, (const uint64_t *)c->offsets.p, n_blocks);
+    std::swap(src, dst);
+  }
+  *sorted = src;
+  return KMC_OK;
+}
+
+// sorted keys → table (t_lo, t_hi, t_cnt); `scratch` must hold (n+1) u64
+template <typename KeyT>
+int rle_to_table(kmc_ctx *c, const KeyT *sorted, uint64_t n, uint64_t *scratch) {
+  c->n_total = n;
+  c->n_distinct = 0;
+  if (n == 0) return KMC_OK;
+  uint32_t blocks = grid_for(n, kRleTile);
+  TRY(ensure(c, c->sums, (size_t)blocks * 8 + 64));
+  LAUNCH(rle_count_kernel<KeyT>, blocks, kRleThreads, 0, sorted, n, (uint64_t *)c->sums.p);
+  // total = last block sum + its exclusive prefix: fetch both sides of the spine scan
+  uint64_t last_cnt = 0, last_ex = 0;
+  CK(cudaMemcpyAsync(&last_cnt, (uint64_t *)c->sums.p + (blocks - 1), 8, cudaMemcpyDeviceToHost, c->stream));
+  LAUNCH(scan_spine_kernel, 1, 1024, 0, (uint64_t *)c->sums.p, (uint64_t)blocks);
+  CK(cudaMemcpyAsync(&last_ex, (uint64_t *)c->sums.p + (blocks - 1), 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  uint64_t d = last_cnt + last_ex;
+  c->n_distinct = d;
+  TRY(ensure(c, c->t_lo, d * 8));
+  if (sizeof(KeyT) == 16) TRY(ensure(c, c->t_hi, d * 8));
+  TRY(ensure(c, c->t_cnt, d * 4));
+  LAUNCH(rle_write_kernel<KeyT>, blocks, kRleThreads, 0, sorted, n, (const uint64_t *)c->sums.p, (uint64_t *)c->t_lo.p,
+         sizeof(KeyT) == 16 ? (uint64_t *)c->t_hi.p : (uint64_t *)nullptr, scratch);
+  LAUNCH(rle_diff_kernel, grid_for(d, 256), 256, 0, (const uint64_t *)scratch, d, n, (uint32_t *)c->t_cnt.p, d_err(c));
+  return KMC_OK;
+}
+
+// ---- key production ----------------------------------------------------------------------------------------
+// contiguous mode: all valid keys of all segments, compacted into keys_a; *n_keys on the host
+template <typename KeyT>
+int extract_all(kmc_ctx *c, uint64_t *n_keys) {
+  uint64_t cap = std::max<uint64_t>(c->total_bases, 1) + 2;
+  TRY(ensure(c, c->keys_a, cap * sizeof(KeyT)));
+  TRY(zero_scalars(c));
+  PHASE_BEGIN("extract");
+  for (size_t i = 0; i < c->n_segs; i++) {
+    Segment &s = c->segs[i];
+    if (!s.n_bases) continue;
+    ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
+    uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
+    uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + 7) / 8, (uint64_t)kNumSMsB200 * 16);
+    auto kfn = extract_compact_kernel<KeyT, true>;
+    LAUNCH(kfn, grid, 256, 0, P, tiles, (KeyT *)c->keys_a.p, d_cursor(c));
+  }
+  PHASE_END();
+  TRY(read_scalars(c, n_keys, nullptr));
+  return KMC_OK;
+}
+
+// lr-gapped mode: count + validate, then fill keys_a
+template <typename KeyT>
+int gapped_all(kmc_ctx *c, uint64_t *n_keys) {
+  const kmc_config &f = c->cfg;
+  TRY(zero_scalars(c));
+  PHASE_BEGIN("extract");
+  uint64_t mx = 1;
+  for (size_t i = 0; i < c->n_segs; i++) mx = std::max<uint64_t>(mx, c->segs[i].n_bases);
+  TRY(ensure(c, c->gap_l, mx * 8));
+  TRY(ensure(c, c->gap_r, mx * 8));
+  TRY(ensure(c, c->gap_f, mx));
+  // pass 1: count and validate (per segment; the per-position arrays are reused)
+  for (size_t i = 0; i < c->n_segs; i++) {
+    Segment &s = c->segs[i];
+    if (!s.n_bases) continue;
+    GapParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, f.l_len, f.r_len, f.d_min, f.d_max};
+    uint32_t g = grid_for(s.n_bases, 256);
+    LAUNCH(gap_mers_kernel, g, 256, 0, P, (uint64_t *)c->gap_l.p, (uint64_t *)c->gap_r.p, (uint8_t *)c->gap_f.p);
+    auto kfn = gap_pairs_kernel<KeyT, false>;
+    LAUNCH(kfn, g, 256, 0, P, (const uint64_t *)c->gap_l.p, (const uint64_t *)c->gap_r.p,
+           (const uint8_t *)c->gap_f.p, (KeyT *)nullptr, d_cursor(c), d_err(c));
+  }
+  uint64_t total = 0;
+  uint32_t err = 0;
+  TRY(read_scalars(c, &total, &err));
+  if (err & 1) return fail(c, KMC_E_BADBASE, "Unexpected character (not one of A,C,G,T) inside an L/R chunk");
+  if (err & 2) return fail(c, KMC_E_BADBASE_OFFSET0, "non-ACGT byte at offset 0 of an L/R chunk cannot be encoded");
+  if (total == 0) return fail(c, KMC_E_EMPTY, "no L/R chunk in the input (every record shorter than %u bases)", f.d_min);
+  TRY(ensure(c, c->keys_a, (total + 2) * sizeof(KeyT)));
+  TRY(zero_scalars(c));
+  for (size_t i = 0; i < c->n_segs; i++) {
+    Segment &s = c->segs[i];
+    if (!s.n_bases) continue;
+    GapParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, f.l_len, f.r_len, f.d_min, f.d_max};
+    uint32_t g = grid_for(s.n_bases, 256);
+    if (c->n_segs > 1)
+      LAUNCH(gap_mers_kernel, g, 256, 0, P, (uint64_t *)c->gap_l.p, (uint64_t *)c->gap_r.p, (uint8_t *)c->gap_f.p);
+    auto kfn = gap_pairs_kernel<KeyT, true>;
+    LAUNCH(kfn, g, 256, 0, P, (const uint64_t *)c->gap_l.p, (const uint64_t *)c->gap_r.p,
+           (const uint8_t *)c->gap_f.p, (KeyT *)c->keys_a.p, d_cursor(c), d_err(c));
+  }
+  PHASE_END();
+  *n_keys = total;
+  return KMC_OK;
+}
+
+template <typename KeyT>
+int produce_keys(kmc_ctx *c, uint64_t *n_keys) {
+  if (!c->ingested.empty()) {
+    uint64_t n = 0;
+    for (auto &e : c->ingested) n += e.second;
+    TRY(ensure(c, c->keys_a, (n + 2) * sizeof(KeyT)));
+    PHASE_BEGIN("gather");
+    uint64_t o = 0;
+    for (auto &e : c->ingested) {
+      if (e.second)
+        CK(cudaMemcpyAsync((KeyT *)c->keys_a.p + o, e.first, e.second * sizeof(KeyT), cudaMemcpyDeviceToDevice, c->stream));
+      o += e.second;
+    }
+    PHASE_END();
+    *n_keys = n;
+    return KMC_OK;
+  }
+  if (c->cfg.mode == KMC_MODE_LR_GAPPED) return gapped_all<KeyT>(c, n_keys);
+  return extract_all<KeyT>(c, n_keys);
+}
+
+// ---- strategies --------------------------------------------------------------------------------------------
+template <typename KeyT>
+int finish_baseline(kmc_ctx *c) {
+  uint64_t n = 0;
+  TRY(produce_keys<KeyT>(c, &n));
+  c->strategy_used = KMC_STRATEGY_SORT_BASELINE;
+  TRY(ensure(c, c->keys_b, (n + 2) * sizeof(KeyT)));
+  KeyT *sorted = nullptr;
+  PHASE_BEGIN("sort");
+  TRY(radix_sort<KeyT>(c, (KeyT *)c->keys_a.p, (KeyT *)c->keys_b.p, n, c->key_bits, &sorted));
+  PHASE_END();
+  PHASE_BEGIN("rle");
+  uint64_t *scratch = (uint64_t *)(sorted == (KeyT *)c->keys_a.p ? c->keys_b.p : c->keys_a.p);
+  TRY(rle_to_table<KeyT>(c, sorted, n, scratch));
+  PHASE_END();
+  return KMC_OK;
+}
+
+template <typename KeyT>
+int finish_impl(kmc_ctx *c) {
+  return finish_baseline<KeyT>(c);
+}
+
+void build_stats(kmc_ctx *c) {
+  std::string s = "{";
+  char buf[256];
+  snprintf(buf, sizeof buf,
+           "\"n_bases\": %llu, \"n_records\": %llu, \"n_total\": %llu, \"n_distinct\": %llu, \"key_bits\": %u, "
+           "\"strategy_used\": %u, \"kernel_launches\": %llu, \"kernel_launches_total\": %llu, \"h2d_bytes\": %llu, \"phases_ms\": {",
+           (unsigned long long)c->total_bases, (unsigned long long)c->total_recs, (unsigned long long)c->n_total,
+           (unsigned long long)c->n_distinct, c->key_bits, c->strategy_used, (unsigned long long)c->launches,
+           (unsigned long long)c->launches_total, (unsigned long long)c->h2d_bytes);
+  s += buf;
+  // sum phases of the same name
+  std::vector<std::pair<std::string, float>> agg;
+  for (auto &p : c->phases) {
+    bool found = false;
+    for (auto &a : agg) if (a.first == p.name) { a.second += p.ms; found = true; }
+    if (!found) agg.emplace_back(p.name, p.ms);
+  }
+  for (size_t i = 0; i < agg.size(); i++) {
+    snprintf(buf, sizeof buf, "%s\"%s\": %.4f", i ? ", " : "", agg[i].first.c_str(), agg[i].second);
+    s += buf;
+  }
+  s += "}}";
+  c->stats = s;
+}
+
+} // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char *kmc_strerror(int code) {
+  switch (code) {
+    case KMC_OK: return "ok";
+    case KMC_E_ARG: return "bad argument or call order";
+    case KMC_E_NO_DEVICE: return "no usable CUDA device";
+    case KMC_E_CUDA: return "CUDA runtime error";
+    case KMC_E_NOMEM: return "out of memory";
+    case KMC_E_BADBASE: return "unexpected character in an L/R chunk";
+    case KMC_E_EMPTY: return "no L/R chunk in the input";
+    case KMC_E_COUNT_OVERFLOW: return "a count exceeds 32 bits";
+    case KMC_E_CAPACITY: return "capacity exceeded";
+    case KMC_E_BADBASE_OFFSET0: return "non-ACGT byte at offset 0 of an L/R chunk";
+    default: return "unknown error";
+  }
+}
+
+const char *kmc_last_error(const kmc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int kmc_create(kmc_ctx **out, const kmc_config *cfg) {
+  kmc_ctx *c = nullptr; // for CK/fail: errors go to g_create_err until the ctx exists
+  if (!out || !cfg) return fail(c, KMC_E_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != KMC_ABI_VERSION) return fail(c, KMC_E_ARG, "abi_version %u != %u", cfg->abi_version, KMC_ABI_VERSION);
+  kmc_config f = *cfg;
+  for (uint32_t r : f.reserved) if (r) return fail(c, KMC_E_ARG, "reserved fields must be zero");
+  if (f.mode == KMC_MODE_CONTIGUOUS) {
+    if (f.k < 1 || f.k > 64) return fail(c, KMC_E_ARG, "k must be 1..64 (got %u)", f.k);
+  } else if (f.mode == KMC_MODE_LR_GAPPED) {
+    if (!f.l_len && !f.r_len) { f.l_len = 27; f.r_len = 27; }       // main.rs:48-49
+    if (!f.d_min && !f.d_max) { f.d_min = 80; f.d_max = 140; }      // main.rs:63
+    if (f.canonical) return fail(c, KMC_E_ARG, "lr-gapped mode is forward-strand only (main.rs:76-78)");
+    if (f.l_len < 1 || f.l_len > 32 || f.r_len < 1 || f.r_len > 32) return fail(c, KMC_E_ARG, "l_len and r_len must be 1..32");
+    if (f.d_min < f.l_len + f.r_len || f.d_max < f.d_min) return fail(c, KMC_E_ARG, "need l_len+r_len <= d_min <= d_max");
+  } else {
+    return fail(c, KMC_E_ARG, "unknown mode %u", f.mode);
+  }
+  if (f.strategy > KMC_STRATEGY_SORT_BASELINE) return fail(c, KMC_E_ARG, "unknown strategy %u", f.strategy);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(c, KMC_E_NO_DEVICE, "no CUDA device: libkmc has no CPU fallback");
+  }
+  int dev = f.device;
+  if (dev < 0) CK(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(c, KMC_E_NO_DEVICE, "device %d of %d", dev, ndev);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(c, KMC_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+  CK(cudaSetDevice(dev));
+  kmc_ctx *x = new (std::nothrow) kmc_ctx();
+  if (!x) return fail(c, KMC_E_NOMEM, "host allocation failed");
+  x->cfg = f;
+  x->device = dev;
+  x->key_bases = f.mode == KMC_MODE_CONTIGUOUS ? f.k : f.l_len + f.r_len;
+  x->key_bits = 2 * x->key_bases;
+  x->wide = x->key_bits > 64;
+  cudaError_t e = cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete x; return fail(c, KMC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  x->own_stream = true;
+  for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&x->copy_done[i], cudaEventDisableTiming);
+  *out = x;
+  return KMC_OK;
+}
+
+void kmc_destroy(kmc_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 2; i++) {
+    if (c->h_bases[i]) cudaFreeHost(c->h_bases[i]);
+    if (c->h_off[i]) cudaFreeHost(c->h_off[i]);
+    if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
+  }
+  for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); }
+  for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
+                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt})
+    release(*b);
+  for (auto ev : c->event_pool) cudaEventDestroy(ev);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int kmc_set_stream(kmc_ctx *c, void *s) {
+  if (!c) return KMC_E_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+  c->stream = (cudaStream_t)s;
+  return KMC_OK;
+}
+
+int kmc_reset(kmc_ctx *c) {
+  if (!c) return KMC_E_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  c->n_segs = 0; c->total_bases = c->total_recs = 0;
+  c->ingested.clear();
+  c->finished = false; c->n_total = c->n_distinct = 0;
+  c->phases.clear(); c->events_used = 0;
+  c->launches_total += c->launches; c->launches = 0; c->h2d_bytes = 0;
+  c->staged = false;
+  return KMC_OK;
+}
+
+uint32_t kmc_key_bases(const kmc_ctx *c) { return c ? c->key_bases : 0; }
+
+int kmc_staging(kmc_ctx *c, size_t want_bases, size_t want_recs, uint8_t **bases, uint64_t **rec_off, size_t *cap_bases,
+                size_t *cap_recs) {
+  if (!c || !bases || !rec_off) return KMC_E_ARG;
+  CK(cudaSetDevice(c->device));
+  want_bases = std::max<size_t>(want_bases, 1 << 20);
+  want_recs = std::max<size_t>(want_recs, 1 << 12);
+  if (want_bases > c->cap_bases || want_recs > c->cap_recs) {
+    CK(cudaStreamSynchronize(c->stream));
+    size_t nb = std::max(want_bases, c->cap_bases), nr = std::max(want_recs, c->cap_recs);
+    for (int i = 0; i < 2; i++) {
+      if (c->h_bases[i]) CK(cudaFreeHost(c->h_bases[i]));
+      if (c->h_off[i]) CK(cudaFreeHost(c->h_off[i]));
+      c->h_bases[i] = nullptr; c->h_off[i] = nullptr;
+      CK(cudaHostAlloc((void **)&c->h_bases[i], nb, cudaHostAllocDefault));
+      CK(cudaHostAlloc((void **)&c->h_off[i], (nr + 1) * 8, cudaHostAllocDefault));
+      c->copy_pending[i] = false;
+    }
+    c->cap_bases = nb; c->cap_recs = nr;
+  }
+  int i = c->cur;
+  if (c->copy_pending[i]) { CK(cudaEventSynchronize(c->copy_done[i])); c->copy_pending[i] = false; }
+  *bases = c->h_bases[i]; *rec_off = c->h_off[i];
+  if (cap_bases) *cap_bases = c->cap_bases;
+  if (cap_recs) *cap_recs = c->cap_recs;
+  c->staged = true;
+  return KMC_OK;
+}
+
+int kmc_submit(kmc_ctx *c, size_t n_bases, size_t n_recs) {
+  if (!c) return KMC_E_ARG;
+  if (!c->staged) return fail(c, KMC_E_ARG, "kmc_submit without kmc_staging");
+  if (n_bases > c->cap_bases || n_recs > c->cap_recs) return fail(c, KMC_E_CAPACITY, "submit larger than the staging buffer");
+  CK(cudaSetDevice(c->device));
+  int i = c->cur;
+  if (c->h_off[i][0] != 0 || c->h_off[i][n_recs] != n_bases) return fail(c, KMC_E_ARG, "rec_off[0] must be 0 and rec_off[n_recs] == n_bases");
+  TRY(submit_from_host(c, c->h_bases[i], c->h_off[i], n_bases, n_recs, c->copy_done[i]));
+  c->copy_pending[i] = true;
+  c->cur ^= 1;
+  c->staged = false;
+  return KMC_OK;
+}
+
+int kmc_submit_host(kmc_ctx *c, const uint8_t *bases, const uint64_t *rec_off, size_t n_bases, size_t n_recs) {
+  if (!c || !rec_off || (!bases && n_bases)) return KMC_E_ARG;
+  if (rec_off[0] != 0 || rec_off[n_recs] != n_bases) return fail(c, KMC_E_ARG, "rec_off[0] must be 0 and rec_off[n_recs] == n_bases");
+  CK(cudaSetDevice(c->device));
+  TRY(submit_from_host(c, bases, rec_off, n_bases, n_recs, nullptr));
+  CK(cudaStreamSynchronize(c->stream)); // caller memory may be pageable / reused right away
+  return KMC_OK;
+}
+
+int kmc_submit_device(kmc_ctx *c, const uint8_t *d_bases, const uint64_t *d_rec_off, size_t n_bases, size_t n_recs) {
+  if (!c || !d_rec_off || (!d_bases && n_bases)) return KMC_E_ARG;
+  if (((uintptr_t)d_bases & 15) != 0) return fail(c, KMC_E_ARG, "d_bases must be 16-byte aligned");
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_submit_device after kmc_finish (call kmc_reset first)");
+  CK(cudaSetDevice(c->device));
+  Segment *s;
+  TRY(new_segment(c, &s));
+  s->bases = d_bases; s->rec_off = d_rec_off; s->n_bases = n_bases; s->n_recs = n_recs;
+  c->total_bases += n_bases; c->total_recs += n_recs;
+  PHASE_BEGIN("mark");
+  TRY(segment_mark(c, *s));
+  PHASE_END();
+  return KMC_OK;
+}
+
+int kmc_ingest_keys(kmc_ctx *c, const void *d_keys, uint64_t n_keys) {
+  if (!c || (!d_keys && n_keys)) return KMC_E_ARG;
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_ingest_keys after kmc_finish");
+  c->ingested.emplace_back(d_keys, n_keys);
+  return KMC_OK;
+}
+
+int kmc_finish(kmc_ctx *c, uint64_t *n_distinct, uint64_t *n_total) {
+  if (!c) return KMC_E_ARG;
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_finish called twice");
+  CK(cudaSetDevice(c->device));
+  int rc = c->wide ? finish_impl<U128>(c) : finish_impl<uint64_t>(c);
+  if (rc) return rc;
+  uint32_t err = 0;
+  TRY(read_scalars(c, nullptr, &err));
+  if (err & 4) return fail(c, KMC_E_COUNT_OVERFLOW, "a k-mer occurs more than 2^32-1 times");
+  for (auto &p : c->phases) cudaEventElapsedTime(&p.ms, p.a, p.b);
+  c->finished = true;
+  if (n_distinct) *n_distinct = c->n_distinct;
+  if (n_total) *n_total = c->n_total;
+  return KMC_OK;
+}
+
+int kmc_read(kmc_ctx *c, uint64_t first, uint64_t n, uint64_t *key_lo, uint64_t *key_hi, uint64_t *count) {
+  if (!c) return KMC_E_ARG;
+  if (!c->finished) return fail(c, KMC_E_ARG, "kmc_read before kmc_finish");
+  if (first > c->n_distinct || n > c->n_distinct - first) return fail(c, KMC_E_ARG, "row range out of bounds");
+  if (!n) return KMC_OK;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (key_lo) CK(cudaMemcpy(key_lo, (uint64_t *)c->t_lo.p + first, n * 8, cudaMemcpyDeviceToHost));
+  if (key_hi) {
+    if (c->wide) CK(cudaMemcpy(key_hi, (uint64_t *)c->t_hi.p + first, n * 8, cudaMemcpyDeviceToHost));
+    else memset(key_hi, 0, n * 8);
+  }
+  if (count) {
+    // widen u32 → u64 in place, back to front
+    uint32_t *tmp = (uint32_t *)count;
+    CK(cudaMemcpy(tmp, (uint32_t *)c->t_cnt.p + first, n * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t i = n; i-- > 0;) count[i] = tmp[i];
+  }
+  return KMC_OK;
+}
+
+int kmc_table_device(kmc_ctx *c, const uint64_t **d_key_lo, const uint64_t **d_key_hi, const uint32_t **d_count) {
+  if (!c) return KMC_E_ARG;
+  if (!c->finished) return fail(c, KMC_E_ARG, "kmc_table_device before kmc_finish");
+  if (d_key_lo) *d_key_lo = c->n_distinct ? (const uint64_t *)c->t_lo.p : nullptr;
+  if (d_key_hi) *d_key_hi = (c->wide && c->n_distinct) ? (const uint64_t *)c->t_hi.p : nullptr;
+  if (d_count) *d_count = c->n_distinct ? (const uint32_t *)c->t_cnt.p : nullptr;
+  return KMC_OK;
+}
+
+int kmc_digest(kmc_ctx *c, uint64_t *digest) {
+  if (!c || !digest) return KMC_E_ARG;
+  if (!c->finished) return fail(c, KMC_E_ARG, "kmc_digest before kmc_finish");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(d_digest(c), 0, 8, c->stream));
+  if (c->n_distinct)
+    LAUNCH(digest_kernel, std::min<uint32_t>(grid_for(c->n_distinct, 256), kNumSMsB200 * 8), 256, 0, (const uint64_t *)c->t_lo.p,
+           c->wide ? (const uint64_t *)c->t_hi.p : (const uint64_t *)nullptr, (const uint32_t *)c->t_cnt.p, c->n_distinct,
+           d_digest(c));
+  unsigned long long h = 0;
+  CK(cudaMemcpyAsync(&h, d_digest(c), 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *digest = h;
+  return KMC_OK;
+}
+
+uint32_t kmc_owner_of(uint64_t key_hi, uint64_t key_lo, uint32_t n_parts) { return owner_of(key_hi, key_lo, n_parts); }
+
+int kmc_route(kmc_ctx *c, uint32_t n_parts, uint64_t *part_off, const void **d_keys, uint32_t *key_bytes) {
+  if (!c) return KMC_E_ARG;
+  return fail(c, KMC_E_ARG, "kmc_route: not built yet");
+}
+
+size_t kmc_stats_json(kmc_ctx *c, char *buf, size_t cap) {
+  if (!c) return 0;
+  build_stats(c);
+  size_t need = c->stats.size() + 1;
+  if (buf && cap) {
+    size_t m = std::min(cap - 1, c->stats.size());
+    memcpy(buf, c->stats.data(), m);
+    buf[m] = 0;
+  }
+  return need;
+}
+
+} // extern "C"

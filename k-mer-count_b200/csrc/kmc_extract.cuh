@@ -1,0 +1,291 @@
+// kmc_extract.cuh — 2-bit packing + k-mer extraction (the GPU form of main.rs:63-81).
+//
+// Layout: a warp covers 32 consecutive 32-base chunks; lane L loads chunk c0+L with two 128-bit
+// loads (32 ASCII bytes), packs it to a 64-bit word of 2-bit codes (first base most significant)
+// plus a 32-bit validity mask, and receives its right-hand neighbours' words by warp shuffle — the
+// hand-off at chunk boundaries.  Lanes whose window would leave the warp (the last 1 or 2) are
+// load-only; consecutive warp tiles overlap by that many chunks.  Every k-mer is then a pair of
+// funnel shifts of registers: no shared memory, no rolling dependency chain.
+//
+// Record boundaries (windows never span records, main.rs:58-81 handles one record at a time) come
+// from a 1-bit-per-base "record starts here" mask built by mark_breaks_kernel.
+#pragma once
+#include "kmc_common.cuh"
+
+namespace kmc {
+
+struct ExtractParams {
+  const uint8_t *bases;  // device, 16-byte aligned
+  const uint32_t *brk;   // 1 bit per base: bit (31 - p%32) of word p/32 set iff p starts a record
+  uint64_t n_bases;
+  uint32_t k;
+  uint32_t canonical;
+};
+
+__global__ void mark_breaks_kernel(const uint64_t *__restrict__ rec_off, uint64_t n_recs, uint64_t base_shift,
+                                   uint32_t *__restrict__ brk) {
+  uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (r >= n_recs) return;
+  uint64_t p = rec_off[r] + base_shift;
+  atomicOr(&brk[p >> 5], 0x80000000u >> (p & 31));
+}
+
+__device__ __forceinline__ uint4 ld_stream16(const uint8_t *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// One 32-base chunk → packed codes + validity.  Positions >= n are invalid.
+template <bool FOLD>
+__device__ __forceinline__ void load_chunk(const uint8_t *__restrict__ bases, uint64_t pos, uint64_t n,
+                                           uint64_t &codes, uint32_t &valid) {
+  uint32_t w[8];
+  if (pos + 32 <= n) {
+    uint4 a = ld_stream16(bases + pos), b = ld_stream16(bases + pos + 16);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      uint32_t x = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint64_t p = pos + q * 4 + j;
+        uint32_t c = (p < n) ? bases[p] : 0u;
+        x |= c << (8 * j);
+      }
+      w[q] = x;
+    }
+  }
+  codes = 0; valid = 0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    uint32_t c, v;
+    pack4<FOLD>(w[q], c, v);
+    codes = (codes << 8) | c;
+    valid = (valid << 4) | v;
+  }
+}
+
+// ---- per-lane window state -----------------------------------------------------------------------
+// K64 : k <= 32, window = 2 chunks (64 positions), 31 productive lanes
+// K128: k <= 64, window = 3 chunks (96 positions), 30 productive lanes
+template <typename KeyT> struct Win;
+
+template <> struct Win<uint64_t> {
+  static constexpr int kLanes = 31;
+  uint64_t w0, w1;
+  uint32_t ok; // start s (0..31) valid <-> bit (31 - s)
+  template <bool FOLD>
+  __device__ __forceinline__ void load(const ExtractParams &P, uint64_t chunk) {
+    uint64_t pos = chunk * 32;
+    uint64_t c = 0; uint32_t v = 0, b = 0;
+    if (pos < P.n_bases) {
+      load_chunk<FOLD>(P.bases, pos, P.n_bases, c, v);
+      b = P.brk ? P.brk[chunk] : 0u;
+    }
+    w0 = c;
+    w1 = __shfl_down_sync(0xffffffffu, c, 1);
+    uint32_t v1 = __shfl_down_sync(0xffffffffu, v, 1), b1 = __shfl_down_sync(0xffffffffu, b, 1);
+    uint64_t E = ((uint64_t)v << 32) | v1;
+    uint64_t NB = ~(((uint64_t)b << 32) | b1);
+    uint64_t g = run_and64(E, P.k);
+    if (P.k > 1) g &= run_and64(NB, P.k - 1) << 1;
+    ok = (lane_id() < kLanes) ? (uint32_t)(g >> 32) : 0u;
+  }
+  __device__ __forceinline__ uint64_t key(uint32_t s, uint32_t k, bool canonical) const {
+    uint64_t f = shl_pair(w0, w1, 2 * s) >> (64 - 2 * k);
+    if (canonical) {
+      uint64_t r = revcomp64(f, k);
+      f = r < f ? r : f;
+    }
+    return f;
+  }
+};
+
+__device__ __forceinline__ unsigned __int128 run_and128(unsigned __int128 x, uint32_t len) {
+  unsigned __int128 r = x;
+  uint32_t have = 1;
+  while (have * 2 <= len) { r &= r << have; have *= 2; }
+  if (len > have) r &= r << (len - have);
+  return r;
+}
+
+template <> struct Win<U128> {
+  static constexpr int kLanes = 30;
+  uint64_t w0, w1, w2;
+  uint32_t ok;
+  template <bool FOLD>
+  __device__ __forceinline__ void load(const ExtractParams &P, uint64_t chunk) {
+    uint64_t pos = chunk * 32;
+    uint64_t c = 0; uint32_t v = 0, b = 0;
+    if (pos < P.n_bases) {
+      load_chunk<FOLD>(P.bases, pos, P.n_bases, c, v);
+      b = P.brk ? P.brk[chunk] : 0u;
+    }
+    w0 = c;
+    w1 = __shfl_down_sync(0xffffffffu, c, 1);
+    w2 = __shfl_down_sync(0xffffffffu, c, 2);
+    uint32_t v1 = __shfl_down_sync(0xffffffffu, v, 1), v2 = __shfl_down_sync(0xffffffffu, v, 2);
+    uint32_t b1 = __shfl_down_sync(0xffffffffu, b, 1), b2 = __shfl_down_sync(0xffffffffu, b, 2);
+    typedef unsigned __int128 u128;
+    u128 E = ((u128)v << 96) | ((u128)v1 << 64) | ((u128)v2 << 32);
+    u128 NB = ~(((u128)b << 96) | ((u128)b1 << 64) | ((u128)b2 << 32));
+    u128 g = run_and128(E, P.k);
+    if (P.k > 1) g &= run_and128(NB, P.k - 1) << 1;
+    ok = (lane_id() < kLanes) ? (uint32_t)(g >> 96) : 0u;
+  }
+  __device__ __forceinline__ U128 key(uint32_t s, uint32_t k, bool canonical) const {
+    uint64_t a = shl_pair(w0, w1, 2 * s), b = shl_pair(w1, w2, 2 * s);
+    uint32_t sh = 128 - 2 * k; // k in 33..64 → 0..62
+    U128 f;
+    if (sh == 0) { f.hi = a; f.lo = b; }
+    else { f.hi = a >> sh; f.lo = (b >> sh) | (a << (64 - sh)); }
+    if (canonical) {
+      U128 r = revcomp128(f, k);
+      if (key_lt(r, f)) f = r;
+    }
+    return f;
+  }
+};
+
+template <typename KeyT> __host__ __device__ constexpr int win_lanes() { return sizeof(KeyT) == 8 ? 31 : 30; }
+
+__host__ inline uint64_t num_warp_tiles(uint64_t n_bases, int lanes) {
+  uint64_t chunks = (n_bases + 31) / 32;
+  return (chunks + lanes - 1) / lanes;
+}
+
+// ---- baseline extraction: all valid keys, compacted, unordered ------------------------------------
+// Warp-aggregated slot allocation (one atomicAdd per warp tile), each lane writes its run of keys.
+template <typename KeyT, bool FOLD>
+__global__ void __launch_bounds__(256) extract_compact_kernel(ExtractParams P, uint64_t n_tiles, KeyT *__restrict__ out,
+                                                               unsigned long long *__restrict__ cursor) {
+  const uint32_t lane = lane_id();
+  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t t = warp0; t < n_tiles; t += nwarps) {
+    Win<KeyT> W;
+    W.template load<FOLD>(P, t * Win<KeyT>::kLanes + lane);
+    uint32_t cnt = __popc(W.ok);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (uint32_t)o) inc += nn;
+    }
+    uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total) base = atomicAdd(cursor, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    uint64_t o = base + (inc - cnt);
+    uint32_t m = W.ok;
+    while (m) {
+      uint32_t s = __clz(m);
+      m &= ~(0x80000000u >> s);
+      out[o++] = W.key(s, P.k, P.canonical != 0);
+    }
+  }
+}
+
+// ---- lr-gapped mode (main.rs:63-80; L/R/gap range generalised) -------------------------------------
+struct GapParams {
+  const uint8_t *bases;
+  const uint32_t *brk;
+  uint64_t n_bases;
+  uint32_t l_len, r_len, d_min, d_max;
+};
+
+// Per-position packed L-mer and R-mer with strict (upper-case ACGT) validity — main.rs:18-23.
+// flags[p]: bit0 L-mer at p valid, bit1 R-mer at p valid, bit2 L-mer valid ignoring its first base.
+__global__ void gap_mers_kernel(GapParams P, uint64_t *__restrict__ lmer, uint64_t *__restrict__ rmer,
+                                uint8_t *__restrict__ flags) {
+  uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (p >= P.n_bases) return;
+  uint32_t mx = P.l_len > P.r_len ? P.l_len : P.r_len;
+  uint64_t acc = 0, lm = 0, rm = 0;
+  uint32_t f = 0;
+  bool ok = true, ok1 = true;
+  for (uint32_t i = 0; i < mx; i++) {
+    uint64_t q = p + i;
+    int c = -1;
+    if (q < P.n_bases) {
+      uint8_t ch = P.bases[q];
+      c = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
+    }
+    if (c < 0) { ok = false; if (i > 0) ok1 = false; c = 0; }
+    acc = (acc << 2) | (uint64_t)c;
+    if (i + 1 == P.l_len) { lm = acc; f |= (ok ? 1u : 0u) | (ok1 ? 4u : 0u); }
+    if (i + 1 == P.r_len) { rm = acc; f |= ok ? 2u : 0u; }
+  }
+  lmer[p] = lm; rmer[p] = rm; flags[p] = (uint8_t)f;
+}
+
+// distance from p to the end of its record, capped at cap
+__device__ __forceinline__ uint32_t room_to_record_end(const uint32_t *__restrict__ brk, uint64_t p, uint64_t n, uint32_t cap) {
+  uint64_t lim = (n - p < cap) ? (n - p) : cap;
+  // first record start in (p, p+lim): scan the break mask
+  for (uint64_t q = p + 1; q < p + lim;) {
+    uint32_t w = brk[q >> 5] & (0xFFFFFFFFu >> (q & 31));
+    if (w) {
+      uint64_t hit = (q & ~31ULL) + __clz(w);
+      return (uint32_t)((hit - p < lim) ? hit - p : lim);
+    }
+    q = (q & ~31ULL) + 32;
+  }
+  return (uint32_t)lim;
+}
+
+// FILL=false: count keys and check validity.  FILL=true: write keys (compacted, unordered).
+// err[0] |= 1 on a bad base at chunk offset >= 1, |= 2 when only offset 0 is bad.
+template <typename KeyT, bool FILL>
+__global__ void __launch_bounds__(256) gap_pairs_kernel(GapParams P, const uint64_t *__restrict__ lmer,
+                                                        const uint64_t *__restrict__ rmer, const uint8_t *__restrict__ flags,
+                                                        KeyT *__restrict__ out, unsigned long long *__restrict__ cursor,
+                                                        uint32_t *__restrict__ err) {
+  uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  uint32_t cnt = 0, room = 0;
+  if (p < P.n_bases) {
+    room = room_to_record_end(P.brk, p, P.n_bases, P.d_max);
+    if (room >= P.d_min) cnt = room - P.d_min + 1;
+  }
+  const uint32_t lane = lane_id();
+  uint32_t inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += nn;
+  }
+  uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+  unsigned long long base = 0;
+  if (lane == 31 && total) base = atomicAdd(cursor, (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (!cnt) return;
+  uint32_t e = 0;
+  if (!FILL) {
+    uint8_t fl = flags[p];
+    for (uint32_t d = P.d_min; d <= room; d++) {
+      uint8_t fr = flags[p + d - P.r_len];
+      if (!(fl & 1) || !(fr & 2)) e |= ((fl & 4) && (fr & 2)) ? 2u : 1u;
+    }
+    if (e) atomicOr(err, e);
+  } else {
+    uint64_t o = base + (inc - cnt);
+    uint64_t L = lmer[p];
+    for (uint32_t d = P.d_min; d <= room; d++) {
+      uint64_t R = rmer[p + d - P.r_len];
+      KeyT key;
+      if constexpr (sizeof(KeyT) == 8) {
+        key = (L << (2 * P.r_len)) | R;
+      } else {
+        uint32_t s = 2 * P.r_len; // 2..64
+        key.lo = (s == 64) ? R : ((L << s) | R);
+        key.hi = (s == 64) ? L : (L >> (64 - s));
+      }
+      out[o++] = key;
+    }
+  }
+}
+
+} // namespace kmc

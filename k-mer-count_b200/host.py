@@ -1,0 +1,226 @@
+"""ctypes binding of include/kmc.h and the Python host object over it.
+
+This mirrors the call chain of the reference's `main` (k-mer-count/src/main.rs:43-92): read records
+(:58-62) → extract windows (:63-81) → order/group (:87) → emit (:88-90), with the middle two on the GPU.
+No computation happens here; arrays are only moved in and out.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from .build import build, lib_path
+
+MODE_CONTIGUOUS, MODE_LR_GAPPED = 0, 1
+STRATEGY_AUTO, STRATEGY_HASH, STRATEGY_SORT, STRATEGY_SORT_BASELINE = 0, 1, 2, 3
+ABI_VERSION = 1
+
+KMC_E_ARG, KMC_E_NO_DEVICE, KMC_E_CUDA, KMC_E_NOMEM, KMC_E_BADBASE, KMC_E_EMPTY = -1, -2, -3, -4, -5, -6
+KMC_E_COUNT_OVERFLOW, KMC_E_CAPACITY, KMC_E_BADBASE_OFFSET0 = -7, -8, -9
+
+# every symbol include/kmc.h declares (tests check the library exports them all)
+SYMBOLS = ["kmc_create", "kmc_destroy", "kmc_last_error", "kmc_strerror", "kmc_set_stream", "kmc_reset",
+           "kmc_staging", "kmc_submit", "kmc_submit_host", "kmc_submit_device", "kmc_finish", "kmc_read",
+           "kmc_table_device", "kmc_digest", "kmc_key_bases", "kmc_route", "kmc_ingest_keys", "kmc_owner_of",
+           "kmc_stats_json"]
+
+
+class KmcConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("mode", C.c_uint32), ("k", C.c_uint32), ("canonical", C.c_uint32),
+                ("strategy", C.c_uint32), ("device", C.c_int32), ("l_len", C.c_uint32), ("r_len", C.c_uint32),
+                ("d_min", C.c_uint32), ("d_max", C.c_uint32), ("expected_bases", C.c_uint64),
+                ("reserved", C.c_uint32 * 8)]
+
+
+class KmcError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"kmc error {code}: {text}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libkmc.so (in-tree).  Raises if it is missing — there is no fallback implementation."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or lib_path()
+    if not os.path.exists(p):
+        raise FileNotFoundError(f"{p} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(p)
+    vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
+    L.kmc_create.argtypes = [C.POINTER(vp), C.POINTER(KmcConfig)]
+    L.kmc_destroy.argtypes = [vp]
+    L.kmc_destroy.restype = None
+    L.kmc_last_error.argtypes = [vp]
+    L.kmc_last_error.restype = C.c_char_p
+    L.kmc_strerror.argtypes = [C.c_int]
+    L.kmc_strerror.restype = C.c_char_p
+    L.kmc_set_stream.argtypes = [vp, vp]
+    L.kmc_reset.argtypes = [vp]
+    L.kmc_staging.argtypes = [vp, C.c_size_t, C.c_size_t, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t),
+                              C.POINTER(C.c_size_t)]
+    L.kmc_submit.argtypes = [vp, C.c_size_t, C.c_size_t]
+    L.kmc_submit_host.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t]
+    L.kmc_submit_device.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t]
+    L.kmc_finish.argtypes = [vp, u64p, u64p]
+    L.kmc_read.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp]
+    L.kmc_table_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.kmc_digest.argtypes = [vp, u64p]
+    L.kmc_key_bases.argtypes = [vp]
+    L.kmc_key_bases.restype = C.c_uint32
+    L.kmc_route.argtypes = [vp, C.c_uint32, vp, C.POINTER(vp), C.POINTER(C.c_uint32)]
+    L.kmc_ingest_keys.argtypes = [vp, vp, C.c_uint64]
+    L.kmc_owner_of.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
+    L.kmc_owner_of.restype = C.c_uint32
+    L.kmc_stats_json.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.kmc_stats_json.restype = C.c_size_t
+    if path is None:
+        _lib = L
+    return L
+
+
+class Table:
+    """Distinct keys ascending by (key_hi, key_lo) with multiplicities — numpy uint64 arrays."""
+
+    def __init__(self, key_hi, key_lo, count, n_total, key_bases):
+        self.key_hi, self.key_lo, self.count = key_hi, key_lo, count
+        self.n_total, self.key_bases = int(n_total), int(key_bases)
+
+    @property
+    def n_distinct(self):
+        return len(self.key_lo)
+
+    def kmers(self):
+        """Decode to ACGT strings (small tables)."""
+        out = []
+        nb = self.key_bases
+        for h, l in zip(self.key_hi.tolist(), self.key_lo.tolist()):
+            v = (h << 64) | l
+            out.append("".join("ACGT"[(v >> (2 * (nb - 1 - i))) & 3] for i in range(nb)))
+        return out
+
+
+class KmerCounter:
+    """One counting context on one GPU (kmc_ctx).  Not thread-safe."""
+
+    def __init__(self, k=31, canonical=True, mode=MODE_CONTIGUOUS, strategy=STRATEGY_AUTO, device=-1,
+                 l_len=0, r_len=0, d_min=0, d_max=0, expected_bases=0):
+        self._L = load_library()
+        cfg = KmcConfig(abi_version=ABI_VERSION, mode=mode, k=k, canonical=int(bool(canonical)), strategy=strategy,
+                        device=device, l_len=l_len, r_len=r_len, d_min=d_min, d_max=d_max,
+                        expected_bases=expected_bases)
+        self._h = C.c_void_p()
+        rc = self._L.kmc_create(C.byref(self._h), C.byref(cfg))
+        if rc:
+            raise KmcError(rc, self._L.kmc_last_error(None).decode())
+        self.key_bases = self._L.kmc_key_bases(self._h)
+
+    # -- plumbing
+    def _ck(self, rc):
+        if rc:
+            raise KmcError(rc, self._L.kmc_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._L.kmc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._L.kmc_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def reset(self):
+        self._ck(self._L.kmc_reset(self._h))
+
+    # -- input
+    def staging(self, n_bases, n_recs):
+        """Pinned staging buffers as numpy views: (bases uint8[cap], rec_off uint64[cap+1])."""
+        b, o = C.c_void_p(), C.c_void_p()
+        cb, cr = C.c_size_t(), C.c_size_t()
+        self._ck(self._L.kmc_staging(self._h, n_bases, n_recs, C.byref(b), C.byref(o), C.byref(cb), C.byref(cr)))
+        bases = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint8)), shape=(cb.value,))
+        off = np.ctypeslib.as_array(C.cast(o, C.POINTER(C.c_uint64)), shape=(cr.value + 1,))
+        return bases, off
+
+    def submit(self, n_bases, n_recs):
+        self._ck(self._L.kmc_submit(self._h, n_bases, n_recs))
+
+    def submit_host(self, bases, rec_off):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        self._ck(self._L.kmc_submit_host(self._h, bases.ctypes.data, rec_off.ctypes.data, len(bases), len(rec_off) - 1))
+
+    def submit_device(self, d_bases_ptr, d_rec_off_ptr, n_bases, n_recs):
+        self._ck(self._L.kmc_submit_device(self._h, C.c_void_p(d_bases_ptr), C.c_void_p(d_rec_off_ptr), n_bases, n_recs))
+
+    # -- hot path
+    def finish(self):
+        d, t = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.kmc_finish(self._h, C.byref(d), C.byref(t)))
+        self.n_distinct, self.n_total = d.value, t.value
+        return d.value, t.value
+
+    # -- output
+    def read(self, first=0, n=None):
+        n = self.n_distinct - first if n is None else n
+        lo, hi, cnt = (np.empty(n, np.uint64) for _ in range(3))
+        self._ck(self._L.kmc_read(self._h, first, n, lo.ctypes.data, hi.ctypes.data, cnt.ctypes.data))
+        return Table(hi, lo, cnt, self.n_total, self.key_bases)
+
+    def table_device(self):
+        lo, hi, cnt = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self._L.kmc_table_device(self._h, C.byref(lo), C.byref(hi), C.byref(cnt)))
+        return lo.value, hi.value, cnt.value
+
+    def digest(self):
+        d = C.c_uint64()
+        self._ck(self._L.kmc_digest(self._h, C.byref(d)))
+        return d.value
+
+    def stats(self):
+        n = self._L.kmc_stats_json(self._h, None, 0)
+        buf = C.create_string_buffer(n)
+        self._L.kmc_stats_json(self._h, buf, n)
+        return json.loads(buf.value.decode())
+
+    # -- multi-GPU routing
+    def route(self, n_parts):
+        off = np.zeros(n_parts + 1, np.uint64)
+        keys, kb = C.c_void_p(), C.c_uint32()
+        self._ck(self._L.kmc_route(self._h, n_parts, off.ctypes.data, C.byref(keys), C.byref(kb)))
+        return off, keys.value, kb.value
+
+    def ingest_keys(self, d_keys_ptr, n_keys):
+        self._ck(self._L.kmc_ingest_keys(self._h, C.c_void_p(d_keys_ptr), n_keys))
+
+
+def count_kmers(bases, rec_off, k, canonical=True, strategy=STRATEGY_AUTO, device=-1):
+    """bases: uint8 ASCII, rec_off: uint64 offsets (n_recs+1).  Returns the sorted Table."""
+    with KmerCounter(k=k, canonical=canonical, strategy=strategy, device=device) as kc:
+        kc.submit_host(bases, rec_off)
+        kc.finish()
+        return kc.read()
+
+
+def count_lr_gapped(bases, rec_off, l_len=0, r_len=0, d_min=0, d_max=0, strategy=STRATEGY_AUTO, device=-1):
+    """The reference's computation (main.rs:63-87): table of L‖R gapped keys."""
+    with KmerCounter(mode=MODE_LR_GAPPED, canonical=False, strategy=strategy, device=device, l_len=l_len, r_len=r_len,
+                     d_min=d_min, d_max=d_max) as kc:
+        kc.submit_host(bases, rec_off)
+        kc.finish()
+        return kc.read()

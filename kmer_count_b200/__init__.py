@@ -1,0 +1,11 @@
+"""Import alias: the product package lives in `k-mer-count_b200/` (named after the reference repo),
+which is not a legal Python identifier.  `import kmer_count_b200` loads that directory as this module."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+_dir = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "k-mer-count_b200")
+_spec = _u.spec_from_file_location(__name__, _os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = _u.module_from_spec(_spec)
+_sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,230 @@
+"""GPU parity tests (B200): libkmc through its C ABI vs the CPU oracle and the reference's golden
+vectors.  Bit-exact: all work here is integer."""
+import gzip
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import assert_tables_equal, expanded_text, random_records, to_arrays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kmc():
+    import kmer_count_b200 as k
+    k.build()
+    k.load_library()
+    return k
+
+
+@pytest.fixture(scope="module")
+def golden(gold_dir):
+    return json.load(open(os.path.join(gold_dir, "compat_golden.json")))
+
+
+STRATEGIES = [3, 0]  # baseline sort, auto
+
+
+# ------------------------------------------------------------------ the reference's own computation
+@pytest.mark.parametrize("strategy", STRATEGIES)
+@pytest.mark.parametrize("name", ["sample", "gen_seed1", "tiny_lengths", "tiny_crlf"])
+def test_lr_gapped_matches_reference_stdout(kmc, orc, gold_dir, golden, name, strategy):
+    bases, off = orc.parse_fasta(os.path.join(gold_dir, name + ".fasta"))
+    tab = kmc.count_lr_gapped(bases, off, strategy=strategy)
+    g = golden[name]
+    assert tab.n_total == g["stdout_lines"] and tab.key_bases == 54
+    text = expanded_text(tab.key_hi, tab.key_lo, tab.count, 54)
+    assert len(text) == g["stdout_bytes"]
+    assert hashlib.sha256(text).hexdigest() == g["stdout_sha256"]
+    assert text[:54].decode() == g["first_line"] and text[-55:-1].decode() == g["last_line"]
+    exp = os.path.join(gold_dir, name + ".expected.txt.gz")
+    if os.path.exists(exp):
+        assert gzip.open(exp).read() == text
+    assert_tables_equal(tab, orc.compat_lr(bases, off))
+
+
+def test_lr_gapped_sample_known_answers(kmc, orc, gold_dir):
+    bases, off = orc.parse_fasta(os.path.join(gold_dir, "sample.fasta"))
+    with kmc.KmerCounter(mode=kmc.MODE_LR_GAPPED, canonical=False) as kc:
+        kc.submit_host(bases, off)
+        d, t = kc.finish()
+        assert (d, t) == (1079497, 3550200)
+        tab = kc.read()
+        assert int(tab.count.max()) == 130 and int((tab.count == 1).sum()) == 559903
+        assert kc.digest() == orc.compat_lr(bases, off).digest()
+        # partial reads
+        part = kc.read(1000, 10)
+        assert np.array_equal(part.key_lo, tab.key_lo[1000:1010]) and np.array_equal(part.count, tab.count[1000:1010])
+
+
+def test_lr_gapped_errors(kmc):
+    def run(recs, **kw):
+        b, o = to_arrays(recs)
+        return kmc.count_lr_gapped(b, o, **kw)
+
+    for recs in ([], ["ACGT" * 10], ["A" * 79, "C" * 79]):
+        with pytest.raises(kmc.KmcError) as e:
+            run(recs)
+        assert e.value.code == -6  # KMC_E_EMPTY  (main.rs:35)
+    s = list("ACGT" * 30)
+    s[40] = "N"
+    with pytest.raises(kmc.KmcError) as e:
+        run(["".join(s)])
+    assert e.value.code == -5  # KMC_E_BADBASE (main.rs:23)
+    with pytest.raises(kmc.KmcError) as e:
+        run(["acgt" * 30])
+    assert e.value.code == -5
+    s = list("ACGT" * 20)
+    s[30] = "N"  # inside the gap of the only chunk: never copied (main.rs:76-77)
+    assert run(["".join(s)]).n_total == 1
+    s = list("ACGT" * 20)
+    s[0] = "N"
+    with pytest.raises(kmc.KmcError) as e:
+        run(["".join(s)])
+    assert e.value.code == -9
+
+
+@pytest.mark.parametrize("l,r,dmin,dmax", [(27, 27, 80, 140), (5, 7, 12, 20), (16, 16, 32, 40), (32, 32, 64, 70), (1, 1, 2, 3)])
+def test_generalised_gapped(kmc, orc, l, r, dmin, dmax):
+    recs = random_records(seed=l * 100 + r, n_recs=40, min_len=0, max_len=180, alphabet="ACGT")
+    b, o = to_arrays(recs)
+    want = orc.gapped_mt(b, o, l, r, dmin, dmax)
+    got = kmc.count_lr_gapped(b, o, l, r, dmin, dmax)
+    assert got.key_bases == l + r
+    assert_tables_equal(got, want)
+
+
+# ------------------------------------------------------------------ contiguous mode (parity unpinned: vs the oracle's definition)
+@pytest.mark.parametrize("strategy", STRATEGIES)
+@pytest.mark.parametrize("k", [1, 2, 5, 16, 21, 31, 32, 33, 47, 63, 64])
+@pytest.mark.parametrize("canonical", [True, False])
+def test_contiguous_small(kmc, orc, k, canonical, strategy):
+    recs = random_records(seed=100 + k, n_recs=60, min_len=0, max_len=300, alphabet="ACGTacgtN", n_rate=0.02)
+    b, o = to_arrays(recs)
+    want = orc.contiguous_def(b, o, k, canonical)
+    got = kmc.count_kmers(b, o, k, canonical, strategy=strategy)
+    assert_tables_equal(got, want)
+
+
+@pytest.mark.parametrize("k,total,distinct,sha", [
+    (21, 76000, 2360, "d6821a8f1b9010573e9009dc86475c1db676fbfa6c2c87cead0bfec2a9a8d248"),
+    (31, 74000, 3260, "f0cd84cb1599b78c53df4b04c274615e63f8a9102f10fe73be34f26979f32cda"),
+    (63, 67600, 6140, "0e4a5e39329606ff25951c3ca5c131d54f0ba30616a1689d229351858fdcc718"),
+])
+def test_contiguous_seeds_on_sample(kmc, orc, gold_dir, k, total, distinct, sha):
+    bases, off = orc.parse_fasta(os.path.join(gold_dir, "sample.fasta"))
+    tab = kmc.count_kmers(bases, off, k, True)
+    assert (tab.n_total, tab.n_distinct) == (total, distinct)
+    txt = "".join(f"{s}\t{c}\n" for s, c in zip(tab.kmers(), tab.count.tolist()))
+    assert hashlib.sha256(txt.encode()).hexdigest() == sha
+
+
+@pytest.mark.parametrize("strategy", STRATEGIES)
+@pytest.mark.parametrize("k,canonical", [(21, True), (31, True), (32, False), (63, True), (40, False)])
+def test_contiguous_medium_vs_oracle_mt(kmc, orc, k, canonical, strategy):
+    """~3 M bases: ragged record lengths, N runs, lower case; compared row by row and by digest."""
+    rng = np.random.default_rng(k)
+    n = 3_000_000
+    bases = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=n)
+    lower = rng.random(n) < 0.01
+    bases[lower] |= 0x20
+    for s in rng.integers(0, n - 200, 300):
+        bases[s:s + int(rng.integers(1, 120))] = ord("N")
+    lens = rng.integers(0, 2500, size=4000)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    off = off[off <= n]
+    off[-1] = n
+    want = orc.contiguous_mt(bases, off, k, canonical)
+    with kmc.KmerCounter(k=k, canonical=canonical, strategy=strategy) as kc:
+        kc.submit_host(bases, off)
+        kc.finish()
+        got = kc.read()
+        assert kc.digest() == want.digest()
+    assert_tables_equal(got, want)
+    assert int(got.count.sum()) == got.n_total
+    key = got.key_hi.astype(object) * (1 << 64) + got.key_lo.astype(object) if k > 32 else got.key_lo
+    assert all(key[i] < key[i + 1] for i in range(0, len(key) - 1, max(1, len(key) // 5000)))
+
+
+def test_low_cardinality_hot_keys(kmc, orc):
+    """Repetitive input (the generator's 10-line pool, random_fasta_generator.py:5-15) — heavy duplicates."""
+    rng = np.random.default_rng(3)
+    pool = [rng.choice(np.frombuffer(b"ACGT", np.uint8), size=80) for _ in range(10)]
+    recs = [np.concatenate([pool[i] for i in rng.integers(0, 10, 5)]) for _ in range(5000)]
+    bases = np.concatenate(recs)
+    off = (np.arange(len(recs) + 1) * 400).astype(np.uint64)
+    for k in (21, 63):
+        want = orc.contiguous_mt(bases, off, k, True)
+        for strategy in STRATEGIES:
+            got = kmc.count_kmers(bases, off, k, True, strategy=strategy)
+            assert_tables_equal(got, want)
+    # one key only: poly-A
+    bases = np.full(200_000, ord("A"), np.uint8)
+    off = np.array([0, 200_000], np.uint64)
+    got = kmc.count_kmers(bases, off, 31, True)
+    assert got.n_distinct == 1 and int(got.count[0]) == 200_000 - 30 and int(got.key_lo[0]) == 0
+
+
+def test_edge_inputs(kmc, orc):
+    # empty input, records shorter than k, exactly k, all-N
+    for recs, k in (([], 21), ([""], 21), (["ACGT"], 21), (["ACGTACGTACGTACGTACGTA"], 21), (["N" * 100], 5), (["ACGTN" * 40], 5)):
+        b, o = to_arrays(recs)
+        want = orc.contiguous_def(b, o, k, True)
+        got = kmc.count_kmers(b, o, k, True)
+        assert_tables_equal(got, want)
+
+
+def test_multi_submit_and_staging(kmc, orc):
+    recs = random_records(seed=9, n_recs=300, min_len=0, max_len=700, alphabet="ACGTN", n_rate=0.01)
+    b, o = to_arrays(recs)
+    want = orc.contiguous_mt(b, o, 31, True)
+    with kmc.KmerCounter(k=31) as kc:
+        # three batches through the pinned staging buffers
+        cuts = [0, 100, 101, 300]
+        for a, z in zip(cuts[:-1], cuts[1:]):
+            lo_b, hi_b = int(o[a]), int(o[z])
+            sb, so = kc.staging(hi_b - lo_b, z - a)
+            sb[:hi_b - lo_b] = b[lo_b:hi_b]
+            so[:z - a + 1] = o[a:z + 1] - o[a]
+            kc.submit(hi_b - lo_b, z - a)
+        kc.finish()
+        assert_tables_equal(kc.read(), want)
+        st = kc.stats()
+        assert st["kernel_launches"] > 0 and st["n_total"] == want.n_total
+        # reuse the ctx
+        kc.reset()
+        kc.submit_host(b, o)
+        kc.finish()
+        assert_tables_equal(kc.read(), want)
+
+
+def test_submit_device_via_torch(kmc, orc):
+    import torch
+    recs = random_records(seed=11, n_recs=200, min_len=50, max_len=900, alphabet="ACGT")
+    b, o = to_arrays(recs)
+    want = orc.contiguous_mt(b, o, 21, True)
+    db = torch.from_numpy(b).cuda()
+    do = torch.from_numpy(o.view(np.int64)).cuda()
+    with kmc.KmerCounter(k=21) as kc:
+        kc.set_stream(torch.cuda.current_stream().cuda_stream)
+        kc.submit_device(db.data_ptr(), do.data_ptr(), len(b), len(o) - 1)
+        kc.finish()
+        assert_tables_equal(kc.read(), want)
+        lo, hi, cnt = kc.table_device()
+        assert lo and cnt and not hi
+
+
+def test_hypothesis_contiguous(kmc, orc):
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.text(alphabet="ACGTNacgt", max_size=90), max_size=8), st.integers(1, 64), st.booleans())
+    def prop(recs, k, canonical):
+        b, o = to_arrays(recs)
+        assert_tables_equal(kmc.count_kmers(b, o, k, canonical), orc.contiguous_def(b, o, k, canonical))
+
+    prop()

@@ -75,3 +75,34 @@ def write_fasta(path, recs, width=80, newline="\n"):
             f.write(f">dummy_sequence_{i:03d} {i}th record{newline}")
             for j in range(0, len(r), width):
                 f.write(r[j:j + width] + newline)
+
+
+def decode_matrix(key_hi, key_lo, n_bases):
+    """(hi, lo) uint64 arrays → (D, n_bases) uint8 matrix of ASCII ACGT (vectorised)."""
+    hi = np.asarray(key_hi, np.uint64)
+    lo = np.asarray(key_lo, np.uint64)
+    out = np.empty((len(lo), n_bases), np.uint8)
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    for i in range(n_bases):
+        bit = 2 * (n_bases - 1 - i)
+        if bit >= 64:
+            c = (hi >> np.uint64(bit - 64)) & np.uint64(3)
+        else:
+            c = (lo >> np.uint64(bit)) & np.uint64(3)
+        out[:, i] = lut[c.astype(np.int64)]
+    return out
+
+
+def expanded_text(key_hi, key_lo, count, n_bases):
+    """The reference's stdout (main.rs:88-90): each key repeated `count` times, one per line."""
+    m = decode_matrix(key_hi, key_lo, n_bases)
+    m = np.concatenate([m, np.full((len(m), 1), 10, np.uint8)], axis=1)
+    return np.repeat(m, np.asarray(count, np.int64), axis=0).tobytes()
+
+
+def assert_tables_equal(got, want):
+    assert got.n_total == want.n_total, (got.n_total, want.n_total)
+    assert got.n_distinct == want.n_distinct, (got.n_distinct, want.n_distinct)
+    assert np.array_equal(got.key_hi, want.key_hi)
+    assert np.array_equal(got.key_lo, want.key_lo)
+    assert np.array_equal(got.count, want.count)

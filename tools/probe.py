@@ -1,0 +1,43 @@
+"""GPU-box probe: per-phase device times of libkmc on synthetic input (development aid)."""
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+import kmer_count_b200 as k
+
+
+def synth(n_bases, rec_len=400, seed=2):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    codes = torch.randint(0, 4, (n_bases,), device="cuda", generator=g, dtype=torch.uint8)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+    bases = lut[codes.long()]
+    off = torch.arange(0, n_bases + 1, rec_len, dtype=torch.int64, device="cuda")
+    if int(off[-1]) != n_bases:
+        off = torch.cat([off, torch.tensor([n_bases], device="cuda")])
+    return bases, off
+
+
+def main():
+    n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
+    kk = int(sys.argv[2]) if len(sys.argv) > 2 else 21
+    strategy = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    bases, off = synth(n)
+    torch.cuda.synchronize()
+    with k.KmerCounter(k=kk, canonical=True, strategy=strategy) as kc:
+        for it in range(3):
+            kc.reset()
+            t0 = time.time()
+            kc.submit_device(bases.data_ptr(), off.data_ptr(), n, len(off) - 1)
+            d, t = kc.finish()
+            dt = time.time() - t0
+            st = kc.stats()
+            print(json.dumps({"iter": it, "n_bases": n, "k": kk, "strategy": strategy, "wall_ms": dt * 1e3,
+                              "Gkmers_per_s": t / dt / 1e9, "n_total": t, "n_distinct": d, **st}))
+
+
+if __name__ == "__main__":
+    main()
