@@ -592,6 +592,7 @@ int kmc_finish(kmc_ctx *c, uint64_t *n_distinct, uint64_t *n_total) {
   if (!c) return KMC_E_ARG;
   if (c->finished) return fail(c, KMC_E_ARG, "kmc_finish called twice");
   CK(cudaSetDevice(c->device));
+  TRY(zero_scalars(c));
   int rc = c->wide ? finish_impl<U128>(c) : finish_impl<uint64_t>(c);
   if (rc) return rc;
   uint32_t err = 0;
