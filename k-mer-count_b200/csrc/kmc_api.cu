@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -38,6 +39,11 @@ struct Phase {
   std::string name;
   cudaEvent_t a = nullptr, b = nullptr;
   float ms = 0.f;
+};
+struct KernelStat {
+  std::string name;
+  uint64_t launches = 0;
+  double ms = 0;
 };
 
 } // namespace
@@ -85,6 +91,10 @@ struct kmc_ctx {
   uint64_t launches = 0, launches_total = 0;
   uint64_t h2d_bytes = 0;
   std::string stats;
+  // optional per-kernel timing (env KMC_KERNEL_TIMING=1): one event pair per launch
+  bool ktiming = false;
+  std::vector<Phase> klaunches;
+  std::vector<KernelStat> kstats;
 };
 
 namespace {
@@ -107,11 +117,16 @@ int fail(kmc_ctx *c, int code, const char *fmt, ...) {
                   cudaGetErrorString(e_), __FILE__, __LINE__);                                           \
   } while (0)
 
+int ktime_begin(kmc_ctx *c, const char *name);
+int ktime_end(kmc_ctx *c);
+
 #define LAUNCH(kern, grid, block, smem, ...)                                                             \
   do {                                                                                                   \
+    if (c->ktiming) { int r_ = ktime_begin(c, #kern); if (r_) return r_; }                               \
     kern<<<(grid), (block), (smem), c->stream>>>(__VA_ARGS__);                                           \
     c->launches++;                                                                                       \
     CK(cudaGetLastError());                                                                              \
+    if (c->ktiming) { int r_ = ktime_end(c); if (r_) return r_; }                                        \
   } while (0)
 
 int ensure(kmc_ctx *c, DevBuf &b, size_t bytes) {
@@ -147,9 +162,28 @@ int phase_end(kmc_ctx *c) {
   CK(cudaEventRecord(c->phases.back().b, c->stream));
   return KMC_OK;
 }
+int ktime_begin(kmc_ctx *c, const char *name) {
+  Phase ph;
+  ph.name = name;
+  for (cudaEvent_t *e : {&ph.a, &ph.b}) {
+    if (c->events_used == c->event_pool.size()) {
+      cudaEvent_t ev;
+      CK(cudaEventCreate(&ev));
+      c->event_pool.push_back(ev);
+    }
+    *e = c->event_pool[c->events_used++];
+  }
+  CK(cudaEventRecord(ph.a, c->stream));
+  c->klaunches.push_back(ph);
+  return KMC_OK;
+}
+int ktime_end(kmc_ctx *c) {
+  CK(cudaEventRecord(c->klaunches.back().b, c->stream));
+  return KMC_OK;
+}
 #define PHASE_BEGIN(name) do { int r_ = phase_begin(c, name); if (r_) return r_; } while (0)
 #define PHASE_END() do { int r_ = phase_end(c); if (r_) return r_; } while (0)
-#define TRY(x) do { int r_ = (x); if (r_) return r_; } while (0)
+#define TRY(...) do { int r_ = (__VA_ARGS__); if (r_) return r_; } while (0)
 
 inline uint32_t grid_for(uint64_t n, uint32_t per_block) { return (uint32_t)std::max<uint64_t>(1, (n + per_block - 1) / per_block); }
 
@@ -215,26 +249,35 @@ int submit_from_host(kmc_ctx *c, const uint8_t *bases, const uint64_t *rec_off, 
 }
 
 // ---- generic radix sort + RLE ---------------------------------------------------------------------------
-// sorts n keys in buffer `a` (scratch `b`) on bits [0,bits); *sorted receives the buffer with the result
-template <typename KeyT>
-int radix_sort(kmc_ctx *c, KeyT *a, KeyT *b, uint64_t n, uint32_t bits, KeyT **sorted) {
-  *sorted = a;
-  if (n <= 1 || bits == 0) return KMC_OK;
+// one stable counting-sort pass of n keys from src to dst by digit(key) < 256
+template <typename KeyT, typename DigitFn>
+int radix_pass(kmc_ctx *c, const KeyT *src, KeyT *dst, uint64_t n, DigitFn digit) {
   uint32_t n_blocks = grid_for(n, kRsTile);
   uint64_t m = (uint64_t)n_blocks * kRadix;
   TRY(ensure(c, c->block_hist, m * 4));
   TRY(ensure(c, c->offsets, m * 8));
   uint32_t scan_blocks = grid_for(m, kScanTile);
   TRY(ensure(c, c->sums, (size_t)std::max<uint64_t>(scan_blocks, grid_for(n, kRleTile)) * 8 + 64));
+  auto rs_hist = rs_hist_kernel<KeyT, DigitFn>;
+  auto rs_scatter = rs_scatter_kernel<KeyT, DigitFn>;
+  LAUNCH(rs_hist, n_blocks, kRsThreads, 0, src, n, digit, (uint32_t *)c->block_hist.p, n_blocks);
+  LAUNCH(scan_reduce_kernel, scan_blocks, kScanThreads, 0, (const uint32_t *)c->block_hist.p, m, (uint64_t *)c->sums.p);
+  LAUNCH(scan_spine_kernel, 1, 1024, 0, (uint64_t *)c->sums.p, (uint64_t)scan_blocks);
+  LAUNCH(scan_apply_kernel, scan_blocks, kScanThreads, 0, (const uint32_t *)c->block_hist.p, m,
+         (const uint64_t *)c->sums.p, (uint64_t *)c->offsets.p);
+  LAUNCH(rs_scatter, n_blocks, kRsThreads, 0, src, dst, n, digit, (const uint64_t *)c->offsets.p, n_blocks);
+  return KMC_OK;
+}
+
+// sorts n keys in buffer `a` (scratch `b`) on bits [0,bits); *sorted receives the buffer with the result
+template <typename KeyT>
+int radix_sort(kmc_ctx *c, KeyT *a, KeyT *b, uint64_t n, uint32_t bits, KeyT **sorted) {
+  *sorted = a;
+  if (n <= 1 || bits == 0) return KMC_OK;
   KeyT *src = a, *dst = b;
   for (uint32_t shift = 0; shift < bits; shift += 8) {
     uint32_t nb = std::min<uint32_t>(8, bits - shift);
-    LAUNCH(rs_hist_kernel<KeyT>, n_blocks, kRsThreads, 0, src, n, shift, nb, (uint32_t *)c->block_hist.p, n_blocks);
-    LAUNCH(scan_reduce_kernel, scan_blocks, kScanThreads, 0, (const uint32_t *)c->block_hist.p, m, (uint64_t *)c->sums.p);
-    LAUNCH(scan_spine_kernel, 1, 1024, 0, (uint64_t *)c->sums.p, (uint64_t)scan_blocks);
-    LAUNCH(scan_apply_kernel, scan_blocks, kScanThreads, 0, (const uint32_t *)c->block_hist.p, m,
-           (const uint64_t *)c->sums.p, (uint64_t *)c->offsets.p);
-    LAUNCH(rs_scatter_kernel<KeyT>, n_blocks, kRsThreads, 0, src, dst, n, shift, nb, (const uint64_t *)c->offsets.p, n_blocks);
+    TRY(radix_pass<KeyT, BitsDigit>(c, src, dst, n, BitsDigit{shift, nb}));
     std::swap(src, dst);
   }
   *sorted = src;
@@ -281,8 +324,8 @@ int extract_all(kmc_ctx *c, uint64_t *n_keys) {
     ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
     uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
     uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + 7) / 8, (uint64_t)kNumSMsB200 * 16);
-    auto kfn = extract_compact_kernel<KeyT, true>;
-    LAUNCH(kfn, grid, 256, 0, P, tiles, (KeyT *)c->keys_a.p, d_cursor(c));
+    auto extract_compact = extract_compact_kernel<KeyT, true>;
+    LAUNCH(extract_compact, grid, 256, 0, P, tiles, (KeyT *)c->keys_a.p, d_cursor(c));
   }
   PHASE_END();
   TRY(read_scalars(c, n_keys, nullptr));
@@ -307,8 +350,8 @@ int gapped_all(kmc_ctx *c, uint64_t *n_keys) {
     GapParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, f.l_len, f.r_len, f.d_min, f.d_max};
     uint32_t g = grid_for(s.n_bases, 256);
     LAUNCH(gap_mers_kernel, g, 256, 0, P, (uint64_t *)c->gap_l.p, (uint64_t *)c->gap_r.p, (uint8_t *)c->gap_f.p);
-    auto kfn = gap_pairs_kernel<KeyT, false>;
-    LAUNCH(kfn, g, 256, 0, P, (const uint64_t *)c->gap_l.p, (const uint64_t *)c->gap_r.p,
+    auto gap_pairs_count = gap_pairs_kernel<KeyT, false>;
+    LAUNCH(gap_pairs_count, g, 256, 0, P, (const uint64_t *)c->gap_l.p, (const uint64_t *)c->gap_r.p,
            (const uint8_t *)c->gap_f.p, (KeyT *)nullptr, d_cursor(c), d_err(c));
   }
   uint64_t total = 0;
@@ -326,8 +369,8 @@ int gapped_all(kmc_ctx *c, uint64_t *n_keys) {
     uint32_t g = grid_for(s.n_bases, 256);
     if (c->n_segs > 1)
       LAUNCH(gap_mers_kernel, g, 256, 0, P, (uint64_t *)c->gap_l.p, (uint64_t *)c->gap_r.p, (uint8_t *)c->gap_f.p);
-    auto kfn = gap_pairs_kernel<KeyT, true>;
-    LAUNCH(kfn, g, 256, 0, P, (const uint64_t *)c->gap_l.p, (const uint64_t *)c->gap_r.p,
+    auto gap_pairs_fill = gap_pairs_kernel<KeyT, true>;
+    LAUNCH(gap_pairs_fill, g, 256, 0, P, (const uint64_t *)c->gap_l.p, (const uint64_t *)c->gap_r.p,
            (const uint8_t *)c->gap_f.p, (KeyT *)c->keys_a.p, d_cursor(c), d_err(c));
   }
   PHASE_END();
@@ -354,6 +397,26 @@ int produce_keys(kmc_ctx *c, uint64_t *n_keys) {
   }
   if (c->cfg.mode == KMC_MODE_LR_GAPPED) return gapped_all<KeyT>(c, n_keys);
   return extract_all<KeyT>(c, n_keys);
+}
+
+// ---- multi-GPU routing: group this rank's keys by owner part ---------------------------------
+template <typename KeyT>
+int route_impl(kmc_ctx *c, uint32_t n_parts, uint64_t *part_off) {
+  uint64_t n = 0;
+  if (c->cfg.mode == KMC_MODE_LR_GAPPED) TRY(gapped_all<KeyT>(c, &n));
+  else TRY(extract_all<KeyT>(c, &n));
+  TRY(ensure(c, c->route_keys, (n + 2) * sizeof(KeyT)));
+  for (uint32_t p = 0; p <= n_parts; p++) part_off[p] = (p == n_parts) ? n : 0;
+  if (n == 0) return KMC_OK;
+  PHASE_BEGIN("route");
+  TRY(radix_pass<KeyT, OwnerDigit>(c, (const KeyT *)c->keys_a.p, (KeyT *)c->route_keys.p, n, OwnerDigit{n_parts}));
+  PHASE_END();
+  // start of part p = scanned offset of (digit p, block 0)
+  uint32_t n_blocks = grid_for(n, kRsTile);
+  CK(cudaMemcpy2DAsync(part_off, 8, c->offsets.p, (size_t)n_blocks * 8, 8, n_parts, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  part_off[n_parts] = n;
+  return KMC_OK;
 }
 
 // ---- strategies --------------------------------------------------------------------------------------------
@@ -398,6 +461,12 @@ void build_stats(kmc_ctx *c) {
   }
   for (size_t i = 0; i < agg.size(); i++) {
     snprintf(buf, sizeof buf, "%s\"%s\": %.4f", i ? ", " : "", agg[i].first.c_str(), agg[i].second);
+    s += buf;
+  }
+  s += "}, \"kernels\": {";
+  for (size_t i = 0; i < c->kstats.size(); i++) {
+    snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %llu, \"ms\": %.4f}", i ? ", " : "", c->kstats[i].name.c_str(),
+             (unsigned long long)c->kstats[i].launches, c->kstats[i].ms);
     s += buf;
   }
   s += "}}";
@@ -468,6 +537,7 @@ int kmc_create(kmc_ctx **out, const kmc_config *cfg) {
   cudaError_t e = cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete x; return fail(c, KMC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   x->own_stream = true;
+  { const char *kt = getenv("KMC_KERNEL_TIMING"); x->ktiming = kt && kt[0] == '1'; }
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&x->copy_done[i], cudaEventDisableTiming);
   *out = x;
   return KMC_OK;
@@ -507,7 +577,7 @@ int kmc_reset(kmc_ctx *c) {
   c->n_segs = 0; c->total_bases = c->total_recs = 0;
   c->ingested.clear();
   c->finished = false; c->n_total = c->n_distinct = 0;
-  c->phases.clear(); c->events_used = 0;
+  c->phases.clear(); c->klaunches.clear(); c->events_used = 0;
   c->launches_total += c->launches; c->launches = 0; c->h2d_bytes = 0;
   c->staged = false;
   return KMC_OK;
@@ -599,6 +669,14 @@ int kmc_finish(kmc_ctx *c, uint64_t *n_distinct, uint64_t *n_total) {
   TRY(read_scalars(c, nullptr, &err));
   if (err & 4) return fail(c, KMC_E_COUNT_OVERFLOW, "a k-mer occurs more than 2^32-1 times");
   for (auto &p : c->phases) cudaEventElapsedTime(&p.ms, p.a, p.b);
+  c->kstats.clear();
+  for (auto &p : c->klaunches) {
+    cudaEventElapsedTime(&p.ms, p.a, p.b);
+    KernelStat *ks = nullptr;
+    for (auto &k : c->kstats) if (k.name == p.name) ks = &k;
+    if (!ks) { c->kstats.emplace_back(); ks = &c->kstats.back(); ks->name = p.name; }
+    ks->launches++; ks->ms += p.ms;
+  }
   c->finished = true;
   if (n_distinct) *n_distinct = c->n_distinct;
   if (n_total) *n_total = c->n_total;
@@ -654,8 +732,16 @@ int kmc_digest(kmc_ctx *c, uint64_t *digest) {
 uint32_t kmc_owner_of(uint64_t key_hi, uint64_t key_lo, uint32_t n_parts) { return owner_of(key_hi, key_lo, n_parts); }
 
 int kmc_route(kmc_ctx *c, uint32_t n_parts, uint64_t *part_off, const void **d_keys, uint32_t *key_bytes) {
-  if (!c) return KMC_E_ARG;
-  return fail(c, KMC_E_ARG, "kmc_route: not built yet");
+  if (!c || !part_off || !d_keys) return KMC_E_ARG;
+  if (n_parts < 1 || n_parts > kRadix) return fail(c, KMC_E_ARG, "n_parts must be 1..%d", kRadix);
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_route after kmc_finish");
+  CK(cudaSetDevice(c->device));
+  TRY(zero_scalars(c));
+  int rc = c->wide ? route_impl<U128>(c, n_parts, part_off) : route_impl<uint64_t>(c, n_parts, part_off);
+  if (rc) return rc;
+  *d_keys = c->route_keys.p;
+  if (key_bytes) *key_bytes = c->wide ? 16 : 8;
+  return KMC_OK;
 }
 
 size_t kmc_stats_json(kmc_ctx *c, char *buf, size_t cap) {

@@ -14,17 +14,28 @@ constexpr int kRsItems = 32;                          // keys per thread per til
 constexpr int kRsTile = kRsThreads * kRsItems;        // 8192 keys per block
 constexpr int kRadix = 256;
 
+// digit functors: a radix digit of the key, or the key's owner part (multi-GPU routing)
+struct BitsDigit {
+  uint32_t shift, nbits;
+  template <typename KeyT> __device__ __forceinline__ uint32_t operator()(const KeyT &k) const { return key_bits(k, shift, nbits); }
+};
+struct OwnerDigit {
+  uint32_t n_parts;
+  template <typename KeyT> __device__ __forceinline__ uint32_t operator()(const KeyT &k) const {
+    return owner_of(key_hi(k), key_lo(k), n_parts);
+  }
+};
+
 // ---- pass 1: per-block digit histogram, laid out [digit][block] ------------------------------------
-template <typename KeyT>
-__global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const KeyT *__restrict__ in, uint64_t n, uint32_t shift,
-                                                             uint32_t nbits, uint32_t *__restrict__ block_hist,
-                                                             uint32_t n_blocks) {
+template <typename KeyT, typename DigitFn>
+__global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const KeyT *__restrict__ in, uint64_t n, DigitFn digit,
+                                                             uint32_t *__restrict__ block_hist, uint32_t n_blocks) {
   __shared__ uint32_t h[kRadix];
   h[threadIdx.x] = 0;
   __syncthreads();
   uint64_t base = (uint64_t)blockIdx.x * kRsTile;
   uint64_t end = base + kRsTile < n ? base + kRsTile : n;
-  for (uint64_t i = base + threadIdx.x; i < end; i += kRsThreads) atomicAdd(&h[key_bits(in[i], shift, nbits)], 1u);
+  for (uint64_t i = base + threadIdx.x; i < end; i += kRsThreads) atomicAdd(&h[digit(in[i])], 1u);
   __syncthreads();
   block_hist[(uint64_t)threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];
 }
@@ -86,9 +97,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
 // the rank of a key among equal digits is (keys of that digit in lower warps) + (lower lanes of the
 // same warp with that digit, from __match_any_sync).  `run[d]` carries the block's running output
 // position for digit d across rounds, so the whole pass is stable.
-template <typename KeyT>
+template <typename KeyT, typename DigitFn>
 __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const KeyT *__restrict__ in, KeyT *__restrict__ out,
-                                                                uint64_t n, uint32_t shift, uint32_t nbits,
+                                                                uint64_t n, DigitFn digit,
                                                                 const uint64_t *__restrict__ offsets, uint32_t n_blocks) {
   constexpr int W = kRsThreads / 32;
   __shared__ uint64_t run[kRadix];
@@ -105,7 +116,7 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const KeyT *__re
     bool have = i < end;
     KeyT key;
     uint32_t d = kRadix; // sentinel digit for idle threads: matches only other idle threads
-    if (have) { key = in[i]; d = key_bits(key, shift, nbits); }
+    if (have) { key = in[i]; d = digit(key); }
     uint32_t peers = __match_any_sync(0xffffffffu, d);
     uint32_t rank = __popc(peers & ((1u << lane) - 1u));
     if (have && rank == 0) cnt[warp][d] = __popc(peers);

@@ -1,0 +1,68 @@
+"""CPU, world_size 2, gloo: the host side of the multi-GPU path — split sizes from kmc_route's part
+offsets and the variable-size all-to-all — delivers every key to the rank that owns it
+(owner = kmc_owner_of, the same function the device uses)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, words, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import kmer_count_b200 as K
+    from kmer_count_b200.dist import exchange, split_sizes
+    L = K.load_library()
+    rng = np.random.default_rng(100 + rank)
+    n = 5000 + 37 * rank
+    lo = rng.integers(0, 1 << 62, n, dtype=np.uint64)
+    hi = rng.integers(0, 1 << 60, n, dtype=np.uint64) if words == 2 else np.zeros(n, np.uint64)
+    owner = np.array([L.kmc_owner_of(int(h), int(l), world) for h, l in zip(hi, lo)])
+    order = np.argsort(owner, kind="stable")           # what kmc_route does on the device
+    lo, hi, owner = lo[order], hi[order], owner[order]
+    part_off = np.searchsorted(owner, np.arange(world + 1)).astype(np.uint64)
+    keys = np.stack([lo, hi], axis=1).reshape(-1) if words == 2 else lo
+    send = torch.from_numpy(keys.view(np.int64).copy())
+    recv, sizes = exchange(torch, dist, send, split_sizes(part_off, words))
+    got = recv.numpy().view(np.uint64).reshape(-1, words)
+    ok = all(L.kmc_owner_of(int(r[1]) if words == 2 else 0, int(r[0]), world) == rank for r in got)
+    q.put((rank, ok, int(part_off[-1]), len(got), int(got[:, 0].astype(object).sum() % (1 << 61)),
+           int(lo.astype(object).sum() % (1 << 61))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("words", [1, 2])
+def test_exchange_delivers_keys_to_owners(words):
+    import kmer_count_b200 as K
+    K.build()
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, words, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res)                       # every received key is owned by the receiver
+    assert sum(r[2] for r in res) == sum(r[3] for r in res)  # nothing lost or duplicated
+    assert sum(r[4] for r in res) % (1 << 61) == sum(r[5] for r in res) % (1 << 61)
+
+
+def test_split_sizes():
+    from kmer_count_b200.dist import split_sizes
+    assert split_sizes(np.array([0, 3, 3, 10], np.uint64), 1) == [3, 0, 7]
+    assert split_sizes(np.array([0, 3, 3, 10], np.uint64), 2) == [6, 0, 14]

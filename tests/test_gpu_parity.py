@@ -228,3 +228,54 @@ def test_hypothesis_contiguous(kmc, orc):
         assert_tables_equal(kmc.count_kmers(b, o, k, canonical), orc.contiguous_def(b, o, k, canonical))
 
     prop()
+
+
+@pytest.mark.parametrize("k,world", [(21, 2), (31, 3), (63, 4)])
+def test_route_and_ingest_emulated_ranks(kmc, orc, k, world):
+    """Multi-GPU path on one GPU: each emulated rank routes its shard of the reads by owner
+    (kmc_route); each owner ingests the parts addressed to it from every rank (what the all-to-all
+    delivers) and counts them.  The union of the owners' tables is the single-GPU table, the owners'
+    key sets are disjoint, and the device owner function equals the host one."""
+    import torch
+    rng = np.random.default_rng(k)
+    n = 400_000
+    bases = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=n, p=[0.2495, 0.2495, 0.2495, 0.2495, 0.002])
+    off = np.arange(0, n + 1, 500, dtype=np.uint64)
+    want = orc.contiguous_mt(bases, off, k, True)
+    L = kmc.load_library()
+    words = 2 if k > 32 else 1
+    rec_cuts = np.linspace(0, len(off) - 1, world + 1).astype(int)
+    routers, parts = [], []
+    for r in range(world):
+        a, z = rec_cuts[r], rec_cuts[r + 1]
+        kc = kmc.KmerCounter(k=k, canonical=True)
+        kc.submit_host(bases[int(off[a]):int(off[z])], off[a:z + 1] - off[a])
+        part_off, ptr, kb = kc.route(world)
+        assert kb == 8 * words
+        from kmer_count_b200.dist import _DevArray
+        t = torch.as_tensor(_DevArray(ptr, max(1, int(part_off[-1]) * words)), device="cuda")[: int(part_off[-1]) * words]
+        routers.append(kc)
+        parts.append((part_off, t.clone()))
+    tables = []
+    for p in range(world):
+        kc = kmc.KmerCounter(k=k, canonical=True)
+        bufs = []
+        for part_off, t in parts:
+            seg = t[int(part_off[p]) * words:int(part_off[p + 1]) * words].contiguous()
+            bufs.append(seg)
+            kc.ingest_keys(seg.data_ptr(), seg.numel() // words)
+        kc.finish()
+        tab = kc.read()
+        for h, l in list(zip(tab.key_hi.tolist(), tab.key_lo.tolist()))[:200]:
+            assert L.kmc_owner_of(h, l, world) == p
+        tables.append(tab)
+        kc.close()
+    for kc in routers:
+        kc.close()
+    hi = np.concatenate([t.key_hi for t in tables])
+    lo = np.concatenate([t.key_lo for t in tables])
+    cnt = np.concatenate([t.count for t in tables])
+    order = np.lexsort((lo, hi))
+    assert sum(t.n_total for t in tables) == want.n_total
+    assert np.array_equal(hi[order], want.key_hi) and np.array_equal(lo[order], want.key_lo)
+    assert np.array_equal(cnt[order], want.count)
