@@ -16,6 +16,8 @@
 #include "kmc_common.cuh"
 #include "kmc_extract.cuh"
 #include "kmc_sort.cuh"
+#include "kmc_fast.cuh"
+#include <cmath>
 
 using namespace kmc;
 
@@ -78,6 +80,9 @@ struct kmc_ctx {
   DevBuf keys_a, keys_b, block_hist, offsets, sums, scalars, route_keys;
   DevBuf gap_l, gap_r, gap_f;
   DevBuf t_lo, t_hi, t_cnt;
+  DevBuf fast_l1, fast_l2, fast_state, fast_tables;
+  std::vector<unsigned char> fast_host; // plan tables staged for upload
+  uint32_t fast_fallbacks = 0;          // times the partitioned path overflowed and the job was recounted
 
   // results
   bool finished = false;
@@ -437,8 +442,195 @@ int finish_baseline(kmc_ctx *c) {
   return KMC_OK;
 }
 
+
+// ---- partitioned fast path (kmc_fast.cuh), 64-bit keys ------------------------------------------------------
+// *used = false: the input does not suit it (tiny, or a bucket overflowed); nothing is left behind and the
+// caller counts with the baseline path.
+int finish_fast(kmc_ctx *c, bool *used) {
+  *used = false;
+  const uint32_t kb = c->key_bits;
+  const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb);
+  const uint32_t ncoarse = 1u << cb;
+  const bool from_array = !c->ingested.empty() || c->cfg.mode == KMC_MODE_LR_GAPPED;
+  uint64_t n_array = 0;
+  if (from_array) TRY(produce_keys<uint64_t>(c, &n_array));
+  // fast_state layout: ghist[4096] u64 | ticket u32 (+pad) | d_total u64 | l1_cursor[kMaxL1] u64 | fine_cursor[nf] u32 | status[nf] u64
+  const size_t off_ticket = 4096 * 8, off_dtotal = off_ticket + 8, off_l1cur = off_dtotal + 8, off_fine = off_l1cur + kMaxL1 * 8;
+  TRY(ensure(c, c->fast_state, off_fine + 64));
+  CK(cudaMemsetAsync(c->fast_state.p, 0, off_fine, c->stream));
+  unsigned long long *ghist = (unsigned long long *)c->fast_state.p;
+  PHASE_BEGIN("fast_hist");
+  if (from_array) {
+    if (n_array) {
+      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(n_array, 256 * 16), (uint64_t)kNumSMsB200 * 8);
+      auto fast_hist_array = fast_hist_array_kernel<uint64_t>;
+      LAUNCH(fast_hist_array, grid, 256, ncoarse * 4, (const uint64_t *)c->keys_a.p, n_array, kb - cb, ncoarse, ghist);
+    }
+  } else {
+    for (size_t i = 0; i < c->n_segs; i++) {
+      Segment &s = c->segs[i];
+      if (!s.n_bases) continue;
+      ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
+      uint64_t tiles = num_warp_tiles(s.n_bases, 31);
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + 7) / 8, (uint64_t)kNumSMsB200 * 8);
+      auto fast_hist = fast_hist_kernel<uint64_t, true>;
+      LAUNCH(fast_hist, grid, 256, ncoarse * 4, P, tiles, kb - cb, ncoarse, ghist);
+    }
+  }
+  PHASE_END();
+  std::vector<uint64_t> hist(ncoarse);
+  CK(cudaMemcpyAsync(hist.data(), ghist, ncoarse * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  uint64_t N = 0;
+  for (uint64_t v : hist) N += v;
+  if (N < (1u << 18)) return KMC_OK; // small job: the generic path is as fast and simpler
+
+  // ---- plan
+  std::vector<uint32_t> e(ncoarse), cap(ncoarse);
+  uint64_t n_fine = 0, l2_keys = 0;
+  for (uint32_t ci = 0; ci < ncoarse; ci++) {
+    uint64_t nc = hist[ci];
+    uint32_t ee = 0;
+    while (((nc + ((1ull << ee) - 1)) >> ee) > (uint64_t)kFineTarget) ee++;
+    if (ee > kb - cb) return KMC_OK; // cannot split far enough: too many keys share a prefix (duplicates)
+    double avg = (double)nc / (double)(1ull << ee);
+    uint32_t cp = (uint32_t)(avg * 1.15 + 6.0 * std::sqrt(avg) + 32.0);
+    cp = (cp + 15) & ~15u;
+    if (cp > (uint32_t)kFineCap) cp = kFineCap;
+    e[ci] = ee; cap[ci] = cp;
+    n_fine += 1ull << ee;
+    l2_keys += (uint64_t)cp << ee;
+  }
+  if (n_fine > (1ull << 30)) return KMC_OK;
+  uint32_t b1_lo = cb > 6 ? cb - 6 : 0, b1_hi = std::min<uint32_t>(cb, 10);
+  uint32_t b1 = (uint32_t)std::lround(std::log2(std::sqrt((double)n_fine)));
+  b1 = std::max(b1_lo, std::min(b1, b1_hi));
+  for (;; b1++) {
+    if (b1 > b1_hi) return KMC_OK;
+    uint64_t mx = 0;
+    for (uint32_t b = 0; b < (1u << b1); b++) {
+      uint64_t nf = 0;
+      for (uint32_t ci = b << (cb - b1); ci < ((b + 1) << (cb - b1)); ci++) nf += 1ull << e[ci];
+      mx = std::max(mx, nf);
+    }
+    if (mx <= (uint64_t)kMaxFinePerL1) break;
+  }
+  const uint32_t n_l1 = 1u << b1;
+  // tables: ctab | fdesc | l1_start | l1_tile0 | l1_fine0
+  const size_t o_ctab = 0, o_fdesc = o_ctab + (size_t)ncoarse * sizeof(CoarseEntry), o_l1s = o_fdesc + n_fine * sizeof(FineDesc),
+               o_t0 = o_l1s + (size_t)(n_l1 + 1) * 8, o_f0 = o_t0 + (((size_t)(n_l1 + 1) * 4 + 15) & ~size_t(15)),
+               tab_bytes = o_f0 + (((size_t)(n_l1 + 1) * 4 + 15) & ~size_t(15));
+  c->fast_host.assign(tab_bytes, 0);
+  CoarseEntry *ctab = (CoarseEntry *)(c->fast_host.data() + o_ctab);
+  FineDesc *fdesc = (FineDesc *)(c->fast_host.data() + o_fdesc);
+  uint64_t *l1s = (uint64_t *)(c->fast_host.data() + o_l1s);
+  uint32_t *t0 = (uint32_t *)(c->fast_host.data() + o_t0), *f0 = (uint32_t *)(c->fast_host.data() + o_f0);
+  uint64_t fs = 0;
+  uint32_t fb = 0;
+  for (uint32_t ci = 0; ci < ncoarse; ci++) {
+    ctab[ci].fstart = fs; ctab[ci].fbase = fb; ctab[ci].cap = (uint16_t)cap[ci]; ctab[ci].e = (uint8_t)e[ci];
+    for (uint32_t sub = 0; sub < (1u << e[ci]); sub++) {
+      fdesc[fb].start = fs; fdesc[fb].cap = (uint16_t)cap[ci]; fdesc[fb].rem = (uint8_t)(kb - cb - e[ci]);
+      fs += cap[ci]; fb++;
+    }
+  }
+  uint64_t l1_keys = 0, tiles2 = 0;
+  for (uint32_t b = 0; b < n_l1; b++) {
+    uint64_t nb = 0;
+    for (uint32_t ci = b << (cb - b1); ci < ((b + 1) << (cb - b1)); ci++) nb += hist[ci];
+    l1s[b] = l1_keys; t0[b] = (uint32_t)tiles2; f0[b] = ctab[b << (cb - b1)].fbase;
+    l1_keys += (nb + 15) & ~15ull;
+    tiles2 += (nb + kPart2Tile - 1) / kPart2Tile;
+  }
+  l1s[n_l1] = l1_keys; t0[n_l1] = (uint32_t)tiles2; f0[n_l1] = (uint32_t)n_fine;
+  if (tiles2 > 0x7FFFFFFFull) return KMC_OK;
+
+  // ---- buffers
+  TRY(ensure(c, c->fast_tables, tab_bytes));
+  TRY(ensure(c, c->fast_state, off_fine + n_fine * 12 + 64));  // (re)allocation keeps nothing: redo the memset below
+  TRY(ensure(c, c->fast_l1, (std::max<uint64_t>(l1_keys, N) + 16) * 8));
+  TRY(ensure(c, c->fast_l2, (l2_keys + 16) * 8));
+  TRY(ensure(c, c->t_cnt, N * 4));
+  const size_t off_status = (off_fine + n_fine * 4 + 15) & ~size_t(15);
+  TRY(ensure(c, c->fast_state, off_status + n_fine * 8 + 64));
+  CK(cudaMemsetAsync(c->fast_state.p, 0, off_status + n_fine * 8, c->stream));
+  CK(cudaMemcpyAsync(c->fast_tables.p, c->fast_host.data(), tab_bytes, cudaMemcpyHostToDevice, c->stream));
+  unsigned char *st = (unsigned char *)c->fast_state.p, *tb = (unsigned char *)c->fast_tables.p;
+  FastPlan pl;
+  pl.kb = kb; pl.cb = cb; pl.b1 = b1; pl.n_l1 = n_l1; pl.n_fine = (uint32_t)n_fine;
+  pl.ctab = (const CoarseEntry *)(tb + o_ctab); pl.fdesc = (const FineDesc *)(tb + o_fdesc);
+  pl.l1_start = (const uint64_t *)(tb + o_l1s); pl.l1_tile0 = (const uint32_t *)(tb + o_t0); pl.l1_fine0 = (const uint32_t *)(tb + o_f0);
+  pl.l1_cursor = (unsigned long long *)(st + off_l1cur); pl.fine_cursor = (uint32_t *)(st + off_fine);
+  unsigned int *ticket = (unsigned int *)(st + off_ticket);
+  unsigned long long *d_total = (unsigned long long *)(st + off_dtotal);
+  unsigned long long *status = (unsigned long long *)(st + off_status);
+
+  // ---- level 1
+  PHASE_BEGIN("fast_part1");
+  if (from_array) {
+    size_t smem = PartSmem::bytes(kPart2Tile, n_l1);
+    CK(cudaFuncSetAttribute(fast_part1_array_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(n_array, kPart2Tile), (uint64_t)kNumSMsB200);
+    auto fast_part1_array = fast_part1_array_kernel;
+    LAUNCH(fast_part1_array, grid, kFastThreads, smem, (const uint64_t *)c->keys_a.p, n_array, pl, (uint64_t *)c->fast_l1.p);
+  } else {
+    size_t smem = PartSmem::bytes(kPart1Stage, n_l1);
+    auto fast_part1 = fast_part1_kernel<true>;
+    CK(cudaFuncSetAttribute(fast_part1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (size_t i = 0; i < c->n_segs; i++) {
+      Segment &s = c->segs[i];
+      if (!s.n_bases) continue;
+      ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
+      uint64_t tiles = num_warp_tiles(s.n_bases, 31);
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
+      LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, (uint64_t *)c->fast_l1.p);
+    }
+  }
+  PHASE_END();
+  // ---- level 2
+  PHASE_BEGIN("fast_part2");
+  {
+    size_t smem = PartSmem::bytes(kPart2Tile, kMaxFinePerL1);
+    CK(cudaFuncSetAttribute(fast_part2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto fast_part2 = fast_part2_kernel;
+    LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const uint64_t *)c->fast_l1.p, (uint64_t *)c->fast_l2.p, d_err(c));
+  }
+  PHASE_END();
+  // ---- finish: the level-1 array is dead after part2 and becomes the table's key column
+  PHASE_BEGIN("fast_finish");
+  {
+    size_t smem = sizeof(FinishSmem);
+    CK(cudaFuncSetAttribute(fast_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2);
+    auto fast_finish = fast_finish_kernel;
+    LAUNCH(fast_finish, grid, kFastThreads, smem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint32_t *)c->t_cnt.p,
+           status, ticket, d_err(c), d_total);
+  }
+  PHASE_END();
+  uint64_t d = 0;
+  uint32_t err = 0;
+  CK(cudaMemcpyAsync(&d, d_total, 8, cudaMemcpyDeviceToHost, c->stream));
+  TRY(read_scalars(c, nullptr, &err));
+  if (err & kFlagSpin) return fail(c, KMC_E_CUDA, "fast_finish: look-back did not make progress");
+  if (err & kFlagOverflow) {
+    c->fast_fallbacks++;
+    TRY(zero_scalars(c));
+    return KMC_OK; // recount with the data-independent path
+  }
+  std::swap(c->t_lo, c->fast_l1);
+  c->n_total = N; c->n_distinct = d;
+  c->strategy_used = KMC_STRATEGY_SORT;
+  *used = true;
+  return KMC_OK;
+}
+
 template <typename KeyT>
 int finish_impl(kmc_ctx *c) {
+  if (sizeof(KeyT) == 8 && c->cfg.strategy != KMC_STRATEGY_SORT_BASELINE) {
+    bool used = false;
+    TRY(finish_fast(c, &used));
+    if (used) return KMC_OK;
+  }
   return finish_baseline<KeyT>(c);
 }
 
@@ -447,9 +639,9 @@ void build_stats(kmc_ctx *c) {
   char buf[256];
   snprintf(buf, sizeof buf,
            "\"n_bases\": %llu, \"n_records\": %llu, \"n_total\": %llu, \"n_distinct\": %llu, \"key_bits\": %u, "
-           "\"strategy_used\": %u, \"kernel_launches\": %llu, \"kernel_launches_total\": %llu, \"h2d_bytes\": %llu, \"phases_ms\": {",
+           "\"strategy_used\": %u, \"fast_fallbacks\": %u, \"kernel_launches\": %llu, \"kernel_launches_total\": %llu, \"h2d_bytes\": %llu, \"phases_ms\": {",
            (unsigned long long)c->total_bases, (unsigned long long)c->total_recs, (unsigned long long)c->n_total,
-           (unsigned long long)c->n_distinct, c->key_bits, c->strategy_used, (unsigned long long)c->launches,
+           (unsigned long long)c->n_distinct, c->key_bits, c->strategy_used, c->fast_fallbacks, (unsigned long long)c->launches,
            (unsigned long long)c->launches_total, (unsigned long long)c->h2d_bytes);
   s += buf;
   // sum phases of the same name
@@ -554,7 +746,7 @@ void kmc_destroy(kmc_ctx *c) {
   }
   for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); }
   for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
-                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt})
+                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables})
     release(*b);
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);

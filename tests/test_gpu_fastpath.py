@@ -1,0 +1,116 @@
+"""GPU tests aimed at the partitioned fast path (kmc_fast.cuh): its plan, both front ends, the
+in-bucket sort including big sub-bins, and the overflow → recount route.  All vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from tests.util import assert_tables_equal
+
+pytestmark = pytest.mark.gpu
+ACGT = np.frombuffer(b"ACGT", np.uint8)
+
+
+@pytest.fixture(scope="module")
+def kmc():
+    import kmer_count_b200 as k
+    k.build()
+    k.load_library()
+    return k
+
+
+def _count(kmc, bases, off, k, canonical=True, strategy=0, **kw):
+    with kmc.KmerCounter(k=k, canonical=canonical, strategy=strategy, **kw) as kc:
+        kc.submit_host(bases, off)
+        kc.finish()
+        return kc.read(), kc.stats(), kc.digest()
+
+
+@pytest.mark.parametrize("k,canonical,n", [(21, True, 20_000_000), (31, True, 8_000_000), (32, False, 5_000_000),
+                                           (11, True, 6_000_000), (5, True, 3_000_000), (16, False, 4_000_000)])
+def test_fast_path_matches_oracle(kmc, orc, k, canonical, n):
+    rng = np.random.default_rng(k * 7 + n % 13)
+    bases = ACGT[rng.integers(0, 4, n)]
+    for s in rng.integers(0, n - 100, n // 20000):
+        bases[s:s + int(rng.integers(1, 60))] = ord("N")
+    off = np.arange(0, n + 1, 400, dtype=np.uint64)
+    want = orc.contiguous_mt(bases, off, k, canonical)
+    got, st, dig = _count(kmc, bases, off, k, canonical)
+    assert_tables_equal(got, want)
+    assert dig == want.digest()
+    if k >= 11:
+        assert st["strategy_used"] == 2 and st["fast_fallbacks"] == 0, st
+    base, _, _ = _count(kmc, bases, off, k, canonical, strategy=3)
+    assert_tables_equal(base, want)
+
+
+def test_fast_path_big_sub_bins(kmc, orc):
+    """5000 distinct k-mers that share their first 13 bases land in one sub-bin of one bucket: the
+    cooperative rank sort of fast_finish; plus a block of 3000 identical k-mers (all-equal shortcut)."""
+    rng = np.random.default_rng(5)
+    k = 21
+    prefix = ACGT[rng.integers(0, 4, 13)]
+    special = [np.concatenate([prefix, ACGT[rng.integers(0, 4, 8)]]) for _ in range(5000)]
+    same = [ACGT[rng.integers(0, 4, 21)]] * 3000
+    filler = ACGT[rng.integers(0, 4, 600_000)]
+    recs = special + same
+    bases = np.concatenate(recs + [filler])
+    off = np.concatenate([np.arange(0, (len(recs) + 1) * 21, 21), [len(bases)]]).astype(np.uint64)
+    want = orc.contiguous_mt(bases, off, k, False)
+    got, st, _ = _count(kmc, bases, off, k, False)
+    assert_tables_equal(got, want)
+    assert st["strategy_used"] == 2, st
+
+
+def test_fast_path_overflow_recounts(kmc, orc):
+    """One k-mer repeated 400k times overflows its bucket: the job is recounted exactly by the generic path."""
+    rng = np.random.default_rng(6)
+    k = 21
+    one = ACGT[rng.integers(0, 4, 21)]
+    hot = np.tile(one, 400_000)
+    filler = ACGT[rng.integers(0, 4, 1_000_000)]
+    bases = np.concatenate([hot, filler])
+    off = np.concatenate([np.arange(0, 400_001 * 21, 21), [len(bases)]]).astype(np.uint64)
+    want = orc.contiguous_mt(bases, off, k, True)
+    got, st, _ = _count(kmc, bases, off, k, True)
+    assert_tables_equal(got, want)
+    assert int(got.count.max()) >= 400_000
+    assert st["strategy_used"] in (1, 3), st
+
+
+def test_fast_path_low_cardinality_pool(kmc, orc):
+    rng = np.random.default_rng(3)
+    pool = [ACGT[rng.integers(0, 4, 80)] for _ in range(10)]
+    recs = [np.concatenate([pool[i] for i in rng.integers(0, 10, 5)]) for _ in range(20000)]
+    bases = np.concatenate(recs)
+    off = (np.arange(len(recs) + 1) * 400).astype(np.uint64)
+    for k in (21, 31):
+        want = orc.contiguous_mt(bases, off, k, True)
+        got, st, _ = _count(kmc, bases, off, k, True)
+        assert_tables_equal(got, want)
+
+
+def test_fast_path_key_array_front_end(kmc, orc):
+    """Ingested keys (multi-GPU path) and 64-bit lr-gapped keys enter through fast_part1_array."""
+    import torch
+    from kmer_count_b200.dist import _DevArray
+    rng = np.random.default_rng(8)
+    n = 3_000_000
+    bases = ACGT[rng.integers(0, 4, n)]
+    off = np.arange(0, n + 1, 500, dtype=np.uint64)
+    want = orc.contiguous_mt(bases, off, 31, True)
+    with kmc.KmerCounter(k=31) as router, kmc.KmerCounter(k=31) as owner:
+        router.submit_host(bases, off)
+        part_off, ptr, kb = router.route(1)
+        t = torch.as_tensor(_DevArray(ptr, int(part_off[-1])), device="cuda")
+        half = int(part_off[-1]) // 2
+        a, b = t[:half].clone(), t[half:].clone()
+        owner.ingest_keys(a.data_ptr(), a.numel())
+        owner.ingest_keys(b.data_ptr(), b.numel())
+        owner.finish()
+        assert_tables_equal(owner.read(), want)
+        assert owner.stats()["strategy_used"] == 2
+    recs_b = ACGT[rng.integers(0, 4, 40_000)]
+    roff = np.arange(0, 40_001, 200, dtype=np.uint64)
+    want = orc.gapped_mt(recs_b, roff, 16, 16, 40, 60)
+    got = kmc.count_lr_gapped(recs_b, roff, 16, 16, 40, 60)
+    assert want.n_total > (1 << 18)
+    assert_tables_equal(got, want)
