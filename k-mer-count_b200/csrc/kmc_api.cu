@@ -444,8 +444,8 @@ int finish_baseline(kmc_ctx *c) {
 
 
 // ---- partitioned fast path (kmc_fast.cuh), 64-bit keys ------------------------------------------------------
-// *used = false: the input does not suit it (tiny, or a bucket overflowed); nothing is left behind and the
-// caller counts with the baseline path.
+// *used = false: the input does not suit it (tiny, duplicate-heavy, or a bucket overflowed); nothing is left
+// behind and the caller counts with the baseline path.
 int finish_fast(kmc_ctx *c, bool *used) {
   *used = false;
   const uint32_t kb = c->key_bits;
@@ -459,12 +459,15 @@ int finish_fast(kmc_ctx *c, bool *used) {
   TRY(ensure(c, c->fast_state, off_fine + 64));
   CK(cudaMemsetAsync(c->fast_state.p, 0, off_fine, c->stream));
   unsigned long long *ghist = (unsigned long long *)c->fast_state.p;
+  // sample so that ~64M keys are looked at (all of them for small inputs)
+  const uint64_t n_in = from_array ? n_array : c->total_bases;
+  const uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
   PHASE_BEGIN("fast_hist");
   if (from_array) {
     if (n_array) {
-      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(n_array, 256 * 16), (uint64_t)kNumSMsB200 * 8);
+      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(n_array, 1024 * step), (uint64_t)kNumSMsB200 * 8);
       auto fast_hist_array = fast_hist_array_kernel<uint64_t>;
-      LAUNCH(fast_hist_array, grid, 256, ncoarse * 4, (const uint64_t *)c->keys_a.p, n_array, kb - cb, ncoarse, ghist);
+      LAUNCH(fast_hist_array, grid, 256, ncoarse * 4, (const uint64_t *)c->keys_a.p, n_array, step, kb - cb, ncoarse, ghist);
     }
   } else {
     for (size_t i = 0; i < c->n_segs; i++) {
@@ -472,94 +475,108 @@ int finish_fast(kmc_ctx *c, bool *used) {
       if (!s.n_bases) continue;
       ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
       uint64_t tiles = num_warp_tiles(s.n_bases, 31);
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + 7) / 8, (uint64_t)kNumSMsB200 * 8);
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)kNumSMsB200 * 8);
       auto fast_hist = fast_hist_kernel<uint64_t, true>;
-      LAUNCH(fast_hist, grid, 256, ncoarse * 4, P, tiles, kb - cb, ncoarse, ghist);
+      LAUNCH(fast_hist, grid, 256, ncoarse * 4, P, tiles, step, kb - cb, ncoarse, ghist);
     }
   }
   PHASE_END();
   std::vector<uint64_t> hist(ncoarse);
   CK(cudaMemcpyAsync(hist.data(), ghist, ncoarse * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  uint64_t N = 0;
-  for (uint64_t v : hist) N += v;
-  if (N < (1u << 18)) return KMC_OK; // small job: the generic path is as fast and simpler
+  // the histogram is a 1-in-step sample: scale it to an upper estimate (+5 sigma of the sampling noise)
+  uint64_t n_est = 0;
+  for (uint64_t &v : hist) {
+    double est = (double)v * step;
+    if (step > 1) est += 5.0 * std::sqrt(est * step) + step;
+    v = (uint64_t)est;
+    n_est += v;
+  }
+  if (n_est < (1u << 18)) return KMC_OK; // small job: the generic path is as fast and simpler
 
   // ---- plan
-  std::vector<uint32_t> e(ncoarse), cap(ncoarse);
-  uint64_t n_fine = 0, l2_keys = 0;
+  std::vector<uint32_t> e(ncoarse);
   for (uint32_t ci = 0; ci < ncoarse; ci++) {
-    uint64_t nc = hist[ci];
     uint32_t ee = 0;
-    while (((nc + ((1ull << ee) - 1)) >> ee) > (uint64_t)kFineTarget) ee++;
+    while (((hist[ci] + ((1ull << ee) - 1)) >> ee) > (uint64_t)kFineTarget) ee++;
     if (ee > kb - cb) return KMC_OK; // cannot split far enough: too many keys share a prefix (duplicates)
-    double avg = (double)nc / (double)(1ull << ee);
-    uint32_t cp = (uint32_t)(avg * 1.15 + 6.0 * std::sqrt(avg) + 32.0);
-    cp = (cp + 15) & ~15u;
-    if (cp > (uint32_t)kFineCap) cp = kFineCap;
-    e[ci] = ee; cap[ci] = cp;
-    n_fine += 1ull << ee;
-    l2_keys += (uint64_t)cp << ee;
+    e[ci] = ee;
   }
-  if (n_fine > (1ull << 30)) return KMC_OK;
   uint32_t b1_lo = cb > 6 ? cb - 6 : 0, b1_hi = std::min<uint32_t>(cb, 10);
-  uint32_t b1 = (uint32_t)std::lround(std::log2(std::sqrt((double)n_fine)));
+  uint64_t nf_guess = 0;
+  for (uint32_t ci = 0; ci < ncoarse; ci++) nf_guess += 1ull << e[ci];
+  uint32_t b1 = (uint32_t)std::lround(std::log2(std::sqrt((double)nf_guess)));
   b1 = std::max(b1_lo, std::min(b1, b1_hi));
+  std::vector<uint8_t> l1e;
   for (;; b1++) {
     if (b1 > b1_hi) return KMC_OK;
-    uint64_t mx = 0;
+    l1e.assign(1u << b1, 0);
+    uint32_t mx = 0;
     for (uint32_t b = 0; b < (1u << b1); b++) {
-      uint64_t nf = 0;
-      for (uint32_t ci = b << (cb - b1); ci < ((b + 1) << (cb - b1)); ci++) nf += 1ull << e[ci];
-      mx = std::max(mx, nf);
+      uint32_t em = 0;
+      for (uint32_t ci = b << (cb - b1); ci < ((b + 1) << (cb - b1)); ci++) em = std::max(em, e[ci]);
+      l1e[b] = (uint8_t)(cb - b1 + em);
+      mx = std::max<uint32_t>(mx, l1e[b]);
     }
-    if (mx <= (uint64_t)kMaxFinePerL1) break;
+    if ((1ull << mx) <= (uint64_t)kMaxFinePerL1) break;
   }
   const uint32_t n_l1 = 1u << b1;
-  // tables: ctab | fdesc | l1_start | l1_tile0 | l1_fine0
-  const size_t o_ctab = 0, o_fdesc = o_ctab + (size_t)ncoarse * sizeof(CoarseEntry), o_l1s = o_fdesc + n_fine * sizeof(FineDesc),
-               o_t0 = o_l1s + (size_t)(n_l1 + 1) * 8, o_f0 = o_t0 + (((size_t)(n_l1 + 1) * 4 + 15) & ~size_t(15)),
-               tab_bytes = o_f0 + (((size_t)(n_l1 + 1) * 4 + 15) & ~size_t(15));
+  uint64_t n_fine = 0;
+  for (uint32_t b = 0; b < n_l1; b++) n_fine += 1ull << l1e[b];
+  if (n_fine > (1ull << 28)) return KMC_OK;
+  // tables: fdesc | l1_start | l1_cap | l1_tile0 | l1_fine0 | l1_e
+  auto al16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+  const size_t o_fdesc = 0, o_l1s = o_fdesc + n_fine * sizeof(FineDesc), o_cap = o_l1s + al16((size_t)(n_l1 + 1) * 8),
+               o_t0 = o_cap + al16((size_t)n_l1 * 8), o_f0 = o_t0 + al16((size_t)(n_l1 + 1) * 4),
+               o_e = o_f0 + al16((size_t)(n_l1 + 1) * 4), tab_bytes = o_e + al16(n_l1);
   c->fast_host.assign(tab_bytes, 0);
-  CoarseEntry *ctab = (CoarseEntry *)(c->fast_host.data() + o_ctab);
   FineDesc *fdesc = (FineDesc *)(c->fast_host.data() + o_fdesc);
-  uint64_t *l1s = (uint64_t *)(c->fast_host.data() + o_l1s);
+  uint64_t *l1s = (uint64_t *)(c->fast_host.data() + o_l1s), *l1cap = (uint64_t *)(c->fast_host.data() + o_cap);
   uint32_t *t0 = (uint32_t *)(c->fast_host.data() + o_t0), *f0 = (uint32_t *)(c->fast_host.data() + o_f0);
-  uint64_t fs = 0;
+  uint8_t *l1ep = c->fast_host.data() + o_e;
+  uint64_t l1_keys = 0, l2_keys = 0, tiles2 = 0;
   uint32_t fb = 0;
-  for (uint32_t ci = 0; ci < ncoarse; ci++) {
-    ctab[ci].fstart = fs; ctab[ci].fbase = fb; ctab[ci].cap = (uint16_t)cap[ci]; ctab[ci].e = (uint8_t)e[ci];
-    for (uint32_t sub = 0; sub < (1u << e[ci]); sub++) {
-      fdesc[fb].start = fs; fdesc[fb].cap = (uint16_t)cap[ci]; fdesc[fb].rem = (uint8_t)(kb - cb - e[ci]);
-      fs += cap[ci]; fb++;
-    }
-  }
-  uint64_t l1_keys = 0, tiles2 = 0;
   for (uint32_t b = 0; b < n_l1; b++) {
     uint64_t nb = 0;
-    for (uint32_t ci = b << (cb - b1); ci < ((b + 1) << (cb - b1)); ci++) nb += hist[ci];
-    l1s[b] = l1_keys; t0[b] = (uint32_t)tiles2; f0[b] = ctab[b << (cb - b1)].fbase;
-    l1_keys += (nb + 15) & ~15ull;
-    tiles2 += (nb + kPart2Tile - 1) / kPart2Tile;
+    const uint32_t sub_bits = l1e[b] - (cb - b1); // fine buckets per coarse bin of this level-1 bucket = 2^sub_bits
+    f0[b] = fb;
+    for (uint32_t ci = b << (cb - b1); ci < ((b + 1) << (cb - b1)); ci++) {
+      nb += hist[ci];
+      double avg = (double)hist[ci] / (double)(1ull << sub_bits);
+      uint32_t cp = (uint32_t)(avg * 1.10 + 6.0 * std::sqrt(avg) + 64.0);
+      cp = std::min<uint32_t>((cp + 15) & ~15u, kFineCap);
+      for (uint32_t sub = 0; sub < (1u << sub_bits); sub++) {
+        fdesc[fb].start = l2_keys; fdesc[fb].cap = (uint16_t)cp; fdesc[fb].rem = (uint8_t)(kb - b1 - l1e[b]);
+        l2_keys += cp; fb++;
+      }
+    }
+    uint64_t cap1 = ((uint64_t)((double)nb * 1.03) + 8192 + 15) & ~15ull;
+    l1s[b] = l1_keys; l1cap[b] = cap1; t0[b] = (uint32_t)tiles2; l1ep[b] = l1e[b];
+    l1_keys += cap1;
+    tiles2 += (cap1 + kPart2Tile - 1) / kPart2Tile;
   }
-  l1s[n_l1] = l1_keys; t0[n_l1] = (uint32_t)tiles2; f0[n_l1] = (uint32_t)n_fine;
+  l1s[n_l1] = l1_keys; t0[n_l1] = (uint32_t)tiles2; f0[n_l1] = fb;
   if (tiles2 > 0x7FFFFFFFull) return KMC_OK;
 
-  // ---- buffers
+  // ---- buffers (each array ends with a trash area of one tile + slack for runs that spill over a bucket end)
+  const uint64_t slack = 2 * kPart2Tile;
   TRY(ensure(c, c->fast_tables, tab_bytes));
-  TRY(ensure(c, c->fast_state, off_fine + n_fine * 12 + 64));  // (re)allocation keeps nothing: redo the memset below
-  TRY(ensure(c, c->fast_l1, (std::max<uint64_t>(l1_keys, N) + 16) * 8));
-  TRY(ensure(c, c->fast_l2, (l2_keys + 16) * 8));
-  TRY(ensure(c, c->t_cnt, N * 4));
+  TRY(ensure(c, c->fast_l1, (l1_keys + slack) * 8));
+  TRY(ensure(c, c->fast_l2, (l2_keys + 2 * slack) * 8));
+  TRY(ensure(c, c->t_cnt, l1_keys * 4));
   const size_t off_status = (off_fine + n_fine * 4 + 15) & ~size_t(15);
-  TRY(ensure(c, c->fast_state, off_status + n_fine * 8 + 64));
+  if (off_status + n_fine * 8 + 64 > c->fast_state.cap) {
+    TRY(ensure(c, c->fast_state, off_status + n_fine * 8 + 64));
+  }
   CK(cudaMemsetAsync(c->fast_state.p, 0, off_status + n_fine * 8, c->stream));
   CK(cudaMemcpyAsync(c->fast_tables.p, c->fast_host.data(), tab_bytes, cudaMemcpyHostToDevice, c->stream));
   unsigned char *st = (unsigned char *)c->fast_state.p, *tb = (unsigned char *)c->fast_tables.p;
   FastPlan pl;
-  pl.kb = kb; pl.cb = cb; pl.b1 = b1; pl.n_l1 = n_l1; pl.n_fine = (uint32_t)n_fine;
-  pl.ctab = (const CoarseEntry *)(tb + o_ctab); pl.fdesc = (const FineDesc *)(tb + o_fdesc);
-  pl.l1_start = (const uint64_t *)(tb + o_l1s); pl.l1_tile0 = (const uint32_t *)(tb + o_t0); pl.l1_fine0 = (const uint32_t *)(tb + o_f0);
+  pl.kb = kb; pl.b1 = b1; pl.n_l1 = n_l1; pl.n_fine = (uint32_t)n_fine;
+  pl.l1_trash = l1_keys; pl.l2_trash = l2_keys + slack;
+  pl.fdesc = (const FineDesc *)(tb + o_fdesc);
+  pl.l1_start = (const uint64_t *)(tb + o_l1s); pl.l1_cap = (const uint64_t *)(tb + o_cap);
+  pl.l1_tile0 = (const uint32_t *)(tb + o_t0); pl.l1_fine0 = (const uint32_t *)(tb + o_f0); pl.l1_e = (const uint8_t *)(tb + o_e);
   pl.l1_cursor = (unsigned long long *)(st + off_l1cur); pl.fine_cursor = (uint32_t *)(st + off_fine);
   unsigned int *ticket = (unsigned int *)(st + off_ticket);
   unsigned long long *d_total = (unsigned long long *)(st + off_dtotal);
@@ -572,7 +589,7 @@ int finish_fast(kmc_ctx *c, bool *used) {
     CK(cudaFuncSetAttribute(fast_part1_array_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(n_array, kPart2Tile), (uint64_t)kNumSMsB200);
     auto fast_part1_array = fast_part1_array_kernel;
-    LAUNCH(fast_part1_array, grid, kFastThreads, smem, (const uint64_t *)c->keys_a.p, n_array, pl, (uint64_t *)c->fast_l1.p);
+    LAUNCH(fast_part1_array, grid, kFastThreads, smem, (const uint64_t *)c->keys_a.p, n_array, pl, (uint64_t *)c->fast_l1.p, d_err(c));
   } else {
     size_t smem = PartSmem::bytes(kPart1Stage, n_l1);
     auto fast_part1 = fast_part1_kernel<true>;
@@ -583,7 +600,7 @@ int finish_fast(kmc_ctx *c, bool *used) {
       ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
       uint64_t tiles = num_warp_tiles(s.n_bases, 31);
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
-      LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, (uint64_t *)c->fast_l1.p);
+      LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, (uint64_t *)c->fast_l1.p, d_err(c));
     }
   }
   PHASE_END();
@@ -609,7 +626,9 @@ int finish_fast(kmc_ctx *c, bool *used) {
   PHASE_END();
   uint64_t d = 0;
   uint32_t err = 0;
+  std::vector<unsigned long long> cur(n_l1);
   CK(cudaMemcpyAsync(&d, d_total, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(cur.data(), pl.l1_cursor, (size_t)n_l1 * 8, cudaMemcpyDeviceToHost, c->stream));
   TRY(read_scalars(c, nullptr, &err));
   if (err & kFlagSpin) return fail(c, KMC_E_CUDA, "fast_finish: look-back did not make progress");
   if (err & kFlagOverflow) {
@@ -617,6 +636,8 @@ int finish_fast(kmc_ctx *c, bool *used) {
     TRY(zero_scalars(c));
     return KMC_OK; // recount with the data-independent path
   }
+  uint64_t N = 0;
+  for (unsigned long long v : cur) N += v;
   std::swap(c->t_lo, c->fast_l1);
   c->n_total = N; c->n_distinct = d;
   c->strategy_used = KMC_STRATEGY_SORT;
