@@ -536,6 +536,8 @@ int finish_fast(kmc_ctx *c, bool *used) {
   uint8_t *l1ep = c->fast_host.data() + o_e;
   uint64_t l1_keys = 0, l2_keys = 0, tiles2 = 0;
   uint32_t fb = 0;
+  bool key32 = true; // every bucket leaves <= 32 key bits: level 2 stores 32-bit suffixes
+  for (uint32_t b = 0; b < n_l1; b++) if (kb - b1 - l1e[b] > 32) key32 = false;
   for (uint32_t b = 0; b < n_l1; b++) {
     uint64_t nb = 0;
     const uint32_t sub_bits = l1e[b] - (cb - b1); // fine buckets per coarse bin of this level-1 bucket = 2^sub_bits
@@ -546,7 +548,11 @@ int finish_fast(kmc_ctx *c, bool *used) {
       uint32_t cp = (uint32_t)(avg * 1.10 + 6.0 * std::sqrt(avg) + 64.0);
       cp = std::min<uint32_t>((cp + 15) & ~15u, kFineCap);
       for (uint32_t sub = 0; sub < (1u << sub_bits); sub++) {
-        fdesc[fb].start = l2_keys; fdesc[fb].cap = (uint16_t)cp; fdesc[fb].rem = (uint8_t)(kb - b1 - l1e[b]);
+        const uint32_t rem = kb - b1 - l1e[b];
+        fdesc[fb].start = l2_keys; fdesc[fb].cap = (uint16_t)cp; fdesc[fb].rem = (uint8_t)rem;
+        // bucket index within the level-1 bucket = the l1e[b] bits right below the b1 prefix
+        const uint64_t within = (uint64_t)(fb - f0[b]);
+        fdesc[fb].prefix = rem >= 64 ? 0 : ((((uint64_t)b << l1e[b]) | within) << rem);
         l2_keys += cp; fb++;
       }
     }
@@ -608,20 +614,49 @@ int finish_fast(kmc_ctx *c, bool *used) {
   PHASE_BEGIN("fast_part2");
   {
     size_t smem = PartSmem::bytes(kPart2Tile, kMaxFinePerL1);
-    CK(cudaFuncSetAttribute(fast_part2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    auto fast_part2 = fast_part2_kernel;
-    LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const uint64_t *)c->fast_l1.p, (uint64_t *)c->fast_l2.p, d_err(c));
+    if (key32) {
+      auto fast_part2 = fast_part2_kernel<uint32_t>;
+      CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const uint64_t *)c->fast_l1.p, (uint32_t *)c->fast_l2.p, d_err(c));
+    } else {
+      auto fast_part2 = fast_part2_kernel<uint64_t>;
+      CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const uint64_t *)c->fast_l1.p, (uint64_t *)c->fast_l2.p, d_err(c));
+    }
   }
   PHASE_END();
   // ---- finish: the level-1 array is dead after part2 and becomes the table's key column
   PHASE_BEGIN("fast_finish");
   {
-    size_t smem = sizeof(FinishSmem);
-    CK(cudaFuncSetAttribute(fast_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2);
-    auto fast_finish = fast_finish_kernel;
-    LAUNCH(fast_finish, grid, kFastThreads, smem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint32_t *)c->t_cnt.p,
-           status, ticket, d_err(c), d_total);
+    unsigned long long *prof = nullptr;
+    static const bool want_prof = getenv("KMC_FINISH_PROF") && getenv("KMC_FINISH_PROF")[0] == '1';
+    if (want_prof) { prof = (unsigned long long *)c->fast_state.p; CK(cudaMemsetAsync(prof, 0, 16 * 8, c->stream)); } // the histogram is dead by now
+    uint32_t grid;
+    if (key32) {
+      size_t smem = sizeof(FinishSmem<uint32_t>);
+      auto fast_finish = fast_finish_kernel<uint32_t>;
+      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 3);
+      LAUNCH(fast_finish, grid, kFastThreads, smem, pl, (const uint32_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint32_t *)c->t_cnt.p,
+             status, ticket, d_err(c), d_total, prof);
+    } else {
+      size_t smem = sizeof(FinishSmem<uint64_t>);
+      auto fast_finish = fast_finish_kernel<uint64_t>;
+      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2);
+      LAUNCH(fast_finish, grid, kFastThreads, smem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint32_t *)c->t_cnt.p,
+             status, ticket, d_err(c), d_total, prof);
+    }
+    if (want_prof) {
+      unsigned long long h[16];
+      CK(cudaMemcpyAsync(h, prof, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      unsigned long long tot = 0;
+      for (int i = 0; i < 10; i++) tot += h[i];
+      fprintf(stderr, "[kmc] fast_finish cycles per phase (thread 0, summed over %u CTAs), %% of total:", grid);
+      for (int i = 0; i < 11; i++) fprintf(stderr, " p%d=%.1f%%", i, 100.0 * (double)h[i] / (double)std::max<unsigned long long>(1, tot));
+      fprintf(stderr, "  total=%.0f cycles/CTA\n", (double)tot / grid);
+    }
   }
   PHASE_END();
   uint64_t d = 0;

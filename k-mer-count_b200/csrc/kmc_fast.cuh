@@ -47,11 +47,15 @@ constexpr uint32_t kFlagOverflow = 8u;   // err flag bits 1,2,4 are used by kmc_
 constexpr uint32_t kFlagSpin = 16u;
 
 struct __align__(16) FineDesc { // one per fine bucket
-  uint64_t start;   // key index in the level-2 array
+  uint64_t start;   // element index in the level-2 array
+  uint64_t prefix;  // the key bits above `rem`, in place (key = prefix | low bits)
   uint16_t cap;     // capacity (multiple of 16, <= kFineCap)
   uint8_t rem;      // key bits below the bucket prefix
-  uint8_t pad[5];
+  uint8_t pad[13];
 };
+// Level-2 element type: when every bucket has rem <= 32 only the low 32 bits of a key are stored (the rest is
+// the bucket's prefix): half the level-2 traffic and half the shared memory of fast_finish.
+template <typename L2T> __device__ __forceinline__ L2T to_l2(uint64_t key) { return (L2T)key; }
 
 struct FastPlan {
   uint32_t kb, b1;          // key bits, level-1 bits
@@ -262,8 +266,9 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part1_array_kernel(const
 }
 
 // One CTA per tile of <= 16384 keys of one level-1 bucket → its 2^e fine buckets (the next e key bits).
+template <typename L2T>
 __global__ void __launch_bounds__(kFastThreads, 1) fast_part2_kernel(FastPlan pl, const uint64_t *__restrict__ l1,
-                                                                      uint64_t *__restrict__ l2, uint32_t *__restrict__ flags) {
+                                                                      L2T *__restrict__ l2, uint32_t *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_b;
   // which level-1 bucket owns this tile: last b with l1_tile0[b] <= tile
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part2_kernel(FastPlan pl
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < total; i += kFastThreads) {
     uint64_t k = S.stage[i];
-    l2[S.gdelta[fmask ? (uint32_t)(k >> fshift) & fmask : 0u] + i] = k;
+    l2[S.gdelta[fmask ? (uint32_t)(k >> fshift) & fmask : 0u] + i] = to_l2<L2T>(k);
   }
 }
 
@@ -341,17 +346,17 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Called by one full warp.  Publishes bucket f's row count d and returns the number of rows of all buckets
-// before f.  Buckets are handed out in ticket order, so every predecessor is running or done.
-__device__ __forceinline__ unsigned long long lookback_warp(unsigned long long *status, uint32_t f, uint32_t d,
-                                                            uint32_t *flags) {
+// Decoupled look-back over the buckets (handed out in ticket order, so every predecessor is running or
+// done).  publish: one thread announces bucket f's row count as soon as it is known.  resolve: one full
+// warp, later, sums the counts of all buckets before f and upgrades f's word to an inclusive prefix.
+__device__ __forceinline__ void lookback_publish(unsigned long long *status, uint32_t f, uint32_t d) {
+  st_status(&status[f], ((f == 0 ? 2ull : 1ull) << 62) | d);
+}
+__device__ __forceinline__ unsigned long long lookback_resolve(unsigned long long *status, uint32_t f, uint32_t d,
+                                                               uint32_t *flags) {
   const uint32_t lane = lane_id();
-  const unsigned long long kIncl = 2ull << 62, kAggr = 1ull << 62, kVal = (1ull << 62) - 1;
-  if (f == 0) {
-    if (lane == 0) st_status(&status[0], kIncl | d);
-    return 0;
-  }
-  if (lane == 0) st_status(&status[f], kAggr | d);
+  const unsigned long long kIncl = 2ull << 62, kVal = (1ull << 62) - 1;
+  if (f == 0) return 0;
   unsigned long long prefix = 0;
   long long top = (long long)f - 1;
   for (;;) {
@@ -378,35 +383,44 @@ __device__ __forceinline__ unsigned long long lookback_warp(unsigned long long *
 
 constexpr int kFinishKPT = kFineCap / kFastThreads; // 16 keys per thread
 
+template <typename L2T>
 struct FinishSmem {
-  uint64_t keys[kFineCap];                 // 64 KB
+  L2T keys[kFineCap];                      // 64 KB (u64) / 32 KB (u32)
   uint32_t bins[kFinishBins / 2];          // packed u16 pairs: counts → starts → (after the scatter) ends
   uint16_t hp[kFineCap + 8];               // head position of every run
   uint32_t scan32[40];
   uint32_t rowcnt[kFinishKPT * kFastWarps];// heads per (row, warp), then their exclusive scan
   uint32_t hard[kMaxHard];
   uint32_t n_hard;
+  uint32_t n_multi;
+  uint32_t n_dups;
   uint32_t ticket;
   unsigned long long goff;
 };
 
 // after the scatter bins[b] holds the END of sub-bin b; its start is the end of sub-bin b-1
-__device__ __forceinline__ uint32_t bin_end(const uint32_t *bins, uint32_t b) { return (bins[b >> 1] >> (16 * (b & 1))) & 0xFFFFu; }
+__device__ __forceinline__ uint32_t bin_end(const uint32_t *bins, uint32_t b) { return reinterpret_cast<const uint16_t *>(bins)[b]; }
 __device__ __forceinline__ uint32_t bin_start(const uint32_t *bins, uint32_t b) { return b ? bin_end(bins, b - 1) : 0u; }
 
-__global__ void __launch_bounds__(kFastThreads, 2) fast_finish_kernel(FastPlan pl, const uint64_t *__restrict__ l2,
+template <typename L2T>
+__global__ void __launch_bounds__(kFastThreads, sizeof(L2T) == 4 ? 3 : 2) fast_finish_kernel(FastPlan pl, const L2T *__restrict__ l2,
                                                                        uint64_t *__restrict__ out_lo, uint32_t *__restrict__ out_cnt,
                                                                        unsigned long long *__restrict__ status,
                                                                        unsigned int *__restrict__ ticket, uint32_t *__restrict__ flags,
-                                                                       unsigned long long *__restrict__ d_total) {
+                                                                       unsigned long long *__restrict__ d_total,
+                                                                       unsigned long long *__restrict__ prof) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FinishSmem &S = *reinterpret_cast<FinishSmem *>(smem_raw);
+  FinishSmem<L2T> &S = *reinterpret_cast<FinishSmem<L2T> *>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // optional phase timeline (development aid, env KMC_FINISH_PROF=1): thread 0 adds the cycles between marks
+  long long t_prev = prof ? clock64() : 0;
+#define FIN_MARK(k) do { if (prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prof[k], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
   for (;;) {
     if (tid == 0) S.ticket = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t f = S.ticket;
     if (f >= pl.n_fine) break;
+    FIN_MARK(0);
     const FineDesc D = pl.fdesc[f];
     uint32_t n = pl.fine_cursor[f];
     if (n > D.cap) n = D.cap; // overflow was flagged by fast_part2; the caller discards this result
@@ -416,24 +430,31 @@ __global__ void __launch_bounds__(kFastThreads, 2) fast_finish_kernel(FastPlan p
       uint4 z = make_uint4(0, 0, 0, 0);
       for (uint32_t i = tid; i < kFinishBins / 8; i += kFastThreads) reinterpret_cast<uint4 *>(S.bins)[i] = z;
     }
-    if (tid == 0) S.n_hard = 0;
+    if (tid == 0) { S.n_hard = 0; S.n_multi = 0; S.n_dups = 0; }
     __syncthreads();
-    // ---- load (thread t owns positions t, t+512, ...) + count per sub-bin
-    uint64_t x[kFinishKPT];
+    FIN_MARK(1);
+    // ---- load (thread t owns positions t, t+512, ...) + count per sub-bin.  The thread that adds the SECOND
+    //      key of a sub-bin puts the sub-bin on the multi-key list (S.hp is free until the run-length encode).
+    const uint32_t rows = (n + kFastThreads - 1) / kFastThreads;
+    L2T x[kFinishKPT];
 #pragma unroll
     for (int j = 0; j < kFinishKPT; j++) {
       uint32_t i = j * kFastThreads + tid;
-      x[j] = i < n ? l2[D.start + i] : 0ull;
+      x[j] = i < n ? l2[D.start + i] : (L2T)0;
     }
 #pragma unroll
     for (int j = 0; j < kFinishKPT; j++) {
+      if ((uint32_t)j >= rows) break;
       uint32_t i = j * kFastThreads + tid;
       if (i < n) {
         uint32_t b = (uint32_t)(x[j] >> bshift) & bmask;
-        atomicAdd(&S.bins[b >> 1], 1u << (16 * (b & 1)));
+        uint32_t sh = 16 * (b & 1);
+        uint32_t old = atomicAdd(&S.bins[b >> 1], 1u << sh);
+        if (((old >> sh) & 0xFFFFu) == 1u) S.hp[atomicAdd(&S.n_multi, 1u)] = (uint16_t)b;
       }
     }
     __syncthreads();
+    FIN_MARK(2);
     // ---- exclusive scan of the 8192 packed counts (16 sub-bins = 8 words per thread), starts written in place
     {
       uint4 a = reinterpret_cast<const uint4 *>(S.bins)[tid * 2], b4 = reinterpret_cast<const uint4 *>(S.bins)[tid * 2 + 1];
@@ -453,67 +474,77 @@ __global__ void __launch_bounds__(kFastThreads, 2) fast_finish_kernel(FastPlan p
       reinterpret_cast<uint4 *>(S.bins)[tid * 2 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
     __syncthreads();
+    FIN_MARK(3);
     // ---- scatter into sub-bin order: a second atomic on the start hands out the slot and leaves the END in bins[]
-    uint32_t slot[kFinishKPT / 2]; // two 16-bit slots per word; later the key's final position
 #pragma unroll
     for (int j = 0; j < kFinishKPT; j++) {
+      if ((uint32_t)j >= rows) break;
       uint32_t i = j * kFastThreads + tid;
-      uint32_t p = 0;
       if (i < n) {
         uint32_t b = (uint32_t)(x[j] >> bshift) & bmask;
         uint32_t sh = 16 * (b & 1);
-        p = (atomicAdd(&S.bins[b >> 1], 1u << sh) >> sh) & 0xFFFFu;
+        uint32_t p = (atomicAdd(&S.bins[b >> 1], 1u << sh) >> sh) & 0xFFFFu;
         S.keys[p] = x[j];
       }
-      if (j & 1) slot[j >> 1] |= p << 16; else slot[j >> 1] = p;
     }
     __syncthreads();
-    // ---- order inside each sub-bin: every key counts the keys of its sub-bin that sort before it
-    uint32_t moved = 0;
-#pragma unroll
-    for (int j = 0; j < kFinishKPT; j++) {
-      uint32_t i = j * kFastThreads + tid;
-      if (i < n) {
-        const uint32_t b = (uint32_t)(x[j] >> bshift) & bmask;
-        const uint32_t s = bin_start(S.bins, b), e = bin_end(S.bins, b);
-        const uint32_t me = (slot[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-        if (e - s >= 2) {
-          if (e - s <= (uint32_t)kSmallBin) {
-            uint32_t r = s;
-            for (uint32_t q = s; q < e; q++) {
-              uint64_t o = S.keys[q];
-              r += (o < x[j]) || (o == x[j] && q < me);
-            }
-            moved |= 1u << j;
-            slot[j >> 1] = (slot[j >> 1] & ~(0xFFFFu << (16 * (j & 1)))) | (r << (16 * (j & 1)));
-          } else if (me == s) { // exactly one key of the sub-bin sits in its first slot: it reports the sub-bin
-            uint32_t h = atomicAdd(&S.n_hard, 1u);
-            if (h < (uint32_t)kMaxHard) S.hard[h] = b;
+    FIN_MARK(4);
+    // ---- order inside the multi-key sub-bins: one thread per listed sub-bin, insertion sort in place.
+    //      Keys of a sub-bin differ only below bit `bshift`: a 32-bit compare is enough when bshift <= 32.
+    {
+      const uint16_t *end16 = reinterpret_cast<const uint16_t *>(S.bins);
+      const uint32_t n_multi = S.n_multi;
+      uint32_t dups = 0; // equal neighbours after sorting = rows that the run-length encode will merge
+      for (uint32_t q = tid; q < n_multi; q += kFastThreads) {
+        const uint32_t b = S.hp[q];
+        const uint32_t s0 = b ? end16[b - 1] : 0u, e0 = end16[b];
+        if (e0 - s0 > (uint32_t)kSmallBin) {
+          uint32_t h = atomicAdd(&S.n_hard, 1u);
+          if (h < (uint32_t)kMaxHard) S.hard[h] = b;
+          continue;
+        }
+        if (sizeof(L2T) == 8 && bshift <= 32) {
+          for (uint32_t i = s0 + 1; i < e0; i++) {
+            const L2T v = S.keys[i];
+            uint32_t jj = i;
+            while (jj > s0 && (uint32_t)S.keys[jj - 1] > (uint32_t)v) { S.keys[jj] = S.keys[jj - 1]; jj--; }
+            S.keys[jj] = v;
+            dups += (jj > s0 && (uint32_t)S.keys[jj - 1] == (uint32_t)v);
+          }
+        } else {
+          for (uint32_t i = s0 + 1; i < e0; i++) {
+            const L2T v = S.keys[i];
+            uint32_t jj = i;
+            while (jj > s0 && S.keys[jj - 1] > v) { S.keys[jj] = S.keys[jj - 1]; jj--; }
+            S.keys[jj] = v;
+            dups += (jj > s0 && S.keys[jj - 1] == v);
           }
         }
       }
+      if (dups) atomicAdd(&S.n_dups, dups);
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kFinishKPT; j++)
-      if (moved & (1u << j)) S.keys[(slot[j >> 1] >> (16 * (j & 1))) & 0xFFFFu] = x[j];
-    __syncthreads();
+    FIN_MARK(5);
     // ---- big sub-bins (duplicates or adversarial input): cooperative rank sort; too many of them → recount
+    // the row count of the bucket is already known unless big sub-bins remain: announce it now, so that by the
+    // time this CTA needs its own offset (after the run-length encode) its predecessors have announced theirs
+    const bool early = S.n_hard == 0;
+    if (early && tid == 0) lookback_publish(status, f, n - S.n_dups);
     {
       uint32_t nh = S.n_hard;
       if (nh > (uint32_t)kMaxHard) { if (tid == 0) atomicOr(flags, kFlagOverflow); nh = 0; }
       for (uint32_t h = 0; h < nh; h++) {
         const uint32_t b = S.hard[h];
         const uint32_t s = bin_start(S.bins, b), m = bin_end(S.bins, b) - s;
-        const uint64_t first = S.keys[s];
+        const L2T first = S.keys[s];
         int differ = 0;
         for (uint32_t i = tid; i < m; i += kFastThreads) differ |= (S.keys[s + i] != first);
         if (__syncthreads_or(differ)) {
           for (uint32_t i = tid; i < m; i += kFastThreads) {
-            const uint64_t v = S.keys[s + i];
+            const L2T v = S.keys[s + i];
             uint32_t r = 0;
             for (uint32_t q = 0; q < m; q++) {
-              uint64_t o = S.keys[s + q];
+              L2T o = S.keys[s + q];
               r += (o < v) || (o == v && q < i);
             }
             S.hp[i] = (uint16_t)r;
@@ -534,6 +565,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fast_finish_kernel(FastPlan p
         }
       }
     }
+    FIN_MARK(6);
     // ---- run-length encode the sorted bucket.  Thread t owns positions t, t+512, ... (bank-conflict free);
     //      a position is a head if its key differs from the one before it.
     uint32_t heads = 0;
@@ -542,11 +574,11 @@ __global__ void __launch_bounds__(kFastThreads, 2) fast_finish_kernel(FastPlan p
     for (int j = 0; j < kFinishKPT; j++) {
       uint32_t p = j * kFastThreads + tid;
       bool h = false;
-      if (p < n) {
+      if ((uint32_t)j < rows && p < n) {
         x[j] = S.keys[p];
         h = (p == 0) || (S.keys[p - 1] != x[j]);
       }
-      uint32_t bal = __ballot_sync(0xffffffffu, h);
+      uint32_t bal = (uint32_t)j < rows ? __ballot_sync(0xffffffffu, h) : 0u;
       if (h) heads |= 1u << j;
       uint32_t lt = __popc(bal & ((1u << lane) - 1u));
       if (j & 3) below[j >> 2] |= lt << (8 * (j & 3)); else below[j >> 2] = lt;
@@ -560,9 +592,14 @@ __global__ void __launch_bounds__(kFastThreads, 2) fast_finish_kernel(FastPlan p
       if (tid < kFinishKPT * kFastWarps) S.rowcnt[tid] = ex;
     }
     __syncthreads();
+    FIN_MARK(7);
     // every thread holds its keys in registers: S.keys can now take the compacted rows.
     if (warp == 0) {
-      unsigned long long prefix = lookback_warp(status, f, d, flags);
+      long long lb0 = prof ? clock64() : 0;
+      if (!early && lane == 0) lookback_publish(status, f, d);
+      if (early && lane == 0 && d != n - S.n_dups) atomicOr(flags, kFlagSpin); // the early count must be the real one
+      unsigned long long prefix = lookback_resolve(status, f, d, flags);
+      if (prof && tid == 0) atomicAdd(&prof[10], (unsigned long long)(clock64() - lb0));
       if (lane == 0) {
         S.goff = prefix;
         if (f + 1 == pl.n_fine) *d_total = prefix + d;
@@ -577,14 +614,17 @@ __global__ void __launch_bounds__(kFastThreads, 2) fast_finish_kernel(FastPlan p
       }
     }
     __syncthreads();
+    FIN_MARK(8);
     const unsigned long long G = S.goff;
     for (uint32_t i = tid; i < d; i += kFastThreads) {
-      out_lo[G + i] = S.keys[i];
+      out_lo[G + i] = D.prefix | (uint64_t)S.keys[i];
       uint32_t nxt = (i + 1 < d) ? S.hp[i + 1] : n;
       out_cnt[G + i] = nxt - S.hp[i];
     }
     __syncthreads();
+    FIN_MARK(9);
   }
+#undef FIN_MARK
 }
 
 } // namespace kmc
