@@ -192,6 +192,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = os.environ.get("KMC_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout: one JSON line
         dist.init_process_group("nccl", device_id=dev)
     os.environ.setdefault("KMC_KERNEL_TIMING", "1")
     K.build()

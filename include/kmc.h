@@ -12,7 +12,10 @@
  *     kmc_create → { kmc_staging → fill → kmc_submit }*  → kmc_finish → kmc_read* → kmc_destroy
  * or, with inputs already resident in HBM:
  *     kmc_create → kmc_submit_device* → kmc_finish → kmc_table_device / kmc_read
- * Multi-GPU (one process per GPU; the exchange itself is done by the host with NCCL):
+ * Multi-GPU (one process per GPU):
+ *     kmc_submit* → kmc_route_to_peers(n_parts)   [keys stored into the owners' buffers over NVLink]
+ *                 → [counts exchanged, ranks synchronised] → kmc_ingest_keys* → kmc_finish
+ *   or, with the exchange done by the host (NCCL all-to-all):
  *     kmc_submit* → kmc_route(n_parts) → [all-to-all of the routed keys] → kmc_ingest_keys* → kmc_finish
  *
  * There is no CPU fallback anywhere behind this ABI: without a CUDA device kmc_create fails with
@@ -117,11 +120,26 @@ int kmc_digest(kmc_ctx *ctx, uint64_t *digest);
 uint32_t kmc_key_bases(const kmc_ctx *ctx);
 
 /* ---- multi-GPU: hash-prefix routing -------------------------------------------
- * kmc_route: extract this rank's keys from the submitted input and group them by owner
- * part = (mix64(key) * n_parts) >> 64 into one device buffer; part p's keys are
- * [part_off[p], part_off[p+1]) (part_off: caller-owned host array of n_parts+1 entries).
- * Keys are 8 bytes (k<=32) or 16 bytes (lo,hi) each; key_bytes tells which.                       */
-int kmc_route(kmc_ctx *ctx, uint32_t n_parts, uint64_t *part_off, const void **d_keys, uint32_t *key_bytes);
+ * kmc_route: extract this rank's keys from the submitted input and group them by owner part
+ * (kmc_owner_of, a hash prefix) in one device buffer; part p's keys are the part_count[p] keys starting
+ * at key index part_begin[p] of *d_keys (both caller-owned host arrays of n_parts entries; the parts need
+ * not be adjacent).  Keys are 8 bytes (k<=32) or 16 bytes (lo,hi) each; key_bytes tells which.      */
+int kmc_route(kmc_ctx *ctx, uint32_t n_parts, uint64_t *part_begin, uint64_t *part_count, const void **d_keys,
+              uint32_t *key_bytes);
+/* Fused route + exchange over NVLink peer memory: like kmc_route, but part p's keys are stored by the
+ * routing kernel straight into d_part_ptr[p] — normally this rank's region of rank p's receive buffer,
+ * mapped with kmc_ipc_open (or any device pointer, e.g. torch symmetric memory).  Each region holds at
+ * most part_cap_keys keys; part_count[p] (host) receives how many were written.  The caller exchanges the
+ * counts and synchronises the ranks before the owners call kmc_ingest_keys on what they received.   */
+int kmc_route_to_peers(kmc_ctx *ctx, uint32_t n_parts, void *const *d_part_ptr, uint64_t part_cap_keys,
+                       uint64_t *part_count);
+/* Library-owned device buffer for received keys (grow-only; 16 bytes per key in 128-bit mode).      */
+int kmc_recv_buffer(kmc_ctx *ctx, uint64_t n_keys, void **d_ptr);
+/* CUDA IPC plumbing for one-process-per-GPU: export a device allocation of this process as a 64-byte
+ * handle; map a peer's handle into this process; unmap it.                                         */
+int kmc_ipc_export(kmc_ctx *ctx, const void *d_ptr, unsigned char handle[64]);
+int kmc_ipc_open(kmc_ctx *ctx, const unsigned char handle[64], void **d_peer_ptr);
+int kmc_ipc_close(kmc_ctx *ctx, void *d_peer_ptr);
 /* Hand the ctx keys it owns (device pointer, same layout as kmc_route's output; referenced until
  * kmc_finish).  kmc_finish then counts the ingested keys instead of extracting from the input.    */
 int kmc_ingest_keys(kmc_ctx *ctx, const void *d_keys, uint64_t n_keys);

@@ -80,7 +80,7 @@ struct kmc_ctx {
   DevBuf keys_a, keys_b, block_hist, offsets, sums, scalars, route_keys;
   DevBuf gap_l, gap_r, gap_f;
   DevBuf t_lo, t_hi, t_cnt;
-  DevBuf fast_l1, fast_l2, fast_state, fast_tables;
+  DevBuf fast_l1, fast_l2, fast_state, fast_tables, recv_keys;
   std::vector<unsigned char> fast_host; // plan tables staged for upload
   uint32_t fast_fallbacks = 0;          // times the partitioned path overflowed and the job was recounted
 
@@ -424,6 +424,64 @@ int route_impl(kmc_ctx *c, uint32_t n_parts, uint64_t *part_off) {
   return KMC_OK;
 }
 
+// fast routing for 64-bit keys: the level-1 scatter of kmc_fast.cuh with bucket = owner part.  Each part gets
+// a region sized from the upper bound (one key per base) with slack; *done = false → use the generic route.
+// part_ptr == nullptr: the parts are regions of c->route_keys (kmc_route).  Otherwise part p is stored at
+// part_ptr[p] — a peer's memory over NVLink (kmc_route_to_peers); positions are then absolute addresses / 8.
+int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *part_count, bool *done,
+               void *const *part_ptr = nullptr, uint64_t peer_cap = 0) {
+  *done = false;
+  if (!part_ptr && (c->total_bases < (1u << 18) || n_parts > (uint32_t)kMaxL1)) return KMC_OK;
+  const uint64_t cap = part_ptr ? peer_cap : (((uint64_t)((double)c->total_bases / n_parts * 1.03) + 65536 + 15) & ~15ull);
+  const uint64_t total = part_ptr ? 0 : cap * n_parts;
+  TRY(ensure(c, c->route_keys, (total + 2 * kPart2Tile) * 8));
+  const size_t o_start = 0, o_cap = o_start + ((size_t)(n_parts + 1) * 8 + 15) / 16 * 16, tab_bytes = o_cap + (size_t)n_parts * 8;
+  c->fast_host.assign(tab_bytes, 0);
+  uint64_t *l1s = (uint64_t *)(c->fast_host.data() + o_start), *l1c = (uint64_t *)(c->fast_host.data() + o_cap);
+  for (uint32_t p = 0; p <= n_parts; p++) l1s[p] = part_ptr ? (p < n_parts ? (uint64_t)(uintptr_t)part_ptr[p] / 8 : 0) : cap * p;
+  for (uint32_t p = 0; p < n_parts; p++) l1c[p] = cap;
+  TRY(ensure(c, c->fast_tables, tab_bytes));
+  TRY(ensure(c, c->fast_state, 4096 * 8 + 16 + kMaxL1 * 8 + 64));
+  const size_t off_l1cur = 4096 * 8 + 16;
+  CK(cudaMemsetAsync((unsigned char *)c->fast_state.p + off_l1cur, 0, kMaxL1 * 8, c->stream));
+  CK(cudaMemcpyAsync(c->fast_tables.p, c->fast_host.data(), tab_bytes, cudaMemcpyHostToDevice, c->stream));
+  FastPlan pl{};
+  pl.kb = c->key_bits; pl.b1 = 0; pl.n_l1 = n_parts; pl.n_fine = 0;
+  pl.l1_trash = part_ptr ? (uint64_t)(uintptr_t)c->route_keys.p / 8 : total;
+  uint64_t *dst = part_ptr ? (uint64_t *)nullptr : (uint64_t *)c->route_keys.p;
+  pl.l1_start = (const uint64_t *)((unsigned char *)c->fast_tables.p + o_start);
+  pl.l1_cap = (const uint64_t *)((unsigned char *)c->fast_tables.p + o_cap);
+  pl.l1_cursor = (unsigned long long *)((unsigned char *)c->fast_state.p + off_l1cur);
+  PHASE_BEGIN("route");
+  {
+    size_t smem = PartSmem::bytes(kPart1Stage, n_parts);
+    auto fast_route = fast_part1_kernel<true, OwnerBucket>;
+    CK(cudaFuncSetAttribute(fast_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const OwnerBucket bucket{n_parts};
+    for (size_t i = 0; i < c->n_segs; i++) {
+      Segment &s = c->segs[i];
+      if (!s.n_bases) continue;
+      ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
+      uint64_t tiles = num_warp_tiles(s.n_bases, 31);
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
+      LAUNCH(fast_route, grid, kFastThreads, smem, P, tiles, pl, bucket, dst, d_err(c));
+    }
+  }
+  PHASE_END();
+  std::vector<unsigned long long> cur(n_parts);
+  uint32_t err = 0;
+  CK(cudaMemcpyAsync(cur.data(), pl.l1_cursor, (size_t)n_parts * 8, cudaMemcpyDeviceToHost, c->stream));
+  TRY(read_scalars(c, nullptr, &err));
+  if (err & kFlagOverflow) {
+    if (part_ptr) return fail(c, KMC_E_CAPACITY, "kmc_route_to_peers: a part exceeded part_cap_keys");
+    TRY(zero_scalars(c));
+    return KMC_OK;
+  }
+  for (uint32_t p = 0; p < n_parts; p++) { if (part_begin) part_begin[p] = cap * p; part_count[p] = cur[p]; }
+  *done = true;
+  return KMC_OK;
+}
+
 // ---- strategies --------------------------------------------------------------------------------------------
 template <typename KeyT>
 int finish_baseline(kmc_ctx *c) {
@@ -453,7 +511,15 @@ int finish_fast(kmc_ctx *c, bool *used) {
   const uint32_t ncoarse = 1u << cb;
   const bool from_array = !c->ingested.empty() || c->cfg.mode == KMC_MODE_LR_GAPPED;
   uint64_t n_array = 0;
-  if (from_array) TRY(produce_keys<uint64_t>(c, &n_array));
+  std::vector<std::pair<const uint64_t *, uint64_t>> arrays; // key arrays are used in place, segment by segment
+  if (from_array) {
+    if (!c->ingested.empty()) {
+      for (auto &e : c->ingested) if (e.second) { arrays.emplace_back((const uint64_t *)e.first, e.second); n_array += e.second; }
+    } else {
+      TRY(produce_keys<uint64_t>(c, &n_array));
+      if (n_array) arrays.emplace_back((const uint64_t *)c->keys_a.p, n_array);
+    }
+  }
   // fast_state layout: ghist[4096] u64 | ticket u32 (+pad) | d_total u64 | l1_cursor[kMaxL1] u64 | fine_cursor[nf] u32 | status[nf] u64
   const size_t off_ticket = 4096 * 8, off_dtotal = off_ticket + 8, off_l1cur = off_dtotal + 8, off_fine = off_l1cur + kMaxL1 * 8;
   TRY(ensure(c, c->fast_state, off_fine + 64));
@@ -464,10 +530,10 @@ int finish_fast(kmc_ctx *c, bool *used) {
   const uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
   PHASE_BEGIN("fast_hist");
   if (from_array) {
-    if (n_array) {
-      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(n_array, 1024 * step), (uint64_t)kNumSMsB200 * 8);
+    for (auto &a : arrays) {
+      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024 * step), (uint64_t)kNumSMsB200 * 8);
       auto fast_hist_array = fast_hist_array_kernel<uint64_t>;
-      LAUNCH(fast_hist_array, grid, 256, ncoarse * 4, (const uint64_t *)c->keys_a.p, n_array, step, kb - cb, ncoarse, ghist);
+      LAUNCH(fast_hist_array, grid, 256, ncoarse * 4, a.first, a.second, step, kb - cb, ncoarse, ghist);
     }
   } else {
     for (size_t i = 0; i < c->n_segs; i++) {
@@ -593,20 +659,23 @@ int finish_fast(kmc_ctx *c, bool *used) {
   if (from_array) {
     size_t smem = PartSmem::bytes(kPart2Tile, n_l1);
     CK(cudaFuncSetAttribute(fast_part1_array_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(n_array, kPart2Tile), (uint64_t)kNumSMsB200);
     auto fast_part1_array = fast_part1_array_kernel;
-    LAUNCH(fast_part1_array, grid, kFastThreads, smem, (const uint64_t *)c->keys_a.p, n_array, pl, (uint64_t *)c->fast_l1.p, d_err(c));
+    for (auto &a : arrays) {
+      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, kPart2Tile), (uint64_t)kNumSMsB200);
+      LAUNCH(fast_part1_array, grid, kFastThreads, smem, a.first, a.second, pl, (uint64_t *)c->fast_l1.p, d_err(c));
+    }
   } else {
     size_t smem = PartSmem::bytes(kPart1Stage, n_l1);
-    auto fast_part1 = fast_part1_kernel<true>;
+    auto fast_part1 = fast_part1_kernel<true, PrefixBucket>;
     CK(cudaFuncSetAttribute(fast_part1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const PrefixBucket bucket{b1, kb - b1};
     for (size_t i = 0; i < c->n_segs; i++) {
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
       ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
       uint64_t tiles = num_warp_tiles(s.n_bases, 31);
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
-      LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, (uint64_t *)c->fast_l1.p, d_err(c));
+      LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (uint64_t *)c->fast_l1.p, d_err(c));
     }
   }
   PHASE_END();
@@ -802,7 +871,7 @@ void kmc_destroy(kmc_ctx *c) {
   }
   for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); }
   for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
-                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables})
+                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->recv_keys})
     release(*b);
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -979,16 +1048,72 @@ int kmc_digest(kmc_ctx *c, uint64_t *digest) {
 
 uint32_t kmc_owner_of(uint64_t key_hi, uint64_t key_lo, uint32_t n_parts) { return owner_of(key_hi, key_lo, n_parts); }
 
-int kmc_route(kmc_ctx *c, uint32_t n_parts, uint64_t *part_off, const void **d_keys, uint32_t *key_bytes) {
-  if (!c || !part_off || !d_keys) return KMC_E_ARG;
+int kmc_route(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *part_count, const void **d_keys,
+              uint32_t *key_bytes) {
+  if (!c || !part_begin || !part_count || !d_keys) return KMC_E_ARG;
   if (n_parts < 1 || n_parts > kRadix) return fail(c, KMC_E_ARG, "n_parts must be 1..%d", kRadix);
   if (c->finished) return fail(c, KMC_E_ARG, "kmc_route after kmc_finish");
   CK(cudaSetDevice(c->device));
   TRY(zero_scalars(c));
-  int rc = c->wide ? route_impl<U128>(c, n_parts, part_off) : route_impl<uint64_t>(c, n_parts, part_off);
-  if (rc) return rc;
+  bool done = false;
+  if (!c->wide && c->cfg.mode == KMC_MODE_CONTIGUOUS) TRY(route_fast(c, n_parts, part_begin, part_count, &done));
+  if (!done) {
+    std::vector<uint64_t> off(n_parts + 1);
+    int rc = c->wide ? route_impl<U128>(c, n_parts, off.data()) : route_impl<uint64_t>(c, n_parts, off.data());
+    if (rc) return rc;
+    for (uint32_t p = 0; p < n_parts; p++) { part_begin[p] = off[p]; part_count[p] = off[p + 1] - off[p]; }
+  }
   *d_keys = c->route_keys.p;
   if (key_bytes) *key_bytes = c->wide ? 16 : 8;
+  return KMC_OK;
+}
+
+int kmc_route_to_peers(kmc_ctx *c, uint32_t n_parts, void *const *d_part_ptr, uint64_t part_cap_keys, uint64_t *part_count) {
+  if (!c || !d_part_ptr || !part_count) return KMC_E_ARG;
+  if (n_parts < 1 || n_parts > kRadix) return fail(c, KMC_E_ARG, "n_parts must be 1..%d", kRadix);
+  if (c->wide || c->cfg.mode != KMC_MODE_CONTIGUOUS)
+    return fail(c, KMC_E_ARG, "kmc_route_to_peers handles 64-bit contiguous-mode keys; use kmc_route + an all-to-all otherwise");
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_route_to_peers after kmc_finish");
+  for (uint32_t p = 0; p < n_parts; p++)
+    if (!d_part_ptr[p] || ((uintptr_t)d_part_ptr[p] & 127)) return fail(c, KMC_E_ARG, "part pointers must be 128-byte aligned device pointers");
+  CK(cudaSetDevice(c->device));
+  TRY(zero_scalars(c));
+  bool done = false;
+  TRY(route_fast(c, n_parts, nullptr, part_count, &done, d_part_ptr, part_cap_keys));
+  return done ? KMC_OK : fail(c, KMC_E_ARG, "kmc_route_to_peers: nothing routed");
+}
+
+int kmc_recv_buffer(kmc_ctx *c, uint64_t n_keys, void **d_ptr) {
+  if (!c || !d_ptr) return KMC_E_ARG;
+  CK(cudaSetDevice(c->device));
+  TRY(ensure(c, c->recv_keys, (n_keys + 16) * (c->wide ? 16 : 8)));
+  *d_ptr = c->recv_keys.p;
+  return KMC_OK;
+}
+
+int kmc_ipc_export(kmc_ctx *c, const void *d_ptr, unsigned char handle[64]) {
+  if (!c || !d_ptr || !handle) return KMC_E_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+  memcpy(handle, &h, 64);
+  return KMC_OK;
+}
+
+int kmc_ipc_open(kmc_ctx *c, const unsigned char handle[64], void **d_peer_ptr) {
+  if (!c || !handle || !d_peer_ptr) return KMC_E_ARG;
+  CK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CK(cudaIpcOpenMemHandle(d_peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return KMC_OK;
+}
+
+int kmc_ipc_close(kmc_ctx *c, void *d_peer_ptr) {
+  if (!c || !d_peer_ptr) return KMC_E_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaIpcCloseMemHandle(d_peer_ptr));
   return KMC_OK;
 }
 

@@ -57,9 +57,15 @@ __host__ __device__ __forceinline__ uint64_t mulhi64(uint64_t a, uint64_t b) {
   return (uint64_t)(((unsigned __int128)a * b) >> 64);
 #endif
 }
-// owner part = top of the hash range, balanced for any n_parts (not only powers of two)
+// owner part of a key (multi-GPU routing): a hash prefix, not a key prefix, so that skewed
+// key distributions stay balanced.  Multiplicative (Fibonacci) hash — the top 32 bits of the product depend
+// on every key bit and cost a handful of instructions in the routing kernel — scaled to n_parts, which
+// need not be a power of two.
 __host__ __device__ __forceinline__ uint32_t owner_of(uint64_t hi, uint64_t lo, uint32_t n_parts) {
-  return (uint32_t)mulhi64(mix_key(hi, lo), (uint64_t)n_parts);
+  uint64_t m = (lo ^ (hi * 0xD6E8FEB86659FD93ULL)) * 0x9E3779B97F4A7C15ULL;
+  m ^= m >> 29;
+  m *= 0xBF58476D1CE4E5B9ULL;
+  return (uint32_t)(((m >> 32) * (uint64_t)n_parts) >> 32);
 }
 
 // ---- ASCII → 2-bit ---------------------------------------------------------------------------------

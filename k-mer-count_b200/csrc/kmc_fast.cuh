@@ -71,9 +71,15 @@ struct FastPlan {
   uint32_t *fine_cursor;    // [n_fine]
 };
 
-__device__ __forceinline__ uint32_t l1_bucket(uint64_t key, uint32_t b1, uint32_t bshift) {
-  return b1 ? (uint32_t)(key >> bshift) : 0u;
-}
+// bucket functions of the level-1 scatter: the top b1 key bits (counting), or the owner part (routing)
+struct PrefixBucket {
+  uint32_t b1, bshift;
+  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return b1 ? (uint32_t)(key >> bshift) : 0u; }
+};
+struct OwnerBucket {
+  uint32_t n_parts;
+  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return owner_of(0, key, n_parts); }
+};
 
 // ------------------------------------------------------------------------------------------------ hist
 // Sampled coarse histogram: warp tiles t with t % step == 0.
@@ -177,14 +183,13 @@ __device__ __forceinline__ void reserve_l1(const FastPlan &pl, PartSmem &S, uint
 }
 
 // Level-1 scatter, extraction front end.  One CTA tile = 16 warp tiles (<= 15872 keys).
-template <bool FOLD>
-__global__ void __launch_bounds__(kFastThreads, 1) fast_part1_kernel(ExtractParams P, uint64_t n_tiles, FastPlan pl,
+template <bool FOLD, typename BucketFn>
+__global__ void __launch_bounds__(kFastThreads, 1) fast_part1_kernel(ExtractParams P, uint64_t n_tiles, FastPlan pl, BucketFn bucket,
                                                                       uint64_t *__restrict__ l1, uint32_t *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t nb = pl.n_l1;
   PartSmem S(smem_raw, kPart1Stage, nb);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  const uint32_t bshift = pl.kb - pl.b1, b1 = pl.b1;
   const uint64_t n_cta_tiles = (n_tiles + kFastWarps - 1) / kFastWarps;
   for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
     for (uint32_t i = threadIdx.x; i < nb; i += kFastThreads) S.hist[i] = 0;
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part1_kernel(ExtractPara
     for (int s = 0; s < 32; s++) {
       key[s] = W.key(s, P.k, P.canonical != 0);
       uint32_t r = 0;
-      if (ok & (0x80000000u >> s)) r = atomicAdd(&S.hist[l1_bucket(key[s], b1, bshift)], 1u);
+      if (ok & (0x80000000u >> s)) r = atomicAdd(&S.hist[bucket(key[s])], 1u);
       if (s & 1) rank[s >> 1] |= r << 16; else rank[s >> 1] = r;
     }
     __syncthreads();
@@ -209,11 +214,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part1_kernel(ExtractPara
 #pragma unroll
     for (int s = 0; s < 32; s++)
       if (ok & (0x80000000u >> s))
-        S.stage[S.loc[l1_bucket(key[s], b1, bshift)] + ((rank[s >> 1] >> (16 * (s & 1))) & 0xFFFFu)] = key[s];
+        S.stage[S.loc[bucket(key[s])] + ((rank[s >> 1] >> (16 * (s & 1))) & 0xFFFFu)] = key[s];
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < total; i += kFastThreads) {
       uint64_t k = S.stage[i];
-      l1[S.gdelta[l1_bucket(k, b1, bshift)] + i] = k;
+      l1[S.gdelta[bucket(k)] + i] = k;
     }
     __syncthreads();
   }
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part1_array_kernel(const
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t nb = pl.n_l1;
   PartSmem S(smem_raw, kPart2Tile, nb);
-  const uint32_t bshift = pl.kb - pl.b1, b1 = pl.b1;
+  const PrefixBucket bucket{pl.b1, pl.kb - pl.b1};
   const uint64_t n_cta_tiles = (n + kPart2Tile - 1) / kPart2Tile;
   for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
     for (uint32_t i = threadIdx.x; i < nb; i += kFastThreads) S.hist[i] = 0;
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part1_array_kernel(const
     for (int j = 0; j < kPart2KPT; j++) {
       uint32_t idx = j * kFastThreads + threadIdx.x;
       uint32_t r = 0;
-      if (idx < cnt) r = atomicAdd(&S.hist[l1_bucket(key[j], b1, bshift)], 1u);
+      if (idx < cnt) r = atomicAdd(&S.hist[bucket(key[j])], 1u);
       if (j & 1) rank[j >> 1] |= r << 16; else rank[j >> 1] = r;
     }
     __syncthreads();
@@ -254,12 +259,12 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part1_array_kernel(const
 #pragma unroll
     for (int j = 0; j < kPart2KPT; j++) {
       uint32_t idx = j * kFastThreads + threadIdx.x;
-      if (idx < cnt) S.stage[S.loc[l1_bucket(key[j], b1, bshift)] + ((rank[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)] = key[j];
+      if (idx < cnt) S.stage[S.loc[bucket(key[j])] + ((rank[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)] = key[j];
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < total; i += kFastThreads) {
       uint64_t k = S.stage[i];
-      l1[S.gdelta[l1_bucket(k, b1, bshift)] + i] = k;
+      l1[S.gdelta[bucket(k)] + i] = k;
     }
     __syncthreads();
   }

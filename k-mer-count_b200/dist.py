@@ -2,9 +2,15 @@
 GPU by hash prefix with one all-to-all.  The exchange is `torch.distributed`
 (NCCL over NVLink on the GPU box; gloo in the CPU tests of the routing arithmetic); everything
 either side of it is libkmc through its C ABI."""
+import os
+import sys
+import time
+
 import numpy as np
 
 from .host import KmerCounter
+
+_PROF = os.environ.get("KMC_DIST_PROF") == "1"
 
 
 class _DevArray:
@@ -14,10 +20,9 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 2}
 
 
-def split_sizes(part_off, words):
-    """Element counts per destination for all_to_all_single, from kmc_route's part offsets."""
-    off = np.asarray(part_off, dtype=np.int64)
-    return ((off[1:] - off[:-1]) * words).tolist()
+def split_sizes(part_count, words):
+    """int64 elements per destination, from kmc_route's part counts (a key is `words` int64s)."""
+    return (np.asarray(part_count, dtype=np.int64) * words).tolist()
 
 
 # Algorithmic bytes moved by each kernel per step (DESIGN.md "kernels"): used for the per-kernel roofline.
@@ -31,33 +36,62 @@ def kernel_bytes(name, n_keys, n_distinct, n_bases, key_bytes, key_bits):
         "rle_count_kernel<KeyT>": n_keys * W,
         "rle_write_kernel<KeyT>": n_keys * W + n_distinct * (W + 8),
         # partitioned fast path (kmc_fast.cuh)
-        "fast_hist": n_bases,
-        "fast_partition": n_bases + n_keys * W,
-        "fast_finish": n_keys * W + n_distinct * (W + 4),
+        "fast_hist": n_bases / 16,
+        "fast_hist_array": n_keys * W / 16,
+        "fast_part1": n_bases + n_keys * W,
+        "fast_part1_array": 2 * n_keys * W,
+        "fast_route": n_bases + n_keys * W,
+        "fast_part2": n_keys * W + n_keys * (4 if key_bits <= 50 else W),
+        "fast_finish": n_keys * (4 if key_bits <= 50 else W) + n_distinct * (W + 4),
     }
     return table.get(name)
 
 
-def exchange(torch, dist, send, send_sizes):
-    """All-to-all of variable-size slices of `send` (a 1-D int64 tensor laid out part by part):
-    first the sizes, then the payload.  Returns (recv, recv_sizes).  Device-agnostic (NCCL or gloo)."""
-    sc = torch.tensor(send_sizes, dtype=torch.int64, device=send.device)
+def exchange(torch, dist, send_parts):
+    """All-to-all of one variable-size 1-D int64 tensor per destination rank: first the sizes, then the
+    payload (grouped send/recv under NCCL).  Returns (recv, recv_sizes) with recv laid out source rank by
+    source rank.  Device-agnostic (NCCL or gloo)."""
+    dev = send_parts[0].device
+    sc = torch.tensor([t.numel() for t in send_parts], dtype=torch.int64, device=dev)
     rc = torch.empty_like(sc)
     dist.all_to_all_single(rc, sc)
     recv_sizes = rc.tolist()
-    recv = torch.empty(sum(recv_sizes), dtype=torch.int64, device=send.device)
-    dist.all_to_all_single(recv, send, output_split_sizes=recv_sizes, input_split_sizes=send_sizes)
+    recv = torch.empty(sum(recv_sizes), dtype=torch.int64, device=dev)
+    outs = list(torch.split(recv, recv_sizes))
+    if dist.get_backend() == "gloo":  # gloo has no list all_to_all: pairwise isend/irecv
+        rank, world = dist.get_rank(), dist.get_world_size()
+        reqs = []
+        for p in range(world):
+            if p == rank:
+                outs[p].copy_(send_parts[p])
+            else:
+                reqs.append(dist.isend(send_parts[p].contiguous(), p))
+                reqs.append(dist.irecv(outs[p], p))
+        for r in reqs:
+            r.wait()
+    else:
+        dist.all_to_all(outs, [t.contiguous() for t in send_parts])
     return recv, recv_sizes
 
 
 class DistCounter:
-    """KmerCounter that, when world > 1, routes keys to owner ranks before counting."""
+    """KmerCounter that, when world > 1, routes keys to their owner ranks before counting.
+
+    64-bit keys: the routing kernel stores every key straight into its owner's receive buffer over NVLink
+    (peer memory mapped with CUDA IPC) — compute and exchange are one kernel; only the per-part counts go
+    through torch.distributed afterwards, which also orders the ranks.  128-bit keys and lr-gapped mode:
+    kmc_route into a local buffer, then an NCCL all-to-all."""
 
     def __init__(self, k, canonical, strategy, device, world=1, rank=0, dist=None, torch=None, **kw):
         self.kc = KmerCounter(k=k, canonical=canonical, strategy=strategy, device=device, **kw)
         self.world, self.rank, self.dist, self.torch = world, rank, dist, torch
         self.key_bits = 2 * self.kc.key_bases
         self._keep = None
+        self._peer = None       # (cap_keys, my recv buffer ptr, [pointer of my region in every rank's recv buffer])
+        self._opened = []
+        self.n_bases = 0
+        self.use_peer = world > 1 and self.key_bits <= 64 and kw.get("mode", 0) == 0 and \
+            os.environ.get("KMC_DIST_EXCHANGE", "peer") == "peer"
 
     def set_stream(self, ptr):
         self.kc.set_stream(ptr)
@@ -65,27 +99,87 @@ class DistCounter:
     def reset(self):
         self.kc.reset()
         self._keep = None
+        self.n_bases = 0
 
-    def submit_device(self, *a):
-        self.kc.submit_device(*a)
+    def submit_device(self, d_bases, d_off, n_bases, n_recs):
+        self.n_bases += n_bases
+        self.kc.submit_device(d_bases, d_off, n_bases, n_recs)
 
-    def submit_host(self, *a):
-        self.kc.submit_host(*a)
+    def submit_host(self, bases, rec_off):
+        self.n_bases += len(bases)
+        self.kc.submit_host(bases, rec_off)
+
+    def _setup_peers(self):
+        """Receive buffer of world regions, one per source rank; map every peer's buffer (CUDA IPC)."""
+        torch, dist = self.torch, self.dist
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nb = torch.tensor([self.n_bases], dtype=torch.int64, device=dev)
+        dist.all_reduce(nb, op=dist.ReduceOp.MAX)
+        cap = (int(int(nb) / self.world * 1.03) + 65536 + 15) // 16 * 16
+        if self._peer is not None and self._peer[0] >= cap:
+            return
+        for p in self._opened:
+            self.kc.ipc_close(p)
+        self._opened = []
+        torch.cuda.synchronize()
+        dist.barrier()
+        mine = self.kc.recv_buffer(cap * self.world)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.kc.ipc_export(mine))
+        regions = []
+        for p in range(self.world):
+            if p == self.rank:
+                base = mine
+            else:
+                base = self.kc.ipc_open(handles[p])
+                self._opened.append(base)
+            regions.append(base + self.rank * cap * 8)
+        self._peer = (cap, mine, regions)
 
     def finish(self):
         if self.world == 1:
             return self.kc.finish()
         torch, dist = self.torch, self.dist
-        part_off, ptr, key_bytes = self.kc.route(self.world)
-        words = key_bytes // 8
-        send_sizes = split_sizes(part_off, words)
+        t = [time.perf_counter()]
+
+        def mark():
+            if _PROF:
+                torch.cuda.synchronize()
+                t.append(time.perf_counter())
+
         dev = torch.device("cuda", torch.cuda.current_device())
-        n_send = int(part_off[-1]) * words
-        send = torch.as_tensor(_DevArray(ptr, max(n_send, 1)), device=dev)[:n_send]
-        recv, _ = exchange(torch, dist, send, send_sizes)
-        self._keep = recv  # referenced by the ctx until finish returns
-        self.kc.ingest_keys(recv.data_ptr(), recv.numel() // words)
-        return self.kc.finish()
+        if self.use_peer:
+            self._setup_peers()
+            cap, mine, regions = self._peer
+            # nobody may still be reading its receive buffer from the previous job
+            dist.barrier()
+            count = self.kc.route_to_peers(regions, cap)
+            mark()
+            sc = torch.from_numpy(count.astype(np.int64)).to(dev)
+            rc = torch.empty_like(sc)
+            dist.all_to_all_single(rc, sc)   # also the hand-over point: every rank's routing kernel is done
+            got = rc.tolist()
+            mark()
+            for src, n in enumerate(got):
+                self.kc.ingest_keys(mine + src * cap * 8, n)
+        else:
+            begin, count, ptr, key_bytes = self.kc.route(self.world)
+            mark()
+            words = key_bytes // 8
+            span = int((begin + count).max()) * words
+            buf = torch.as_tensor(_DevArray(ptr, max(span, 1)), device=dev)
+            parts = [buf[int(b) * words:(int(b) + int(n)) * words] for b, n in zip(begin, count)]
+            recv, _ = exchange(torch, dist, parts)
+            mark()
+            self._keep = recv  # referenced by the ctx until finish returns
+            self.kc.ingest_keys(recv.data_ptr(), recv.numel() // words)
+        out = self.kc.finish()
+        mark()
+        if _PROF and self.rank == 0:
+            d = [1e3 * (b - a) for a, b in zip(t[:-1], t[1:])]
+            print(f"[kmc dist] route {d[0]:.2f} ms, exchange {d[1]:.2f} ms, count {d[2]:.2f} ms "
+                  f"({'peer stores' if self.use_peer else 'nccl all-to-all'})", file=sys.stderr)
+        return out
 
     def digest(self):
         return self.kc.digest()
@@ -100,4 +194,10 @@ class DistCounter:
         return kernel_bytes(name, n_keys, n_distinct, n_bases, key_bytes, self.key_bits)
 
     def close(self):
+        for p in self._opened:
+            try:
+                self.kc.ipc_close(p)
+            except Exception:
+                pass
+        self._opened = []
         self.kc.close()

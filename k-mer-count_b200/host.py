@@ -23,7 +23,8 @@ KMC_E_COUNT_OVERFLOW, KMC_E_CAPACITY, KMC_E_BADBASE_OFFSET0 = -7, -8, -9
 SYMBOLS = ["kmc_create", "kmc_destroy", "kmc_last_error", "kmc_strerror", "kmc_set_stream", "kmc_reset",
            "kmc_staging", "kmc_submit", "kmc_submit_host", "kmc_submit_device", "kmc_finish", "kmc_read",
            "kmc_table_device", "kmc_digest", "kmc_key_bases", "kmc_route", "kmc_ingest_keys", "kmc_owner_of",
-           "kmc_stats_json"]
+           "kmc_stats_json", "kmc_route_to_peers", "kmc_recv_buffer", "kmc_ipc_export", "kmc_ipc_open",
+           "kmc_ipc_close"]
 
 
 class KmcConfig(C.Structure):
@@ -72,8 +73,13 @@ def load_library(path=None):
     L.kmc_digest.argtypes = [vp, u64p]
     L.kmc_key_bases.argtypes = [vp]
     L.kmc_key_bases.restype = C.c_uint32
-    L.kmc_route.argtypes = [vp, C.c_uint32, vp, C.POINTER(vp), C.POINTER(C.c_uint32)]
+    L.kmc_route.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(vp), C.POINTER(C.c_uint32)]
     L.kmc_ingest_keys.argtypes = [vp, vp, C.c_uint64]
+    L.kmc_route_to_peers.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.c_uint64, vp]
+    L.kmc_recv_buffer.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    L.kmc_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    L.kmc_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.kmc_ipc_close.argtypes = [vp, vp]
     L.kmc_owner_of.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
     L.kmc_owner_of.restype = C.c_uint32
     L.kmc_stats_json.argtypes = [vp, C.c_char_p, C.c_size_t]
@@ -200,10 +206,37 @@ class KmerCounter:
 
     # -- multi-GPU routing
     def route(self, n_parts):
-        off = np.zeros(n_parts + 1, np.uint64)
+        """→ (part_begin, part_count) in keys, device pointer of the routed keys, bytes per key."""
+        begin, count = np.zeros(n_parts, np.uint64), np.zeros(n_parts, np.uint64)
         keys, kb = C.c_void_p(), C.c_uint32()
-        self._ck(self._L.kmc_route(self._h, n_parts, off.ctypes.data, C.byref(keys), C.byref(kb)))
-        return off, keys.value, kb.value
+        self._ck(self._L.kmc_route(self._h, n_parts, begin.ctypes.data, count.ctypes.data, C.byref(keys), C.byref(kb)))
+        return begin, count, keys.value, kb.value
+
+    def route_to_peers(self, part_ptrs, part_cap_keys):
+        """Route straight into the given device pointers (peers' receive regions).  → part_count."""
+        n = len(part_ptrs)
+        arr = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in part_ptrs])
+        count = np.zeros(n, np.uint64)
+        self._ck(self._L.kmc_route_to_peers(self._h, n, arr, part_cap_keys, count.ctypes.data))
+        return count
+
+    def recv_buffer(self, n_keys):
+        p = C.c_void_p()
+        self._ck(self._L.kmc_recv_buffer(self._h, n_keys, C.byref(p)))
+        return p.value
+
+    def ipc_export(self, d_ptr):
+        h = C.create_string_buffer(64)
+        self._ck(self._L.kmc_ipc_export(self._h, C.c_void_p(d_ptr), h))
+        return h.raw
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        self._ck(self._L.kmc_ipc_open(self._h, C.create_string_buffer(bytes(handle), 64), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, d_peer_ptr):
+        self._ck(self._L.kmc_ipc_close(self._h, C.c_void_p(d_peer_ptr)))
 
     def ingest_keys(self, d_keys_ptr, n_keys):
         self._ck(self._L.kmc_ingest_keys(self._h, C.c_void_p(d_keys_ptr), n_keys))

@@ -35,7 +35,8 @@ def _worker(rank, world, port, words, q):
     part_off = np.searchsorted(owner, np.arange(world + 1)).astype(np.uint64)
     keys = np.stack([lo, hi], axis=1).reshape(-1) if words == 2 else lo
     send = torch.from_numpy(keys.view(np.int64).copy())
-    recv, sizes = exchange(torch, dist, send, split_sizes(part_off, words))
+    sizes = split_sizes(part_off[1:] - part_off[:-1], words)
+    recv, sizes = exchange(torch, dist, list(torch.split(send, sizes)))
     got = recv.numpy().view(np.uint64).reshape(-1, words)
     ok = all(L.kmc_owner_of(int(r[1]) if words == 2 else 0, int(r[0]), world) == rank for r in got)
     q.put((rank, ok, int(part_off[-1]), len(got), int(got[:, 0].astype(object).sum() % (1 << 61)),
@@ -64,5 +65,5 @@ def test_exchange_delivers_keys_to_owners(words):
 
 def test_split_sizes():
     from kmer_count_b200.dist import split_sizes
-    assert split_sizes(np.array([0, 3, 3, 10], np.uint64), 1) == [3, 0, 7]
-    assert split_sizes(np.array([0, 3, 3, 10], np.uint64), 2) == [6, 0, 14]
+    assert split_sizes(np.array([3, 0, 7], np.uint64), 1) == [3, 0, 7]
+    assert split_sizes(np.array([3, 0, 7], np.uint64), 2) == [6, 0, 14]

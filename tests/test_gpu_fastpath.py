@@ -99,9 +99,9 @@ def test_fast_path_key_array_front_end(kmc, orc):
     want = orc.contiguous_mt(bases, off, 31, True)
     with kmc.KmerCounter(k=31) as router, kmc.KmerCounter(k=31) as owner:
         router.submit_host(bases, off)
-        part_off, ptr, kb = router.route(1)
-        t = torch.as_tensor(_DevArray(ptr, int(part_off[-1])), device="cuda")
-        half = int(part_off[-1]) // 2
+        begin, count, ptr, kb = router.route(1)
+        t = torch.as_tensor(_DevArray(ptr, int(begin[0] + count[0])), device="cuda")[int(begin[0]):]
+        half = int(count[0]) // 2
         a, b = t[:half].clone(), t[half:].clone()
         owner.ingest_keys(a.data_ptr(), a.numel())
         owner.ingest_keys(b.data_ptr(), b.numel())

@@ -230,15 +230,14 @@ def test_hypothesis_contiguous(kmc, orc):
     prop()
 
 
-@pytest.mark.parametrize("k,world", [(21, 2), (31, 3), (63, 4)])
-def test_route_and_ingest_emulated_ranks(kmc, orc, k, world):
+@pytest.mark.parametrize("k,world,n", [(21, 2, 400_000), (31, 3, 400_000), (63, 4, 400_000), (21, 8, 3_000_000), (31, 5, 2_500_000)])
+def test_route_and_ingest_emulated_ranks(kmc, orc, k, world, n):
     """Multi-GPU path on one GPU: each emulated rank routes its shard of the reads by owner
     (kmc_route); each owner ingests the parts addressed to it from every rank (what the all-to-all
     delivers) and counts them.  The union of the owners' tables is the single-GPU table, the owners'
     key sets are disjoint, and the device owner function equals the host one."""
     import torch
     rng = np.random.default_rng(k)
-    n = 400_000
     bases = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=n, p=[0.2495, 0.2495, 0.2495, 0.2495, 0.002])
     off = np.arange(0, n + 1, 500, dtype=np.uint64)
     want = orc.contiguous_mt(bases, off, k, True)
@@ -250,18 +249,19 @@ def test_route_and_ingest_emulated_ranks(kmc, orc, k, world):
         a, z = rec_cuts[r], rec_cuts[r + 1]
         kc = kmc.KmerCounter(k=k, canonical=True)
         kc.submit_host(bases[int(off[a]):int(off[z])], off[a:z + 1] - off[a])
-        part_off, ptr, kb = kc.route(world)
+        begin, count, ptr, kb = kc.route(world)
         assert kb == 8 * words
         from kmer_count_b200.dist import _DevArray
-        t = torch.as_tensor(_DevArray(ptr, max(1, int(part_off[-1]) * words)), device="cuda")[: int(part_off[-1]) * words]
+        span = max(1, int((begin + count).max()) * words)
+        t = torch.as_tensor(_DevArray(ptr, span), device="cuda")
         routers.append(kc)
-        parts.append((part_off, t.clone()))
+        parts.append([t[int(b) * words:(int(b) + int(n)) * words].clone() for b, n in zip(begin, count)])
     tables = []
     for p in range(world):
         kc = kmc.KmerCounter(k=k, canonical=True)
         bufs = []
-        for part_off, t in parts:
-            seg = t[int(part_off[p]) * words:int(part_off[p + 1]) * words].contiguous()
+        for plist in parts:
+            seg = plist[p].contiguous()
             bufs.append(seg)
             kc.ingest_keys(seg.data_ptr(), seg.numel() // words)
         kc.finish()
@@ -279,3 +279,70 @@ def test_route_and_ingest_emulated_ranks(kmc, orc, k, world):
     assert sum(t.n_total for t in tables) == want.n_total
     assert np.array_equal(hi[order], want.key_hi) and np.array_equal(lo[order], want.key_lo)
     assert np.array_equal(cnt[order], want.count)
+
+
+def test_route_to_peers_emulated(kmc, orc):
+    """kmc_route_to_peers on one GPU: the 'peer' regions are plain device buffers of this process.  Each
+    emulated rank stores part p of its keys into region [rank] of owner p's buffer; owners count."""
+    import torch
+    k, world, n = 31, 4, 3_000_000
+    rng = np.random.default_rng(77)
+    bases = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=n, p=[0.2495, 0.2495, 0.2495, 0.2495, 0.002])
+    off = np.arange(0, n + 1, 500, dtype=np.uint64)
+    want = orc.contiguous_mt(bases, off, k, True)
+    cap = (int(n / world / world * 1.2) + 65536 + 15) // 16 * 16
+    recv = [torch.zeros(cap * world, dtype=torch.int64, device="cuda") for _ in range(world)]
+    rec_cuts = np.linspace(0, len(off) - 1, world + 1).astype(int)
+    counts = np.zeros((world, world), np.int64)
+    for r in range(world):
+        a, z = rec_cuts[r], rec_cuts[r + 1]
+        with kmc.KmerCounter(k=k, canonical=True) as kc:
+            kc.submit_host(bases[int(off[a]):int(off[z])], off[a:z + 1] - off[a])
+            counts[r] = kc.route_to_peers([recv[p].data_ptr() + r * cap * 8 for p in range(world)], cap)
+    torch.cuda.synchronize()
+    tables = []
+    for p in range(world):
+        with kmc.KmerCounter(k=k, canonical=True) as kc:
+            for r in range(world):
+                kc.ingest_keys(recv[p].data_ptr() + r * cap * 8, int(counts[r, p]))
+            kc.finish()
+            tables.append(kc.read())
+    hi = np.concatenate([t.key_hi for t in tables])
+    lo = np.concatenate([t.key_lo for t in tables])
+    cnt = np.concatenate([t.count for t in tables])
+    order = np.lexsort((lo, hi))
+    assert sum(t.n_total for t in tables) == want.n_total
+    assert np.array_equal(lo[order], want.key_lo) and np.array_equal(cnt[order], want.count)
+
+
+def test_cli_drop_in(kmc, gold_dir, golden, tmp_path):
+    """The kmer-count binary with no arguments is the reference binary: reads ./sample.fasta from the CWD
+    (main.rs:44) and prints the sorted chunks (main.rs:87-90); panics (exit 101) where the reference does."""
+    import shutil
+    import subprocess
+    from kmer_count_b200.build import cli_path
+    cli = cli_path()
+    assert os.path.exists(cli)
+    shutil.copy(os.path.join(gold_dir, "sample.fasta"), tmp_path / "sample.fasta")
+    r = subprocess.run([cli], cwd=tmp_path, capture_output=True)
+    assert r.returncode == 0 and r.stderr == b""
+    assert hashlib.sha256(r.stdout).hexdigest() == golden["sample"]["stdout_sha256"]
+    # argv forms: explicit path, -o, contiguous mode
+    out = tmp_path / "out.txt"
+    r = subprocess.run([cli, os.path.join(gold_dir, "tiny_lengths.fasta"), "--mode", "lr-gapped", "-o", str(out)], capture_output=True)
+    assert r.returncode == 0
+    assert out.read_bytes() == gzip.open(os.path.join(gold_dir, "tiny_lengths.expected.txt.gz")).read()
+    r = subprocess.run([cli, os.path.join(gold_dir, "sample.fasta"), "-k", "21"], capture_output=True)
+    assert r.returncode == 0
+    assert hashlib.sha256(r.stdout).hexdigest() == "d6821a8f1b9010573e9009dc86475c1db676fbfa6c2c87cead0bfec2a9a8d248"
+    # the reference's panics
+    empty = tmp_path / "e"
+    empty.mkdir()
+    assert subprocess.run([cli], cwd=empty, capture_output=True).returncode == 101       # missing file, main.rs:44
+    (empty / "sample.fasta").write_text("ACGT\n")
+    assert subprocess.run([cli], cwd=empty, capture_output=True).returncode == 101       # no '>', main.rs:59
+    (empty / "sample.fasta").write_text(">a\n" + "ACGT" * 10 + "\n")
+    assert subprocess.run([cli], cwd=empty, capture_output=True).returncode == 101       # no chunk, main.rs:35
+    (empty / "sample.fasta").write_text(">a\n" + "ACGT" * 10 + "N" + "ACGT" * 20 + "\n")
+    r = subprocess.run([cli], cwd=empty, capture_output=True)
+    assert r.returncode == 101 and r.stdout == b""                                        # bad base, main.rs:23
