@@ -625,7 +625,7 @@ int finish_fast(kmc_ctx *c, bool *used) {
     uint64_t cap1 = ((uint64_t)((double)nb * 1.03) + 8192 + 15) & ~15ull;
     l1s[b] = l1_keys; l1cap[b] = cap1; t0[b] = (uint32_t)tiles2; l1ep[b] = l1e[b];
     l1_keys += cap1;
-    tiles2 += (cap1 + kPart2Tile - 1) / kPart2Tile;
+    tiles2 += (cap1 + kP2Tile - 1) / kP2Tile;
   }
   l1s[n_l1] = l1_keys; t0[n_l1] = (uint32_t)tiles2; f0[n_l1] = fb;
   if (tiles2 > 0x7FFFFFFFull) return KMC_OK;
@@ -682,7 +682,7 @@ int finish_fast(kmc_ctx *c, bool *used) {
   // ---- level 2
   PHASE_BEGIN("fast_part2");
   {
-    size_t smem = PartSmem::bytes(kPart2Tile, kMaxFinePerL1);
+    size_t smem = PartSmem::bytes(kP2Tile, kMaxFinePerL1);
     if (key32) {
       auto fast_part2 = fast_part2_kernel<uint32_t>;
       CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -705,15 +705,15 @@ int finish_fast(kmc_ctx *c, bool *used) {
       size_t smem = sizeof(FinishSmem<uint32_t>);
       auto fast_finish = fast_finish_kernel<uint32_t>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 3);
-      LAUNCH(fast_finish, grid, kFastThreads, smem, pl, (const uint32_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint32_t *)c->t_cnt.p,
+      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB32);
+      LAUNCH(fast_finish, grid, kFinThreads, smem, pl, (const uint32_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint32_t *)c->t_cnt.p,
              status, ticket, d_err(c), d_total, prof);
     } else {
       size_t smem = sizeof(FinishSmem<uint64_t>);
       auto fast_finish = fast_finish_kernel<uint64_t>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2);
-      LAUNCH(fast_finish, grid, kFastThreads, smem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint32_t *)c->t_cnt.p,
+      LAUNCH(fast_finish, grid, kFinThreads, smem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint32_t *)c->t_cnt.p,
              status, ticket, d_err(c), d_total, prof);
     }
     if (want_prof) {

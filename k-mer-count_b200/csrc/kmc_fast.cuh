@@ -163,6 +163,7 @@ __device__ __forceinline__ uint32_t scan_bins(const uint32_t *hist, uint32_t *lo
     if (b < nb) loc[b] = ex;
     ex += v[j];
   }
+  __syncthreads(); // loc[] is read next by other threads (bucket b is reserved by thread b, not by its writer b/4)
   return total;
 }
 
@@ -270,9 +271,14 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part1_array_kernel(const
   }
 }
 
-// One CTA per tile of <= 16384 keys of one level-1 bucket → its 2^e fine buckets (the next e key bits).
+// One CTA per tile of kP2Tile keys of one level-1 bucket → its 2^e fine buckets (the next e key bits).
+#ifndef KMC_PART2_KPT
+#define KMC_PART2_KPT 16
+#endif
+constexpr int kP2KPT = KMC_PART2_KPT;              // keys per thread
+constexpr int kP2Tile = kFastThreads * kP2KPT;     // 8192 keys at 16 per thread: 96 KB of smem, two CTAs per SM
 template <typename L2T>
-__global__ void __launch_bounds__(kFastThreads, 1) fast_part2_kernel(FastPlan pl, const uint64_t *__restrict__ l1,
+__global__ void __launch_bounds__(kFastThreads, kP2KPT <= 16 ? 2 : 1) fast_part2_kernel(FastPlan pl, const uint64_t *__restrict__ l1,
                                                                       L2T *__restrict__ l2, uint32_t *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_b;
@@ -289,25 +295,25 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part2_kernel(FastPlan pl
   const uint32_t b = s_b;
   unsigned long long n_b = pl.l1_cursor[b];
   if (n_b > pl.l1_cap[b]) n_b = pl.l1_cap[b];
-  const uint64_t toff = (uint64_t)(blockIdx.x - pl.l1_tile0[b]) * kPart2Tile;
+  const uint64_t toff = (uint64_t)(blockIdx.x - pl.l1_tile0[b]) * kP2Tile;
   if (toff >= n_b) return; // tiles are laid out over the capacity; this one is past the fill
   const uint32_t e = pl.l1_e[b];
   const uint32_t fshift = pl.kb - pl.b1 - e, fmask = (1u << e) - 1u; // e == 0 → fmask 0 → fine index 0
   const uint32_t fine0 = pl.l1_fine0[b], nb = 1u << e;
-  PartSmem S(smem_raw, kPart2Tile, kMaxFinePerL1);
+  PartSmem S(smem_raw, kP2Tile, kMaxFinePerL1);
   for (uint32_t i = threadIdx.x; i < nb; i += kFastThreads) S.hist[i] = 0;
   __syncthreads();
   const uint64_t base = pl.l1_start[b] + toff;
-  const uint32_t cnt = (uint32_t)((n_b - toff < (uint64_t)kPart2Tile) ? n_b - toff : kPart2Tile);
-  uint64_t key[kPart2KPT];
-  uint32_t rank[kPart2KPT / 2];
+  const uint32_t cnt = (uint32_t)((n_b - toff < (uint64_t)kP2Tile) ? n_b - toff : kP2Tile);
+  uint64_t key[kP2KPT];
+  uint32_t rank[kP2KPT / 2];
 #pragma unroll
-  for (int j = 0; j < kPart2KPT; j++) {
+  for (int j = 0; j < kP2KPT; j++) {
     uint32_t idx = j * kFastThreads + threadIdx.x;
     key[j] = idx < cnt ? l1[base + idx] : 0ull;
   }
 #pragma unroll
-  for (int j = 0; j < kPart2KPT; j++) {
+  for (int j = 0; j < kP2KPT; j++) {
     uint32_t idx = j * kFastThreads + threadIdx.x;
     uint32_t r = 0;
     if (idx < cnt) r = atomicAdd(&S.hist[fmask ? (uint32_t)(key[j] >> fshift) & fmask : 0u], 1u);
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part2_kernel(FastPlan pl
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < kPart2KPT; j++) {
+  for (int j = 0; j < kP2KPT; j++) {
     uint32_t idx = j * kFastThreads + threadIdx.x;
     if (idx < cnt)
       S.stage[S.loc[fmask ? (uint32_t)(key[j] >> fshift) & fmask : 0u] + ((rank[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)] = key[j];
@@ -386,7 +392,14 @@ __device__ __forceinline__ unsigned long long lookback_resolve(unsigned long lon
   return prefix;
 }
 
-constexpr int kFinishKPT = kFineCap / kFastThreads; // 16 keys per thread
+#ifndef KMC_FINISH_THREADS
+#define KMC_FINISH_THREADS 512
+#endif
+constexpr int kFinThreads = KMC_FINISH_THREADS;      // threads per CTA of fast_finish
+constexpr int kFinWarps = kFinThreads / 32;
+constexpr int kFinishKPT = kFineCap / kFinThreads;   // keys per thread (16 at 512 threads)
+constexpr int kFinWordsPT = kFinishBins / 2 / kFinThreads; // packed bin words per thread in the scan (8 at 512 threads)
+static_assert(kFinishKPT <= 32 && kFinishKPT * kFinWarps <= kFinThreads && kFinWordsPT % 4 == 0, "fast_finish shape");
 
 template <typename L2T>
 struct FinishSmem {
@@ -394,7 +407,7 @@ struct FinishSmem {
   uint32_t bins[kFinishBins / 2];          // packed u16 pairs: counts → starts → (after the scatter) ends
   uint16_t hp[kFineCap + 8];               // head position of every run
   uint32_t scan32[40];
-  uint32_t rowcnt[kFinishKPT * kFastWarps];// heads per (row, warp), then their exclusive scan
+  uint32_t rowcnt[kFinishKPT * kFinWarps];// heads per (row, warp), then their exclusive scan
   uint32_t hard[kMaxHard];
   uint32_t n_hard;
   uint32_t n_multi;
@@ -407,8 +420,11 @@ struct FinishSmem {
 __device__ __forceinline__ uint32_t bin_end(const uint32_t *bins, uint32_t b) { return reinterpret_cast<const uint16_t *>(bins)[b]; }
 __device__ __forceinline__ uint32_t bin_start(const uint32_t *bins, uint32_t b) { return b ? bin_end(bins, b - 1) : 0u; }
 
+#ifndef KMC_FINISH_MINB32
+#define KMC_FINISH_MINB32 3
+#endif
 template <typename L2T>
-__global__ void __launch_bounds__(kFastThreads, sizeof(L2T) == 4 ? 3 : 2) fast_finish_kernel(FastPlan pl, const L2T *__restrict__ l2,
+__global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MINB32 : 2) fast_finish_kernel(FastPlan pl, const L2T *__restrict__ l2,
                                                                        uint64_t *__restrict__ out_lo, uint32_t *__restrict__ out_cnt,
                                                                        unsigned long long *__restrict__ status,
                                                                        unsigned int *__restrict__ ticket, uint32_t *__restrict__ flags,
@@ -433,24 +449,24 @@ __global__ void __launch_bounds__(kFastThreads, sizeof(L2T) == 4 ? 3 : 2) fast_f
     const uint32_t bshift = D.rem - sb, bmask = (1u << sb) - 1u;
     {
       uint4 z = make_uint4(0, 0, 0, 0);
-      for (uint32_t i = tid; i < kFinishBins / 8; i += kFastThreads) reinterpret_cast<uint4 *>(S.bins)[i] = z;
+      for (uint32_t i = tid; i < kFinishBins / 8; i += kFinThreads) reinterpret_cast<uint4 *>(S.bins)[i] = z;
     }
     if (tid == 0) { S.n_hard = 0; S.n_multi = 0; S.n_dups = 0; }
     __syncthreads();
     FIN_MARK(1);
     // ---- load (thread t owns positions t, t+512, ...) + count per sub-bin.  The thread that adds the SECOND
     //      key of a sub-bin puts the sub-bin on the multi-key list (S.hp is free until the run-length encode).
-    const uint32_t rows = (n + kFastThreads - 1) / kFastThreads;
+    const uint32_t rows = (n + kFinThreads - 1) / kFinThreads;
     L2T x[kFinishKPT];
 #pragma unroll
     for (int j = 0; j < kFinishKPT; j++) {
-      uint32_t i = j * kFastThreads + tid;
+      uint32_t i = j * kFinThreads + tid;
       x[j] = i < n ? l2[D.start + i] : (L2T)0;
     }
 #pragma unroll
     for (int j = 0; j < kFinishKPT; j++) {
       if ((uint32_t)j >= rows) break;
-      uint32_t i = j * kFastThreads + tid;
+      uint32_t i = j * kFinThreads + tid;
       if (i < n) {
         uint32_t b = (uint32_t)(x[j] >> bshift) & bmask;
         uint32_t sh = 16 * (b & 1);
@@ -462,21 +478,26 @@ __global__ void __launch_bounds__(kFastThreads, sizeof(L2T) == 4 ? 3 : 2) fast_f
     FIN_MARK(2);
     // ---- exclusive scan of the 8192 packed counts (16 sub-bins = 8 words per thread), starts written in place
     {
-      uint4 a = reinterpret_cast<const uint4 *>(S.bins)[tid * 2], b4 = reinterpret_cast<const uint4 *>(S.bins)[tid * 2 + 1];
-      uint32_t w[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+      uint32_t w[kFinWordsPT];
+#pragma unroll
+      for (int q = 0; q < kFinWordsPT / 4; q++) {
+        uint4 a = reinterpret_cast<const uint4 *>(S.bins)[tid * (kFinWordsPT / 4) + q];
+        w[4 * q] = a.x; w[4 * q + 1] = a.y; w[4 * q + 2] = a.z; w[4 * q + 3] = a.w;
+      }
       uint32_t s = 0;
 #pragma unroll
-      for (int q = 0; q < 8; q++) s += (w[q] & 0xFFFFu) + (w[q] >> 16);
+      for (int q = 0; q < kFinWordsPT; q++) s += (w[q] & 0xFFFFu) + (w[q] >> 16);
       uint32_t total;
-      uint32_t ex = block_excl_scan<uint32_t, kFastThreads>(s, S.scan32, total);
+      uint32_t ex = block_excl_scan<uint32_t, kFinThreads>(s, S.scan32, total);
 #pragma unroll
-      for (int q = 0; q < 8; q++) {
+      for (int q = 0; q < kFinWordsPT; q++) {
         uint32_t c0 = w[q] & 0xFFFFu, c1 = w[q] >> 16;
         w[q] = ex | ((ex + c0) << 16);
         ex += c0 + c1;
       }
-      reinterpret_cast<uint4 *>(S.bins)[tid * 2] = make_uint4(w[0], w[1], w[2], w[3]);
-      reinterpret_cast<uint4 *>(S.bins)[tid * 2 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+#pragma unroll
+      for (int q = 0; q < kFinWordsPT / 4; q++)
+        reinterpret_cast<uint4 *>(S.bins)[tid * (kFinWordsPT / 4) + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
     }
     __syncthreads();
     FIN_MARK(3);
@@ -484,7 +505,7 @@ __global__ void __launch_bounds__(kFastThreads, sizeof(L2T) == 4 ? 3 : 2) fast_f
 #pragma unroll
     for (int j = 0; j < kFinishKPT; j++) {
       if ((uint32_t)j >= rows) break;
-      uint32_t i = j * kFastThreads + tid;
+      uint32_t i = j * kFinThreads + tid;
       if (i < n) {
         uint32_t b = (uint32_t)(x[j] >> bshift) & bmask;
         uint32_t sh = 16 * (b & 1);
@@ -500,7 +521,7 @@ __global__ void __launch_bounds__(kFastThreads, sizeof(L2T) == 4 ? 3 : 2) fast_f
       const uint16_t *end16 = reinterpret_cast<const uint16_t *>(S.bins);
       const uint32_t n_multi = S.n_multi;
       uint32_t dups = 0; // equal neighbours after sorting = rows that the run-length encode will merge
-      for (uint32_t q = tid; q < n_multi; q += kFastThreads) {
+      for (uint32_t q = tid; q < n_multi; q += kFinThreads) {
         const uint32_t b = S.hp[q];
         const uint32_t s0 = b ? end16[b - 1] : 0u, e0 = end16[b];
         if (e0 - s0 > (uint32_t)kSmallBin) {
@@ -543,9 +564,9 @@ __global__ void __launch_bounds__(kFastThreads, sizeof(L2T) == 4 ? 3 : 2) fast_f
         const uint32_t s = bin_start(S.bins, b), m = bin_end(S.bins, b) - s;
         const L2T first = S.keys[s];
         int differ = 0;
-        for (uint32_t i = tid; i < m; i += kFastThreads) differ |= (S.keys[s + i] != first);
+        for (uint32_t i = tid; i < m; i += kFinThreads) differ |= (S.keys[s + i] != first);
         if (__syncthreads_or(differ)) {
-          for (uint32_t i = tid; i < m; i += kFastThreads) {
+          for (uint32_t i = tid; i < m; i += kFinThreads) {
             const L2T v = S.keys[s + i];
             uint32_t r = 0;
             for (uint32_t q = 0; q < m; q++) {
@@ -557,13 +578,13 @@ __global__ void __launch_bounds__(kFastThreads, sizeof(L2T) == 4 ? 3 : 2) fast_f
           __syncthreads();
 #pragma unroll
           for (int j = 0; j < kFinishKPT; j++) {
-            uint32_t i = j * kFastThreads + tid;
+            uint32_t i = j * kFinThreads + tid;
             if (i < m) x[j] = S.keys[s + i];
           }
           __syncthreads();
 #pragma unroll
           for (int j = 0; j < kFinishKPT; j++) {
-            uint32_t i = j * kFastThreads + tid;
+            uint32_t i = j * kFinThreads + tid;
             if (i < m) S.keys[s + S.hp[i]] = x[j];
           }
           __syncthreads();
@@ -574,10 +595,9 @@ __global__ void __launch_bounds__(kFastThreads, sizeof(L2T) == 4 ? 3 : 2) fast_f
     // ---- run-length encode the sorted bucket.  Thread t owns positions t, t+512, ... (bank-conflict free);
     //      a position is a head if its key differs from the one before it.
     uint32_t heads = 0;
-    uint32_t below[kFinishKPT / 4]; // heads in lower lanes of the same warp row, 8 bits each
 #pragma unroll
     for (int j = 0; j < kFinishKPT; j++) {
-      uint32_t p = j * kFastThreads + tid;
+      uint32_t p = j * kFinThreads + tid;
       bool h = false;
       if ((uint32_t)j < rows && p < n) {
         x[j] = S.keys[p];
@@ -585,16 +605,14 @@ __global__ void __launch_bounds__(kFastThreads, sizeof(L2T) == 4 ? 3 : 2) fast_f
       }
       uint32_t bal = (uint32_t)j < rows ? __ballot_sync(0xffffffffu, h) : 0u;
       if (h) heads |= 1u << j;
-      uint32_t lt = __popc(bal & ((1u << lane) - 1u));
-      if (j & 3) below[j >> 2] |= lt << (8 * (j & 3)); else below[j >> 2] = lt;
-      if (lane == 0) S.rowcnt[j * kFastWarps + warp] = __popc(bal);
+      if (lane == 0) S.rowcnt[j * kFinWarps + warp] = __popc(bal);
     }
     __syncthreads();
     uint32_t d;
     {
-      uint32_t v = tid < kFinishKPT * kFastWarps ? S.rowcnt[tid] : 0u;
-      uint32_t ex = block_excl_scan<uint32_t, kFastThreads>(v, S.scan32, d);
-      if (tid < kFinishKPT * kFastWarps) S.rowcnt[tid] = ex;
+      uint32_t v = tid < kFinishKPT * kFinWarps ? S.rowcnt[tid] : 0u;
+      uint32_t ex = block_excl_scan<uint32_t, kFinThreads>(v, S.scan32, d);
+      if (tid < kFinishKPT * kFinWarps) S.rowcnt[tid] = ex;
     }
     __syncthreads();
     FIN_MARK(7);
@@ -612,16 +630,19 @@ __global__ void __launch_bounds__(kFastThreads, sizeof(L2T) == 4 ? 3 : 2) fast_f
     }
 #pragma unroll
     for (int j = 0; j < kFinishKPT; j++) {
-      if (heads & (1u << j)) {
-        uint32_t u = S.rowcnt[j * kFastWarps + warp] + ((below[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+      if ((uint32_t)j >= rows) break;
+      const bool h = (heads >> j) & 1u;
+      const uint32_t bal = __ballot_sync(0xffffffffu, h); // same vote as in the head pass
+      if (h) {
+        uint32_t u = S.rowcnt[j * kFinWarps + warp] + __popc(bal & ((1u << lane) - 1u));
         S.keys[u] = x[j];
-        S.hp[u] = (uint16_t)(j * kFastThreads + tid);
+        S.hp[u] = (uint16_t)(j * kFinThreads + tid);
       }
     }
     __syncthreads();
     FIN_MARK(8);
     const unsigned long long G = S.goff;
-    for (uint32_t i = tid; i < d; i += kFastThreads) {
+    for (uint32_t i = tid; i < d; i += kFinThreads) {
       out_lo[G + i] = D.prefix | (uint64_t)S.keys[i];
       uint32_t nxt = (i + 1 < d) ? S.hp[i + 1] : n;
       out_cnt[G + i] = nxt - S.hp[i];
