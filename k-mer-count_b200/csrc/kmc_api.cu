@@ -17,6 +17,7 @@
 #include "kmc_extract.cuh"
 #include "kmc_sort.cuh"
 #include "kmc_fast.cuh"
+#include "kmc_hash.cuh"
 #include <cmath>
 
 using namespace kmc;
@@ -81,6 +82,8 @@ struct kmc_ctx {
   DevBuf gap_l, gap_r, gap_f;
   DevBuf t_lo, t_hi, t_cnt;
   DevBuf fast_l1, fast_l2, fast_state, fast_tables, recv_keys;
+  DevBuf hash_keys, hash_counts, hash_scalars;
+  uint32_t hash_aborts = 0;
   std::vector<unsigned char> fast_host; // plan tables staged for upload
   uint32_t fast_fallbacks = 0;          // times the partitioned path overflowed and the job was recounted
 
@@ -501,6 +504,137 @@ int finish_baseline(kmc_ctx *c) {
 }
 
 
+// 64-bit key sources of a job: either the submitted segments (keys are extracted on the fly) or key arrays
+// (ingested keys are used in place; lr-gapped keys are materialised first).
+struct KeyArrays {
+  bool from_array = false;
+  uint64_t n = 0;
+  std::vector<std::pair<const uint64_t *, uint64_t>> arrays;
+};
+int key_sources(kmc_ctx *c, KeyArrays *ka) {
+  ka->from_array = !c->ingested.empty() || c->cfg.mode == KMC_MODE_LR_GAPPED;
+  ka->n = 0; ka->arrays.clear();
+  if (!ka->from_array) return KMC_OK;
+  if (!c->ingested.empty()) {
+    for (auto &e : c->ingested) if (e.second) { ka->arrays.emplace_back((const uint64_t *)e.first, e.second); ka->n += e.second; }
+  } else {
+    TRY(produce_keys<uint64_t>(c, &ka->n));
+    if (ka->n) ka->arrays.emplace_back((const uint64_t *)c->keys_a.p, ka->n);
+  }
+  return KMC_OK;
+}
+
+// ---- hash strategy (kmc_hash.cuh), 64-bit keys ---------------------------------------------------------------
+// step > 1: cardinality probe on a sample (table stays, nothing else is produced); *ok = table did not fill.
+int hash_run(kmc_ctx *c, const KeyArrays &ka, uint32_t log2_slots, uint64_t limit, uint32_t step, bool *ok, HashTable *out) {
+  *ok = false;
+  // the fill limit is only checked between tiles: keep the keys in flight (one tile per resident warp) well below
+  // the table size, or a high-cardinality input would swamp the table before anybody notices
+  const uint64_t max_warps = std::max<uint64_t>(64, (1ull << log2_slots) / 4 / 992);
+  const uint32_t max_ctas = (uint32_t)std::min<uint64_t>((uint64_t)kNumSMsB200 * 8, std::max<uint64_t>(8, max_warps / 8));
+  const uint64_t slots = 1ull << log2_slots;
+  TRY(ensure(c, c->hash_keys, slots * 8));
+  TRY(ensure(c, c->hash_counts, slots * 4));
+  TRY(ensure(c, c->hash_scalars, 64));
+  CK(cudaMemsetAsync(c->hash_keys.p, 0xFF, slots * 8, c->stream));
+  CK(cudaMemsetAsync(c->hash_counts.p, 0, slots * 4, c->stream));
+  CK(cudaMemsetAsync(c->hash_scalars.p, 0, 64, c->stream));
+  HashTable T;
+  T.keys = (uint64_t *)c->hash_keys.p; T.counts = (uint32_t *)c->hash_counts.p;
+  T.mask = slots - 1; T.shift = 64 - log2_slots;
+  T.n_used = (unsigned long long *)c->hash_scalars.p; T.n_total = T.n_used + 1; T.n_ones = T.n_used + 2;
+  T.limit = limit; T.flags = d_err(c);
+  if (ka.from_array) {
+    for (auto &a : ka.arrays) {
+      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024ull * step), (uint64_t)max_ctas);
+      LAUNCH(hash_count_array_kernel, grid, 256, 0, a.first, a.second, step, T);
+    }
+  } else {
+    for (size_t i = 0; i < c->n_segs; i++) {
+      Segment &s = c->segs[i];
+      if (!s.n_bases) continue;
+      ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
+      uint64_t tiles = num_warp_tiles(s.n_bases, 31);
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)max_ctas);
+      auto hash_count = hash_count_kernel<true>;
+      LAUNCH(hash_count, grid, 256, 0, P, tiles, step, T);
+    }
+  }
+  uint32_t err = 0;
+  TRY(read_scalars(c, nullptr, &err));
+  if (err & kFlagHashFull) {
+    CK(cudaMemsetAsync(d_err(c), 0, 4, c->stream)); // a full table is not an error: the caller picks another route
+    return KMC_OK;
+  }
+  *ok = true;
+  if (out) *out = T;
+  return KMC_OK;
+}
+
+int finish_hash(kmc_ctx *c, uint32_t log2_slots, uint64_t limit, bool *used) {
+  *used = false;
+  KeyArrays ka;
+  TRY(key_sources(c, &ka));
+  HashTable T;
+  bool ok = false;
+  PHASE_BEGIN("hash_count");
+  TRY(hash_run(c, ka, log2_slots, limit, 1, &ok, &T));
+  PHASE_END();
+  if (!ok) { c->hash_aborts++; return KMC_OK; }
+  unsigned long long sc[3];
+  CK(cudaMemcpyAsync(sc, c->hash_scalars.p, sizeof sc, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const uint64_t d = sc[0], n_total = sc[1], n_ones = sc[2];
+  if (n_ones > 0xFFFFFFFFull) return fail(c, KMC_E_COUNT_OVERFLOW, "a k-mer occurs more than 2^32-1 times");
+  PHASE_BEGIN("hash_sort");
+  // distinct keys → dense array → sorted; the key arrays of key_sources() are no longer needed
+  uint64_t *dense = nullptr, *scratch = nullptr, *sorted = nullptr;
+  TRY(ensure(c, c->t_lo, (d + 2) * 8));
+  TRY(ensure(c, c->keys_b, (d + 2) * 8));
+  TRY(ensure(c, c->t_cnt, (d + 2) * 4));
+  dense = (uint64_t *)c->t_lo.p; scratch = (uint64_t *)c->keys_b.p;
+  if (d) {
+    CK(cudaMemsetAsync(d_cursor(c), 0, 8, c->stream));
+    LAUNCH(hash_compact_kernel, std::min<uint32_t>(grid_for(T.mask + 1, 256), kNumSMsB200 * 16), 256, 0, T, dense, d_cursor(c));
+    TRY(radix_sort<uint64_t>(c, dense, scratch, d, c->key_bits, &sorted));
+    if (sorted != dense) CK(cudaMemcpyAsync(dense, sorted, d * 8, cudaMemcpyDeviceToDevice, c->stream));
+    LAUNCH(hash_lookup_kernel, std::min<uint32_t>(grid_for(d, 256), kNumSMsB200 * 16), 256, 0, T, (const uint64_t *)dense, d,
+           (uint32_t *)c->t_cnt.p);
+  }
+  uint64_t rows = d;
+  if (n_ones) { // the all-ones key (k = 32) sorts last
+    uint64_t k1 = kHashEmpty;
+    uint32_t c1 = (uint32_t)n_ones;
+    CK(cudaMemcpyAsync(dense + d, &k1, 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync((uint32_t *)c->t_cnt.p + d, &c1, 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    rows++;
+  }
+  PHASE_END();
+  c->n_total = n_total; c->n_distinct = rows;
+  c->strategy_used = KMC_STRATEGY_HASH;
+  *used = true;
+  return KMC_OK;
+}
+
+// AUTO: is the number of distinct keys small enough for an L2-resident table?  Insert a sample into a small table.
+int hash_probe(kmc_ctx *c, bool *low_cardinality) {
+  *low_cardinality = false;
+  KeyArrays ka;
+  ka.from_array = !c->ingested.empty();
+  if (c->cfg.mode == KMC_MODE_LR_GAPPED) return KMC_OK; // keys would have to be materialised first: skip the probe
+  if (ka.from_array) for (auto &e : c->ingested) if (e.second) { ka.arrays.emplace_back((const uint64_t *)e.first, e.second); ka.n += e.second; }
+  const uint64_t n_in = ka.from_array ? ka.n : c->total_bases;
+  if (n_in < (1u << 18)) return KMC_OK;
+  const uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
+  bool ok = false;
+  PHASE_BEGIN("hash_probe");
+  TRY(hash_run(c, ka, 23, 1ull << 21, step, &ok, nullptr));
+  PHASE_END();
+  *low_cardinality = ok;
+  return KMC_OK;
+}
+
 // ---- partitioned fast path (kmc_fast.cuh), 64-bit keys ------------------------------------------------------
 // *used = false: the input does not suit it (tiny, duplicate-heavy, or a bucket overflowed); nothing is left
 // behind and the caller counts with the baseline path.
@@ -509,17 +643,11 @@ int finish_fast(kmc_ctx *c, bool *used) {
   const uint32_t kb = c->key_bits;
   const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb);
   const uint32_t ncoarse = 1u << cb;
-  const bool from_array = !c->ingested.empty() || c->cfg.mode == KMC_MODE_LR_GAPPED;
-  uint64_t n_array = 0;
-  std::vector<std::pair<const uint64_t *, uint64_t>> arrays; // key arrays are used in place, segment by segment
-  if (from_array) {
-    if (!c->ingested.empty()) {
-      for (auto &e : c->ingested) if (e.second) { arrays.emplace_back((const uint64_t *)e.first, e.second); n_array += e.second; }
-    } else {
-      TRY(produce_keys<uint64_t>(c, &n_array));
-      if (n_array) arrays.emplace_back((const uint64_t *)c->keys_a.p, n_array);
-    }
-  }
+  KeyArrays ka;
+  TRY(key_sources(c, &ka));
+  const bool from_array = ka.from_array;
+  const uint64_t n_array = ka.n;
+  const auto &arrays = ka.arrays;
   // fast_state layout: ghist[4096] u64 | ticket u32 (+pad) | d_total u64 | l1_cursor[kMaxL1] u64 | fine_cursor[nf] u32 | status[nf] u64
   const size_t off_ticket = 4096 * 8, off_dtotal = off_ticket + 8, off_l1cur = off_dtotal + 8, off_fine = off_l1cur + kMaxL1 * 8;
   TRY(ensure(c, c->fast_state, off_fine + 64));
@@ -751,8 +879,26 @@ int finish_fast(kmc_ctx *c, bool *used) {
 
 template <typename KeyT>
 int finish_impl(kmc_ctx *c) {
-  if (sizeof(KeyT) == 8 && c->cfg.strategy != KMC_STRATEGY_SORT_BASELINE) {
+  const uint32_t strat = c->cfg.strategy;
+  if (sizeof(KeyT) == 8 && strat != KMC_STRATEGY_SORT_BASELINE) {
     bool used = false;
+    if (strat == KMC_STRATEGY_HASH) {
+      // forced: size the table for the worst case (every key distinct), at most 2^32 slots
+      uint64_t n_in = 0;
+      for (auto &e : c->ingested) n_in += e.second;
+      if (c->ingested.empty()) n_in = c->cfg.mode == KMC_MODE_LR_GAPPED ? c->total_bases * (c->cfg.d_max - c->cfg.d_min + 1) : c->total_bases;
+      uint32_t lg = 20;
+      while (lg < 32 && (1ull << lg) < 2 * n_in) lg++;
+      TRY(finish_hash(c, lg, (1ull << lg) / 10 * 7, &used));
+      if (used) return KMC_OK;
+    } else if (strat == KMC_STRATEGY_AUTO) {
+      bool low = false;
+      TRY(hash_probe(c, &low));
+      if (low) {
+        TRY(finish_hash(c, 25, 1ull << 24, &used));
+        if (used) return KMC_OK;
+      }
+    }
     TRY(finish_fast(c, &used));
     if (used) return KMC_OK;
   }
@@ -764,9 +910,9 @@ void build_stats(kmc_ctx *c) {
   char buf[256];
   snprintf(buf, sizeof buf,
            "\"n_bases\": %llu, \"n_records\": %llu, \"n_total\": %llu, \"n_distinct\": %llu, \"key_bits\": %u, "
-           "\"strategy_used\": %u, \"fast_fallbacks\": %u, \"kernel_launches\": %llu, \"kernel_launches_total\": %llu, \"h2d_bytes\": %llu, \"phases_ms\": {",
+           "\"strategy_used\": %u, \"fast_fallbacks\": %u, \"hash_aborts\": %u, \"kernel_launches\": %llu, \"kernel_launches_total\": %llu, \"h2d_bytes\": %llu, \"phases_ms\": {",
            (unsigned long long)c->total_bases, (unsigned long long)c->total_recs, (unsigned long long)c->n_total,
-           (unsigned long long)c->n_distinct, c->key_bits, c->strategy_used, c->fast_fallbacks, (unsigned long long)c->launches,
+           (unsigned long long)c->n_distinct, c->key_bits, c->strategy_used, c->fast_fallbacks, c->hash_aborts, (unsigned long long)c->launches,
            (unsigned long long)c->launches_total, (unsigned long long)c->h2d_bytes);
   s += buf;
   // sum phases of the same name
@@ -871,7 +1017,7 @@ void kmc_destroy(kmc_ctx *c) {
   }
   for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); }
   for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
-                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->recv_keys})
+                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->recv_keys, &c->hash_keys, &c->hash_counts, &c->hash_scalars})
     release(*b);
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);

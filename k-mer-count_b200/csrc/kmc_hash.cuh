@@ -1,0 +1,155 @@
+// kmc_hash.cuh — the hash strategy for low-cardinality input (few distinct keys, each seen many times):
+// the GPU form of main.rs:87 when sorting every occurrence would be wasted work.
+//
+// An open-addressing table (linear probing) in HBM — small enough to live in the 126 MB L2 for the inputs this
+// strategy is chosen for — keyed by the 64-bit k-mer, with a 32-bit count per slot.  Insert = find/claim the
+// slot (atomicCAS on the key word) + atomicAdd on the count; a lane first combines equal keys it holds itself
+// (runs of identical k-mers: homopolymers, tandem repeats), which removes the hottest atomics.  Afterwards the
+// occupied slots are compacted, the distinct keys sorted with the generic radix sort (they are few), and their
+// counts looked up again.  The same kernel, run on a sample with a small table and a low fill limit, is the
+// cardinality probe of the AUTO strategy.
+//
+// All-ones is the empty marker; it is a real key only for k = 32, where it gets its own counter.
+#pragma once
+#include "kmc_common.cuh"
+#include "kmc_extract.cuh"
+
+namespace kmc {
+
+constexpr uint64_t kHashEmpty = ~0ull;
+constexpr uint32_t kFlagHashFull = 32u;   // err flag bits 1..16 are used elsewhere
+
+struct HashTable {
+  uint64_t *keys;            // [slots], kHashEmpty = free
+  uint32_t *counts;          // [slots]
+  uint64_t mask;             // slots - 1 (slots is a power of two)
+  uint32_t shift;            // 64 - log2(slots)
+  unsigned long long *n_used;   // occupied slots
+  unsigned long long *n_total;  // key occurrences inserted
+  unsigned long long *n_ones;   // occurrences of the all-ones key (k = 32 only)
+  uint64_t limit;            // stop (and flag) when more than this many slots are occupied
+  uint32_t *flags;
+};
+
+__device__ __forceinline__ uint64_t hash_slot(const HashTable &T, uint64_t key) {
+  return ((key ^ (key >> 29)) * 0x9E3779B97F4A7C15ULL) >> T.shift;
+}
+
+// returns 1 when the key claimed a new slot (the caller accumulates these and reports them per tile: one
+// atomic per warp tile on the shared fill counter instead of one per new key)
+__device__ __forceinline__ uint32_t hash_add(const HashTable &T, uint64_t key, uint32_t inc) {
+  if (key == kHashEmpty) { atomicAdd(T.n_ones, (unsigned long long)inc); return 0; }
+  uint64_t h = hash_slot(T, key);
+  for (uint32_t probe = 0; probe < 128; probe++) { // longer than this means the table is overloaded
+    uint64_t cur = T.keys[h];
+    uint32_t claimed = 0;
+    if (cur == kHashEmpty) {
+      cur = atomicCAS((unsigned long long *)&T.keys[h], (unsigned long long)kHashEmpty, (unsigned long long)key);
+      if (cur == kHashEmpty) { cur = key; claimed = 1; }
+    }
+    if (cur == key) {
+      uint32_t old = atomicAdd(&T.counts[h], inc);
+      if (old + inc < old) atomicOr(T.flags, 4u); // 32-bit count overflow (KMC_E_COUNT_OVERFLOW)
+      return claimed;
+    }
+    h = (h + 1) & T.mask;
+  }
+  atomicOr(T.flags, kFlagHashFull);
+  return 0;
+}
+
+// warp-wide: add the new slots of this tile to the fill counter; flag the table when it passes its limit
+__device__ __forceinline__ void hash_report(const HashTable &T, uint32_t claimed) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+  if (lane_id() == 0 && claimed)
+    if (atomicAdd(T.n_used, (unsigned long long)claimed) + claimed > T.limit) atomicOr(T.flags, kFlagHashFull);
+}
+
+// extraction front end: warp tiles t with t % step == 0 (step = 1: everything)
+template <bool FOLD>
+__global__ void __launch_bounds__(256) hash_count_kernel(ExtractParams P, uint64_t n_tiles, uint32_t step, HashTable T) {
+  const uint32_t lane = lane_id();
+  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t n_samp = (n_tiles + step - 1) / step;
+  unsigned long long mine = 0;
+  for (uint64_t ts = warp0; ts < n_samp; ts += nwarps) {
+    if (*(volatile uint32_t *)T.flags & kFlagHashFull) break;
+    Win<uint64_t> W{};
+    W.template load<FOLD>(P, ts * step * Win<uint64_t>::kLanes + lane);
+    uint32_t m = W.ok;
+    mine += __popc(m);
+    // a lane's k-mers are consecutive windows: merge runs of equal keys before touching the table
+    uint64_t prev = 0;
+    uint32_t run = 0, claimed = 0;
+    while (m) {
+      uint32_t s = __clz(m);
+      m &= ~(0x80000000u >> s);
+      uint64_t key = W.key(s, P.k, P.canonical != 0);
+      if (run && key == prev) { run++; continue; }
+      if (run) claimed += hash_add(T, prev, run);
+      prev = key; run = 1;
+    }
+    if (run) claimed += hash_add(T, prev, run);
+    hash_report(T, claimed);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (lane == 0 && mine) atomicAdd(T.n_total, mine);
+}
+
+// key-array front end
+__global__ void __launch_bounds__(256) hash_count_array_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t step,
+                                                                HashTable T) {
+  const uint64_t n_chunks = (n + 1023) / 1024, n_samp = (n_chunks + step - 1) / step;
+  unsigned long long mine = 0;
+  for (uint64_t cs = blockIdx.x; cs < n_samp; cs += gridDim.x) {
+    if (*(volatile uint32_t *)T.flags & kFlagHashFull) break;
+    const uint64_t base = cs * step * 1024;
+    uint32_t claimed = 0;
+    for (uint32_t j = threadIdx.x; j < 1024; j += 256)
+      if (base + j < n) { claimed += hash_add(T, keys[base + j], 1u); mine++; }
+    hash_report(T, claimed);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(T.n_total, mine);
+}
+
+// occupied slots → dense key array (unordered); *cursor ends at the number of distinct keys
+__global__ void __launch_bounds__(256) hash_compact_kernel(HashTable T, uint64_t *__restrict__ out,
+                                                            unsigned long long *__restrict__ cursor) {
+  const uint32_t lane = lane_id();
+  const uint64_t slots = T.mask + 1;
+  for (uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ull; i0 < slots; i0 += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t i = i0 + lane;
+    uint64_t key = i < slots ? T.keys[i] : kHashEmpty;
+    bool occ = key != kHashEmpty;
+    uint32_t bal = __ballot_sync(0xffffffffu, occ);
+    if (!bal) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (occ) out[base + __popc(bal & ((1u << lane) - 1u))] = key;
+  }
+}
+
+// counts of the sorted distinct keys (every key is in the table)
+__global__ void __launch_bounds__(256) hash_lookup_kernel(HashTable T, const uint64_t *__restrict__ keys, uint64_t n,
+                                                           uint32_t *__restrict__ counts) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = keys[i];
+    uint64_t h = hash_slot(T, key);
+    uint32_t c = 0;
+    for (uint32_t probe = 0; probe < 4096; probe++) {
+      uint64_t cur = T.keys[h];
+      if (cur == key) { c = T.counts[h]; break; }
+      if (cur == kHashEmpty) break;
+      h = (h + 1) & T.mask;
+    }
+    counts[i] = c;
+  }
+}
+
+} // namespace kmc

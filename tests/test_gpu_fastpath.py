@@ -36,8 +36,12 @@ def test_fast_path_matches_oracle(kmc, orc, k, canonical, n):
     got, st, dig = _count(kmc, bases, off, k, canonical)
     assert_tables_equal(got, want)
     assert dig == want.digest()
-    if k >= 11:
+    if k >= 16:   # smaller k has few distinct keys: AUTO picks the hash table
         assert st["strategy_used"] == 2 and st["fast_fallbacks"] == 0, st
+    if k == 11:
+        fast, st2, _ = _count(kmc, bases, off, k, canonical, strategy=2)
+        assert_tables_equal(fast, want)
+        assert st2["strategy_used"] == 2, st2
     base, _, _ = _count(kmc, bases, off, k, canonical, strategy=3)
     assert_tables_equal(base, want)
 
@@ -55,9 +59,11 @@ def test_fast_path_big_sub_bins(kmc, orc):
     bases = np.concatenate(recs + [filler])
     off = np.concatenate([np.arange(0, (len(recs) + 1) * 21, 21), [len(bases)]]).astype(np.uint64)
     want = orc.contiguous_mt(bases, off, k, False)
-    got, st, _ = _count(kmc, bases, off, k, False)
+    got, st, _ = _count(kmc, bases, off, k, False, strategy=2)
     assert_tables_equal(got, want)
     assert st["strategy_used"] == 2, st
+    auto, _, _ = _count(kmc, bases, off, k, False)
+    assert_tables_equal(auto, want)
 
 
 def test_fast_path_overflow_recounts(kmc, orc):
@@ -113,4 +119,47 @@ def test_fast_path_key_array_front_end(kmc, orc):
     want = orc.gapped_mt(recs_b, roff, 16, 16, 40, 60)
     got = kmc.count_lr_gapped(recs_b, roff, 16, 16, 40, 60)
     assert want.n_total > (1 << 18)
+    assert_tables_equal(got, want)
+
+
+def test_hash_strategy(kmc, orc):
+    """Low-cardinality input goes to the HBM hash table under AUTO; the forced hash strategy is exact on
+    high-cardinality input too; k=32 all-ones key (the table's empty marker) has its own counter."""
+    rng = np.random.default_rng(31)
+    # 1. repetitive reads: 1 Mbase 'genome', 150-base reads from both strands, ~40x coverage
+    genome = ACGT[rng.integers(0, 4, 200_000)]
+    comp = np.zeros(256, np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    starts = rng.integers(0, len(genome) - 150, 50_000)
+    reads = [genome[s:s + 150] for s in starts]
+    reads = [comp[r[::-1]] if rng.random() < 0.5 else r for r in reads]
+    bases = np.concatenate(reads)
+    off = (np.arange(len(reads) + 1) * 150).astype(np.uint64)
+    for k in (21, 31):
+        want = orc.contiguous_mt(bases, off, k, True)
+        got, st, dig = _count(kmc, bases, off, k, True)
+        assert_tables_equal(got, want)
+        assert st["strategy_used"] == 1, st
+        assert dig == want.digest()
+    # 2. forced hash on all-distinct keys
+    n = 3_000_000
+    b2 = ACGT[rng.integers(0, 4, n)]
+    o2 = np.arange(0, n + 1, 400, dtype=np.uint64)
+    want = orc.contiguous_mt(b2, o2, 31, True)
+    got, st, _ = _count(kmc, b2, o2, 31, True, strategy=1)
+    assert_tables_equal(got, want)
+    assert st["strategy_used"] == 1
+    # 3. k=32, forward strand, poly-T: the all-ones key
+    b3 = np.concatenate([np.full(500_000, ord("T"), np.uint8), ACGT[rng.integers(0, 4, 300_000)]])
+    o3 = np.array([0, 500_000, 800_000], np.uint64)
+    want = orc.contiguous_mt(b3, o3, 32, False)
+    for strategy in (0, 1):
+        got, st, _ = _count(kmc, b3, o3, 32, False, strategy=strategy)
+        assert_tables_equal(got, want)
+    assert int(want.key_lo[-1]) == 2**64 - 1 and int(want.count[-1]) == 500_000 - 31
+    # 4. lr-gapped keys of <= 64 bits through the forced hash strategy
+    b4 = ACGT[rng.integers(0, 4, 40_000)]
+    o4 = np.arange(0, 40_001, 200, dtype=np.uint64)
+    want = orc.gapped_mt(b4, o4, 16, 16, 40, 60)
+    got = kmc.count_lr_gapped(b4, o4, 16, 16, 40, 60, strategy=1)
     assert_tables_equal(got, want)
