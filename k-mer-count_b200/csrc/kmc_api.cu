@@ -82,7 +82,9 @@ struct kmc_ctx {
   DevBuf gap_l, gap_r, gap_f;
   DevBuf t_lo, t_hi, t_cnt;
   DevBuf fast_l1, fast_l2, fast_state, fast_tables, recv_keys;
-  DevBuf hash_keys, hash_counts, hash_scalars;
+  DevBuf hash_slots, hash_scalars, hash_hot;
+  uint64_t probe_distinct = 0;
+  uint32_t n_hot = 0;
   uint32_t hash_aborts = 0;
   std::vector<unsigned char> fast_host; // plan tables staged for upload
   uint32_t fast_fallbacks = 0;          // times the partitioned path overflowed and the job was recounted
@@ -526,28 +528,31 @@ int key_sources(kmc_ctx *c, KeyArrays *ka) {
 
 // ---- hash strategy (kmc_hash.cuh), 64-bit keys ---------------------------------------------------------------
 // step > 1: cardinality probe on a sample (table stays, nothing else is produced); *ok = table did not fill.
-int hash_run(kmc_ctx *c, const KeyArrays &ka, uint32_t log2_slots, uint64_t limit, uint32_t step, bool *ok, HashTable *out) {
+int hash_run(kmc_ctx *c, const KeyArrays &ka, uint32_t log2_slots, uint64_t limit, uint32_t step, bool *ok, HashTable *out,
+             uint32_t n_hot = 0, bool throttle = true) {
   *ok = false;
+  TRY(ensure(c, c->hash_hot, kHotMax * 8 + 64));
+  const uint64_t *hot = (const uint64_t *)c->hash_hot.p;
   // the fill limit is only checked between tiles: keep the keys in flight (one tile per resident warp) well below
   // the table size, or a high-cardinality input would swamp the table before anybody notices
+  // (the real run's table is sized from the probe, so only the probe itself — step > 1 or forced — is throttled)
   const uint64_t max_warps = std::max<uint64_t>(64, (1ull << log2_slots) / 4 / 992);
-  const uint32_t max_ctas = (uint32_t)std::min<uint64_t>((uint64_t)kNumSMsB200 * 8, std::max<uint64_t>(8, max_warps / 8));
+  const uint32_t max_ctas = throttle ? (uint32_t)std::min<uint64_t>((uint64_t)kNumSMsB200 * 8, std::max<uint64_t>(8, max_warps / 8))
+                                     : (uint32_t)kNumSMsB200 * 8;
   const uint64_t slots = 1ull << log2_slots;
-  TRY(ensure(c, c->hash_keys, slots * 8));
-  TRY(ensure(c, c->hash_counts, slots * 4));
+  TRY(ensure(c, c->hash_slots, slots * sizeof(HashSlot)));
   TRY(ensure(c, c->hash_scalars, 64));
-  CK(cudaMemsetAsync(c->hash_keys.p, 0xFF, slots * 8, c->stream));
-  CK(cudaMemsetAsync(c->hash_counts.p, 0, slots * 4, c->stream));
+  LAUNCH(hash_init_kernel, std::min<uint32_t>(grid_for(slots, 256), kNumSMsB200 * 16), 256, 0, (HashSlot *)c->hash_slots.p, slots);
   CK(cudaMemsetAsync(c->hash_scalars.p, 0, 64, c->stream));
   HashTable T;
-  T.keys = (uint64_t *)c->hash_keys.p; T.counts = (uint32_t *)c->hash_counts.p;
+  T.slots = (HashSlot *)c->hash_slots.p;
   T.mask = slots - 1; T.shift = 64 - log2_slots;
   T.n_used = (unsigned long long *)c->hash_scalars.p; T.n_total = T.n_used + 1; T.n_ones = T.n_used + 2;
   T.limit = limit; T.flags = d_err(c);
   if (ka.from_array) {
     for (auto &a : ka.arrays) {
       uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024ull * step), (uint64_t)max_ctas);
-      LAUNCH(hash_count_array_kernel, grid, 256, 0, a.first, a.second, step, T);
+      LAUNCH(hash_count_array_kernel, grid, 256, 0, a.first, a.second, step, T, hot, n_hot);
     }
   } else {
     for (size_t i = 0; i < c->n_segs; i++) {
@@ -557,7 +562,7 @@ int hash_run(kmc_ctx *c, const KeyArrays &ka, uint32_t log2_slots, uint64_t limi
       uint64_t tiles = num_warp_tiles(s.n_bases, 31);
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)max_ctas);
       auto hash_count = hash_count_kernel<true>;
-      LAUNCH(hash_count, grid, 256, 0, P, tiles, step, T);
+      LAUNCH(hash_count, grid, 256, 0, P, tiles, step, T, hot, n_hot);
     }
   }
   uint32_t err = 0;
@@ -578,7 +583,7 @@ int finish_hash(kmc_ctx *c, uint32_t log2_slots, uint64_t limit, bool *used) {
   HashTable T;
   bool ok = false;
   PHASE_BEGIN("hash_count");
-  TRY(hash_run(c, ka, log2_slots, limit, 1, &ok, &T));
+  TRY(hash_run(c, ka, log2_slots, limit, 1, &ok, &T, c->n_hot, /*throttle=*/c->probe_distinct == 0));
   PHASE_END();
   if (!ok) { c->hash_aborts++; return KMC_OK; }
   unsigned long long sc[3];
@@ -620,6 +625,7 @@ int finish_hash(kmc_ctx *c, uint32_t log2_slots, uint64_t limit, bool *used) {
 // AUTO: is the number of distinct keys small enough for an L2-resident table?  Insert a sample into a small table.
 int hash_probe(kmc_ctx *c, bool *low_cardinality) {
   *low_cardinality = false;
+  c->probe_distinct = 0;
   KeyArrays ka;
   ka.from_array = !c->ingested.empty();
   if (c->cfg.mode == KMC_MODE_LR_GAPPED) return KMC_OK; // keys would have to be materialised first: skip the probe
@@ -628,8 +634,25 @@ int hash_probe(kmc_ctx *c, bool *low_cardinality) {
   if (n_in < (1u << 18)) return KMC_OK;
   const uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
   bool ok = false;
+  HashTable T;
+  c->n_hot = 0;
   PHASE_BEGIN("hash_probe");
-  TRY(hash_run(c, ka, 23, 1ull << 21, step, &ok, nullptr));
+  TRY(hash_run(c, ka, 23, 1ull << 21, step, &ok, &T));
+  if (ok) {
+    // keys that make up more than 1/50000 of the sampled occurrences get private shared-memory counters later
+    unsigned long long sc[3];
+    CK(cudaMemcpyAsync(sc, c->hash_scalars.p, sizeof sc, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const uint32_t thr = (uint32_t)std::max<uint64_t>(64, sc[1] / 50000);
+    unsigned int *d_nhot = (unsigned int *)((unsigned char *)c->hash_hot.p + kHotMax * 8);
+    CK(cudaMemsetAsync(d_nhot, 0, 4, c->stream));
+    LAUNCH(hash_hot_kernel, kNumSMsB200 * 8, 256, 0, T, thr, (uint64_t *)c->hash_hot.p, d_nhot);
+    unsigned int nh = 0;
+    CK(cudaMemcpyAsync(&nh, d_nhot, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->n_hot = std::min<uint32_t>(nh, kHotMax);
+    c->probe_distinct = sc[0];
+  }
   PHASE_END();
   *low_cardinality = ok;
   return KMC_OK;
@@ -887,6 +910,8 @@ int finish_impl(kmc_ctx *c) {
       uint64_t n_in = 0;
       for (auto &e : c->ingested) n_in += e.second;
       if (c->ingested.empty()) n_in = c->cfg.mode == KMC_MODE_LR_GAPPED ? c->total_bases * (c->cfg.d_max - c->cfg.d_min + 1) : c->total_bases;
+      bool low = false;
+      TRY(hash_probe(c, &low)); // also finds the hot keys
       uint32_t lg = 20;
       while (lg < 32 && (1ull << lg) < 2 * n_in) lg++;
       TRY(finish_hash(c, lg, (1ull << lg) / 10 * 7, &used));
@@ -895,8 +920,16 @@ int finish_impl(kmc_ctx *c) {
       bool low = false;
       TRY(hash_probe(c, &low));
       if (low) {
-        TRY(finish_hash(c, 25, 1ull << 24, &used));
+        // a table sized from the sample stays in L2 (a 2^25-slot one does not: 512 MB of randomly touched lines);
+        // if the full input has more distinct keys than that, retry once with the big table
+        uint32_t lg = 20;
+        while (lg < 25 && (1ull << lg) < 4 * c->probe_distinct) lg++;
+        TRY(finish_hash(c, lg, (1ull << lg) / 2, &used));
         if (used) return KMC_OK;
+        if (lg < 25) {
+          TRY(finish_hash(c, 25, 1ull << 24, &used));
+          if (used) return KMC_OK;
+        }
       }
     }
     TRY(finish_fast(c, &used));
@@ -907,12 +940,12 @@ int finish_impl(kmc_ctx *c) {
 
 void build_stats(kmc_ctx *c) {
   std::string s = "{";
-  char buf[256];
+  char buf[1024];
   snprintf(buf, sizeof buf,
            "\"n_bases\": %llu, \"n_records\": %llu, \"n_total\": %llu, \"n_distinct\": %llu, \"key_bits\": %u, "
-           "\"strategy_used\": %u, \"fast_fallbacks\": %u, \"hash_aborts\": %u, \"kernel_launches\": %llu, \"kernel_launches_total\": %llu, \"h2d_bytes\": %llu, \"phases_ms\": {",
+           "\"strategy_used\": %u, \"fast_fallbacks\": %u, \"hash_aborts\": %u, \"hot_keys\": %u, \"kernel_launches\": %llu, \"kernel_launches_total\": %llu, \"h2d_bytes\": %llu, \"phases_ms\": {",
            (unsigned long long)c->total_bases, (unsigned long long)c->total_recs, (unsigned long long)c->n_total,
-           (unsigned long long)c->n_distinct, c->key_bits, c->strategy_used, c->fast_fallbacks, c->hash_aborts, (unsigned long long)c->launches,
+           (unsigned long long)c->n_distinct, c->key_bits, c->strategy_used, c->fast_fallbacks, c->hash_aborts, c->n_hot, (unsigned long long)c->launches,
            (unsigned long long)c->launches_total, (unsigned long long)c->h2d_bytes);
   s += buf;
   // sum phases of the same name
@@ -1017,7 +1050,7 @@ void kmc_destroy(kmc_ctx *c) {
   }
   for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); }
   for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
-                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->recv_keys, &c->hash_keys, &c->hash_counts, &c->hash_scalars})
+                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot})
     release(*b);
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);

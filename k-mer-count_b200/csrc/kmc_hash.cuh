@@ -19,9 +19,12 @@ namespace kmc {
 constexpr uint64_t kHashEmpty = ~0ull;
 constexpr uint32_t kFlagHashFull = 32u;   // err flag bits 1..16 are used elsewhere
 
+struct __align__(16) HashSlot { // key and count share one 32 B sector: the count update hits the line the probe just fetched
+  uint64_t key;              // kHashEmpty = free
+  unsigned long long count;  // 64-bit: a fire-and-forget add (no return value to wait for) that cannot wrap
+};
 struct HashTable {
-  uint64_t *keys;            // [slots], kHashEmpty = free
-  uint32_t *counts;          // [slots]
+  HashSlot *slots;           // [mask + 1]
   uint64_t mask;             // slots - 1 (slots is a power of two)
   uint32_t shift;            // 64 - log2(slots)
   unsigned long long *n_used;   // occupied slots
@@ -30,6 +33,11 @@ struct HashTable {
   uint64_t limit;            // stop (and flag) when more than this many slots are occupied
   uint32_t *flags;
 };
+
+__global__ void __launch_bounds__(256) hash_init_kernel(HashSlot *__restrict__ slots, uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    *reinterpret_cast<ulonglong2 *>(&slots[i]) = make_ulonglong2(kHashEmpty, 0ull);
+}
 
 __device__ __forceinline__ uint64_t hash_slot(const HashTable &T, uint64_t key) {
   return ((key ^ (key >> 29)) * 0x9E3779B97F4A7C15ULL) >> T.shift;
@@ -41,15 +49,14 @@ __device__ __forceinline__ uint32_t hash_add(const HashTable &T, uint64_t key, u
   if (key == kHashEmpty) { atomicAdd(T.n_ones, (unsigned long long)inc); return 0; }
   uint64_t h = hash_slot(T, key);
   for (uint32_t probe = 0; probe < 128; probe++) { // longer than this means the table is overloaded
-    uint64_t cur = T.keys[h];
+    uint64_t cur = T.slots[h].key;
     uint32_t claimed = 0;
     if (cur == kHashEmpty) {
-      cur = atomicCAS((unsigned long long *)&T.keys[h], (unsigned long long)kHashEmpty, (unsigned long long)key);
+      cur = atomicCAS((unsigned long long *)&T.slots[h].key, (unsigned long long)kHashEmpty, (unsigned long long)key);
       if (cur == kHashEmpty) { cur = key; claimed = 1; }
     }
     if (cur == key) {
-      uint32_t old = atomicAdd(&T.counts[h], inc);
-      if (old + inc < old) atomicOr(T.flags, 4u); // 32-bit count overflow (KMC_E_COUNT_OVERFLOW)
+      atomicAdd(&T.slots[h].count, (unsigned long long)inc); // result unused → RED, nothing to wait for
       return claimed;
     }
     h = (h + 1) & T.mask;
@@ -66,16 +73,76 @@ __device__ __forceinline__ void hash_report(const HashTable &T, uint32_t claimed
     if (atomicAdd(T.n_used, (unsigned long long)claimed) + claimed > T.limit) atomicOr(T.flags, kFlagHashFull);
 }
 
+// Hot keys (SURVEY §7 "hot keys": poly-A, tandem repeats — keys that occur millions of times).  Their atomics
+// would serialise on one L2 address (measured: 50 ms on a 1e9-base repetitive input).  The cardinality probe's
+// sample table already knows them: keys above a frequency threshold are copied to a short list, and every CTA
+// of the counting kernel gives them private counters in shared memory (a small read-only dictionary built at
+// kernel start), flushed to the table once at the end.
+constexpr int kHotMax = 1024;          // listed hot keys at most
+constexpr int kHotSlots = 4096;        // per-CTA dictionary (open addressing, <= 25 % full)
+struct HotDict {
+  uint64_t key[kHotSlots];
+  uint32_t cnt[kHotSlots];
+};
+__device__ __forceinline__ uint32_t hot_slot(uint64_t key) { return (uint32_t)(((key ^ (key >> 31)) * 0xD6E8FEB86659FD93ULL) >> 52); }
+
+__global__ void __launch_bounds__(256) hash_hot_kernel(HashTable T, uint32_t threshold, uint64_t *__restrict__ hot_keys,
+                                                        unsigned int *__restrict__ n_hot) {
+  const uint64_t slots = T.mask + 1;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (T.slots[i].count >= threshold && T.slots[i].key != kHashEmpty) {
+      unsigned int j = atomicAdd(n_hot, 1u);
+      if (j < (unsigned)kHotMax) hot_keys[j] = T.slots[i].key;
+    }
+  }
+}
+
+__device__ __forceinline__ void hot_build(HotDict &H, const uint64_t *__restrict__ hot_keys, uint32_t n_hot) {
+  for (uint32_t i = threadIdx.x; i < kHotSlots; i += blockDim.x) { H.key[i] = kHashEmpty; H.cnt[i] = 0; }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n_hot; i += blockDim.x) {
+    const uint64_t key = hot_keys[i];
+    uint32_t s = hot_slot(key);
+    for (;;) {
+      uint64_t cur = atomicCAS((unsigned long long *)&H.key[s], (unsigned long long)kHashEmpty, (unsigned long long)key);
+      if (cur == kHashEmpty || cur == key) break;
+      s = (s + 1) & (kHotSlots - 1);
+    }
+  }
+  __syncthreads();
+}
+// true: the key is hot and was counted in shared memory
+__device__ __forceinline__ bool hot_add(HotDict &H, uint64_t key, uint32_t inc) {
+  uint32_t s = hot_slot(key);
+  for (;;) {
+    uint64_t cur = H.key[s];
+    if (cur == key) { atomicAdd(&H.cnt[s], inc); return true; }
+    if (cur == kHashEmpty) return false;
+    s = (s + 1) & (kHotSlots - 1);
+  }
+}
+__device__ __forceinline__ void hot_flush(HotDict &H, const HashTable &T) {
+  __syncthreads();
+  uint32_t claimed = 0;
+  for (uint32_t i = threadIdx.x; i < kHotSlots; i += blockDim.x)
+    if (H.key[i] != kHashEmpty && H.cnt[i]) claimed += hash_add(T, H.key[i], H.cnt[i]);
+  hash_report(T, claimed);
+}
+
 // extraction front end: warp tiles t with t % step == 0 (step = 1: everything)
 template <bool FOLD>
-__global__ void __launch_bounds__(256) hash_count_kernel(ExtractParams P, uint64_t n_tiles, uint32_t step, HashTable T) {
+__global__ void __launch_bounds__(256) hash_count_kernel(ExtractParams P, uint64_t n_tiles, uint32_t step, HashTable T,
+                                                          const uint64_t *__restrict__ hot_keys, uint32_t n_hot) {
+  __shared__ HotDict H;
+  if (n_hot) hot_build(H, hot_keys, n_hot);
   const uint32_t lane = lane_id();
   const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const uint64_t n_samp = (n_tiles + step - 1) / step;
   unsigned long long mine = 0;
   for (uint64_t ts = warp0; ts < n_samp; ts += nwarps) {
-    if (*(volatile uint32_t *)T.flags & kFlagHashFull) break;
+    // warp-uniform exit: the lanes must stay together for the shuffles below
+    if (__any_sync(0xffffffffu, *(volatile uint32_t *)T.flags & kFlagHashFull)) break;
     Win<uint64_t> W{};
     W.template load<FOLD>(P, ts * step * Win<uint64_t>::kLanes + lane);
     uint32_t m = W.ok;
@@ -88,12 +155,13 @@ __global__ void __launch_bounds__(256) hash_count_kernel(ExtractParams P, uint64
       m &= ~(0x80000000u >> s);
       uint64_t key = W.key(s, P.k, P.canonical != 0);
       if (run && key == prev) { run++; continue; }
-      if (run) claimed += hash_add(T, prev, run);
+      if (run && !(n_hot && hot_add(H, prev, run))) claimed += hash_add(T, prev, run);
       prev = key; run = 1;
     }
-    if (run) claimed += hash_add(T, prev, run);
+    if (run && !(n_hot && hot_add(H, prev, run))) claimed += hash_add(T, prev, run);
     hash_report(T, claimed);
   }
+  if (n_hot) hot_flush(H, T);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
   if (lane == 0 && mine) atomicAdd(T.n_total, mine);
@@ -101,17 +169,25 @@ __global__ void __launch_bounds__(256) hash_count_kernel(ExtractParams P, uint64
 
 // key-array front end
 __global__ void __launch_bounds__(256) hash_count_array_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t step,
-                                                                HashTable T) {
+                                                                HashTable T, const uint64_t *__restrict__ hot_keys,
+                                                                uint32_t n_hot) {
+  __shared__ HotDict H;
+  if (n_hot) hot_build(H, hot_keys, n_hot);
   const uint64_t n_chunks = (n + 1023) / 1024, n_samp = (n_chunks + step - 1) / step;
   unsigned long long mine = 0;
   for (uint64_t cs = blockIdx.x; cs < n_samp; cs += gridDim.x) {
-    if (*(volatile uint32_t *)T.flags & kFlagHashFull) break;
+    if (__any_sync(0xffffffffu, *(volatile uint32_t *)T.flags & kFlagHashFull)) break; // warp-uniform exit
     const uint64_t base = cs * step * 1024;
     uint32_t claimed = 0;
     for (uint32_t j = threadIdx.x; j < 1024; j += 256)
-      if (base + j < n) { claimed += hash_add(T, keys[base + j], 1u); mine++; }
+      if (base + j < n) {
+        const uint64_t key = keys[base + j];
+        if (!(n_hot && hot_add(H, key, 1u))) claimed += hash_add(T, key, 1u);
+        mine++;
+      }
     hash_report(T, claimed);
   }
+  if (n_hot) hot_flush(H, T);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(T.n_total, mine);
@@ -124,7 +200,7 @@ __global__ void __launch_bounds__(256) hash_compact_kernel(HashTable T, uint64_t
   const uint64_t slots = T.mask + 1;
   for (uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ull; i0 < slots; i0 += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t i = i0 + lane;
-    uint64_t key = i < slots ? T.keys[i] : kHashEmpty;
+    uint64_t key = i < slots ? T.slots[i].key : kHashEmpty;
     bool occ = key != kHashEmpty;
     uint32_t bal = __ballot_sync(0xffffffffu, occ);
     if (!bal) continue;
@@ -135,20 +211,21 @@ __global__ void __launch_bounds__(256) hash_compact_kernel(HashTable T, uint64_t
   }
 }
 
-// counts of the sorted distinct keys (every key is in the table)
+// counts of the sorted distinct keys (every key is in the table); a count beyond 32 bits raises flag 4
 __global__ void __launch_bounds__(256) hash_lookup_kernel(HashTable T, const uint64_t *__restrict__ keys, uint64_t n,
                                                            uint32_t *__restrict__ counts) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t key = keys[i];
     uint64_t h = hash_slot(T, key);
-    uint32_t c = 0;
+    unsigned long long c = 0;
     for (uint32_t probe = 0; probe < 4096; probe++) {
-      uint64_t cur = T.keys[h];
-      if (cur == key) { c = T.counts[h]; break; }
+      uint64_t cur = T.slots[h].key;
+      if (cur == key) { c = T.slots[h].count; break; }
       if (cur == kHashEmpty) break;
       h = (h + 1) & T.mask;
     }
-    counts[i] = c;
+    if (c > 0xFFFFFFFFull) { atomicOr(T.flags, 4u); c = 0xFFFFFFFFull; }
+    counts[i] = (uint32_t)c;
   }
 }
 

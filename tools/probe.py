@@ -21,11 +21,40 @@ def synth(n_bases, rec_len=400, seed=2):
     return bases, off
 
 
+def synth_genome(n_bases, genome_len=1_000_000, read_len=150, seed=5):
+    """cfg5-like: reads sampled uniformly from both strands of a fixed random genome (5% of it homopolymer/tandem)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+    codes = torch.randint(0, 4, (genome_len,), device="cuda", generator=g)
+    rep = genome_len // 20
+    codes[:rep // 2] = 0                                   # poly-A
+    codes[rep // 2:rep] = torch.arange(rep - rep // 2, device="cuda") % 2  # (AC)n tandem repeat
+    fwd = lut[codes]
+    rc = lut[(3 - codes).flip(0)]
+    both = torch.cat([fwd, rc])
+    n_reads = n_bases // read_len
+    out = torch.empty(n_reads * read_len, dtype=torch.uint8, device="cuda")
+    CH = 1 << 20
+    ar = torch.arange(read_len, device="cuda")
+    for s in range(0, n_reads, CH):
+        e = min(n_reads, s + CH)
+        st = torch.randint(0, genome_len - read_len, (e - s,), device="cuda", generator=g)
+        strand = torch.randint(0, 2, (e - s,), device="cuda", generator=g) * genome_len
+        idx = (st + strand)[:, None] + ar[None, :]
+        out[s * read_len:e * read_len] = both[idx].reshape(-1)
+    off = torch.arange(0, n_reads * read_len + 1, read_len, dtype=torch.int64, device="cuda")
+    return out, off
+
+
 def main():
     n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
     kk = int(sys.argv[2]) if len(sys.argv) > 2 else 21
     strategy = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-    bases, off = synth(n)
+    if len(sys.argv) > 4 and sys.argv[4] == "genome":
+        bases, off = synth_genome(n)
+        n = bases.numel()
+    else:
+        bases, off = synth(n)
     torch.cuda.synchronize()
     with k.KmerCounter(k=kk, canonical=True, strategy=strategy) as kc:
         for it in range(3):
