@@ -439,7 +439,7 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
   if (!part_ptr && (c->total_bases < (1u << 18) || n_parts > (uint32_t)kMaxL1)) return KMC_OK;
   const uint64_t cap = part_ptr ? peer_cap : (((uint64_t)((double)c->total_bases / n_parts * 1.03) + 65536 + 15) & ~15ull);
   const uint64_t total = part_ptr ? 0 : cap * n_parts;
-  TRY(ensure(c, c->route_keys, (total + 2 * kPart2Tile) * 8));
+  TRY(ensure(c, c->route_keys, (total + 2 * kMaxTile) * 8));
   const size_t o_start = 0, o_cap = o_start + ((size_t)(n_parts + 1) * 8 + 15) / 16 * 16, tab_bytes = o_cap + (size_t)n_parts * 8;
   c->fast_host.assign(tab_bytes, 0);
   uint64_t *l1s = (uint64_t *)(c->fast_host.data() + o_start), *l1c = (uint64_t *)(c->fast_host.data() + o_cap);
@@ -459,8 +459,8 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
   pl.l1_cursor = (unsigned long long *)((unsigned char *)c->fast_state.p + off_l1cur);
   PHASE_BEGIN("route");
   {
-    size_t smem = PartSmem::bytes(kPart1Stage, n_parts);
-    auto fast_route = fast_part1_kernel<true, OwnerBucket>;
+    size_t smem = PartSmem<uint64_t>::bytes(part1_stage<uint64_t>(), n_parts);
+    auto fast_route = fast_part1_kernel<uint64_t, true, OwnerBucket>;
     CK(cudaFuncSetAttribute(fast_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const OwnerBucket bucket{n_parts};
     for (size_t i = 0; i < c->n_segs; i++) {
@@ -511,17 +511,18 @@ int finish_baseline(kmc_ctx *c) {
 struct KeyArrays {
   bool from_array = false;
   uint64_t n = 0;
-  std::vector<std::pair<const uint64_t *, uint64_t>> arrays;
+  std::vector<std::pair<const void *, uint64_t>> arrays;
 };
+template <typename KeyT>
 int key_sources(kmc_ctx *c, KeyArrays *ka) {
   ka->from_array = !c->ingested.empty() || c->cfg.mode == KMC_MODE_LR_GAPPED;
   ka->n = 0; ka->arrays.clear();
   if (!ka->from_array) return KMC_OK;
   if (!c->ingested.empty()) {
-    for (auto &e : c->ingested) if (e.second) { ka->arrays.emplace_back((const uint64_t *)e.first, e.second); ka->n += e.second; }
+    for (auto &e : c->ingested) if (e.second) { ka->arrays.emplace_back(e.first, e.second); ka->n += e.second; }
   } else {
-    TRY(produce_keys<uint64_t>(c, &ka->n));
-    if (ka->n) ka->arrays.emplace_back((const uint64_t *)c->keys_a.p, ka->n);
+    TRY(produce_keys<KeyT>(c, &ka->n));
+    if (ka->n) ka->arrays.emplace_back((const void *)c->keys_a.p, ka->n);
   }
   return KMC_OK;
 }
@@ -552,7 +553,7 @@ int hash_run(kmc_ctx *c, const KeyArrays &ka, uint32_t log2_slots, uint64_t limi
   if (ka.from_array) {
     for (auto &a : ka.arrays) {
       uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024ull * step), (uint64_t)max_ctas);
-      LAUNCH(hash_count_array_kernel, grid, 256, 0, a.first, a.second, step, T, hot, n_hot);
+      LAUNCH(hash_count_array_kernel, grid, 256, 0, (const uint64_t *)a.first, a.second, step, T, hot, n_hot);
     }
   } else {
     for (size_t i = 0; i < c->n_segs; i++) {
@@ -579,7 +580,7 @@ int hash_run(kmc_ctx *c, const KeyArrays &ka, uint32_t log2_slots, uint64_t limi
 int finish_hash(kmc_ctx *c, uint32_t log2_slots, uint64_t limit, bool *used) {
   *used = false;
   KeyArrays ka;
-  TRY(key_sources(c, &ka));
+  TRY(key_sources<uint64_t>(c, &ka));
   HashTable T;
   bool ok = false;
   PHASE_BEGIN("hash_count");
@@ -629,7 +630,7 @@ int hash_probe(kmc_ctx *c, bool *low_cardinality) {
   KeyArrays ka;
   ka.from_array = !c->ingested.empty();
   if (c->cfg.mode == KMC_MODE_LR_GAPPED) return KMC_OK; // keys would have to be materialised first: skip the probe
-  if (ka.from_array) for (auto &e : c->ingested) if (e.second) { ka.arrays.emplace_back((const uint64_t *)e.first, e.second); ka.n += e.second; }
+  if (ka.from_array) for (auto &e : c->ingested) if (e.second) { ka.arrays.emplace_back(e.first, e.second); ka.n += e.second; }
   const uint64_t n_in = ka.from_array ? ka.n : c->total_bases;
   if (n_in < (1u << 18)) return KMC_OK;
   const uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
@@ -658,16 +659,19 @@ int hash_probe(kmc_ctx *c, bool *low_cardinality) {
   return KMC_OK;
 }
 
-// ---- partitioned fast path (kmc_fast.cuh), 64-bit keys ------------------------------------------------------
+// ---- partitioned fast path (kmc_fast.cuh) --------------------------------------------------------------------
 // *used = false: the input does not suit it (tiny, duplicate-heavy, or a bucket overflowed); nothing is left
 // behind and the caller counts with the baseline path.
+template <typename KeyT>
 int finish_fast(kmc_ctx *c, bool *used) {
+  constexpr bool kWide = sizeof(KeyT) == 16;
+  constexpr int kTarget = kWide ? 3200 : kFineTarget, kCap = kWide ? 4096 : kFineCap;
   *used = false;
   const uint32_t kb = c->key_bits;
   const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb);
   const uint32_t ncoarse = 1u << cb;
   KeyArrays ka;
-  TRY(key_sources(c, &ka));
+  TRY(key_sources<KeyT>(c, &ka));
   const bool from_array = ka.from_array;
   const uint64_t n_array = ka.n;
   const auto &arrays = ka.arrays;
@@ -683,17 +687,17 @@ int finish_fast(kmc_ctx *c, bool *used) {
   if (from_array) {
     for (auto &a : arrays) {
       uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024 * step), (uint64_t)kNumSMsB200 * 8);
-      auto fast_hist_array = fast_hist_array_kernel<uint64_t>;
-      LAUNCH(fast_hist_array, grid, 256, ncoarse * 4, a.first, a.second, step, kb - cb, ncoarse, ghist);
+      auto fast_hist_array = fast_hist_array_kernel<KeyT>;
+      LAUNCH(fast_hist_array, grid, 256, ncoarse * 4, (const KeyT *)a.first, a.second, step, kb - cb, ncoarse, ghist);
     }
   } else {
     for (size_t i = 0; i < c->n_segs; i++) {
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
       ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
-      uint64_t tiles = num_warp_tiles(s.n_bases, 31);
+      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)kNumSMsB200 * 8);
-      auto fast_hist = fast_hist_kernel<uint64_t, true>;
+      auto fast_hist = fast_hist_kernel<KeyT, true>;
       LAUNCH(fast_hist, grid, 256, ncoarse * 4, P, tiles, step, kb - cb, ncoarse, ghist);
     }
   }
@@ -715,7 +719,7 @@ int finish_fast(kmc_ctx *c, bool *used) {
   std::vector<uint32_t> e(ncoarse);
   for (uint32_t ci = 0; ci < ncoarse; ci++) {
     uint32_t ee = 0;
-    while (((hist[ci] + ((1ull << ee) - 1)) >> ee) > (uint64_t)kFineTarget) ee++;
+    while (((hist[ci] + ((1ull << ee) - 1)) >> ee) > (uint64_t)kTarget) ee++;
     if (ee > kb - cb) return KMC_OK; // cannot split far enough: too many keys share a prefix (duplicates)
     e[ci] = ee;
   }
@@ -753,7 +757,7 @@ int finish_fast(kmc_ctx *c, bool *used) {
   uint8_t *l1ep = c->fast_host.data() + o_e;
   uint64_t l1_keys = 0, l2_keys = 0, tiles2 = 0;
   uint32_t fb = 0;
-  bool key32 = true; // every bucket leaves <= 32 key bits: level 2 stores 32-bit suffixes
+  bool key32 = !kWide; // every bucket leaves <= 32 key bits: level 2 stores 32-bit suffixes
   for (uint32_t b = 0; b < n_l1; b++) if (kb - b1 - l1e[b] > 32) key32 = false;
   for (uint32_t b = 0; b < n_l1; b++) {
     uint64_t nb = 0;
@@ -763,29 +767,30 @@ int finish_fast(kmc_ctx *c, bool *used) {
       nb += hist[ci];
       double avg = (double)hist[ci] / (double)(1ull << sub_bits);
       uint32_t cp = (uint32_t)(avg * 1.10 + 6.0 * std::sqrt(avg) + 64.0);
-      cp = std::min<uint32_t>((cp + 15) & ~15u, kFineCap);
+      cp = std::min<uint32_t>((cp + 15) & ~15u, kCap);
       for (uint32_t sub = 0; sub < (1u << sub_bits); sub++) {
         const uint32_t rem = kb - b1 - l1e[b];
         fdesc[fb].start = l2_keys; fdesc[fb].cap = (uint16_t)cp; fdesc[fb].rem = (uint8_t)rem;
         // bucket index within the level-1 bucket = the l1e[b] bits right below the b1 prefix
         const uint64_t within = (uint64_t)(fb - f0[b]);
-        fdesc[fb].prefix = rem >= 64 ? 0 : ((((uint64_t)b << l1e[b]) | within) << rem);
+        fdesc[fb].prefix = (kWide || rem >= 64) ? 0 : ((((uint64_t)b << l1e[b]) | within) << rem); // 128-bit keys stay whole
         l2_keys += cp; fb++;
       }
     }
     uint64_t cap1 = ((uint64_t)((double)nb * 1.03) + 8192 + 15) & ~15ull;
     l1s[b] = l1_keys; l1cap[b] = cap1; t0[b] = (uint32_t)tiles2; l1ep[b] = l1e[b];
     l1_keys += cap1;
-    tiles2 += (cap1 + kP2Tile - 1) / kP2Tile;
+    tiles2 += (cap1 + p2_tile<KeyT>() - 1) / p2_tile<KeyT>();
   }
   l1s[n_l1] = l1_keys; t0[n_l1] = (uint32_t)tiles2; f0[n_l1] = fb;
   if (tiles2 > 0x7FFFFFFFull) return KMC_OK;
 
   // ---- buffers (each array ends with a trash area of one tile + slack for runs that spill over a bucket end)
-  const uint64_t slack = 2 * kPart2Tile;
+  const uint64_t slack = 2 * kMaxTile;
   TRY(ensure(c, c->fast_tables, tab_bytes));
-  TRY(ensure(c, c->fast_l1, (l1_keys + slack) * 8));
-  TRY(ensure(c, c->fast_l2, (l2_keys + 2 * slack) * 8));
+  TRY(ensure(c, c->fast_l1, (l1_keys + slack) * sizeof(KeyT)));
+  TRY(ensure(c, c->fast_l2, (l2_keys + 2 * slack) * sizeof(KeyT)));
+  if (kWide) { TRY(ensure(c, c->t_lo, l1_keys * 8)); TRY(ensure(c, c->t_hi, l1_keys * 8)); }
   TRY(ensure(c, c->t_cnt, l1_keys * 4));
   const size_t off_status = (off_fine + n_fine * 4 + 15) & ~size_t(15);
   if (off_status + n_fine * 8 + 64 > c->fast_state.cap) {
@@ -808,64 +813,75 @@ int finish_fast(kmc_ctx *c, bool *used) {
   // ---- level 1
   PHASE_BEGIN("fast_part1");
   if (from_array) {
-    size_t smem = PartSmem::bytes(kPart2Tile, n_l1);
-    CK(cudaFuncSetAttribute(fast_part1_array_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    auto fast_part1_array = fast_part1_array_kernel;
+    size_t smem = PartSmem<KeyT>::bytes(arr_tile<KeyT>(), n_l1);
+    auto fast_part1_array = fast_part1_array_kernel<KeyT>;
+    CK(cudaFuncSetAttribute(fast_part1_array, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (auto &a : arrays) {
-      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, kPart2Tile), (uint64_t)kNumSMsB200);
-      LAUNCH(fast_part1_array, grid, kFastThreads, smem, a.first, a.second, pl, (uint64_t *)c->fast_l1.p, d_err(c));
+      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, arr_tile<KeyT>()), (uint64_t)kNumSMsB200);
+      LAUNCH(fast_part1_array, grid, kFastThreads, smem, (const KeyT *)a.first, a.second, pl, (KeyT *)c->fast_l1.p, d_err(c));
     }
   } else {
-    size_t smem = PartSmem::bytes(kPart1Stage, n_l1);
-    auto fast_part1 = fast_part1_kernel<true, PrefixBucket>;
+    size_t smem = PartSmem<KeyT>::bytes(part1_stage<KeyT>(), n_l1);
+    auto fast_part1 = fast_part1_kernel<KeyT, true, PrefixBucket>;
     CK(cudaFuncSetAttribute(fast_part1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const PrefixBucket bucket{b1, kb - b1};
     for (size_t i = 0; i < c->n_segs; i++) {
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
       ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
-      uint64_t tiles = num_warp_tiles(s.n_bases, 31);
+      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
-      LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (uint64_t *)c->fast_l1.p, d_err(c));
+      LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->fast_l1.p, d_err(c));
     }
   }
   PHASE_END();
   // ---- level 2
   PHASE_BEGIN("fast_part2");
   {
-    size_t smem = PartSmem::bytes(kP2Tile, kMaxFinePerL1);
-    if (key32) {
-      auto fast_part2 = fast_part2_kernel<uint32_t>;
+    size_t smem = PartSmem<KeyT>::bytes(p2_tile<KeyT>(), kMaxFinePerL1);
+    if constexpr (kWide) {
+      auto fast_part2 = fast_part2_kernel<U128, U128>;
+      CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const U128 *)c->fast_l1.p, (U128 *)c->fast_l2.p, d_err(c));
+    } else if (key32) {
+      auto fast_part2 = fast_part2_kernel<uint64_t, uint32_t>;
       CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const uint64_t *)c->fast_l1.p, (uint32_t *)c->fast_l2.p, d_err(c));
     } else {
-      auto fast_part2 = fast_part2_kernel<uint64_t>;
+      auto fast_part2 = fast_part2_kernel<uint64_t, uint64_t>;
       CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const uint64_t *)c->fast_l1.p, (uint64_t *)c->fast_l2.p, d_err(c));
     }
   }
   PHASE_END();
-  // ---- finish: the level-1 array is dead after part2 and becomes the table's key column
+  // ---- finish: the level-1 array is dead after part2 and (64-bit keys) becomes the table's key column
   PHASE_BEGIN("fast_finish");
   {
     unsigned long long *prof = nullptr;
     static const bool want_prof = getenv("KMC_FINISH_PROF") && getenv("KMC_FINISH_PROF")[0] == '1';
     if (want_prof) { prof = (unsigned long long *)c->fast_state.p; CK(cudaMemsetAsync(prof, 0, 16 * 8, c->stream)); } // the histogram is dead by now
     uint32_t grid;
-    if (key32) {
-      size_t smem = sizeof(FinishSmem<uint32_t>);
-      auto fast_finish = fast_finish_kernel<uint32_t>;
-      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB32);
-      LAUNCH(fast_finish, grid, kFinThreads, smem, pl, (const uint32_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint32_t *)c->t_cnt.p,
-             status, ticket, d_err(c), d_total, prof);
-    } else {
-      size_t smem = sizeof(FinishSmem<uint64_t>);
-      auto fast_finish = fast_finish_kernel<uint64_t>;
-      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if constexpr (kWide) {
+      size_t fsmem = sizeof(FinishSmem<U128>);
+      auto fast_finish = fast_finish_kernel<U128>;
+      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2);
-      LAUNCH(fast_finish, grid, kFinThreads, smem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint32_t *)c->t_cnt.p,
-             status, ticket, d_err(c), d_total, prof);
+      LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const U128 *)c->fast_l2.p, (uint64_t *)c->t_lo.p, (uint64_t *)c->t_hi.p,
+             (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
+    } else if (key32) {
+      size_t fsmem = sizeof(FinishSmem<uint32_t>);
+      auto fast_finish = fast_finish_kernel<uint32_t>;
+      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB32);
+      LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint32_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
+             (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
+    } else {
+      size_t fsmem = sizeof(FinishSmem<uint64_t>);
+      auto fast_finish = fast_finish_kernel<uint64_t>;
+      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2);
+      LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
+             (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
     }
     if (want_prof) {
       unsigned long long h[16];
@@ -893,7 +909,7 @@ int finish_fast(kmc_ctx *c, bool *used) {
   }
   uint64_t N = 0;
   for (unsigned long long v : cur) N += v;
-  std::swap(c->t_lo, c->fast_l1);
+  if (!kWide) std::swap(c->t_lo, c->fast_l1);
   c->n_total = N; c->n_distinct = d;
   c->strategy_used = KMC_STRATEGY_SORT;
   *used = true;
@@ -903,36 +919,38 @@ int finish_fast(kmc_ctx *c, bool *used) {
 template <typename KeyT>
 int finish_impl(kmc_ctx *c) {
   const uint32_t strat = c->cfg.strategy;
-  if (sizeof(KeyT) == 8 && strat != KMC_STRATEGY_SORT_BASELINE) {
+  if (strat != KMC_STRATEGY_SORT_BASELINE) {
     bool used = false;
-    if (strat == KMC_STRATEGY_HASH) {
-      // forced: size the table for the worst case (every key distinct), at most 2^32 slots
-      uint64_t n_in = 0;
-      for (auto &e : c->ingested) n_in += e.second;
-      if (c->ingested.empty()) n_in = c->cfg.mode == KMC_MODE_LR_GAPPED ? c->total_bases * (c->cfg.d_max - c->cfg.d_min + 1) : c->total_bases;
-      bool low = false;
-      TRY(hash_probe(c, &low)); // also finds the hot keys
-      uint32_t lg = 20;
-      while (lg < 32 && (1ull << lg) < 2 * n_in) lg++;
-      TRY(finish_hash(c, lg, (1ull << lg) / 10 * 7, &used));
-      if (used) return KMC_OK;
-    } else if (strat == KMC_STRATEGY_AUTO) {
-      bool low = false;
-      TRY(hash_probe(c, &low));
-      if (low) {
-        // a table sized from the sample stays in L2 (a 2^25-slot one does not: 512 MB of randomly touched lines);
-        // if the full input has more distinct keys than that, retry once with the big table
+    if constexpr (sizeof(KeyT) == 8) {
+      if (strat == KMC_STRATEGY_HASH) {
+        // forced: size the table for the worst case (every key distinct), at most 2^32 slots
+        uint64_t n_in = 0;
+        for (auto &e : c->ingested) n_in += e.second;
+        if (c->ingested.empty()) n_in = c->cfg.mode == KMC_MODE_LR_GAPPED ? c->total_bases * (c->cfg.d_max - c->cfg.d_min + 1) : c->total_bases;
+        bool low = false;
+        TRY(hash_probe(c, &low)); // also finds the hot keys
         uint32_t lg = 20;
-        while (lg < 25 && (1ull << lg) < 4 * c->probe_distinct) lg++;
-        TRY(finish_hash(c, lg, (1ull << lg) / 2, &used));
+        while (lg < 32 && (1ull << lg) < 2 * n_in) lg++;
+        TRY(finish_hash(c, lg, (1ull << lg) / 10 * 7, &used));
         if (used) return KMC_OK;
-        if (lg < 25) {
-          TRY(finish_hash(c, 25, 1ull << 24, &used));
+      } else if (strat == KMC_STRATEGY_AUTO) {
+        bool low = false;
+        TRY(hash_probe(c, &low));
+        if (low) {
+          // a table sized from the sample stays in L2 (a 2^25-slot one does not: 512 MB of randomly touched lines);
+          // if the full input has more distinct keys than that, retry once with the big table
+          uint32_t lg = 20;
+          while (lg < 25 && (1ull << lg) < 4 * c->probe_distinct) lg++;
+          TRY(finish_hash(c, lg, (1ull << lg) / 2, &used));
           if (used) return KMC_OK;
+          if (lg < 25) {
+            TRY(finish_hash(c, 25, 1ull << 24, &used));
+            if (used) return KMC_OK;
+          }
         }
       }
     }
-    TRY(finish_fast(c, &used));
+    TRY(finish_fast<KeyT>(c, &used));
     if (used) return KMC_OK;
   }
   return finish_baseline<KeyT>(c);

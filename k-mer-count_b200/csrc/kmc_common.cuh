@@ -35,6 +35,17 @@ __host__ __device__ __forceinline__ uint32_t key_bits(const U128 &k, uint32_t sh
   return (uint32_t)v & ((1u << nbits) - 1u);
 }
 
+// low 32 bits of (key >> shift).  shift < 64 for 64-bit keys, < 128 for 128-bit keys, < 32 for 32-bit suffixes.
+__host__ __device__ __forceinline__ uint32_t key_shr32(uint32_t k, uint32_t shift) { return k >> shift; }
+__host__ __device__ __forceinline__ uint32_t key_shr32(uint64_t k, uint32_t shift) { return (uint32_t)(k >> shift); }
+__host__ __device__ __forceinline__ uint32_t key_shr32(const U128 &k, uint32_t shift) {
+  if (shift >= 64) return (uint32_t)(k.hi >> (shift - 64));
+  if (shift == 0) return (uint32_t)k.lo;
+  return (uint32_t)((k.lo >> shift) | (k.hi << (64 - shift)));
+}
+__host__ __device__ __forceinline__ bool key_eq(uint32_t a, uint32_t b) { return a == b; }
+__host__ __device__ __forceinline__ bool key_lt(uint32_t a, uint32_t b) { return a < b; }
+
 // ---- mixing: the digest of SURVEY §8d and the owner function of §8e ------------------------------
 // (restated on the CPU in oracle/kmc_oracle.c orc_mix; the two must agree bit for bit)
 __host__ __device__ __forceinline__ uint64_t fmix64(uint64_t x) {

@@ -34,9 +34,7 @@ constexpr int kCoarseBitsMax = 12;
 constexpr int kHistSampleMax = 16;       // fast_hist looks at every step-th tile, step <= 16
 constexpr int kFineTarget = 6400;        // aimed keys per fine bucket
 constexpr int kFineCap = 8192;           // smem capacity of fast_finish (keys)
-constexpr int kPart2KPT = 32;            // keys per thread in fast_part2
-constexpr int kPart2Tile = kFastThreads * kPart2KPT; // 16384
-constexpr int kPart1Stage = kFastWarps * 31 * 32;    // 15872 keys per CTA tile
+constexpr int kMaxTile = 16384;           // largest tile of any partition kernel (sizes the trash areas)
 constexpr int kMaxL1 = 1024;             // level-1 buckets (smem histogram size in fast_part1)
 constexpr int kMaxFinePerL1 = 2048;      // fine buckets under one level-1 bucket (smem histogram in fast_part2)
 constexpr int kFinishBins = 8192;        // sub-bins of fast_finish (13 bits)
@@ -56,6 +54,11 @@ struct __align__(16) FineDesc { // one per fine bucket
 // Level-2 element type: when every bucket has rem <= 32 only the low 32 bits of a key are stored (the rest is
 // the bucket's prefix): half the level-2 traffic and half the shared memory of fast_finish.
 template <typename L2T> __device__ __forceinline__ L2T to_l2(uint64_t key) { return (L2T)key; }
+template <typename L2T> __device__ __forceinline__ L2T to_l2(const U128 &key) { return key; }
+// table row from a level-2 element: the bucket prefix supplies the stripped bits
+__device__ __forceinline__ void emit_key(uint64_t *lo, uint64_t *, uint64_t i, const FineDesc &D, uint32_t x) { lo[i] = D.prefix | x; }
+__device__ __forceinline__ void emit_key(uint64_t *lo, uint64_t *, uint64_t i, const FineDesc &D, uint64_t x) { lo[i] = D.prefix | x; }
+__device__ __forceinline__ void emit_key(uint64_t *lo, uint64_t *hi, uint64_t i, const FineDesc &, const U128 &x) { lo[i] = x.lo; hi[i] = x.hi; }
 
 struct FastPlan {
   uint32_t kb, b1;          // key bits, level-1 bits
@@ -74,12 +77,32 @@ struct FastPlan {
 // bucket functions of the level-1 scatter: the top b1 key bits (counting), or the owner part (routing)
 struct PrefixBucket {
   uint32_t b1, bshift;
-  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return b1 ? (uint32_t)(key >> bshift) : 0u; }
+  template <typename KeyT> __device__ __forceinline__ uint32_t operator()(const KeyT &key) const { return b1 ? key_shr32(key, bshift) : 0u; }
 };
 struct OwnerBucket {
   uint32_t n_parts;
-  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return owner_of(0, key, n_parts); }
+  template <typename KeyT> __device__ __forceinline__ uint32_t operator()(const KeyT &key) const {
+    return owner_of(key_hi(key), key_lo(key), n_parts);
+  }
 };
+
+// shapes per key width: 128-bit keys take twice the registers and shared memory, so half the keys per tile
+template <typename KeyT> struct FastShape;
+template <> struct FastShape<uint64_t> {
+  static constexpr int kHalves = 1;                      // fast_part1: all 32 window starts of a lane in one tile
+  static constexpr int kLanes = 31;
+  static constexpr int kArrKPT = 32;                     // fast_part1_array keys per thread
+  static constexpr int kP2KPT = 16;                      // fast_part2 keys per thread
+};
+template <> struct FastShape<U128> {
+  static constexpr int kHalves = 2;
+  static constexpr int kLanes = 30;
+  static constexpr int kArrKPT = 16;
+  static constexpr int kP2KPT = 8;
+};
+template <typename KeyT> __host__ __device__ constexpr int part1_stage() { return kFastWarps * FastShape<KeyT>::kLanes * (32 / FastShape<KeyT>::kHalves); }
+template <typename KeyT> __host__ __device__ constexpr int arr_tile() { return kFastThreads * FastShape<KeyT>::kArrKPT; }
+template <typename KeyT> __host__ __device__ constexpr int p2_tile() { return kFastThreads * FastShape<KeyT>::kP2KPT; }
 
 // ------------------------------------------------------------------------------------------------ hist
 // Sampled coarse histogram: warp tiles t with t % step == 0.
@@ -132,17 +155,18 @@ __global__ void __launch_bounds__(256) fast_hist_array_kernel(const KeyT *__rest
 // ------------------------------------------------------------------------------------------------ part1 / part2
 // Shared-memory layout of the partition kernels (dynamic smem):
 //   stage[STAGE] keys | gdelta[NB] u64 | hist[NB] u32 | loc[NB] u32 | scan scratch
+template <typename KeyT>
 struct PartSmem {
-  uint64_t *stage; uint64_t *gdelta; uint32_t *hist; uint32_t *loc; uint32_t *scan;
+  KeyT *stage; uint64_t *gdelta; uint32_t *hist; uint32_t *loc; uint32_t *scan;
   __device__ PartSmem(unsigned char *base, uint32_t stage_keys, uint32_t nb) {
-    stage = (uint64_t *)base;
-    gdelta = stage + stage_keys;
+    stage = (KeyT *)base;
+    gdelta = (uint64_t *)(stage + stage_keys);
     hist = (uint32_t *)(gdelta + nb);
     loc = hist + nb;
     scan = loc + nb;
   }
   static __host__ __device__ size_t bytes(uint32_t stage_keys, uint32_t nb) {
-    return (size_t)stage_keys * 8 + (size_t)nb * 16 + 64 * 4;
+    return (size_t)stage_keys * sizeof(KeyT) + (size_t)nb * 16 + 64 * 4;
   }
 };
 
@@ -168,7 +192,8 @@ __device__ __forceinline__ uint32_t scan_bins(const uint32_t *hist, uint32_t *lo
 }
 
 // reserve room for the tile's run of every level-1 bucket; runs that do not fit go to the trash area
-__device__ __forceinline__ void reserve_l1(const FastPlan &pl, PartSmem &S, uint32_t nb, uint32_t *flags) {
+template <typename KeyT>
+__device__ __forceinline__ void reserve_l1(const FastPlan &pl, PartSmem<KeyT> &S, uint32_t nb, uint32_t *flags) {
   for (uint32_t b = threadIdx.x; b < nb; b += kFastThreads) {
     uint32_t c = S.hist[b];
     if (c) {
@@ -183,105 +208,99 @@ __device__ __forceinline__ void reserve_l1(const FastPlan &pl, PartSmem &S, uint
   }
 }
 
-// Level-1 scatter, extraction front end.  One CTA tile = 16 warp tiles (<= 15872 keys).
-template <bool FOLD, typename BucketFn>
+// rank (smem atomics) → scan → reserve → stage in bucket order → write runs: the common back end of the
+// level-1 scatters.  key[]/valid describe this thread's NK keys.
+template <typename KeyT, int NK, typename BucketFn>
+__device__ __forceinline__ void scatter_tile_l1(const FastPlan &pl, PartSmem<KeyT> &S, uint32_t nb, const BucketFn &bucket,
+                                                const KeyT (&key)[NK], uint32_t valid, KeyT *__restrict__ l1, uint32_t *flags) {
+  uint32_t rank[NK / 2]; // two 16-bit ranks per word
+#pragma unroll
+  for (int s = 0; s < NK; s++) {
+    uint32_t r = 0;
+    if (valid & (1u << s)) r = atomicAdd(&S.hist[bucket(key[s])], 1u);
+    if (s & 1) rank[s >> 1] |= r << 16; else rank[s >> 1] = r;
+  }
+  __syncthreads();
+  uint32_t total = scan_bins(S.hist, S.loc, nb, S.scan);
+  reserve_l1(pl, S, nb, flags);
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < NK; s++)
+    if (valid & (1u << s)) S.stage[S.loc[bucket(key[s])] + ((rank[s >> 1] >> (16 * (s & 1))) & 0xFFFFu)] = key[s];
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < total; i += kFastThreads) {
+    KeyT k = S.stage[i];
+    l1[S.gdelta[bucket(k)] + i] = k;
+  }
+  __syncthreads();
+}
+
+// Level-1 scatter, extraction front end.  One CTA tile = 16 warp tiles (u64: all 32 starts of every lane,
+// <= 15872 keys; u128: 16 starts at a time, two tiles per load).
+template <typename KeyT, bool FOLD, typename BucketFn>
 __global__ void __launch_bounds__(kFastThreads, 1) fast_part1_kernel(ExtractParams P, uint64_t n_tiles, FastPlan pl, BucketFn bucket,
-                                                                      uint64_t *__restrict__ l1, uint32_t *__restrict__ flags) {
+                                                                      KeyT *__restrict__ l1, uint32_t *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kHalves = FastShape<KeyT>::kHalves, kSPH = 32 / kHalves;
   const uint32_t nb = pl.n_l1;
-  PartSmem S(smem_raw, kPart1Stage, nb);
+  PartSmem<KeyT> S(smem_raw, part1_stage<KeyT>(), nb);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   const uint64_t n_cta_tiles = (n_tiles + kFastWarps - 1) / kFastWarps;
   for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
-    for (uint32_t i = threadIdx.x; i < nb; i += kFastThreads) S.hist[i] = 0;
-    __syncthreads();
     uint64_t t = ct * kFastWarps + warp;
-    Win<uint64_t> W{};
-    W.template load<FOLD>(P, t * Win<uint64_t>::kLanes + lane);
+    Win<KeyT> W{};
+    W.template load<FOLD>(P, t * Win<KeyT>::kLanes + lane);
     const uint32_t ok = t < n_tiles ? W.ok : 0u;
-    uint64_t key[32];
-    uint32_t rank[16]; // two 16-bit ranks per word
+#pragma unroll 1
+    for (int half = 0; half < kHalves; half++) {
+      for (uint32_t i = threadIdx.x; i < nb; i += kFastThreads) S.hist[i] = 0;
+      __syncthreads();
+      KeyT key[kSPH];
+      uint32_t valid = 0;
 #pragma unroll
-    for (int s = 0; s < 32; s++) {
-      key[s] = W.key(s, P.k, P.canonical != 0);
-      uint32_t r = 0;
-      if (ok & (0x80000000u >> s)) r = atomicAdd(&S.hist[bucket(key[s])], 1u);
-      if (s & 1) rank[s >> 1] |= r << 16; else rank[s >> 1] = r;
+      for (int s = 0; s < kSPH; s++) {
+        key[s] = W.key(half * kSPH + s, P.k, P.canonical != 0);
+        if (ok & (0x80000000u >> (half * kSPH + s))) valid |= 1u << s;
+      }
+      scatter_tile_l1<KeyT, kSPH>(pl, S, nb, bucket, key, valid, l1, flags);
     }
-    __syncthreads();
-    uint32_t total = scan_bins(S.hist, S.loc, nb, S.scan);
-    reserve_l1(pl, S, nb, flags);
-    __syncthreads();
-#pragma unroll
-    for (int s = 0; s < 32; s++)
-      if (ok & (0x80000000u >> s))
-        S.stage[S.loc[bucket(key[s])] + ((rank[s >> 1] >> (16 * (s & 1))) & 0xFFFFu)] = key[s];
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < total; i += kFastThreads) {
-      uint64_t k = S.stage[i];
-      l1[S.gdelta[bucket(k)] + i] = k;
-    }
-    __syncthreads();
   }
 }
 
 // Level-1 scatter, key-array front end (ingested keys of the multi-GPU path, lr-gapped keys).
-__global__ void __launch_bounds__(kFastThreads, 1) fast_part1_array_kernel(const uint64_t *__restrict__ keys, uint64_t n,
-                                                                            FastPlan pl, uint64_t *__restrict__ l1,
+template <typename KeyT>
+__global__ void __launch_bounds__(kFastThreads, 1) fast_part1_array_kernel(const KeyT *__restrict__ keys, uint64_t n,
+                                                                            FastPlan pl, KeyT *__restrict__ l1,
                                                                             uint32_t *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kKPT = FastShape<KeyT>::kArrKPT, kTile = arr_tile<KeyT>();
   const uint32_t nb = pl.n_l1;
-  PartSmem S(smem_raw, kPart2Tile, nb);
+  PartSmem<KeyT> S(smem_raw, kTile, nb);
   const PrefixBucket bucket{pl.b1, pl.kb - pl.b1};
-  const uint64_t n_cta_tiles = (n + kPart2Tile - 1) / kPart2Tile;
+  const uint64_t n_cta_tiles = (n + kTile - 1) / kTile;
   for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
     for (uint32_t i = threadIdx.x; i < nb; i += kFastThreads) S.hist[i] = 0;
     __syncthreads();
-    const uint64_t base = ct * kPart2Tile;
-    const uint32_t cnt = (uint32_t)((n - base < (uint64_t)kPart2Tile) ? n - base : kPart2Tile);
-    uint64_t key[kPart2KPT];
-    uint32_t rank[kPart2KPT / 2];
+    const uint64_t base = ct * kTile;
+    const uint32_t cnt = (uint32_t)((n - base < (uint64_t)kTile) ? n - base : kTile);
+    KeyT key[kKPT];
+    uint32_t valid = 0;
 #pragma unroll
-    for (int j = 0; j < kPart2KPT; j++) {
+    for (int j = 0; j < kKPT; j++) {
       uint32_t idx = j * kFastThreads + threadIdx.x;
-      key[j] = idx < cnt ? keys[base + idx] : 0ull;
+      if (idx < cnt) { key[j] = keys[base + idx]; valid |= 1u << j; } else key[j] = KeyT{};
     }
-#pragma unroll
-    for (int j = 0; j < kPart2KPT; j++) {
-      uint32_t idx = j * kFastThreads + threadIdx.x;
-      uint32_t r = 0;
-      if (idx < cnt) r = atomicAdd(&S.hist[bucket(key[j])], 1u);
-      if (j & 1) rank[j >> 1] |= r << 16; else rank[j >> 1] = r;
-    }
-    __syncthreads();
-    uint32_t total = scan_bins(S.hist, S.loc, nb, S.scan);
-    reserve_l1(pl, S, nb, flags);
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kPart2KPT; j++) {
-      uint32_t idx = j * kFastThreads + threadIdx.x;
-      if (idx < cnt) S.stage[S.loc[bucket(key[j])] + ((rank[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)] = key[j];
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < total; i += kFastThreads) {
-      uint64_t k = S.stage[i];
-      l1[S.gdelta[bucket(k)] + i] = k;
-    }
-    __syncthreads();
+    scatter_tile_l1<KeyT, kKPT>(pl, S, nb, bucket, key, valid, l1, flags);
   }
 }
 
-// One CTA per tile of kP2Tile keys of one level-1 bucket → its 2^e fine buckets (the next e key bits).
-#ifndef KMC_PART2_KPT
-#define KMC_PART2_KPT 16
-#endif
-constexpr int kP2KPT = KMC_PART2_KPT;              // keys per thread
-constexpr int kP2Tile = kFastThreads * kP2KPT;     // 8192 keys at 16 per thread: 96 KB of smem, two CTAs per SM
-template <typename L2T>
-__global__ void __launch_bounds__(kFastThreads, kP2KPT <= 16 ? 2 : 1) fast_part2_kernel(FastPlan pl, const uint64_t *__restrict__ l1,
+// One CTA per tile of p2_tile<KeyT>() keys of one level-1 bucket → its 2^e fine buckets (the next e key bits).
+template <typename KeyT, typename L2T>
+__global__ void __launch_bounds__(kFastThreads, 2) fast_part2_kernel(FastPlan pl, const KeyT *__restrict__ l1,
                                                                       L2T *__restrict__ l2, uint32_t *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_b;
+  constexpr int kKPT = FastShape<KeyT>::kP2KPT, kTile = p2_tile<KeyT>();
   // which level-1 bucket owns this tile: last b with l1_tile0[b] <= tile
   if (threadIdx.x == 0) {
     uint32_t lo = 0, hi = pl.n_l1;
@@ -295,28 +314,28 @@ __global__ void __launch_bounds__(kFastThreads, kP2KPT <= 16 ? 2 : 1) fast_part2
   const uint32_t b = s_b;
   unsigned long long n_b = pl.l1_cursor[b];
   if (n_b > pl.l1_cap[b]) n_b = pl.l1_cap[b];
-  const uint64_t toff = (uint64_t)(blockIdx.x - pl.l1_tile0[b]) * kP2Tile;
+  const uint64_t toff = (uint64_t)(blockIdx.x - pl.l1_tile0[b]) * kTile;
   if (toff >= n_b) return; // tiles are laid out over the capacity; this one is past the fill
   const uint32_t e = pl.l1_e[b];
   const uint32_t fshift = pl.kb - pl.b1 - e, fmask = (1u << e) - 1u; // e == 0 → fmask 0 → fine index 0
   const uint32_t fine0 = pl.l1_fine0[b], nb = 1u << e;
-  PartSmem S(smem_raw, kP2Tile, kMaxFinePerL1);
+  PartSmem<KeyT> S(smem_raw, kTile, kMaxFinePerL1);
   for (uint32_t i = threadIdx.x; i < nb; i += kFastThreads) S.hist[i] = 0;
   __syncthreads();
   const uint64_t base = pl.l1_start[b] + toff;
-  const uint32_t cnt = (uint32_t)((n_b - toff < (uint64_t)kP2Tile) ? n_b - toff : kP2Tile);
-  uint64_t key[kP2KPT];
-  uint32_t rank[kP2KPT / 2];
+  const uint32_t cnt = (uint32_t)((n_b - toff < (uint64_t)kTile) ? n_b - toff : kTile);
+  KeyT key[kKPT];
+  uint32_t rank[kKPT / 2];
 #pragma unroll
-  for (int j = 0; j < kP2KPT; j++) {
+  for (int j = 0; j < kKPT; j++) {
     uint32_t idx = j * kFastThreads + threadIdx.x;
-    key[j] = idx < cnt ? l1[base + idx] : 0ull;
+    if (idx < cnt) key[j] = l1[base + idx]; else key[j] = KeyT{};
   }
 #pragma unroll
-  for (int j = 0; j < kP2KPT; j++) {
+  for (int j = 0; j < kKPT; j++) {
     uint32_t idx = j * kFastThreads + threadIdx.x;
     uint32_t r = 0;
-    if (idx < cnt) r = atomicAdd(&S.hist[fmask ? (uint32_t)(key[j] >> fshift) & fmask : 0u], 1u);
+    if (idx < cnt) r = atomicAdd(&S.hist[fmask ? key_shr32(key[j], fshift) & fmask : 0u], 1u);
     if (j & 1) rank[j >> 1] |= r << 16; else rank[j >> 1] = r;
   }
   __syncthreads();
@@ -334,15 +353,15 @@ __global__ void __launch_bounds__(kFastThreads, kP2KPT <= 16 ? 2 : 1) fast_part2
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < kP2KPT; j++) {
+  for (int j = 0; j < kKPT; j++) {
     uint32_t idx = j * kFastThreads + threadIdx.x;
     if (idx < cnt)
-      S.stage[S.loc[fmask ? (uint32_t)(key[j] >> fshift) & fmask : 0u] + ((rank[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)] = key[j];
+      S.stage[S.loc[fmask ? key_shr32(key[j], fshift) & fmask : 0u] + ((rank[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)] = key[j];
   }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < total; i += kFastThreads) {
-    uint64_t k = S.stage[i];
-    l2[S.gdelta[fmask ? (uint32_t)(k >> fshift) & fmask : 0u] + i] = to_l2<L2T>(k);
+    KeyT k = S.stage[i];
+    l2[S.gdelta[fmask ? key_shr32(k, fshift) & fmask : 0u] + i] = to_l2<L2T>(k);
   }
 }
 
@@ -397,17 +416,20 @@ __device__ __forceinline__ unsigned long long lookback_resolve(unsigned long lon
 #endif
 constexpr int kFinThreads = KMC_FINISH_THREADS;      // threads per CTA of fast_finish
 constexpr int kFinWarps = kFinThreads / 32;
-constexpr int kFinishKPT = kFineCap / kFinThreads;   // keys per thread (16 at 512 threads)
 constexpr int kFinWordsPT = kFinishBins / 2 / kFinThreads; // packed bin words per thread in the scan (8 at 512 threads)
-static_assert(kFinishKPT <= 32 && kFinishKPT * kFinWarps <= kFinThreads && kFinWordsPT % 4 == 0, "fast_finish shape");
+// keys per fine bucket that fast_finish can hold: 8192 32/64-bit elements, 4096 128-bit keys (64 KB either way
+// for the widest; 32 KB for 32-bit suffixes)
+template <typename L2T> __host__ __device__ constexpr int fin_cap() { return sizeof(L2T) == 16 ? 4096 : kFineCap; }
+template <typename L2T> __host__ __device__ constexpr int fin_kpt() { return fin_cap<L2T>() / kFinThreads; }
+static_assert(fin_kpt<uint32_t>() <= 32 && fin_kpt<uint32_t>() * kFinWarps <= kFinThreads && kFinWordsPT % 4 == 0, "fast_finish shape");
 
 template <typename L2T>
 struct FinishSmem {
-  L2T keys[kFineCap];                      // 64 KB (u64) / 32 KB (u32)
+  L2T keys[fin_cap<L2T>()];                // 64 KB (u64, u128) / 32 KB (u32)
   uint32_t bins[kFinishBins / 2];          // packed u16 pairs: counts → starts → (after the scatter) ends
-  uint16_t hp[kFineCap + 8];               // head position of every run
+  uint16_t hp[kFineCap + 8];               // multi-key sub-bin list, then head position of every run
   uint32_t scan32[40];
-  uint32_t rowcnt[kFinishKPT * kFinWarps];// heads per (row, warp), then their exclusive scan
+  uint32_t rowcnt[fin_kpt<L2T>() * kFinWarps];// heads per (row, warp), then their exclusive scan
   uint32_t hard[kMaxHard];
   uint32_t n_hard;
   uint32_t n_multi;
@@ -425,13 +447,15 @@ __device__ __forceinline__ uint32_t bin_start(const uint32_t *bins, uint32_t b) 
 #endif
 template <typename L2T>
 __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MINB32 : 2) fast_finish_kernel(FastPlan pl, const L2T *__restrict__ l2,
-                                                                       uint64_t *__restrict__ out_lo, uint32_t *__restrict__ out_cnt,
+                                                                       uint64_t *__restrict__ out_lo, uint64_t *__restrict__ out_hi,
+                                                                       uint32_t *__restrict__ out_cnt,
                                                                        unsigned long long *__restrict__ status,
                                                                        unsigned int *__restrict__ ticket, uint32_t *__restrict__ flags,
                                                                        unsigned long long *__restrict__ d_total,
                                                                        unsigned long long *__restrict__ prof) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FinishSmem<L2T> &S = *reinterpret_cast<FinishSmem<L2T> *>(smem_raw);
+  constexpr int kFinishKPT = fin_kpt<L2T>();
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // optional phase timeline (development aid, env KMC_FINISH_PROF=1): thread 0 adds the cycles between marks
   long long t_prev = prof ? clock64() : 0;
@@ -446,7 +470,7 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
     uint32_t n = pl.fine_cursor[f];
     if (n > D.cap) n = D.cap; // overflow was flagged by fast_part2; the caller discards this result
     const uint32_t sb = D.rem < 13 ? D.rem : 13;
-    const uint32_t bshift = D.rem - sb, bmask = (1u << sb) - 1u;
+    const uint32_t bshift = D.rem - sb, bmask = (1u << sb) - 1u; // sb == 0 → every key in sub-bin 0
     {
       uint4 z = make_uint4(0, 0, 0, 0);
       for (uint32_t i = tid; i < kFinishBins / 8; i += kFinThreads) reinterpret_cast<uint4 *>(S.bins)[i] = z;
@@ -461,14 +485,14 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
 #pragma unroll
     for (int j = 0; j < kFinishKPT; j++) {
       uint32_t i = j * kFinThreads + tid;
-      x[j] = i < n ? l2[D.start + i] : (L2T)0;
+      if (i < n) x[j] = l2[D.start + i]; else x[j] = L2T{};
     }
 #pragma unroll
     for (int j = 0; j < kFinishKPT; j++) {
       if ((uint32_t)j >= rows) break;
       uint32_t i = j * kFinThreads + tid;
       if (i < n) {
-        uint32_t b = (uint32_t)(x[j] >> bshift) & bmask;
+        uint32_t b = key_shr32(x[j], bshift) & bmask;
         uint32_t sh = 16 * (b & 1);
         uint32_t old = atomicAdd(&S.bins[b >> 1], 1u << sh);
         if (((old >> sh) & 0xFFFFu) == 1u) S.hp[atomicAdd(&S.n_multi, 1u)] = (uint16_t)b;
@@ -507,7 +531,7 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
       if ((uint32_t)j >= rows) break;
       uint32_t i = j * kFinThreads + tid;
       if (i < n) {
-        uint32_t b = (uint32_t)(x[j] >> bshift) & bmask;
+        uint32_t b = key_shr32(x[j], bshift) & bmask;
         uint32_t sh = 16 * (b & 1);
         uint32_t p = (atomicAdd(&S.bins[b >> 1], 1u << sh) >> sh) & 0xFFFFu;
         S.keys[p] = x[j];
@@ -529,22 +553,12 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
           if (h < (uint32_t)kMaxHard) S.hard[h] = b;
           continue;
         }
-        if (sizeof(L2T) == 8 && bshift <= 32) {
-          for (uint32_t i = s0 + 1; i < e0; i++) {
-            const L2T v = S.keys[i];
-            uint32_t jj = i;
-            while (jj > s0 && (uint32_t)S.keys[jj - 1] > (uint32_t)v) { S.keys[jj] = S.keys[jj - 1]; jj--; }
-            S.keys[jj] = v;
-            dups += (jj > s0 && (uint32_t)S.keys[jj - 1] == (uint32_t)v);
-          }
-        } else {
-          for (uint32_t i = s0 + 1; i < e0; i++) {
-            const L2T v = S.keys[i];
-            uint32_t jj = i;
-            while (jj > s0 && S.keys[jj - 1] > v) { S.keys[jj] = S.keys[jj - 1]; jj--; }
-            S.keys[jj] = v;
-            dups += (jj > s0 && S.keys[jj - 1] == v);
-          }
+        for (uint32_t i = s0 + 1; i < e0; i++) {
+          const L2T v = S.keys[i];
+          uint32_t jj = i;
+          while (jj > s0 && key_lt(v, S.keys[jj - 1])) { S.keys[jj] = S.keys[jj - 1]; jj--; }
+          S.keys[jj] = v;
+          dups += (jj > s0 && key_eq(S.keys[jj - 1], v));
         }
       }
       if (dups) atomicAdd(&S.n_dups, dups);
@@ -564,14 +578,14 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
         const uint32_t s = bin_start(S.bins, b), m = bin_end(S.bins, b) - s;
         const L2T first = S.keys[s];
         int differ = 0;
-        for (uint32_t i = tid; i < m; i += kFinThreads) differ |= (S.keys[s + i] != first);
+        for (uint32_t i = tid; i < m; i += kFinThreads) differ |= !key_eq(S.keys[s + i], first);
         if (__syncthreads_or(differ)) {
           for (uint32_t i = tid; i < m; i += kFinThreads) {
             const L2T v = S.keys[s + i];
             uint32_t r = 0;
             for (uint32_t q = 0; q < m; q++) {
               L2T o = S.keys[s + q];
-              r += (o < v) || (o == v && q < i);
+              r += key_lt(o, v) || (key_eq(o, v) && q < i);
             }
             S.hp[i] = (uint16_t)r;
           }
@@ -601,7 +615,7 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
       bool h = false;
       if ((uint32_t)j < rows && p < n) {
         x[j] = S.keys[p];
-        h = (p == 0) || (S.keys[p - 1] != x[j]);
+        h = (p == 0) || !key_eq(S.keys[p - 1], x[j]);
       }
       uint32_t bal = (uint32_t)j < rows ? __ballot_sync(0xffffffffu, h) : 0u;
       if (h) heads |= 1u << j;
@@ -643,7 +657,7 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
     FIN_MARK(8);
     const unsigned long long G = S.goff;
     for (uint32_t i = tid; i < d; i += kFinThreads) {
-      out_lo[G + i] = D.prefix | (uint64_t)S.keys[i];
+      emit_key(out_lo, out_hi, G + i, D, S.keys[i]);
       uint32_t nxt = (i + 1 < d) ? S.hp[i + 1] : n;
       out_cnt[G + i] = nxt - S.hp[i];
     }

@@ -163,3 +163,23 @@ def test_hash_strategy(kmc, orc):
     want = orc.gapped_mt(b4, o4, 16, 16, 40, 60)
     got = kmc.count_lr_gapped(b4, o4, 16, 16, 40, 60, strategy=1)
     assert_tables_equal(got, want)
+
+
+@pytest.mark.parametrize("k,canonical,n", [(63, True, 8_000_000), (47, False, 5_000_000), (33, True, 4_000_000), (64, True, 3_000_000)])
+def test_fast_path_128bit_keys(kmc, orc, k, canonical, n):
+    """k > 32: the partitioned path on 128-bit keys (BASELINE config 4's shape: ragged reads, N runs)."""
+    rng = np.random.default_rng(k)
+    bases = ACGT[rng.integers(0, 4, n)]
+    for s in rng.integers(0, n - 100, n // 10000):
+        bases[s:s + int(rng.integers(1, 120))] = ord("N")
+    lens = rng.integers(100, 10000, size=n // 100)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    off = off[off < n]
+    off = np.append(off, np.uint64(n))
+    want = orc.contiguous_mt(bases, off, k, canonical)
+    got, st, dig = _count(kmc, bases, off, k, canonical)
+    assert_tables_equal(got, want)
+    assert dig == want.digest()
+    assert st["strategy_used"] == 2 and st["fast_fallbacks"] == 0, st
+    base, _, _ = _count(kmc, bases, off, k, canonical, strategy=3)
+    assert_tables_equal(base, want)
