@@ -31,11 +31,16 @@ struct DevBuf {
   size_t cap = 0;
 };
 
-struct Segment {            // one submit's worth of input, resident in HBM
+struct Segment {            // one piece of input, resident in HBM (a submit, or a chunk of a large pinned submit)
   DevBuf own_bases, own_off, brk;
   const uint8_t *bases = nullptr;   // points into own_bases or at caller memory (submit_device)
   const uint64_t *rec_off = nullptr;
   uint64_t n_bases = 0, n_recs = 0;
+  uint64_t off_shift = 0;           // added to rec_off[] values to make them relative to this segment (chunks share one array)
+  const uint8_t *host_alias = nullptr; // the same bases in pinned host memory (readable by kernels): sampling passes use
+                                       // it so that they need not wait for the copy
+  cudaEvent_t ready = nullptr;      // recorded on the copy stream after this segment's H2D
+  bool wait_ready = false;
 };
 
 struct Phase {
@@ -57,6 +62,10 @@ struct kmc_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;
+  unsigned char *mailbox = nullptr, *mailbox_dev = nullptr; // pinned + mapped: small results written by kernels
+  unsigned char *upbox = nullptr, *upbox_dev = nullptr;     // pinned + mapped: small uploads pulled by a kernel
+  size_t upbox_cap = 0;
+  cudaStream_t copy_stream = nullptr; // chunked H2D of large pinned submits, overlapped with the level-1 scatter
   uint32_t key_bits = 0, key_bases = 0;
   bool wide = false; // 128-bit keys
 
@@ -202,6 +211,52 @@ unsigned long long *d_cursor(kmc_ctx *c) { return (unsigned long long *)c->scala
 unsigned long long *d_digest(kmc_ctx *c) { return (unsigned long long *)c->scalars.p + 1; }
 uint32_t *d_err(kmc_ctx *c) { return (uint32_t *)((unsigned long long *)c->scalars.p + 2); }
 
+// Small device→host reads go through a pinned, device-mapped mailbox written by a kernel, not through the copy
+// engines: a cudaMemcpy D2H queues behind the 64 MB H2D chunks of a large submit and would stall the compute
+// stream until every chunk has landed (measured: +6 ms per job).  Synchronises the compute stream.
+__global__ void mailbox_copy_kernel(const unsigned char *__restrict__ src, unsigned char *__restrict__ dst, uint32_t bytes) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < bytes; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+constexpr size_t kMailboxBytes = 64 << 10;
+int d2h_small(kmc_ctx *c, void *dst, const void *d_src, size_t bytes, size_t mailbox_off = 0) {
+  if (!c->mailbox) {
+    CK(cudaHostAlloc((void **)&c->mailbox, kMailboxBytes, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void **)&c->mailbox_dev, c->mailbox, 0));
+  }
+  if (mailbox_off + bytes > kMailboxBytes) return fail(c, KMC_E_ARG, "d2h_small: %zu bytes do not fit the mailbox", bytes);
+  LAUNCH(mailbox_copy_kernel, std::max<uint32_t>(1, (uint32_t)std::min<size_t>(bytes / 256, 32)), 256, 0, (const unsigned char *)d_src,
+         c->mailbox_dev + mailbox_off, (uint32_t)bytes);
+  c->launches--; // plumbing, not part of the hot path's launch count
+  CK(cudaStreamSynchronize(c->stream));
+  memcpy(dst, c->mailbox + mailbox_off, bytes);
+  return KMC_OK;
+}
+
+// ... and small host→device uploads (plan tables) likewise: staged in pinned mapped memory and pulled by a kernel,
+// because a cudaMemcpy H2D would queue behind the chunk copies on the same engine.
+__global__ void upload_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, uint64_t n16) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+int h2d_small(kmc_ctx *c, void *d_dst, const void *src, size_t bytes) {
+  size_t need = (bytes + 15) & ~size_t(15);
+  if (need > c->upbox_cap) {
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->upbox) CK(cudaFreeHost(c->upbox));
+    c->upbox = nullptr; c->upbox_cap = 0;
+    size_t cap = std::max<size_t>(need * 2, 1 << 20);
+    CK(cudaHostAlloc((void **)&c->upbox, cap, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void **)&c->upbox_dev, c->upbox, 0));
+    c->upbox_cap = cap;
+  } else {
+    CK(cudaStreamSynchronize(c->stream)); // the previous upload kernel may still be reading the box
+  }
+  memcpy(c->upbox, src, bytes);
+  LAUNCH(upload_kernel, (uint32_t)std::min<size_t>(std::max<size_t>(1, need / 16 / 256), (size_t)kNumSMsB200 * 4), 256, 0,
+         (const uint4 *)c->upbox_dev, (uint4 *)d_dst, (uint64_t)(need / 16));
+  c->launches--;
+  return KMC_OK;
+}
+
 int zero_scalars(kmc_ctx *c) {
   TRY(ensure(c, c->scalars, 64));
   CK(cudaMemsetAsync(c->scalars.p, 0, 64, c->stream));
@@ -209,8 +264,7 @@ int zero_scalars(kmc_ctx *c) {
 }
 int read_scalars(kmc_ctx *c, uint64_t *cursor, uint32_t *err) {
   unsigned long long h[4];
-  CK(cudaMemcpyAsync(h, c->scalars.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  TRY(d2h_small(c, h, c->scalars.p, sizeof h));
   if (cursor) *cursor = h[0];
   if (err) *err = (uint32_t)h[2];
   return KMC_OK;
@@ -221,6 +275,7 @@ int new_segment(kmc_ctx *c, Segment **out) {
   if (c->n_segs == c->segs.size()) c->segs.emplace_back();
   Segment &s = c->segs[c->n_segs++];
   s.bases = nullptr; s.rec_off = nullptr; s.n_bases = s.n_recs = 0;
+  s.off_shift = 0; s.host_alias = nullptr; s.wait_ready = false;
   *out = &s;
   return KMC_OK;
 }
@@ -231,13 +286,94 @@ int segment_mark(kmc_ctx *c, Segment &s) {
   TRY(ensure(c, s.brk, words * 4));
   CK(cudaMemsetAsync(s.brk.p, 0, words * 4, c->stream));
   if (s.n_recs)
-    LAUNCH(mark_breaks_kernel, grid_for(s.n_recs, 256), 256, 0, s.rec_off, s.n_recs, 0ull, (uint32_t *)s.brk.p);
+    LAUNCH(mark_breaks_kernel, grid_for(s.n_recs, 256), 256, 0, s.rec_off, s.n_recs, (unsigned long long)s.off_shift, (uint32_t *)s.brk.p);
+  return KMC_OK;
+}
+
+// kernels that read a segment's bases from HBM must not start before its copy has landed
+int seg_wait(kmc_ctx *c, Segment &s) {
+  if (s.wait_ready) { CK(cudaStreamWaitEvent(c->stream, s.ready, 0)); s.wait_ready = false; }
+  return KMC_OK;
+}
+
+// A large submit from PINNED host memory: cut it at record boundaries into ~64 MB chunks, one segment each, copied
+// on a separate stream.  kmc_finish's sampling passes read the pinned memory directly (1/16 of it), and the level-1
+// scatter of chunk i runs while chunk i+1 is still on the bus.  The caller's buffer must stay unchanged until
+// kmc_finish returns (library staging buffers: until the next kmc_staging hands them out again).
+constexpr size_t kChunkBases = (size_t)64 << 20;
+int submit_chunked(kmc_ctx *c, const uint8_t *bases, const uint8_t *bases_dev_alias, const uint64_t *rec_off, size_t n_bases,
+                   size_t n_recs, cudaEvent_t done) {
+  if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  c->segs.reserve(c->segs.size() + 2 * (n_bases / kChunkBases) + 4); // Segment pointers below must stay valid
+  // everything queued so far on the compute stream (e.g. a reset's tail) precedes the copies
+  Segment *first;
+  TRY(new_segment(c, &first));
+  TRY(ensure(c, first->own_off, (n_recs + 1) * 8));
+  if (!first->ready) CK(cudaEventCreateWithFlags(&first->ready, cudaEventDisableTiming));
+  CK(cudaEventRecord(first->ready, c->stream));
+  CK(cudaStreamWaitEvent(c->copy_stream, first->ready, 0));
+  {
+    int r_ = phase_begin(c, "h2d"); // events of this phase live on the copy stream
+    if (r_) return r_;
+    CK(cudaEventRecord(c->phases.back().a, c->copy_stream));
+  }
+  const size_t h2d_phase = c->phases.size() - 1;
+  CK(cudaMemcpyAsync(first->own_off.p, rec_off, (n_recs + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+  const uint64_t *d_off = (const uint64_t *)first->own_off.p;
+  size_t r0 = 0;
+  Segment *s = first;
+  bool is_first = true;
+  while (r0 < n_recs || is_first) {
+    // records [r0, r1): as many as fit the chunk (at least one)
+    size_t lo = r0 + 1, hi = n_recs;
+    const uint64_t limit = rec_off[r0] + kChunkBases;
+    while (lo < hi) { size_t mid = (lo + hi + 1) / 2; if (rec_off[mid] <= limit) lo = mid; else hi = mid - 1; }
+    size_t r1 = n_recs ? std::min(std::max(lo, r0 + 1), n_recs) : 0;
+    if (!is_first) TRY(new_segment(c, &s));
+    const uint64_t b0 = n_recs ? rec_off[r0] : 0, b1 = n_recs ? rec_off[r1] : 0;
+    TRY(ensure(c, s->own_bases, (b1 - b0) + 64));
+    if (!s->ready) CK(cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
+    if (b1 > b0) CK(cudaMemcpyAsync(s->own_bases.p, bases + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventRecord(s->ready, c->copy_stream));
+    s->wait_ready = true;
+    s->bases = (const uint8_t *)s->own_bases.p;
+    s->host_alias = bases_dev_alias + b0;
+    s->rec_off = d_off + r0;
+    s->off_shift = (uint64_t)0 - b0;
+    s->n_bases = b1 - b0; s->n_recs = r1 - r0;
+    is_first = false;
+    r0 = r1;
+    if (!n_recs) break;
+  }
+  if (done) CK(cudaEventRecord(done, c->copy_stream));
+  CK(cudaEventRecord(c->phases[h2d_phase].b, c->copy_stream));
+  c->h2d_bytes += n_bases + (n_recs + 1) * 8;
+  c->total_bases += n_bases; c->total_recs += n_recs;
+  // record-start masks need only the offsets: wait for that copy (the first event on the copy stream after it)
+  PHASE_BEGIN("mark");
+  for (size_t i = 0; i < c->n_segs; i++) {
+    Segment &g = c->segs[i];
+    if (g.rec_off < d_off || g.rec_off > d_off + n_recs) continue; // a segment of an earlier submit
+    // the offsets copy precedes this segment's bases copy on the copy stream, so its ready event covers both
+    CK(cudaStreamWaitEvent(c->stream, first->ready, 0));
+    TRY(segment_mark(c, g));
+  }
+  PHASE_END();
   return KMC_OK;
 }
 
 int submit_from_host(kmc_ctx *c, const uint8_t *bases, const uint64_t *rec_off, size_t n_bases, size_t n_recs,
                      cudaEvent_t done) {
   if (c->finished) return fail(c, KMC_E_ARG, "kmc_submit after kmc_finish (call kmc_reset first)");
+  if (n_bases >= 4 * kChunkBases && n_recs >= 2 && !getenv("KMC_NO_CHUNKED_H2D")) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, bases) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+      cudaPointerAttributes at2;
+      if (cudaPointerGetAttributes(&at2, rec_off) == cudaSuccess && at2.type == cudaMemoryTypeHost)
+        return submit_chunked(c, bases, (const uint8_t *)at.devicePointer, rec_off, n_bases, n_recs, done);
+    }
+    cudaGetLastError();
+  }
   Segment *s;
   TRY(new_segment(c, &s));
   TRY(ensure(c, s->own_bases, n_bases + 64));
@@ -331,6 +467,7 @@ int extract_all(kmc_ctx *c, uint64_t *n_keys) {
   for (size_t i = 0; i < c->n_segs; i++) {
     Segment &s = c->segs[i];
     if (!s.n_bases) continue;
+    TRY(seg_wait(c, s));
     ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
     uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
     uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + 7) / 8, (uint64_t)kNumSMsB200 * 16);
@@ -357,6 +494,7 @@ int gapped_all(kmc_ctx *c, uint64_t *n_keys) {
   for (size_t i = 0; i < c->n_segs; i++) {
     Segment &s = c->segs[i];
     if (!s.n_bases) continue;
+    TRY(seg_wait(c, s));
     GapParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, f.l_len, f.r_len, f.d_min, f.d_max};
     uint32_t g = grid_for(s.n_bases, 256);
     LAUNCH(gap_mers_kernel, g, 256, 0, P, (uint64_t *)c->gap_l.p, (uint64_t *)c->gap_r.p, (uint8_t *)c->gap_f.p);
@@ -449,7 +587,7 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
   TRY(ensure(c, c->fast_state, 4096 * 8 + 16 + kMaxL1 * 8 + 64));
   const size_t off_l1cur = 4096 * 8 + 16;
   CK(cudaMemsetAsync((unsigned char *)c->fast_state.p + off_l1cur, 0, kMaxL1 * 8, c->stream));
-  CK(cudaMemcpyAsync(c->fast_tables.p, c->fast_host.data(), tab_bytes, cudaMemcpyHostToDevice, c->stream));
+  TRY(h2d_small(c, c->fast_tables.p, c->fast_host.data(), tab_bytes));
   FastPlan pl{};
   pl.kb = c->key_bits; pl.b1 = 0; pl.n_l1 = n_parts; pl.n_fine = 0;
   pl.l1_trash = part_ptr ? (uint64_t)(uintptr_t)c->route_keys.p / 8 : total;
@@ -466,6 +604,7 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
     for (size_t i = 0; i < c->n_segs; i++) {
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
+      TRY(seg_wait(c, s));
       ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
       uint64_t tiles = num_warp_tiles(s.n_bases, 31);
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
@@ -475,7 +614,7 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
   PHASE_END();
   std::vector<unsigned long long> cur(n_parts);
   uint32_t err = 0;
-  CK(cudaMemcpyAsync(cur.data(), pl.l1_cursor, (size_t)n_parts * 8, cudaMemcpyDeviceToHost, c->stream));
+  TRY(d2h_small(c, cur.data(), pl.l1_cursor, (size_t)n_parts * 8));
   TRY(read_scalars(c, nullptr, &err));
   if (err & kFlagOverflow) {
     if (part_ptr) return fail(c, KMC_E_CAPACITY, "kmc_route_to_peers: a part exceeded part_cap_keys");
@@ -559,7 +698,9 @@ int hash_run(kmc_ctx *c, const KeyArrays &ka, uint32_t log2_slots, uint64_t limi
     for (size_t i = 0; i < c->n_segs; i++) {
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
-      ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
+      const bool sample_host = step > 1 && s.host_alias && s.wait_ready;
+      if (!sample_host) TRY(seg_wait(c, s));
+      ExtractParams P{sample_host ? s.host_alias : s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
       uint64_t tiles = num_warp_tiles(s.n_bases, 31);
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)max_ctas);
       auto hash_count = hash_count_kernel<true>;
@@ -588,8 +729,7 @@ int finish_hash(kmc_ctx *c, uint32_t log2_slots, uint64_t limit, bool *used) {
   PHASE_END();
   if (!ok) { c->hash_aborts++; return KMC_OK; }
   unsigned long long sc[3];
-  CK(cudaMemcpyAsync(sc, c->hash_scalars.p, sizeof sc, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  TRY(d2h_small(c, sc, c->hash_scalars.p, sizeof sc));
   const uint64_t d = sc[0], n_total = sc[1], n_ones = sc[2];
   if (n_ones > 0xFFFFFFFFull) return fail(c, KMC_E_COUNT_OVERFLOW, "a k-mer occurs more than 2^32-1 times");
   PHASE_BEGIN("hash_sort");
@@ -633,7 +773,8 @@ int hash_probe(kmc_ctx *c, bool *low_cardinality) {
   if (ka.from_array) for (auto &e : c->ingested) if (e.second) { ka.arrays.emplace_back(e.first, e.second); ka.n += e.second; }
   const uint64_t n_in = ka.from_array ? ka.n : c->total_bases;
   if (n_in < (1u << 18)) return KMC_OK;
-  const uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
+  uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
+  if (!ka.from_array) for (size_t i = 0; i < c->n_segs; i++) if (c->segs[i].wait_ready && c->segs[i].host_alias && step > 1) { step = std::min<uint32_t>(64, step * 4); break; }
   bool ok = false;
   HashTable T;
   c->n_hot = 0;
@@ -642,15 +783,13 @@ int hash_probe(kmc_ctx *c, bool *low_cardinality) {
   if (ok) {
     // keys that make up more than 1/50000 of the sampled occurrences get private shared-memory counters later
     unsigned long long sc[3];
-    CK(cudaMemcpyAsync(sc, c->hash_scalars.p, sizeof sc, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    TRY(d2h_small(c, sc, c->hash_scalars.p, sizeof sc));
     const uint32_t thr = (uint32_t)std::max<uint64_t>(64, sc[1] / 50000);
     unsigned int *d_nhot = (unsigned int *)((unsigned char *)c->hash_hot.p + kHotMax * 8);
     CK(cudaMemsetAsync(d_nhot, 0, 4, c->stream));
     LAUNCH(hash_hot_kernel, kNumSMsB200 * 8, 256, 0, T, thr, (uint64_t *)c->hash_hot.p, d_nhot);
     unsigned int nh = 0;
-    CK(cudaMemcpyAsync(&nh, d_nhot, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    TRY(d2h_small(c, &nh, d_nhot, 4));
     c->n_hot = std::min<uint32_t>(nh, kHotMax);
     c->probe_distinct = sc[0];
   }
@@ -682,7 +821,9 @@ int finish_fast(kmc_ctx *c, bool *used) {
   unsigned long long *ghist = (unsigned long long *)c->fast_state.p;
   // sample so that ~64M keys are looked at (all of them for small inputs)
   const uint64_t n_in = from_array ? n_array : c->total_bases;
-  const uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
+  uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
+  // chunks still on their way are sampled straight from pinned host memory: read 4x less of it over the bus
+  if (!from_array) for (size_t i = 0; i < c->n_segs; i++) if (c->segs[i].wait_ready && c->segs[i].host_alias && step > 1) { step = std::min<uint32_t>(64, step * 4); break; }
   PHASE_BEGIN("fast_hist");
   if (from_array) {
     for (auto &a : arrays) {
@@ -694,7 +835,9 @@ int finish_fast(kmc_ctx *c, bool *used) {
     for (size_t i = 0; i < c->n_segs; i++) {
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
-      ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
+      const bool sample_host = step > 1 && s.host_alias && s.wait_ready;
+      if (!sample_host) TRY(seg_wait(c, s));
+      ExtractParams P{sample_host ? s.host_alias : s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)kNumSMsB200 * 8);
       auto fast_hist = fast_hist_kernel<KeyT, true>;
@@ -703,8 +846,7 @@ int finish_fast(kmc_ctx *c, bool *used) {
   }
   PHASE_END();
   std::vector<uint64_t> hist(ncoarse);
-  CK(cudaMemcpyAsync(hist.data(), ghist, ncoarse * 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  TRY(d2h_small(c, hist.data(), ghist, ncoarse * 8));
   // the histogram is a 1-in-step sample: scale it to an upper estimate (+5 sigma of the sampling noise)
   uint64_t n_est = 0;
   for (uint64_t &v : hist) {
@@ -797,7 +939,7 @@ int finish_fast(kmc_ctx *c, bool *used) {
     TRY(ensure(c, c->fast_state, off_status + n_fine * 8 + 64));
   }
   CK(cudaMemsetAsync(c->fast_state.p, 0, off_status + n_fine * 8, c->stream));
-  CK(cudaMemcpyAsync(c->fast_tables.p, c->fast_host.data(), tab_bytes, cudaMemcpyHostToDevice, c->stream));
+  TRY(h2d_small(c, c->fast_tables.p, c->fast_host.data(), tab_bytes));
   unsigned char *st = (unsigned char *)c->fast_state.p, *tb = (unsigned char *)c->fast_tables.p;
   FastPlan pl;
   pl.kb = kb; pl.b1 = b1; pl.n_l1 = n_l1; pl.n_fine = (uint32_t)n_fine;
@@ -828,6 +970,7 @@ int finish_fast(kmc_ctx *c, bool *used) {
     for (size_t i = 0; i < c->n_segs; i++) {
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
+      TRY(seg_wait(c, s));
       ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
@@ -898,8 +1041,8 @@ int finish_fast(kmc_ctx *c, bool *used) {
   uint64_t d = 0;
   uint32_t err = 0;
   std::vector<unsigned long long> cur(n_l1);
-  CK(cudaMemcpyAsync(&d, d_total, 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(cur.data(), pl.l1_cursor, (size_t)n_l1 * 8, cudaMemcpyDeviceToHost, c->stream));
+  TRY(d2h_small(c, &d, d_total, 8));
+  TRY(d2h_small(c, cur.data(), pl.l1_cursor, (size_t)n_l1 * 8));
   TRY(read_scalars(c, nullptr, &err));
   if (err & kFlagSpin) return fail(c, KMC_E_CUDA, "fast_finish: look-back did not make progress");
   if (err & kFlagOverflow) {
@@ -1066,7 +1209,10 @@ void kmc_destroy(kmc_ctx *c) {
     if (c->h_off[i]) cudaFreeHost(c->h_off[i]);
     if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
   }
-  for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); }
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->mailbox) cudaFreeHost(c->mailbox);
+  if (c->upbox) cudaFreeHost(c->upbox);
+  for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); if (s.ready) cudaEventDestroy(s.ready); }
   for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
                     &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot})
     release(*b);
@@ -1088,6 +1234,7 @@ int kmc_reset(kmc_ctx *c) {
   if (!c) return KMC_E_ARG;
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
+  if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
   c->n_segs = 0; c->total_bases = c->total_recs = 0;
   c->ingested.clear();
   c->finished = false; c->n_total = c->n_distinct = 0;
@@ -1145,8 +1292,11 @@ int kmc_submit_host(kmc_ctx *c, const uint8_t *bases, const uint64_t *rec_off, s
   if (!c || !rec_off || (!bases && n_bases)) return KMC_E_ARG;
   if (rec_off[0] != 0 || rec_off[n_recs] != n_bases) return fail(c, KMC_E_ARG, "rec_off[0] must be 0 and rec_off[n_recs] == n_bases");
   CK(cudaSetDevice(c->device));
+  const size_t segs_before = c->n_segs;
   TRY(submit_from_host(c, bases, rec_off, n_bases, n_recs, nullptr));
-  CK(cudaStreamSynchronize(c->stream)); // caller memory may be pageable / reused right away
+  // pageable memory was copied synchronously enough to be reused; a chunked (pinned) submit stays asynchronous and
+  // the caller's buffer must stay unchanged until kmc_finish returns
+  if (!(c->n_segs > segs_before && c->segs[segs_before].wait_ready)) CK(cudaStreamSynchronize(c->stream));
   return KMC_OK;
 }
 
@@ -1237,8 +1387,7 @@ int kmc_digest(kmc_ctx *c, uint64_t *digest) {
            c->wide ? (const uint64_t *)c->t_hi.p : (const uint64_t *)nullptr, (const uint32_t *)c->t_cnt.p, c->n_distinct,
            d_digest(c));
   unsigned long long h = 0;
-  CK(cudaMemcpyAsync(&h, d_digest(c), 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  TRY(d2h_small(c, &h, d_digest(c), 8));
   *digest = h;
   return KMC_OK;
 }

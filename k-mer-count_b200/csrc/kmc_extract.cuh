@@ -42,9 +42,24 @@ template <bool FOLD>
 __device__ __forceinline__ void load_chunk(const uint8_t *__restrict__ bases, uint64_t pos, uint64_t n,
                                            uint64_t &codes, uint32_t &valid) {
   uint32_t w[8];
-  if (pos + 32 <= n) {
+  const uint32_t mis = (uint32_t)((uintptr_t)(bases + pos) & 15); // the same for every chunk of a segment (pos % 32 == 0)
+  if (mis == 0 && pos + 32 <= n) {
     uint4 a = ld_stream16(bases + pos), b = ld_stream16(bases + pos + 16);
     w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  } else if (mis != 0 && pos + 48 <= n) {
+    // segment base not 16-byte aligned (a chunk of a pinned host buffer cut at a record boundary): three aligned
+    // loads around the 32 bytes, then a byte-granular funnel shift
+    const uint8_t *p0 = bases + pos - mis;
+    uint4 a = ld_stream16(p0), b = ld_stream16(p0 + 16), c = ld_stream16(p0 + 32);
+    uint32_t v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    const uint32_t wo = mis >> 2, bo = (mis & 3) * 8;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int t = 0; t < 4; t++) { if (wo == (uint32_t)t) { lo = v[q + t]; hi = v[q + t + 1]; } }
+      w[q] = __funnelshift_r(lo, hi, bo);
+    }
   } else {
 #pragma unroll
     for (int q = 0; q < 8; q++) {

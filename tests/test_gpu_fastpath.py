@@ -183,3 +183,37 @@ def test_fast_path_128bit_keys(kmc, orc, k, canonical, n):
     assert st["strategy_used"] == 2 and st["fast_fallbacks"] == 0, st
     base, _, _ = _count(kmc, bases, off, k, canonical, strategy=3)
     assert_tables_equal(base, want)
+
+
+def test_chunked_pinned_submit(kmc, orc):
+    """A submit of >= 256 MB from pinned host memory is cut into chunks copied on a second stream while earlier
+    chunks are already being scattered; results are the same as for the device-resident input."""
+    import torch
+    n, k = 300_000_000, 31
+    g = torch.Generator(device="cuda").manual_seed(9)
+    c = torch.randint(0, 4, (n,), device="cuda", generator=g, dtype=torch.uint8)
+    bases = 65 + 2 * c + 2 * (c == 2).to(torch.uint8) + 13 * (c == 3).to(torch.uint8)
+    bases[torch.randint(0, n, (3000,), device="cuda", generator=g)] = 78
+    lens = torch.randint(50, 3000, (n // 1000,), device="cuda", generator=g)
+    off = torch.cumsum(lens, 0)
+    off = torch.cat([torch.zeros(1, dtype=torch.int64, device="cuda"), off[off < n], torch.tensor([n], device="cuda")])
+    hb = torch.empty(n, dtype=torch.uint8).pin_memory()
+    ho = torch.empty(off.numel(), dtype=torch.int64).pin_memory()
+    hb.copy_(bases)
+    ho.copy_(off)
+    torch.cuda.synchronize()
+    with kmc.KmerCounter(k=k) as kc:
+        kc.submit_device(bases.data_ptr(), off.data_ptr(), n, off.numel() - 1)
+        ref = kc.finish()
+        ref_dig = kc.digest()
+        for strategy_run in range(2):
+            kc.reset()
+            kc.submit_host(hb.numpy(), ho.numpy().view(np.uint64))
+            assert kc.finish() == ref and kc.digest() == ref_dig
+    # the generic path waits for all chunks too
+    with kmc.KmerCounter(k=k, strategy=3) as kc:
+        kc.submit_host(hb.numpy()[:280_000_000], np.append(ho.numpy().view(np.uint64)[ho.numpy() < 280_000_000], np.uint64(280_000_000)))
+        d3, t3 = kc.finish()
+    with kmc.KmerCounter(k=k) as kc:
+        kc.submit_host(hb.numpy()[:280_000_000], np.append(ho.numpy().view(np.uint64)[ho.numpy() < 280_000_000], np.uint64(280_000_000)))
+        assert kc.finish() == (d3, t3)
