@@ -152,6 +152,9 @@ int ensure(kmc_ctx *c, DevBuf &b, size_t bytes) {
   if (bytes <= b.cap && b.p) return KMC_OK;
   if (b.p) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
   size_t want = std::max<size_t>(bytes, 256);
+  // sizes derived from sampled estimates wobble by a fraction of a percent from job to job: leave headroom so that
+  // a slightly larger next job does not free and reallocate gigabytes (cudaFree/cudaMalloc stall the host for tens of ms)
+  if (want > ((size_t)16 << 20)) want += want / 16;
   want = (want + 255) & ~size_t(255);
   CK(cudaMalloc(&b.p, want));
   b.cap = want;
@@ -571,17 +574,18 @@ int route_impl(kmc_ctx *c, uint32_t n_parts, uint64_t *part_off) {
 // a region sized from the upper bound (one key per base) with slack; *done = false → use the generic route.
 // part_ptr == nullptr: the parts are regions of c->route_keys (kmc_route).  Otherwise part p is stored at
 // part_ptr[p] — a peer's memory over NVLink (kmc_route_to_peers); positions are then absolute addresses / 8.
+template <typename KeyT>
 int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *part_count, bool *done,
                void *const *part_ptr = nullptr, uint64_t peer_cap = 0) {
   *done = false;
   if (!part_ptr && (c->total_bases < (1u << 18) || n_parts > (uint32_t)kMaxL1)) return KMC_OK;
   const uint64_t cap = part_ptr ? peer_cap : (((uint64_t)((double)c->total_bases / n_parts * 1.03) + 65536 + 15) & ~15ull);
   const uint64_t total = part_ptr ? 0 : cap * n_parts;
-  TRY(ensure(c, c->route_keys, (total + 2 * kMaxTile) * 8));
+  TRY(ensure(c, c->route_keys, (total + 2 * kMaxTile) * sizeof(KeyT)));
   const size_t o_start = 0, o_cap = o_start + ((size_t)(n_parts + 1) * 8 + 15) / 16 * 16, tab_bytes = o_cap + (size_t)n_parts * 8;
   c->fast_host.assign(tab_bytes, 0);
   uint64_t *l1s = (uint64_t *)(c->fast_host.data() + o_start), *l1c = (uint64_t *)(c->fast_host.data() + o_cap);
-  for (uint32_t p = 0; p <= n_parts; p++) l1s[p] = part_ptr ? (p < n_parts ? (uint64_t)(uintptr_t)part_ptr[p] / 8 : 0) : cap * p;
+  for (uint32_t p = 0; p <= n_parts; p++) l1s[p] = part_ptr ? (p < n_parts ? (uint64_t)(uintptr_t)part_ptr[p] / sizeof(KeyT) : 0) : cap * p;
   for (uint32_t p = 0; p < n_parts; p++) l1c[p] = cap;
   TRY(ensure(c, c->fast_tables, tab_bytes));
   TRY(ensure(c, c->fast_state, 4096 * 8 + 16 + kMaxL1 * 8 + 64));
@@ -590,15 +594,15 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
   TRY(h2d_small(c, c->fast_tables.p, c->fast_host.data(), tab_bytes));
   FastPlan pl{};
   pl.kb = c->key_bits; pl.b1 = 0; pl.n_l1 = n_parts; pl.n_fine = 0;
-  pl.l1_trash = part_ptr ? (uint64_t)(uintptr_t)c->route_keys.p / 8 : total;
-  uint64_t *dst = part_ptr ? (uint64_t *)nullptr : (uint64_t *)c->route_keys.p;
+  pl.l1_trash = part_ptr ? (uint64_t)(uintptr_t)c->route_keys.p / sizeof(KeyT) : total;
+  KeyT *dst = part_ptr ? (KeyT *)nullptr : (KeyT *)c->route_keys.p;
   pl.l1_start = (const uint64_t *)((unsigned char *)c->fast_tables.p + o_start);
   pl.l1_cap = (const uint64_t *)((unsigned char *)c->fast_tables.p + o_cap);
   pl.l1_cursor = (unsigned long long *)((unsigned char *)c->fast_state.p + off_l1cur);
   PHASE_BEGIN("route");
   {
-    size_t smem = PartSmem<uint64_t>::bytes(part1_stage<uint64_t>(), n_parts);
-    auto fast_route = fast_part1_kernel<uint64_t, true, OwnerBucket>;
+    size_t smem = PartSmem<KeyT>::bytes(part1_stage<KeyT>(), n_parts);
+    auto fast_route = fast_part1_kernel<KeyT, true, OwnerBucket>;
     CK(cudaFuncSetAttribute(fast_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const OwnerBucket bucket{n_parts};
     for (size_t i = 0; i < c->n_segs; i++) {
@@ -606,7 +610,7 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
       if (!s.n_bases) continue;
       TRY(seg_wait(c, s));
       ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
-      uint64_t tiles = num_warp_tiles(s.n_bases, 31);
+      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
       LAUNCH(fast_route, grid, kFastThreads, smem, P, tiles, pl, bucket, dst, d_err(c));
     }
@@ -1402,7 +1406,10 @@ int kmc_route(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *part
   CK(cudaSetDevice(c->device));
   TRY(zero_scalars(c));
   bool done = false;
-  if (!c->wide && c->cfg.mode == KMC_MODE_CONTIGUOUS) TRY(route_fast(c, n_parts, part_begin, part_count, &done));
+  if (c->cfg.mode == KMC_MODE_CONTIGUOUS) {
+    if (c->wide) TRY(route_fast<U128>(c, n_parts, part_begin, part_count, &done));
+    else TRY(route_fast<uint64_t>(c, n_parts, part_begin, part_count, &done));
+  }
   if (!done) {
     std::vector<uint64_t> off(n_parts + 1);
     int rc = c->wide ? route_impl<U128>(c, n_parts, off.data()) : route_impl<uint64_t>(c, n_parts, off.data());
@@ -1417,15 +1424,16 @@ int kmc_route(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *part
 int kmc_route_to_peers(kmc_ctx *c, uint32_t n_parts, void *const *d_part_ptr, uint64_t part_cap_keys, uint64_t *part_count) {
   if (!c || !d_part_ptr || !part_count) return KMC_E_ARG;
   if (n_parts < 1 || n_parts > kRadix) return fail(c, KMC_E_ARG, "n_parts must be 1..%d", kRadix);
-  if (c->wide || c->cfg.mode != KMC_MODE_CONTIGUOUS)
-    return fail(c, KMC_E_ARG, "kmc_route_to_peers handles 64-bit contiguous-mode keys; use kmc_route + an all-to-all otherwise");
+  if (c->cfg.mode != KMC_MODE_CONTIGUOUS)
+    return fail(c, KMC_E_ARG, "kmc_route_to_peers handles contiguous mode; use kmc_route + an all-to-all for lr-gapped keys");
   if (c->finished) return fail(c, KMC_E_ARG, "kmc_route_to_peers after kmc_finish");
   for (uint32_t p = 0; p < n_parts; p++)
     if (!d_part_ptr[p] || ((uintptr_t)d_part_ptr[p] & 127)) return fail(c, KMC_E_ARG, "part pointers must be 128-byte aligned device pointers");
   CK(cudaSetDevice(c->device));
   TRY(zero_scalars(c));
   bool done = false;
-  TRY(route_fast(c, n_parts, nullptr, part_count, &done, d_part_ptr, part_cap_keys));
+  if (c->wide) TRY(route_fast<U128>(c, n_parts, nullptr, part_count, &done, d_part_ptr, part_cap_keys));
+  else TRY(route_fast<uint64_t>(c, n_parts, nullptr, part_count, &done, d_part_ptr, part_cap_keys));
   return done ? KMC_OK : fail(c, KMC_E_ARG, "kmc_route_to_peers: nothing routed");
 }
 

@@ -77,10 +77,10 @@ def exchange(torch, dist, send_parts):
 class DistCounter:
     """KmerCounter that, when world > 1, routes keys to their owner ranks before counting.
 
-    64-bit keys: the routing kernel stores every key straight into its owner's receive buffer over NVLink
+    Contiguous mode: the routing kernel stores every key straight into its owner's receive buffer over NVLink
     (peer memory mapped with CUDA IPC) — compute and exchange are one kernel; only the per-part counts go
-    through torch.distributed afterwards, which also orders the ranks.  128-bit keys and lr-gapped mode:
-    kmc_route into a local buffer, then an NCCL all-to-all."""
+    through torch.distributed afterwards, which also orders the ranks.  lr-gapped mode (or
+    KMC_DIST_EXCHANGE=nccl): kmc_route into a local buffer, then an NCCL all-to-all."""
 
     def __init__(self, k, canonical, strategy, device, world=1, rank=0, dist=None, torch=None, **kw):
         self.kc = KmerCounter(k=k, canonical=canonical, strategy=strategy, device=device, **kw)
@@ -89,9 +89,10 @@ class DistCounter:
         self._keep = None
         self._peer = None       # (cap_keys, my recv buffer ptr, [pointer of my region in every rank's recv buffer])
         self._opened = []
+        self._peer_bases = None
         self.n_bases = 0
-        self.use_peer = world > 1 and self.key_bits <= 64 and kw.get("mode", 0) == 0 and \
-            os.environ.get("KMC_DIST_EXCHANGE", "peer") == "peer"
+        self.key_bytes = 8 if self.key_bits <= 64 else 16
+        self.use_peer = world > 1 and kw.get("mode", 0) == 0 and os.environ.get("KMC_DIST_EXCHANGE", "peer") == "peer"
 
     def set_stream(self, ptr):
         self.kc.set_stream(ptr)
@@ -113,6 +114,8 @@ class DistCounter:
         """Receive buffer of world regions, one per source rank; map every peer's buffer (CUDA IPC)."""
         torch, dist = self.torch, self.dist
         dev = torch.device("cuda", torch.cuda.current_device())
+        # one small all-reduce per job: agrees on the region size, and is the point after which nobody is still
+        # reading its receive buffer from the previous job (every rank has returned from its last kmc_finish)
         nb = torch.tensor([self.n_bases], dtype=torch.int64, device=dev)
         dist.all_reduce(nb, op=dist.ReduceOp.MAX)
         cap = (int(int(nb) / self.world * 1.03) + 65536 + 15) // 16 * 16
@@ -133,7 +136,7 @@ class DistCounter:
             else:
                 base = self.kc.ipc_open(handles[p])
                 self._opened.append(base)
-            regions.append(base + self.rank * cap * 8)
+            regions.append(base + self.rank * cap * self.key_bytes)
         self._peer = (cap, mine, regions)
 
     def finish(self):
@@ -151,8 +154,7 @@ class DistCounter:
         if self.use_peer:
             self._setup_peers()
             cap, mine, regions = self._peer
-            # nobody may still be reading its receive buffer from the previous job
-            dist.barrier()
+            mark()
             count = self.kc.route_to_peers(regions, cap)
             mark()
             sc = torch.from_numpy(count.astype(np.int64)).to(dev)
@@ -161,7 +163,7 @@ class DistCounter:
             got = rc.tolist()
             mark()
             for src, n in enumerate(got):
-                self.kc.ingest_keys(mine + src * cap * 8, n)
+                self.kc.ingest_keys(mine + src * cap * self.key_bytes, n)
         else:
             begin, count, ptr, key_bytes = self.kc.route(self.world)
             mark()
@@ -175,10 +177,13 @@ class DistCounter:
             self.kc.ingest_keys(recv.data_ptr(), recv.numel() // words)
         out = self.kc.finish()
         mark()
-        if _PROF and self.rank == 0:
+        if _PROF:
             d = [1e3 * (b - a) for a, b in zip(t[:-1], t[1:])]
-            print(f"[kmc dist] route {d[0]:.2f} ms, exchange {d[1]:.2f} ms, count {d[2]:.2f} ms "
-                  f"({'peer stores' if self.use_peer else 'nccl all-to-all'})", file=sys.stderr)
+            names = ["setup+barrier", "route", "exchange", "count"] if self.use_peer else ["route", "exchange", "count"]
+            print(f"[kmc dist r{self.rank}] " + ", ".join(f"{n} {v:.2f} ms" for n, v in zip(names, d)) +
+                  f" ({'peer stores' if self.use_peer else 'nccl all-to-all'}) end@{time.time() % 100:.4f} "
+                  f"strategy={self.kc.stats().get('strategy_used')} fallbacks={self.kc.stats().get('fast_fallbacks')} "
+                  f"phases={self.kc.stats().get('phases_ms')}", file=sys.stderr)
         return out
 
     def digest(self):

@@ -281,30 +281,32 @@ def test_route_and_ingest_emulated_ranks(kmc, orc, k, world, n):
     assert np.array_equal(cnt[order], want.count)
 
 
-def test_route_to_peers_emulated(kmc, orc):
+@pytest.mark.parametrize("k", [31, 63])
+def test_route_to_peers_emulated(kmc, orc, k):
     """kmc_route_to_peers on one GPU: the 'peer' regions are plain device buffers of this process.  Each
     emulated rank stores part p of its keys into region [rank] of owner p's buffer; owners count."""
     import torch
-    k, world, n = 31, 4, 3_000_000
+    world, n = 4, 3_000_000
+    kb = 8 if k <= 32 else 16
     rng = np.random.default_rng(77)
     bases = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=n, p=[0.2495, 0.2495, 0.2495, 0.2495, 0.002])
     off = np.arange(0, n + 1, 500, dtype=np.uint64)
     want = orc.contiguous_mt(bases, off, k, True)
     cap = (int(n / world / world * 1.2) + 65536 + 15) // 16 * 16
-    recv = [torch.zeros(cap * world, dtype=torch.int64, device="cuda") for _ in range(world)]
+    recv = [torch.zeros(cap * world * (kb // 8), dtype=torch.int64, device="cuda") for _ in range(world)]
     rec_cuts = np.linspace(0, len(off) - 1, world + 1).astype(int)
     counts = np.zeros((world, world), np.int64)
     for r in range(world):
         a, z = rec_cuts[r], rec_cuts[r + 1]
         with kmc.KmerCounter(k=k, canonical=True) as kc:
             kc.submit_host(bases[int(off[a]):int(off[z])], off[a:z + 1] - off[a])
-            counts[r] = kc.route_to_peers([recv[p].data_ptr() + r * cap * 8 for p in range(world)], cap)
+            counts[r] = kc.route_to_peers([recv[p].data_ptr() + r * cap * kb for p in range(world)], cap)
     torch.cuda.synchronize()
     tables = []
     for p in range(world):
         with kmc.KmerCounter(k=k, canonical=True) as kc:
             for r in range(world):
-                kc.ingest_keys(recv[p].data_ptr() + r * cap * 8, int(counts[r, p]))
+                kc.ingest_keys(recv[p].data_ptr() + r * cap * kb, int(counts[r, p]))
             kc.finish()
             tables.append(kc.read())
     hi = np.concatenate([t.key_hi for t in tables])
@@ -313,6 +315,7 @@ def test_route_to_peers_emulated(kmc, orc):
     order = np.lexsort((lo, hi))
     assert sum(t.n_total for t in tables) == want.n_total
     assert np.array_equal(lo[order], want.key_lo) and np.array_equal(cnt[order], want.count)
+    assert np.array_equal(hi[order], want.key_hi)
 
 
 def test_cli_drop_in(kmc, gold_dir, golden, tmp_path):
