@@ -44,9 +44,11 @@ enum {
   KMC_E_EMPTY = -6,          /* lr-gapped mode: no chunk at all: main.rs:35 source[0] panics       */
   KMC_E_COUNT_OVERFLOW = -7, /* a multiplicity does not fit the table's 32-bit count               */
   KMC_E_CAPACITY = -8,       /* more input than the ctx was sized for and it could not grow        */
-  KMC_E_BADBASE_OFFSET0 = -9 /* lr-gapped mode: non-ACGT byte only at chunk offset 0, which
+  KMC_E_BADBASE_OFFSET0 = -9,/* lr-gapped mode: non-ACGT byte only at chunk offset 0, which
                                 main.rs:36 never inspects and would print verbatim; a 2-bit key
                                 cannot hold it, so this build refuses (documented divergence)      */
+  KMC_E_FORMAT = -10         /* FASTA text does not start with '>': main.rs:59 `reader.read(..).unwrap()`
+                                ("Expected > at record start.")                                      */
 };
 
 /* ---- configuration ---------------------------------------------------------------------------- */
@@ -96,6 +98,12 @@ int kmc_staging(kmc_ctx *ctx, size_t want_bases, size_t want_recs, uint8_t **bas
 int kmc_submit(kmc_ctx *ctx, size_t n_bases, size_t n_recs);
 /* Same, from caller-owned HOST memory (pageable or pinned); copies synchronously if pageable.     */
 int kmc_submit_host(kmc_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, size_t n_bases, size_t n_recs);
+/* Raw FASTA text (the bytes of the file, HOST memory): parsed ON THE DEVICE into sequence bytes + record
+ * offsets with the rules of bio's fasta::Reader as main.rs:45,59-62 uses it (header lines start with '>',
+ * sequence lines are appended with trailing whitespace trimmed, the first all-empty record ends the input),
+ * then submitted.  Replaces the host-side line parser in front of kmc_submit.  n_bases/n_recs (optional)
+ * receive what was found.                                                                           */
+int kmc_submit_fasta(kmc_ctx *ctx, const uint8_t *fasta_text, size_t n_bytes, uint64_t *n_bases, uint64_t *n_recs);
 /* Same, but the input is already in HBM (device pointers, `bases` 16-byte aligned).  The buffers
  * are referenced, not copied, and must stay valid and unchanged until kmc_finish returns.         */
 int kmc_submit_device(kmc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, size_t n_bases, size_t n_recs);

@@ -18,6 +18,7 @@
 #include "kmc_sort.cuh"
 #include "kmc_fast.cuh"
 #include "kmc_hash.cuh"
+#include "kmc_fasta.cuh"
 #include <cmath>
 
 using namespace kmc;
@@ -92,6 +93,7 @@ struct kmc_ctx {
   DevBuf t_lo, t_hi, t_cnt;
   DevBuf fast_l1, fast_l2, fast_state, fast_tables, recv_keys;
   DevBuf hash_slots, hash_scalars, hash_hot;
+  DevBuf fa_raw, fa_tiles, fa_flags;
   uint64_t probe_distinct = 0;
   uint32_t n_hot = 0;
   uint32_t hash_aborts = 0;
@@ -977,7 +979,8 @@ int finish_fast(kmc_ctx *c, bool *used) {
       TRY(seg_wait(c, s));
       ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps,
+                                                   (uint64_t)kNumSMsB200 * ((sizeof(KeyT) == 8 && FastShape<KeyT>::kHalves == 2) ? 2 : 1));
       LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->fast_l1.p, d_err(c));
     }
   }
@@ -1151,6 +1154,7 @@ const char *kmc_strerror(int code) {
     case KMC_E_COUNT_OVERFLOW: return "a count exceeds 32 bits";
     case KMC_E_CAPACITY: return "capacity exceeded";
     case KMC_E_BADBASE_OFFSET0: return "non-ACGT byte at offset 0 of an L/R chunk";
+    case KMC_E_FORMAT: return "FASTA text does not start with '>'";
     default: return "unknown error";
   }
 }
@@ -1218,7 +1222,7 @@ void kmc_destroy(kmc_ctx *c) {
   if (c->upbox) cudaFreeHost(c->upbox);
   for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); if (s.ready) cudaEventDestroy(s.ready); }
   for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
-                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot})
+                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot, &c->fa_raw, &c->fa_tiles, &c->fa_flags})
     release(*b);
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1301,6 +1305,87 @@ int kmc_submit_host(kmc_ctx *c, const uint8_t *bases, const uint64_t *rec_off, s
   // pageable memory was copied synchronously enough to be reused; a chunked (pinned) submit stays asynchronous and
   // the caller's buffer must stay unchanged until kmc_finish returns
   if (!(c->n_segs > segs_before && c->segs[segs_before].wait_ready)) CK(cudaStreamSynchronize(c->stream));
+  return KMC_OK;
+}
+
+// exclusive scan of m u32 counts into u64 offsets (three kernels, uses c->sums)
+static int scan_u32(kmc_ctx *c, const uint32_t *in, uint64_t m, uint64_t *out) {
+  uint32_t blocks = grid_for(m, kScanTile);
+  TRY(ensure(c, c->sums, (size_t)blocks * 8 + 64));
+  LAUNCH(scan_reduce_kernel, blocks, kScanThreads, 0, in, m, (uint64_t *)c->sums.p);
+  LAUNCH(scan_spine_kernel, 1, 1024, 0, (uint64_t *)c->sums.p, (uint64_t)blocks);
+  LAUNCH(scan_apply_kernel, blocks, kScanThreads, 0, in, m, (const uint64_t *)c->sums.p, out);
+  return KMC_OK;
+}
+
+int kmc_submit_fasta(kmc_ctx *c, const uint8_t *text, size_t n, uint64_t *n_bases_out, uint64_t *n_recs_out) {
+  if (!c || (!text && n)) return KMC_E_ARG;
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_submit_fasta after kmc_finish (call kmc_reset first)");
+  if (n && text[0] != '>') return fail(c, KMC_E_FORMAT, "Expected > at record start.");
+  CK(cudaSetDevice(c->device));
+  Segment *s;
+  TRY(new_segment(c, &s));
+  uint64_t n_seq = 0, n_hdr = 0;
+  if (n) {
+    const uint64_t tiles = (n + kFaTile - 1) / kFaTile;
+    // tile arrays: prev_nl i64 | seq_off u64 | hdr_off u64 | tile_seq u32 | tile_hdr u32
+    TRY(ensure(c, c->fa_raw, n + 64));
+    TRY(ensure(c, c->fa_tiles, tiles * 32 + 256));
+    long long *prev_nl = (long long *)c->fa_tiles.p;
+    uint64_t *seq_off = (uint64_t *)(prev_nl + tiles), *hdr_off = seq_off + tiles;
+    uint32_t *tile_seq = (uint32_t *)(hdr_off + tiles), *tile_hdr = tile_seq + tiles;
+    PHASE_BEGIN("h2d");
+    CK(cudaMemcpyAsync(c->fa_raw.p, text, n, cudaMemcpyHostToDevice, c->stream));
+    PHASE_END();
+    c->h2d_bytes += n;
+    PHASE_BEGIN("fasta_parse");
+    const uint8_t *raw = (const uint8_t *)c->fa_raw.p;
+    LAUNCH(fasta_lastnl_kernel, (uint32_t)tiles, kFaThreads, 0, raw, (uint64_t)n, prev_nl);
+    LAUNCH(fasta_scan_nl_kernel, 1, 1024, 0, prev_nl, tiles);
+    LAUNCH(fasta_count_kernel, (uint32_t)tiles, kFaThreads, 0, raw, (uint64_t)n, (const long long *)prev_nl, tile_seq, tile_hdr);
+    TRY(scan_u32(c, tile_seq, tiles, seq_off));
+    TRY(scan_u32(c, tile_hdr, tiles, hdr_off));
+    uint64_t last_off[2];
+    uint32_t last_cnt[2];
+    TRY(d2h_small(c, &last_off[0], seq_off + (tiles - 1), 8, 0));
+    TRY(d2h_small(c, &last_off[1], hdr_off + (tiles - 1), 8, 64));
+    TRY(d2h_small(c, &last_cnt[0], tile_seq + (tiles - 1), 4, 128));
+    TRY(d2h_small(c, &last_cnt[1], tile_hdr + (tiles - 1), 4, 192));
+    n_seq = last_off[0] + last_cnt[0];
+    n_hdr = last_off[1] + last_cnt[1];
+    TRY(ensure(c, s->own_bases, n_seq + 64));
+    TRY(ensure(c, s->own_off, (n_hdr + 2) * 8));
+    TRY(ensure(c, c->fa_flags, n_hdr + 64));
+    LAUNCH(fasta_write_kernel, (uint32_t)tiles, kFaThreads, 0, raw, (uint64_t)n, (const long long *)prev_nl, (const uint64_t *)seq_off,
+           (const uint64_t *)hdr_off, (uint8_t *)s->own_bases.p, (uint64_t *)s->own_off.p, (uint8_t *)c->fa_flags.p);
+    CK(cudaMemcpyAsync((uint64_t *)s->own_off.p + n_hdr, &n_seq, 8, cudaMemcpyHostToDevice, c->stream));
+    // main.rs:60-62: stop at the first record that is entirely empty
+    TRY(zero_scalars(c));
+    CK(cudaMemsetAsync(d_cursor(c), 0xFF, 8, c->stream));
+    if (n_hdr)
+      LAUNCH(fasta_first_empty_kernel, grid_for(n_hdr, 256), 256, 0, (const uint64_t *)s->own_off.p, (const uint8_t *)c->fa_flags.p, n_hdr, d_cursor(c));
+    uint64_t first_empty = ~0ull;
+    TRY(read_scalars(c, &first_empty, nullptr));
+    if (first_empty < n_hdr) {
+      n_hdr = first_empty;
+      TRY(d2h_small(c, &n_seq, (uint64_t *)s->own_off.p + n_hdr, 8));
+    }
+    PHASE_END();
+  } else {
+    TRY(ensure(c, s->own_off, 64));
+    CK(cudaMemsetAsync(s->own_off.p, 0, 8, c->stream));
+    TRY(ensure(c, s->own_bases, 64));
+  }
+  s->bases = (const uint8_t *)s->own_bases.p;
+  s->rec_off = (const uint64_t *)s->own_off.p;
+  s->n_bases = n_seq; s->n_recs = n_hdr;
+  c->total_bases += n_seq; c->total_recs += n_hdr;
+  PHASE_BEGIN("mark");
+  TRY(segment_mark(c, *s));
+  PHASE_END();
+  CK(cudaStreamSynchronize(c->stream)); // the caller's text may be pageable / reused right away
+  if (n_bases_out) *n_bases_out = n_seq;
+  if (n_recs_out) *n_recs_out = n_hdr;
   return KMC_OK;
 }
 

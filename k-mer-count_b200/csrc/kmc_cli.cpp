@@ -31,6 +31,7 @@ struct Options {
   uint32_t strategy = KMC_STRATEGY_AUTO;
   uint32_t l_len = 0, r_len = 0, d_min = 0, d_max = 0;
   int device = -1;
+  bool host_parse = false; // --host-parse: parse FASTA on the host (default: on the device, kmc_submit_fasta)
   bool expanded = true; // lr-gapped: repeat each key `count` times (the reference's output); --counts switches it off
 };
 
@@ -43,6 +44,7 @@ struct Options {
 void usage() {
   fputs("usage: kmer-count [FASTA] [-k K] [-o OUT] [--mode lr-gapped|contiguous] [--canonical|--no-canonical]\n"
         "                  [--strategy auto|hash|sort|baseline] [--lr L R DMIN DMAX] [--counts] [--device N] [--stats FILE]\n"
+        "                  [--host-parse]\n"
         "  no arguments: read ./sample.fasta and print the reference's output (sorted L27+R27 gapped chunks)\n",
         stderr);
 }
@@ -64,6 +66,7 @@ Options parse_args(int argc, char **argv) {
     else if (a == "--canonical") { o.canonical = 1; canon_given = true; }
     else if (a == "--no-canonical") { o.canonical = 0; canon_given = true; }
     else if (a == "--counts") o.expanded = false;
+    else if (a == "--host-parse") o.host_parse = true;
     else if (a == "--strategy") {
       need(1); std::string s = argv[++i];
       o.strategy = s == "hash" ? KMC_STRATEGY_HASH : s == "sort" ? KMC_STRATEGY_SORT : s == "baseline" ? KMC_STRATEGY_SORT_BASELINE : KMC_STRATEGY_AUTO;
@@ -113,6 +116,12 @@ void feed_fasta(const Options &o, kmc_ctx *ctx, Feeder &fd) {
   std::vector<unsigned char> buf((size_t)(sz > 0 ? sz : 0));
   if (sz > 0 && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) panic("read failed", o.fasta);
   fclose(f);
+  if (!o.host_parse) { // the file's bytes go to the GPU as they are; records are found there
+    int rc = kmc_submit_fasta(ctx, buf.data(), buf.size(), &fd.total_bases, &fd.total_recs);
+    if (rc == KMC_E_FORMAT) panic("called `Result::unwrap()` on an `Err` value", "Expected > at record start."); // main.rs:59
+    if (rc) panic("kmc_submit_fasta", kmc_last_error(ctx));
+    return;
+  }
   const size_t batch = (size_t)256 << 20;
   fd.ctx = ctx;
   fd.acquire(std::min<size_t>(batch, (size_t)sz + 1024), 1 << 16);

@@ -88,8 +88,11 @@ struct OwnerBucket {
 
 // shapes per key width: 128-bit keys take twice the registers and shared memory, so half the keys per tile
 template <typename KeyT> struct FastShape;
+#ifndef KMC_PART1_HALVES64
+#define KMC_PART1_HALVES64 1
+#endif
 template <> struct FastShape<uint64_t> {
-  static constexpr int kHalves = 1;                      // fast_part1: all 32 window starts of a lane in one tile
+  static constexpr int kHalves = KMC_PART1_HALVES64;     // fast_part1: all 32 window starts of a lane in one tile
   static constexpr int kLanes = 31;
   static constexpr int kArrKPT = 32;                     // fast_part1_array keys per thread
   static constexpr int kP2KPT = 16;                      // fast_part2 keys per thread
@@ -238,7 +241,7 @@ __device__ __forceinline__ void scatter_tile_l1(const FastPlan &pl, PartSmem<Key
 // Level-1 scatter, extraction front end.  One CTA tile = 16 warp tiles (u64: all 32 starts of every lane,
 // <= 15872 keys; u128: 16 starts at a time, two tiles per load).
 template <typename KeyT, bool FOLD, typename BucketFn>
-__global__ void __launch_bounds__(kFastThreads, 1) fast_part1_kernel(ExtractParams P, uint64_t n_tiles, FastPlan pl, BucketFn bucket,
+__global__ void __launch_bounds__(kFastThreads, (sizeof(KeyT) == 8 && FastShape<KeyT>::kHalves == 2) ? 2 : 1) fast_part1_kernel(ExtractParams P, uint64_t n_tiles, FastPlan pl, BucketFn bucket,
                                                                       KeyT *__restrict__ l1, uint32_t *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kHalves = FastShape<KeyT>::kHalves, kSPH = 32 / kHalves;

@@ -17,14 +17,14 @@ STRATEGY_AUTO, STRATEGY_HASH, STRATEGY_SORT, STRATEGY_SORT_BASELINE = 0, 1, 2, 3
 ABI_VERSION = 1
 
 KMC_E_ARG, KMC_E_NO_DEVICE, KMC_E_CUDA, KMC_E_NOMEM, KMC_E_BADBASE, KMC_E_EMPTY = -1, -2, -3, -4, -5, -6
-KMC_E_COUNT_OVERFLOW, KMC_E_CAPACITY, KMC_E_BADBASE_OFFSET0 = -7, -8, -9
+KMC_E_COUNT_OVERFLOW, KMC_E_CAPACITY, KMC_E_BADBASE_OFFSET0, KMC_E_FORMAT = -7, -8, -9, -10
 
 # every symbol include/kmc.h declares (tests check the library exports them all)
 SYMBOLS = ["kmc_create", "kmc_destroy", "kmc_last_error", "kmc_strerror", "kmc_set_stream", "kmc_reset",
            "kmc_staging", "kmc_submit", "kmc_submit_host", "kmc_submit_device", "kmc_finish", "kmc_read",
            "kmc_table_device", "kmc_digest", "kmc_key_bases", "kmc_route", "kmc_ingest_keys", "kmc_owner_of",
            "kmc_stats_json", "kmc_route_to_peers", "kmc_recv_buffer", "kmc_ipc_export", "kmc_ipc_open",
-           "kmc_ipc_close"]
+           "kmc_ipc_close", "kmc_submit_fasta"]
 
 
 class KmcConfig(C.Structure):
@@ -67,6 +67,7 @@ def load_library(path=None):
     L.kmc_submit.argtypes = [vp, C.c_size_t, C.c_size_t]
     L.kmc_submit_host.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t]
     L.kmc_submit_device.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t]
+    L.kmc_submit_fasta.argtypes = [vp, vp, C.c_size_t, u64p, u64p]
     L.kmc_finish.argtypes = [vp, u64p, u64p]
     L.kmc_read.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp]
     L.kmc_table_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
@@ -170,6 +171,13 @@ class KmerCounter:
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
         self._ck(self._L.kmc_submit_host(self._h, bases.ctypes.data, rec_off.ctypes.data, len(bases), len(rec_off) - 1))
+
+    def submit_fasta(self, text):
+        """Raw FASTA text (bytes / uint8 array): parsed on the device.  → (n_bases, n_recs)."""
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, np.uint8)
+        nb, nr = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.kmc_submit_fasta(self._h, buf.ctypes.data if len(buf) else None, len(buf), C.byref(nb), C.byref(nr)))
+        return nb.value, nr.value
 
     def submit_device(self, d_bases_ptr, d_rec_off_ptr, n_bases, n_recs):
         self._ck(self._L.kmc_submit_device(self._h, C.c_void_p(d_bases_ptr), C.c_void_p(d_rec_off_ptr), n_bases, n_recs))

@@ -349,3 +349,50 @@ def test_cli_drop_in(kmc, gold_dir, golden, tmp_path):
     (empty / "sample.fasta").write_text(">a\n" + "ACGT" * 10 + "N" + "ACGT" * 20 + "\n")
     r = subprocess.run([cli], cwd=empty, capture_output=True)
     assert r.returncode == 101 and r.stdout == b""                                        # bad base, main.rs:23
+
+
+def _fasta_cases(gold_dir):
+    rng = np.random.default_rng(12)
+
+    def seq(n):
+        return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+
+    cases = {name: open(os.path.join(gold_dir, name + ".fasta"), "rb").read()
+             for name in ("sample", "tiny_lengths", "tiny_crlf")}
+    cases["crlf_blank_trailing"] = (">a one\r\n" + seq(70) + "  \r\n\r\n" + seq(50) + "\t \n>b\n" + seq(120) + "\n\n>c empty\n>d\n" + seq(90)).encode()
+    cases["gt_inside_line"] = (">a\n" + seq(40) + ">" + seq(40) + "\n>b\n" + seq(100) + "\n").encode()
+    cases["long_single_line"] = (">chr1 long\n" + seq(30000) + "\n>chr2\n" + seq(9000) + "\n" + seq(5000)).encode()
+    cases["many_short"] = "".join(f">r{i}\n{seq(int(rng.integers(0, 130)))}\n" for i in range(3000)).encode()
+    cases["all_empty_record_stops"] = (">a\n" + seq(100) + "\n>\n>b\n" + seq(100) + "\n").encode()
+    cases["header_only"] = b">x\n"
+    cases["no_final_newline_ws"] = (">a\n" + seq(95) + " ").encode()
+    cases["interior_space"] = (">a\n" + seq(50) + " " + seq(50) + "\n").encode()
+    return cases
+
+
+def test_device_fasta_parse(kmc, orc, gold_dir, tmp_path):
+    """kmc_submit_fasta parses raw FASTA text on the GPU with the rules of the reference's reader (bio, via
+    main.rs:45,59-62): same sequence bytes, same record boundaries, hence the same table as the oracle's parser."""
+    for name, text in _fasta_cases(gold_dir).items():
+        p = tmp_path / (name + ".fa")
+        p.write_bytes(text)
+        bases, off = orc.parse_fasta(str(p))
+        want = orc.contiguous_def(bases, off, 21, True) if len(bases) < 200_000 else orc.contiguous_mt(bases, off, 21, True)
+        with kmc.KmerCounter(k=21) as kc:
+            nb, nr = kc.submit_fasta(text)
+            assert (nb, nr) == (len(bases), len(off) - 1), name
+            kc.finish()
+            assert_tables_equal(kc.read(), want)
+    # the reference's own computation from raw text
+    text = open(os.path.join(gold_dir, "sample.fasta"), "rb").read()
+    bases, off = orc.parse_fasta(os.path.join(gold_dir, "sample.fasta"))
+    with kmc.KmerCounter(mode=kmc.MODE_LR_GAPPED, canonical=False) as kc:
+        kc.submit_fasta(text)
+        assert kc.finish() == (1079497, 3550200)
+        assert kc.digest() == orc.compat_lr(bases, off).digest()
+    # first byte is not '>' → main.rs:59 unwrap panics
+    with kmc.KmerCounter(k=21) as kc:
+        with pytest.raises(kmc.KmcError) as e:
+            kc.submit_fasta(b"ACGT\n>a\nACGT\n")
+        assert e.value.code == -10
+        assert kc.submit_fasta(b"") == (0, 0)
