@@ -119,6 +119,11 @@ int kmc_finish(kmc_ctx *ctx, uint64_t *n_distinct, uint64_t *n_total);
  * keys of <= 64 bits.  Key encoding: A=0,C=1,G=2,T=3, first base most significant, so ascending
  * integer order is the bytewise String order of main.rs:87.                                        */
 int kmc_read(kmc_ctx *ctx, uint64_t first, uint64_t n, uint64_t *key_lo, uint64_t *key_hi, uint64_t *count);
+/* Rows [first, first+n) as text, formatted ON THE DEVICE into a library-owned pinned host buffer (*text, *len
+ * bytes; valid until the next call on this ctx).  expanded != 0: each key as letters + '\n', repeated `count`
+ * times — exactly what main.rs:88-90 prints; expanded == 0: "<kmer>\t<count>\n".  Returns KMC_E_CAPACITY when
+ * the text of these rows exceeds max_bytes (ask for fewer rows).                                    */
+int kmc_format(kmc_ctx *ctx, uint64_t first, uint64_t n, int expanded, size_t max_bytes, const char **text, size_t *len);
 /* Device pointers of the table (valid until reset/destroy).  d_key_hi is NULL for 64-bit keys.    */
 int kmc_table_device(kmc_ctx *ctx, const uint64_t **d_key_lo, const uint64_t **d_key_hi, const uint32_t **d_count);
 /* Order-independent 64-bit digest of the table, computed on the device:

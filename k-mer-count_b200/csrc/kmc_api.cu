@@ -19,6 +19,7 @@
 #include "kmc_fast.cuh"
 #include "kmc_hash.cuh"
 #include "kmc_fasta.cuh"
+#include "kmc_format.cuh"
 #include <cmath>
 
 using namespace kmc;
@@ -94,6 +95,9 @@ struct kmc_ctx {
   DevBuf fast_l1, fast_l2, fast_state, fast_tables, recv_keys;
   DevBuf hash_slots, hash_scalars, hash_hot;
   DevBuf fa_raw, fa_tiles, fa_flags;
+  DevBuf fmt_len, fmt_off, fmt_text;
+  char *fmt_host = nullptr;
+  size_t fmt_host_cap = 0;
   uint64_t probe_distinct = 0;
   uint32_t n_hot = 0;
   uint32_t hash_aborts = 0;
@@ -1106,6 +1110,16 @@ int finish_impl(kmc_ctx *c) {
   return finish_baseline<KeyT>(c);
 }
 
+// exclusive scan of m u32 counts into u64 offsets (three kernels, uses c->sums)
+int scan_u32(kmc_ctx *c, const uint32_t *in, uint64_t m, uint64_t *out) {
+  uint32_t blocks = grid_for(m, kScanTile);
+  TRY(ensure(c, c->sums, (size_t)blocks * 8 + 64));
+  LAUNCH(scan_reduce_kernel, blocks, kScanThreads, 0, in, m, (uint64_t *)c->sums.p);
+  LAUNCH(scan_spine_kernel, 1, 1024, 0, (uint64_t *)c->sums.p, (uint64_t)blocks);
+  LAUNCH(scan_apply_kernel, blocks, kScanThreads, 0, in, m, (const uint64_t *)c->sums.p, out);
+  return KMC_OK;
+}
+
 void build_stats(kmc_ctx *c) {
   std::string s = "{";
   char buf[1024];
@@ -1220,9 +1234,10 @@ void kmc_destroy(kmc_ctx *c) {
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->mailbox) cudaFreeHost(c->mailbox);
   if (c->upbox) cudaFreeHost(c->upbox);
+  if (c->fmt_host) cudaFreeHost(c->fmt_host);
   for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); if (s.ready) cudaEventDestroy(s.ready); }
   for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
-                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot, &c->fa_raw, &c->fa_tiles, &c->fa_flags})
+                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot, &c->fa_raw, &c->fa_tiles, &c->fa_flags, &c->fmt_len, &c->fmt_off, &c->fmt_text})
     release(*b);
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1305,16 +1320,6 @@ int kmc_submit_host(kmc_ctx *c, const uint8_t *bases, const uint64_t *rec_off, s
   // pageable memory was copied synchronously enough to be reused; a chunked (pinned) submit stays asynchronous and
   // the caller's buffer must stay unchanged until kmc_finish returns
   if (!(c->n_segs > segs_before && c->segs[segs_before].wait_ready)) CK(cudaStreamSynchronize(c->stream));
-  return KMC_OK;
-}
-
-// exclusive scan of m u32 counts into u64 offsets (three kernels, uses c->sums)
-static int scan_u32(kmc_ctx *c, const uint32_t *in, uint64_t m, uint64_t *out) {
-  uint32_t blocks = grid_for(m, kScanTile);
-  TRY(ensure(c, c->sums, (size_t)blocks * 8 + 64));
-  LAUNCH(scan_reduce_kernel, blocks, kScanThreads, 0, in, m, (uint64_t *)c->sums.p);
-  LAUNCH(scan_spine_kernel, 1, 1024, 0, (uint64_t *)c->sums.p, (uint64_t)blocks);
-  LAUNCH(scan_apply_kernel, blocks, kScanThreads, 0, in, m, (const uint64_t *)c->sums.p, out);
   return KMC_OK;
 }
 
@@ -1454,6 +1459,43 @@ int kmc_read(kmc_ctx *c, uint64_t first, uint64_t n, uint64_t *key_lo, uint64_t 
     CK(cudaMemcpy(tmp, (uint32_t *)c->t_cnt.p + first, n * 4, cudaMemcpyDeviceToHost));
     for (uint64_t i = n; i-- > 0;) count[i] = tmp[i];
   }
+  return KMC_OK;
+}
+
+int kmc_format(kmc_ctx *c, uint64_t first, uint64_t n, int expanded, size_t max_bytes, const char **text, size_t *len) {
+  if (!c || !text || !len) return KMC_E_ARG;
+  if (!c->finished) return fail(c, KMC_E_ARG, "kmc_format before kmc_finish");
+  if (first > c->n_distinct || n > c->n_distinct - first) return fail(c, KMC_E_ARG, "row range out of bounds");
+  *text = ""; *len = 0;
+  if (!n) return KMC_OK;
+  CK(cudaSetDevice(c->device));
+  const uint32_t nb = c->key_bases;
+  TRY(ensure(c, c->fmt_len, n * 4));
+  TRY(ensure(c, c->fmt_off, n * 8));
+  const uint32_t *cnt = (const uint32_t *)c->t_cnt.p + first;
+  LAUNCH(fmt_len_kernel, grid_for(n, 256), 256, 0, cnt, n, nb, expanded, (uint32_t *)c->fmt_len.p);
+  TRY(scan_u32(c, (const uint32_t *)c->fmt_len.p, n, (uint64_t *)c->fmt_off.p));
+  uint64_t last_off = 0;
+  uint32_t last_len = 0;
+  TRY(d2h_small(c, &last_off, (uint64_t *)c->fmt_off.p + (n - 1), 8, 0));
+  TRY(d2h_small(c, &last_len, (uint32_t *)c->fmt_len.p + (n - 1), 4, 64));
+  const uint64_t bytes = expanded ? (last_off + last_len) * (uint64_t)(nb + 1) : last_off + last_len;
+  if (bytes > max_bytes) return fail(c, KMC_E_CAPACITY, "the text of %llu rows is %llu bytes (> %zu)", (unsigned long long)n,
+                                     (unsigned long long)bytes, max_bytes);
+  TRY(ensure(c, c->fmt_text, bytes + 64));
+  if (bytes > c->fmt_host_cap) {
+    if (c->fmt_host) CK(cudaFreeHost(c->fmt_host));
+    c->fmt_host = nullptr; c->fmt_host_cap = 0;
+    size_t cap = std::max<size_t>(bytes + bytes / 8, 1 << 20);
+    CK(cudaHostAlloc((void **)&c->fmt_host, cap, cudaHostAllocDefault));
+    c->fmt_host_cap = cap;
+  }
+  LAUNCH(fmt_write_kernel, std::min<uint32_t>(grid_for(n, 8), kNumSMsB200 * 16), 256, 0, (const uint64_t *)c->t_lo.p + first,
+         c->wide ? (const uint64_t *)c->t_hi.p + first : (const uint64_t *)nullptr, cnt, (const uint64_t *)c->fmt_off.p, n, nb, expanded,
+         (char *)c->fmt_text.p);
+  CK(cudaMemcpyAsync(c->fmt_host, c->fmt_text.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *text = c->fmt_host; *len = bytes;
   return KMC_OK;
 }
 

@@ -166,35 +166,36 @@ void feed_fasta(const Options &o, kmc_ctx *ctx, Feeder &fd) {
   fd.flush();
 }
 
-// table rows → text.  expanded: each key `count` times, one per line (main.rs:88-90); else "kmer\tcount".
+// table rows → text, formatted on the device (kmc_format) chunk by chunk.  expanded: each key `count` times, one per
+// line (main.rs:88-90); else "kmer\tcount".
 void emit(const Options &o, kmc_ctx *ctx, uint64_t n_distinct) {
   FILE *out = o.out.empty() ? stdout : fopen(o.out.c_str(), "wb");
   if (!out) panic("cannot open output", o.out);
-  const uint32_t nbases = kmc_key_bases(ctx);
-  const bool expanded = o.mode == KMC_MODE_LR_GAPPED && o.expanded;
-  const uint64_t chunk = 1 << 20;
-  std::vector<uint64_t> lo(chunk), hi(chunk), cnt(chunk);
-  std::vector<char> text;
-  text.reserve(64 << 20);
-  char line[160];
-  for (uint64_t first = 0; first < n_distinct; first += chunk) {
+  const int expanded = o.mode == KMC_MODE_LR_GAPPED && o.expanded;
+  const size_t max_bytes = (size_t)1 << 30;
+  uint64_t chunk = 1 << 22;
+  for (uint64_t first = 0; first < n_distinct;) {
     uint64_t n = std::min<uint64_t>(chunk, n_distinct - first);
-    int rc = kmc_read(ctx, first, n, lo.data(), hi.data(), cnt.data());
-    if (rc) panic("kmc_read", kmc_last_error(ctx));
-    for (uint64_t i = 0; i < n; i++) {
-      unsigned __int128 v = ((unsigned __int128)hi[i] << 64) | lo[i];
-      for (uint32_t b = 0; b < nbases; b++) { line[nbases - 1 - b] = "ACGT"[(unsigned)(v & 3)]; v >>= 2; }
-      if (expanded) {
-        line[nbases] = '\n';
-        for (uint64_t c = 0; c < cnt[i]; c++) text.insert(text.end(), line, line + nbases + 1);
-      } else {
-        int m = snprintf(line + nbases, sizeof line - nbases, "\t%llu\n", (unsigned long long)cnt[i]);
-        text.insert(text.end(), line, line + nbases + m);
-      }
-      if (text.size() > (48u << 20)) { fwrite(text.data(), 1, text.size(), out); text.clear(); }
+    const char *text = nullptr;
+    size_t len = 0;
+    int rc = kmc_format(ctx, first, n, expanded, max_bytes, &text, &len);
+    if (rc == KMC_E_CAPACITY && n > 1) { chunk = std::max<uint64_t>(1, n / 4); continue; } // huge multiplicities: fewer rows at a time
+    if (rc == KMC_E_CAPACITY) { // a single row whose expansion exceeds the buffer: expand it here
+      uint64_t lo = 0, hi = 0, cnt = 0;
+      if (kmc_read(ctx, first, 1, &lo, &hi, &cnt)) panic("kmc_read", kmc_last_error(ctx));
+      const uint32_t nb = kmc_key_bases(ctx);
+      char line[160];
+      unsigned __int128 v = ((unsigned __int128)hi << 64) | lo;
+      for (uint32_t b = 0; b < nb; b++) { line[nb - 1 - b] = "ACGT"[(unsigned)(v & 3)]; v >>= 2; }
+      line[nb] = '\n';
+      for (uint64_t c = 0; c < cnt; c++) fwrite(line, 1, nb + 1, out);
+      first += 1;
+      continue;
     }
+    if (rc) panic("kmc_format", kmc_last_error(ctx));
+    fwrite(text, 1, len, out);
+    first += n;
   }
-  if (!text.empty()) fwrite(text.data(), 1, text.size(), out);
   if (out == stdout) fflush(out); else fclose(out);
 }
 

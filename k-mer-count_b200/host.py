@@ -24,7 +24,7 @@ SYMBOLS = ["kmc_create", "kmc_destroy", "kmc_last_error", "kmc_strerror", "kmc_s
            "kmc_staging", "kmc_submit", "kmc_submit_host", "kmc_submit_device", "kmc_finish", "kmc_read",
            "kmc_table_device", "kmc_digest", "kmc_key_bases", "kmc_route", "kmc_ingest_keys", "kmc_owner_of",
            "kmc_stats_json", "kmc_route_to_peers", "kmc_recv_buffer", "kmc_ipc_export", "kmc_ipc_open",
-           "kmc_ipc_close", "kmc_submit_fasta"]
+           "kmc_ipc_close", "kmc_submit_fasta", "kmc_format"]
 
 
 class KmcConfig(C.Structure):
@@ -70,6 +70,7 @@ def load_library(path=None):
     L.kmc_submit_fasta.argtypes = [vp, vp, C.c_size_t, u64p, u64p]
     L.kmc_finish.argtypes = [vp, u64p, u64p]
     L.kmc_read.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp]
+    L.kmc_format.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t)]
     L.kmc_table_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.kmc_digest.argtypes = [vp, u64p]
     L.kmc_key_bases.argtypes = [vp]
@@ -195,6 +196,13 @@ class KmerCounter:
         lo, hi, cnt = (np.empty(n, np.uint64) for _ in range(3))
         self._ck(self._L.kmc_read(self._h, first, n, lo.ctypes.data, hi.ctypes.data, cnt.ctypes.data))
         return Table(hi, lo, cnt, self.n_total, self.key_bases)
+
+    def format(self, first=0, n=None, expanded=False, max_bytes=1 << 30):
+        """Rows as text formatted on the device: expanded = the reference's stdout, else kmer<TAB>count lines."""
+        n = self.n_distinct - first if n is None else n
+        p, ln = C.c_char_p(), C.c_size_t()
+        self._ck(self._L.kmc_format(self._h, first, n, int(expanded), max_bytes, C.byref(p), C.byref(ln)))
+        return C.string_at(p, ln.value)
 
     def table_device(self):
         lo, hi, cnt = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -396,3 +396,32 @@ def test_device_fasta_parse(kmc, orc, gold_dir, tmp_path):
             kc.submit_fasta(b"ACGT\n>a\nACGT\n")
         assert e.value.code == -10
         assert kc.submit_fasta(b"") == (0, 0)
+
+
+def test_device_text_formatting(kmc, orc, gold_dir, golden):
+    """kmc_format: the table as text, produced on the device — the reference's stdout (expanded) and kmer<TAB>count."""
+    bases, off = orc.parse_fasta(os.path.join(gold_dir, "sample.fasta"))
+    with kmc.KmerCounter(mode=kmc.MODE_LR_GAPPED, canonical=False) as kc:
+        kc.submit_host(bases, off)
+        d, t = kc.finish()
+        h = hashlib.sha256()
+        for first in range(0, d, 300_000):
+            h.update(kc.format(first, min(300_000, d - first), expanded=True))
+        assert h.hexdigest() == golden["sample"]["stdout_sha256"]
+        txt = kc.format(expanded=False)
+        assert hashlib.sha256(txt).hexdigest() == "696a3c9cdcc963513511e5ae95d0d0faa057177a1ce726136dd777ec3d00ef9c"
+        with pytest.raises(kmc.KmcError) as e:
+            kc.format(0, d, expanded=True, max_bytes=1000)
+        assert e.value.code == -8
+    for k, sha in ((21, "d6821a8f1b9010573e9009dc86475c1db676fbfa6c2c87cead0bfec2a9a8d248"),
+                   (63, "0e4a5e39329606ff25951c3ca5c131d54f0ba30616a1689d229351858fdcc718")):
+        with kmc.KmerCounter(k=k) as kc:
+            kc.submit_host(bases, off)
+            kc.finish()
+            assert hashlib.sha256(kc.format()).hexdigest() == sha
+    # counts with many digits
+    b = np.full(1_234_567, ord("A"), np.uint8)
+    with kmc.KmerCounter(k=5) as kc:
+        kc.submit_host(b, np.array([0, len(b)], np.uint64))
+        kc.finish()
+        assert kc.format() == b"AAAAA\t1234563\n"
