@@ -220,20 +220,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()   # nvidia-smi needs ~100 ms to produce its first row: start it before the warm-up steps
     for _ in range(args.warmup):
         step_device()
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    kstats, totals = [], None
+    kstats, totals, step_wall = [], None, []
     for _ in range(args.steps):
+        t_s = time.perf_counter()
         totals = step_device()
+        step_wall.append(round(1e3 * (time.perf_counter() - t_s), 2))
         kstats.append(dc.stats())
     ev1.record(stream)
     barrier()
+    if rank == 0 and not sampler.rows:
+        time.sleep(0.15)  # very short runs: let the sampler deliver at least one row (GPU still warm)
     clocks = sampler.stop() if rank == 0 else None
     ms_local = ev0.elapsed_time(ev1) / args.steps
     digest = dc.digest()
@@ -267,6 +271,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     ms, e2e_ms = float(t[0]), float(t[1])
+    all_walls = [step_wall]
+    if dist is not None and os.environ.get("KMC_BENCH_STEPS") == "1":
+        all_walls = [None] * world
+        dist.all_gather_object(all_walls, step_wall)
     n_total, n_distinct = int(cnt[0]), int(cnt[1])
 
     if rank == 0:
@@ -316,6 +324,7 @@ def main():
             "kernels_ms_per_step": {kname: v[1] / args.steps for kname, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
             "phases_ms": kstats[-1].get("phases_ms"),
             "clocks": clocks,
+            "step_wall_ms": all_walls if os.environ.get("KMC_BENCH_STEPS") == "1" else step_wall,
         }
         if not args.no_cpu:
             from oracle import orc  # cpu_baseline leg only

@@ -160,7 +160,7 @@ int ensure(kmc_ctx *c, DevBuf &b, size_t bytes) {
   size_t want = std::max<size_t>(bytes, 256);
   // sizes derived from sampled estimates wobble by a fraction of a percent from job to job: leave headroom so that
   // a slightly larger next job does not free and reallocate gigabytes (cudaFree/cudaMalloc stall the host for tens of ms)
-  if (want > ((size_t)16 << 20)) want += want / 16;
+  if (want > ((size_t)16 << 20)) want += want / 8;
   want = (want + 255) & ~size_t(255);
   CK(cudaMalloc(&b.p, want));
   b.cap = want;
@@ -941,6 +941,9 @@ int finish_fast(kmc_ctx *c, bool *used) {
   const uint64_t slack = 2 * kMaxTile;
   TRY(ensure(c, c->fast_tables, tab_bytes));
   TRY(ensure(c, c->fast_l1, (l1_keys + slack) * sizeof(KeyT)));
+  // the level-1 array and the table's key column trade places after every job (64-bit keys): size both, or the
+  // smaller one would be freed and reallocated on alternate jobs
+  if (!kWide) TRY(ensure(c, c->t_lo, (l1_keys + slack) * sizeof(KeyT)));
   TRY(ensure(c, c->fast_l2, (l2_keys + 2 * slack) * sizeof(KeyT)));
   if (kWide) { TRY(ensure(c, c->t_lo, l1_keys * 8)); TRY(ensure(c, c->t_hi, l1_keys * 8)); }
   TRY(ensure(c, c->t_cnt, l1_keys * 4));
