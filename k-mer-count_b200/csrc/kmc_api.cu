@@ -811,10 +811,13 @@ int hash_probe(kmc_ctx *c, bool *low_cardinality) {
 // ---- partitioned fast path (kmc_fast.cuh) --------------------------------------------------------------------
 // *used = false: the input does not suit it (tiny, duplicate-heavy, or a bucket overflowed); nothing is left
 // behind and the caller counts with the baseline path.
+// relax = 1: aim at half-full buckets (retry after an overflow: input whose keys come in many copies spreads
+// less evenly than the plan's Poisson slack assumes).
 template <typename KeyT>
-int finish_fast(kmc_ctx *c, bool *used) {
+int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   constexpr bool kWide = sizeof(KeyT) == 16;
-  constexpr int kTarget = kWide ? 3200 : kFineTarget, kCap = kWide ? 4096 : kFineCap;
+  constexpr int kCap = kWide ? 4096 : kFineCap;
+  const int kTarget = (kWide ? 3200 : kFineTarget) >> relax;
   *used = false;
   const uint32_t kb = c->key_bits;
   const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb);
@@ -918,7 +921,7 @@ int finish_fast(kmc_ctx *c, bool *used) {
     for (uint32_t ci = b << (cb - b1); ci < ((b + 1) << (cb - b1)); ci++) {
       nb += hist[ci];
       double avg = (double)hist[ci] / (double)(1ull << sub_bits);
-      uint32_t cp = (uint32_t)(avg * 1.10 + 6.0 * std::sqrt(avg) + 64.0);
+      uint32_t cp = relax ? (uint32_t)kCap : (uint32_t)(avg * 1.10 + 6.0 * std::sqrt(avg) + 64.0);
       cp = std::min<uint32_t>((cp + 15) & ~15u, kCap);
       for (uint32_t sub = 0; sub < (1u << sub_bits); sub++) {
         const uint32_t rem = kb - b1 - l1e[b];
@@ -1107,8 +1110,13 @@ int finish_impl(kmc_ctx *c) {
         }
       }
     }
+    const uint32_t fallbacks = c->fast_fallbacks;
     TRY(finish_fast<KeyT>(c, &used));
     if (used) return KMC_OK;
+    if (c->fast_fallbacks != fallbacks) { // a bucket overflowed: once more with half-full buckets of full capacity
+      TRY(finish_fast<KeyT>(c, &used, 1));
+      if (used) return KMC_OK;
+    }
   }
   return finish_baseline<KeyT>(c);
 }

@@ -552,6 +552,12 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
         const uint32_t b = S.hp[q];
         const uint32_t s0 = b ? end16[b - 1] : 0u, e0 = end16[b];
         if (e0 - s0 > (uint32_t)kSmallBin) {
+          // many keys in one sub-bin are almost always copies of one key (input with coverage > 1): a linear check
+          // settles those without sorting; only sub-bins with several distinct keys go to the cooperative sort
+          const L2T first = S.keys[s0];
+          bool same = true;
+          for (uint32_t i = s0 + 1; i < e0; i++) if (!key_eq(S.keys[i], first)) { same = false; break; }
+          if (same) { dups += e0 - s0 - 1; continue; }
           uint32_t h = atomicAdd(&S.n_hard, 1u);
           if (h < (uint32_t)kMaxHard) S.hard[h] = b;
           continue;

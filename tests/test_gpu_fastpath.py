@@ -217,3 +217,19 @@ def test_chunked_pinned_submit(kmc, orc):
     with kmc.KmerCounter(k=k) as kc:
         kc.submit_host(hb.numpy()[:280_000_000], np.append(ho.numpy().view(np.uint64)[ho.numpy() < 280_000_000], np.uint64(280_000_000)))
         assert kc.finish() == (d3, t3)
+
+
+def test_fast_path_with_coverage_duplicates(kmc, orc):
+    """Reads at ~40x coverage of a 1.5 Mbase genome: every key ~40 times.  Forced through the partitioned path
+    (AUTO would pick the hash table): sub-bins hold many copies of one key and are settled by a linear check."""
+    rng = np.random.default_rng(41)
+    genome = ACGT[rng.integers(0, 4, 1_500_000)]
+    starts = rng.integers(0, len(genome) - 150, 400_000)
+    bases = np.concatenate([genome[s:s + 150] for s in starts])
+    off = (np.arange(len(starts) + 1) * 150).astype(np.uint64)
+    for k, canonical in ((21, False), (31, True)):
+        want = orc.contiguous_mt(bases, off, k, canonical)
+        got, st, _ = _count(kmc, bases, off, k, canonical, strategy=2)
+        assert_tables_equal(got, want)
+        assert st["strategy_used"] == 2, st   # possibly after one retry with half-full buckets
+        assert float(want.count.mean()) > 20
