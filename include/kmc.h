@@ -10,6 +10,8 @@
  *
  * Call chain (one ctx per GPU, one host thread per ctx; a ctx is not thread-safe):
  *     kmc_create → { kmc_staging → fill → kmc_submit }*  → kmc_finish → kmc_read* → kmc_destroy
+ * or, when keys + table exceed HBM, in key-range passes over the resident input:
+ *     kmc_submit* → { kmc_finish_part(p, P) → kmc_read* }  for p = 0..P-1
  * or, with inputs already resident in HBM:
  *     kmc_create → kmc_submit_device* → kmc_finish → kmc_table_device / kmc_read
  * Multi-GPU (one process per GPU):
@@ -113,6 +115,15 @@ int kmc_submit_device(kmc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_re
  * multiplicities — resident in HBM.  n_total = number of key occurrences (lines the reference would
  * print), n_distinct = rows.                                                                       */
 int kmc_finish(kmc_ctx *ctx, uint64_t *n_distinct, uint64_t *n_total);
+/* The same for inputs whose keys or table do not fit in HBM at once (BASELINE.json configs 3-4 on ONE GPU:
+ * 1e10 k-mers are 80-160 GB of keys): count in n_parts passes over the resident input.  The key space is cut
+ * into n_parts consecutive key ranges of about equal population (from a histogram of the submitted input, so the
+ * same input always gives the same ranges); this call counts range `part` only and leaves ITS table — n_total =
+ * the key occurrences inside the range.  Ranges ascend with `part`: reading the tables of part 0, 1, ...,
+ * n_parts-1 in turn yields exactly the rows kmc_finish would have produced, in the same order (main.rs:87-90),
+ * and the kmc_digest values add up (mod 2^64).  The input stays submitted between calls; the previous part's
+ * table is dropped.  Errors that concern the whole input (main.rs:23,35) are raised by every part.           */
+int kmc_finish_part(kmc_ctx *ctx, uint32_t part, uint32_t n_parts, uint64_t *n_distinct, uint64_t *n_total);
 
 /* ---- output: what main.rs:88-90 prints, as arrays --------------------------------------------
  * Rows [first, first+n) into caller-owned HOST arrays (any of them may be NULL).  key_hi is zero for

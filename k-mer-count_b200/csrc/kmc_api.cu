@@ -104,6 +104,13 @@ struct kmc_ctx {
   std::vector<unsigned char> fast_host; // plan tables staged for upload
   uint32_t fast_fallbacks = 0;          // times the partitioned path overflowed and the job was recounted
 
+  // partial count (kmc_finish_part): the coarse-bin range [range_lo, range_lo + range_n) being counted, and the
+  // coarse histogram of the whole input it is cut from (computed once per input)
+  bool range_on = false;
+  uint32_t range_lo = 0, range_n = 0;
+  std::vector<uint64_t> part_hist; // raw (sampled) counts per coarse bin
+  uint32_t part_hist_step = 0;     // sampling step of part_hist; 0 = not computed yet
+
   // results
   bool finished = false;
   uint64_t n_total = 0, n_distinct = 0;
@@ -219,6 +226,7 @@ inline uint32_t grid_for(uint64_t n, uint32_t per_block) { return (uint32_t)std:
 unsigned long long *d_cursor(kmc_ctx *c) { return (unsigned long long *)c->scalars.p; }
 unsigned long long *d_digest(kmc_ctx *c) { return (unsigned long long *)c->scalars.p + 1; }
 uint32_t *d_err(kmc_ctx *c) { return (uint32_t *)((unsigned long long *)c->scalars.p + 2); }
+unsigned long long *d_total_all(kmc_ctx *c) { return (unsigned long long *)c->scalars.p + 3; }
 
 // Small device→host reads go through a pinned, device-mapped mailbox written by a kernel, not through the copy
 // engines: a cudaMemcpy D2H queues behind the 64 MB H2D chunks of a large submit and would stall the compute
@@ -271,12 +279,29 @@ int zero_scalars(kmc_ctx *c) {
   CK(cudaMemsetAsync(c->scalars.p, 0, 64, c->stream));
   return KMC_OK;
 }
-int read_scalars(kmc_ctx *c, uint64_t *cursor, uint32_t *err) {
+int read_scalars(kmc_ctx *c, uint64_t *cursor, uint32_t *err, uint64_t *total_all = nullptr) {
   unsigned long long h[4];
   TRY(d2h_small(c, h, c->scalars.p, sizeof h));
   if (cursor) *cursor = h[0];
   if (err) *err = (uint32_t)h[2];
+  if (total_all) *total_all = h[3];
   return KMC_OK;
+}
+
+// coarse bins (kmc_fast.cuh): the top min(12, key_bits) bits of a key
+uint32_t coarse_bits(const kmc_ctx *c) { return std::min<uint32_t>(kCoarseBitsMax, c->key_bits); }
+
+// kernel parameters of one segment; host_alias: read the pinned host copy (sampling passes before the H2D has landed)
+ExtractParams seg_params(const kmc_ctx *c, const Segment &s, bool host_alias = false) {
+  ExtractParams P{host_alias ? s.host_alias : s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical, 0, 0, 0, 0};
+  if (c->range_on) { P.range_on = 1; P.range_shift = c->key_bits - coarse_bits(c); P.range_lo = c->range_lo; P.range_n = c->range_n; }
+  return P;
+}
+GapParams gap_params(const kmc_ctx *c, const Segment &s) {
+  const kmc_config &f = c->cfg;
+  GapParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, f.l_len, f.r_len, f.d_min, f.d_max, 0, 0, 0, 0};
+  if (c->range_on) { P.range_on = 1; P.range_shift = c->key_bits - coarse_bits(c); P.range_lo = c->range_lo; P.range_n = c->range_n; }
+  return P;
 }
 
 // ---- input segments ------------------------------------------------------------------------------------
@@ -285,6 +310,7 @@ int new_segment(kmc_ctx *c, Segment **out) {
   Segment &s = c->segs[c->n_segs++];
   s.bases = nullptr; s.rec_off = nullptr; s.n_bases = s.n_recs = 0;
   s.off_shift = 0; s.host_alias = nullptr; s.wait_ready = false;
+  c->part_hist_step = 0; // new input: the partial-count histogram is stale
   *out = &s;
   return KMC_OK;
 }
@@ -477,7 +503,7 @@ int extract_all(kmc_ctx *c, uint64_t *n_keys) {
     Segment &s = c->segs[i];
     if (!s.n_bases) continue;
     TRY(seg_wait(c, s));
-    ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
+    ExtractParams P = seg_params(c, s);
     uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
     uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + 7) / 8, (uint64_t)kNumSMsB200 * 16);
     auto extract_compact = extract_compact_kernel<KeyT, true>;
@@ -504,31 +530,31 @@ int gapped_all(kmc_ctx *c, uint64_t *n_keys) {
     Segment &s = c->segs[i];
     if (!s.n_bases) continue;
     TRY(seg_wait(c, s));
-    GapParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, f.l_len, f.r_len, f.d_min, f.d_max};
+    GapParams P = gap_params(c, s);
     uint32_t g = grid_for(s.n_bases, 256);
     LAUNCH(gap_mers_kernel, g, 256, 0, P, (uint64_t *)c->gap_l.p, (uint64_t *)c->gap_r.p, (uint8_t *)c->gap_f.p);
     auto gap_pairs_count = gap_pairs_kernel<KeyT, false>;
     LAUNCH(gap_pairs_count, g, 256, 0, P, (const uint64_t *)c->gap_l.p, (const uint64_t *)c->gap_r.p,
-           (const uint8_t *)c->gap_f.p, (KeyT *)nullptr, d_cursor(c), d_err(c));
+           (const uint8_t *)c->gap_f.p, (KeyT *)nullptr, d_cursor(c), d_total_all(c), d_err(c));
   }
-  uint64_t total = 0;
+  uint64_t total = 0, total_all = 0; // keys of this part / of the whole input
   uint32_t err = 0;
-  TRY(read_scalars(c, &total, &err));
+  TRY(read_scalars(c, &total, &err, &total_all));
   if (err & 1) return fail(c, KMC_E_BADBASE, "Unexpected character (not one of A,C,G,T) inside an L/R chunk");
   if (err & 2) return fail(c, KMC_E_BADBASE_OFFSET0, "non-ACGT byte at offset 0 of an L/R chunk cannot be encoded");
-  if (total == 0) return fail(c, KMC_E_EMPTY, "no L/R chunk in the input (every record shorter than %u bases)", f.d_min);
+  if (total_all == 0) return fail(c, KMC_E_EMPTY, "no L/R chunk in the input (every record shorter than %u bases)", f.d_min);
   TRY(ensure(c, c->keys_a, (total + 2) * sizeof(KeyT)));
   TRY(zero_scalars(c));
   for (size_t i = 0; i < c->n_segs; i++) {
     Segment &s = c->segs[i];
     if (!s.n_bases) continue;
-    GapParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, f.l_len, f.r_len, f.d_min, f.d_max};
+    GapParams P = gap_params(c, s);
     uint32_t g = grid_for(s.n_bases, 256);
     if (c->n_segs > 1)
       LAUNCH(gap_mers_kernel, g, 256, 0, P, (uint64_t *)c->gap_l.p, (uint64_t *)c->gap_r.p, (uint8_t *)c->gap_f.p);
     auto gap_pairs_fill = gap_pairs_kernel<KeyT, true>;
     LAUNCH(gap_pairs_fill, g, 256, 0, P, (const uint64_t *)c->gap_l.p, (const uint64_t *)c->gap_r.p,
-           (const uint8_t *)c->gap_f.p, (KeyT *)c->keys_a.p, d_cursor(c), d_err(c));
+           (const uint8_t *)c->gap_f.p, (KeyT *)c->keys_a.p, d_cursor(c), d_total_all(c), d_err(c));
   }
   PHASE_END();
   *n_keys = total;
@@ -615,7 +641,7 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
       TRY(seg_wait(c, s));
-      ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
+      ExtractParams P = seg_params(c, s);
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
       LAUNCH(fast_route, grid, kFastThreads, smem, P, tiles, pl, bucket, dst, d_err(c));
@@ -710,7 +736,7 @@ int hash_run(kmc_ctx *c, const KeyArrays &ka, uint32_t log2_slots, uint64_t limi
       if (!s.n_bases) continue;
       const bool sample_host = step > 1 && s.host_alias && s.wait_ready;
       if (!sample_host) TRY(seg_wait(c, s));
-      ExtractParams P{sample_host ? s.host_alias : s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
+      ExtractParams P = seg_params(c, s, sample_host);
       uint64_t tiles = num_warp_tiles(s.n_bases, 31);
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)max_ctas);
       auto hash_count = hash_count_kernel<true>;
@@ -808,6 +834,75 @@ int hash_probe(kmc_ctx *c, bool *low_cardinality) {
   return KMC_OK;
 }
 
+// Sampled histogram of the top coarse_bits() key bits of the job's keys (raw counts; *step_out = sampling step).
+// Uses the head of c->fast_state.
+template <typename KeyT>
+int coarse_hist(kmc_ctx *c, const KeyArrays &ka, std::vector<uint64_t> &hist, uint32_t *step_out) {
+  const uint32_t kb = c->key_bits, cb = coarse_bits(c), ncoarse = 1u << cb;
+  TRY(ensure(c, c->fast_state, 4096 * 8 + 64));
+  CK(cudaMemsetAsync(c->fast_state.p, 0, 4096 * 8, c->stream));
+  unsigned long long *ghist = (unsigned long long *)c->fast_state.p;
+  // sample so that ~64M keys are looked at (all of them for small inputs)
+  const uint64_t n_in = ka.from_array ? ka.n : c->total_bases;
+  uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
+  // chunks still on their way are sampled straight from pinned host memory: read 4x less of it over the bus
+  if (!ka.from_array) for (size_t i = 0; i < c->n_segs; i++) if (c->segs[i].wait_ready && c->segs[i].host_alias && step > 1) { step = std::min<uint32_t>(64, step * 4); break; }
+  PHASE_BEGIN("fast_hist");
+  if (ka.from_array) {
+    for (auto &a : ka.arrays) {
+      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024 * step), (uint64_t)kNumSMsB200 * 8);
+      auto fast_hist_array = fast_hist_array_kernel<KeyT>;
+      LAUNCH(fast_hist_array, grid, 256, ncoarse * 4, (const KeyT *)a.first, a.second, step, kb - cb, ncoarse, ghist);
+    }
+  } else {
+    for (size_t i = 0; i < c->n_segs; i++) {
+      Segment &s = c->segs[i];
+      if (!s.n_bases) continue;
+      const bool sample_host = step > 1 && s.host_alias && s.wait_ready;
+      if (!sample_host) TRY(seg_wait(c, s));
+      ExtractParams P = seg_params(c, s, sample_host);
+      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)kNumSMsB200 * 8);
+      auto fast_hist = fast_hist_kernel<KeyT, true>;
+      LAUNCH(fast_hist, grid, 256, ncoarse * 4, P, tiles, step, kb - cb, ncoarse, ghist);
+    }
+  }
+  PHASE_END();
+  hist.assign(ncoarse, 0);
+  TRY(d2h_small(c, hist.data(), ghist, ncoarse * 8));
+  *step_out = step;
+  return KMC_OK;
+}
+
+// lr-gapped keys are never materialised as a whole in a partial count: exact histogram straight from the L/R-mers
+template <typename KeyT>
+int coarse_hist_gapped(kmc_ctx *c, std::vector<uint64_t> &hist) {
+  const uint32_t kb = c->key_bits, cb = coarse_bits(c), ncoarse = 1u << cb;
+  TRY(ensure(c, c->fast_state, 4096 * 8 + 64));
+  CK(cudaMemsetAsync(c->fast_state.p, 0, 4096 * 8, c->stream));
+  uint64_t mx = 1;
+  for (size_t i = 0; i < c->n_segs; i++) mx = std::max<uint64_t>(mx, c->segs[i].n_bases);
+  TRY(ensure(c, c->gap_l, mx * 8));
+  TRY(ensure(c, c->gap_r, mx * 8));
+  TRY(ensure(c, c->gap_f, mx));
+  PHASE_BEGIN("fast_hist");
+  for (size_t i = 0; i < c->n_segs; i++) {
+    Segment &s = c->segs[i];
+    if (!s.n_bases) continue;
+    TRY(seg_wait(c, s));
+    GapParams P = gap_params(c, s);
+    uint32_t g = grid_for(s.n_bases, 256);
+    LAUNCH(gap_mers_kernel, g, 256, 0, P, (uint64_t *)c->gap_l.p, (uint64_t *)c->gap_r.p, (uint8_t *)c->gap_f.p);
+    auto gap_hist = gap_hist_kernel<KeyT>;
+    LAUNCH(gap_hist, g, 256, ncoarse * 4, P, (const uint64_t *)c->gap_l.p, (const uint64_t *)c->gap_r.p, kb - cb, ncoarse,
+           (unsigned long long *)c->fast_state.p);
+  }
+  PHASE_END();
+  hist.assign(ncoarse, 0);
+  TRY(d2h_small(c, hist.data(), c->fast_state.p, ncoarse * 8));
+  return KMC_OK;
+}
+
 // ---- partitioned fast path (kmc_fast.cuh) --------------------------------------------------------------------
 // *used = false: the input does not suit it (tiny, duplicate-heavy, or a bucket overflowed); nothing is left
 // behind and the caller counts with the baseline path.
@@ -825,41 +920,20 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   KeyArrays ka;
   TRY(key_sources<KeyT>(c, &ka));
   const bool from_array = ka.from_array;
-  const uint64_t n_array = ka.n;
   const auto &arrays = ka.arrays;
   // fast_state layout: ghist[4096] u64 | ticket u32 (+pad) | d_total u64 | l1_cursor[kMaxL1] u64 | fine_cursor[nf] u32 | status[nf] u64
   const size_t off_ticket = 4096 * 8, off_dtotal = off_ticket + 8, off_l1cur = off_dtotal + 8, off_fine = off_l1cur + kMaxL1 * 8;
   TRY(ensure(c, c->fast_state, off_fine + 64));
   CK(cudaMemsetAsync(c->fast_state.p, 0, off_fine, c->stream));
-  unsigned long long *ghist = (unsigned long long *)c->fast_state.p;
-  // sample so that ~64M keys are looked at (all of them for small inputs)
-  const uint64_t n_in = from_array ? n_array : c->total_bases;
-  uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
-  // chunks still on their way are sampled straight from pinned host memory: read 4x less of it over the bus
-  if (!from_array) for (size_t i = 0; i < c->n_segs; i++) if (c->segs[i].wait_ready && c->segs[i].host_alias && step > 1) { step = std::min<uint32_t>(64, step * 4); break; }
-  PHASE_BEGIN("fast_hist");
-  if (from_array) {
-    for (auto &a : arrays) {
-      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024 * step), (uint64_t)kNumSMsB200 * 8);
-      auto fast_hist_array = fast_hist_array_kernel<KeyT>;
-      LAUNCH(fast_hist_array, grid, 256, ncoarse * 4, (const KeyT *)a.first, a.second, step, kb - cb, ncoarse, ghist);
-    }
-  } else {
-    for (size_t i = 0; i < c->n_segs; i++) {
-      Segment &s = c->segs[i];
-      if (!s.n_bases) continue;
-      const bool sample_host = step > 1 && s.host_alias && s.wait_ready;
-      if (!sample_host) TRY(seg_wait(c, s));
-      ExtractParams P{sample_host ? s.host_alias : s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
-      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)kNumSMsB200 * 8);
-      auto fast_hist = fast_hist_kernel<KeyT, true>;
-      LAUNCH(fast_hist, grid, 256, ncoarse * 4, P, tiles, step, kb - cb, ncoarse, ghist);
-    }
-  }
-  PHASE_END();
-  std::vector<uint64_t> hist(ncoarse);
-  TRY(d2h_small(c, hist.data(), ghist, ncoarse * 8));
+  std::vector<uint64_t> hist;
+  uint32_t step = 1;
+  if (c->range_on && c->part_hist_step) { hist = c->part_hist; step = c->part_hist_step; } // partial count: computed once per input
+  else TRY(coarse_hist<KeyT>(c, ka, hist, &step));
+  // a partial count sees only the coarse bins of its key range
+  const bool ranged = c->range_on;
+  const uint32_t c_lo = ranged ? c->range_lo : 0u, c_hi = ranged ? c->range_lo + c->range_n : ncoarse;
+  if (ranged) for (uint32_t ci = 0; ci < ncoarse; ci++) if (ci < c_lo || ci >= c_hi) hist[ci] = 0;
+  if (c_hi <= c_lo) return KMC_OK; // empty range: the generic path returns the empty table
   // the histogram is a 1-in-step sample: scale it to an upper estimate (+5 sigma of the sampling noise)
   uint64_t n_est = 0;
   for (uint64_t &v : hist) {
@@ -878,25 +952,36 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
     if (ee > kb - cb) return KMC_OK; // cannot split far enough: too many keys share a prefix (duplicates)
     e[ci] = ee;
   }
-  uint32_t b1_lo = cb > 6 ? cb - 6 : 0, b1_hi = std::min<uint32_t>(cb, 10);
+  // Level 1 = the top b1 key bits.  Only the level-1 buckets that meet the key range exist, numbered from l1_base
+  // (all 2^b1 of them unless this is a partial count — which may therefore use more level-1 bits: what is bounded
+  // is the number of buckets the scatter kernel ranks in shared memory, kMaxL1).
+  uint32_t b1_lo = cb > 6 ? cb - 6 : 0, b1_hi = ranged ? cb : std::min<uint32_t>(cb, 10);
   uint64_t nf_guess = 0;
-  for (uint32_t ci = 0; ci < ncoarse; ci++) nf_guess += 1ull << e[ci];
-  uint32_t b1 = (uint32_t)std::lround(std::log2(std::sqrt((double)nf_guess)));
+  for (uint32_t ci = c_lo; ci < c_hi; ci++) nf_guess += 1ull << e[ci];
+  uint32_t b1 = (uint32_t)std::lround(std::log2(std::sqrt((double)nf_guess) * (double)ncoarse / (double)(c_hi - c_lo)));
   b1 = std::max(b1_lo, std::min(b1, b1_hi));
+  auto l1_span = [&](uint32_t bits, uint32_t *base) { // level-1 buckets met by the coarse range at `bits` level-1 bits
+    *base = c_lo >> (cb - bits);
+    return ((c_hi - 1) >> (cb - bits)) + 1 - *base;
+  };
   std::vector<uint8_t> l1e;
+  uint32_t l1_base = 0, n_l1 = 0;
+  while (b1 > b1_lo && l1_span(b1, &l1_base) > (uint32_t)kMaxL1) b1--;
   for (;; b1++) {
     if (b1 > b1_hi) return KMC_OK;
-    l1e.assign(1u << b1, 0);
+    n_l1 = l1_span(b1, &l1_base);
+    if (n_l1 > (uint32_t)kMaxL1) return KMC_OK; // too many keys for two levels of this size
+    l1e.assign(n_l1, 0);
     uint32_t mx = 0;
-    for (uint32_t b = 0; b < (1u << b1); b++) {
+    for (uint32_t rb = 0; rb < n_l1; rb++) {
+      const uint32_t b = l1_base + rb;
       uint32_t em = 0;
       for (uint32_t ci = b << (cb - b1); ci < ((b + 1) << (cb - b1)); ci++) em = std::max(em, e[ci]);
-      l1e[b] = (uint8_t)(cb - b1 + em);
-      mx = std::max<uint32_t>(mx, l1e[b]);
+      l1e[rb] = (uint8_t)(cb - b1 + em);
+      mx = std::max<uint32_t>(mx, l1e[rb]);
     }
     if ((1ull << mx) <= (uint64_t)kMaxFinePerL1) break;
   }
-  const uint32_t n_l1 = 1u << b1;
   uint64_t n_fine = 0;
   for (uint32_t b = 0; b < n_l1; b++) n_fine += 1ull << l1e[b];
   if (n_fine > (1ull << 28)) return KMC_OK;
@@ -914,11 +999,12 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   uint32_t fb = 0;
   bool key32 = !kWide; // every bucket leaves <= 32 key bits: level 2 stores 32-bit suffixes
   for (uint32_t b = 0; b < n_l1; b++) if (kb - b1 - l1e[b] > 32) key32 = false;
-  for (uint32_t b = 0; b < n_l1; b++) {
+  for (uint32_t b = 0; b < n_l1; b++) { // b: index among the existing level-1 buckets; b_abs: its key prefix
+    const uint32_t b_abs = l1_base + b;
     uint64_t nb = 0;
     const uint32_t sub_bits = l1e[b] - (cb - b1); // fine buckets per coarse bin of this level-1 bucket = 2^sub_bits
     f0[b] = fb;
-    for (uint32_t ci = b << (cb - b1); ci < ((b + 1) << (cb - b1)); ci++) {
+    for (uint32_t ci = b_abs << (cb - b1); ci < ((b_abs + 1) << (cb - b1)); ci++) {
       nb += hist[ci];
       double avg = (double)hist[ci] / (double)(1ull << sub_bits);
       uint32_t cp = relax ? (uint32_t)kCap : (uint32_t)(avg * 1.10 + 6.0 * std::sqrt(avg) + 64.0);
@@ -928,7 +1014,7 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
         fdesc[fb].start = l2_keys; fdesc[fb].cap = (uint16_t)cp; fdesc[fb].rem = (uint8_t)rem;
         // bucket index within the level-1 bucket = the l1e[b] bits right below the b1 prefix
         const uint64_t within = (uint64_t)(fb - f0[b]);
-        fdesc[fb].prefix = (kWide || rem >= 64) ? 0 : ((((uint64_t)b << l1e[b]) | within) << rem); // 128-bit keys stay whole
+        fdesc[fb].prefix = (kWide || rem >= 64) ? 0 : ((((uint64_t)b_abs << l1e[b]) | within) << rem); // 128-bit keys stay whole
         l2_keys += cp; fb++;
       }
     }
@@ -958,7 +1044,7 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   TRY(h2d_small(c, c->fast_tables.p, c->fast_host.data(), tab_bytes));
   unsigned char *st = (unsigned char *)c->fast_state.p, *tb = (unsigned char *)c->fast_tables.p;
   FastPlan pl;
-  pl.kb = kb; pl.b1 = b1; pl.n_l1 = n_l1; pl.n_fine = (uint32_t)n_fine;
+  pl.kb = kb; pl.b1 = b1; pl.n_l1 = n_l1; pl.n_fine = (uint32_t)n_fine; pl.l1_base = l1_base;
   pl.l1_trash = l1_keys; pl.l2_trash = l2_keys + slack;
   pl.fdesc = (const FineDesc *)(tb + o_fdesc);
   pl.l1_start = (const uint64_t *)(tb + o_l1s); pl.l1_cap = (const uint64_t *)(tb + o_cap);
@@ -981,17 +1067,21 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   } else {
     size_t smem = PartSmem<KeyT>::bytes(part1_stage<KeyT>(), n_l1);
     auto fast_part1 = fast_part1_kernel<KeyT, true, PrefixBucket>;
-    CK(cudaFuncSetAttribute(fast_part1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const PrefixBucket bucket{b1, kb - b1};
+    auto fast_part1_ranged = fast_part1_kernel<KeyT, true, PrefixBucketT<true>>;
+    if (ranged) CK(cudaFuncSetAttribute(fast_part1_ranged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CK(cudaFuncSetAttribute(fast_part1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const PrefixBucket bucket{b1, kb - b1, 0, 0, 0, 0};
+    const PrefixBucketT<true> bucket_ranged{b1, kb - b1, l1_base, kb - cb, c_lo, c_hi - c_lo};
     for (size_t i = 0; i < c->n_segs; i++) {
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
       TRY(seg_wait(c, s));
-      ExtractParams P{s.bases, (const uint32_t *)s.brk.p, s.n_bases, c->cfg.k, c->cfg.canonical};
+      ExtractParams P = seg_params(c, s);
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps,
                                                    (uint64_t)kNumSMsB200 * ((sizeof(KeyT) == 8 && FastShape<KeyT>::kHalves == 2) ? 2 : 1));
-      LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->fast_l1.p, d_err(c));
+      if (ranged) LAUNCH(fast_part1_ranged, grid, kFastThreads, smem, P, tiles, pl, bucket_ranged, (KeyT *)c->fast_l1.p, d_err(c));
+      else LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->fast_l1.p, d_err(c));
     }
   }
   PHASE_END();
@@ -1272,6 +1362,7 @@ int kmc_reset(kmc_ctx *c) {
   c->n_segs = 0; c->total_bases = c->total_recs = 0;
   c->ingested.clear();
   c->finished = false; c->n_total = c->n_distinct = 0;
+  c->range_on = false; c->part_hist_step = 0;
   c->phases.clear(); c->klaunches.clear(); c->events_used = 0;
   c->launches_total += c->launches; c->launches = 0; c->h2d_bytes = 0;
   c->staged = false;
@@ -1427,10 +1518,7 @@ int kmc_ingest_keys(kmc_ctx *c, const void *d_keys, uint64_t n_keys) {
   return KMC_OK;
 }
 
-int kmc_finish(kmc_ctx *c, uint64_t *n_distinct, uint64_t *n_total) {
-  if (!c) return KMC_E_ARG;
-  if (c->finished) return fail(c, KMC_E_ARG, "kmc_finish called twice");
-  CK(cudaSetDevice(c->device));
+static int finish_common(kmc_ctx *c, uint64_t *n_distinct, uint64_t *n_total) {
   TRY(zero_scalars(c));
   int rc = c->wide ? finish_impl<U128>(c) : finish_impl<uint64_t>(c);
   if (rc) return rc;
@@ -1450,6 +1538,57 @@ int kmc_finish(kmc_ctx *c, uint64_t *n_distinct, uint64_t *n_total) {
   if (n_distinct) *n_distinct = c->n_distinct;
   if (n_total) *n_total = c->n_total;
   return KMC_OK;
+}
+
+int kmc_finish(kmc_ctx *c, uint64_t *n_distinct, uint64_t *n_total) {
+  if (!c) return KMC_E_ARG;
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_finish called twice");
+  CK(cudaSetDevice(c->device));
+  return finish_common(c, n_distinct, n_total);
+}
+
+int kmc_finish_part(kmc_ctx *c, uint32_t part, uint32_t n_parts, uint64_t *n_distinct, uint64_t *n_total) {
+  if (!c) return KMC_E_ARG;
+  const uint32_t ncoarse = 1u << coarse_bits(c);
+  if (n_parts == 0 || part >= n_parts) return fail(c, KMC_E_ARG, "kmc_finish_part: need part < n_parts");
+  if (n_parts > ncoarse) return fail(c, KMC_E_ARG, "kmc_finish_part: at most %u parts for %u-bit keys", ncoarse, c->key_bits);
+  if (!c->ingested.empty()) return fail(c, KMC_E_ARG, "kmc_finish_part: ingested keys are one part of a multi-GPU job already");
+  CK(cudaSetDevice(c->device));
+  if (c->finished) { // the previous part's table goes, the submitted input stays
+    CK(cudaStreamSynchronize(c->stream));
+    c->finished = false; c->n_total = c->n_distinct = 0;
+    c->phases.clear(); c->klaunches.clear(); c->events_used = 0;
+  }
+  if (n_parts == 1) return finish_common(c, n_distinct, n_total);
+  if (!c->part_hist_step) { // once per input: where the keys are
+    c->range_on = false;
+    if (c->cfg.mode == KMC_MODE_LR_GAPPED) {
+      TRY(c->wide ? coarse_hist_gapped<U128>(c, c->part_hist) : coarse_hist_gapped<uint64_t>(c, c->part_hist));
+      c->part_hist_step = 1;
+    } else {
+      KeyArrays ka;
+      uint32_t step = 1;
+      TRY(c->wide ? coarse_hist<U128>(c, ka, c->part_hist, &step) : coarse_hist<uint64_t>(c, ka, c->part_hist, &step));
+      c->part_hist_step = step;
+    }
+  }
+  // part p = coarse bins [B(p), B(p+1)), B(p) = the first bin with at least p/n_parts of the keys before it
+  unsigned __int128 total = 0;
+  for (uint64_t v : c->part_hist) total += v;
+  auto boundary = [&](uint32_t p) -> uint32_t {
+    if (p == 0) return 0;
+    if (p >= n_parts) return ncoarse;
+    const unsigned __int128 want = (total * p + n_parts - 1) / n_parts;
+    unsigned __int128 before = 0;
+    uint32_t idx = 0;
+    while (idx < ncoarse && before < want) before += c->part_hist[idx++];
+    return idx;
+  };
+  const uint32_t lo = boundary(part), hi = boundary(part + 1);
+  c->range_on = true; c->range_lo = lo; c->range_n = hi - lo;
+  int rc = finish_common(c, n_distinct, n_total);
+  c->range_on = false;
+  return rc;
 }
 
 int kmc_read(kmc_ctx *c, uint64_t first, uint64_t n, uint64_t *key_lo, uint64_t *key_hi, uint64_t *count) {

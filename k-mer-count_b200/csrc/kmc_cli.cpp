@@ -31,6 +31,7 @@ struct Options {
   uint32_t strategy = KMC_STRATEGY_AUTO;
   uint32_t l_len = 0, r_len = 0, d_min = 0, d_max = 0;
   int device = -1;
+  int parts = 1;           // --parts P: count in P key-range passes (kmc_finish_part)
   bool host_parse = false; // --host-parse: parse FASTA on the host (default: on the device, kmc_submit_fasta)
   bool expanded = true; // lr-gapped: repeat each key `count` times (the reference's output); --counts switches it off
 };
@@ -44,7 +45,7 @@ struct Options {
 void usage() {
   fputs("usage: kmer-count [FASTA] [-k K] [-o OUT] [--mode lr-gapped|contiguous] [--canonical|--no-canonical]\n"
         "                  [--strategy auto|hash|sort|baseline] [--lr L R DMIN DMAX] [--counts] [--device N] [--stats FILE]\n"
-        "                  [--host-parse]\n"
+        "                  [--host-parse] [--parts P]\n"
         "  no arguments: read ./sample.fasta and print the reference's output (sorted L27+R27 gapped chunks)\n",
         stderr);
 }
@@ -67,6 +68,7 @@ Options parse_args(int argc, char **argv) {
     else if (a == "--no-canonical") { o.canonical = 0; canon_given = true; }
     else if (a == "--counts") o.expanded = false;
     else if (a == "--host-parse") o.host_parse = true;
+    else if (a == "--parts") { need(1); o.parts = atoi(argv[++i]); if (o.parts < 1) { usage(); exit(2); } }
     else if (a == "--strategy") {
       need(1); std::string s = argv[++i];
       o.strategy = s == "hash" ? KMC_STRATEGY_HASH : s == "sort" ? KMC_STRATEGY_SORT : s == "baseline" ? KMC_STRATEGY_SORT_BASELINE : KMC_STRATEGY_AUTO;
@@ -168,9 +170,7 @@ void feed_fasta(const Options &o, kmc_ctx *ctx, Feeder &fd) {
 
 // table rows → text, formatted on the device (kmc_format) chunk by chunk.  expanded: each key `count` times, one per
 // line (main.rs:88-90); else "kmer\tcount".
-void emit(const Options &o, kmc_ctx *ctx, uint64_t n_distinct) {
-  FILE *out = o.out.empty() ? stdout : fopen(o.out.c_str(), "wb");
-  if (!out) panic("cannot open output", o.out);
+void emit(const Options &o, kmc_ctx *ctx, uint64_t n_distinct, FILE *out) {
   const int expanded = o.mode == KMC_MODE_LR_GAPPED && o.expanded;
   const size_t max_bytes = (size_t)1 << 30;
   uint64_t chunk = 1 << 22;
@@ -196,7 +196,6 @@ void emit(const Options &o, kmc_ctx *ctx, uint64_t n_distinct) {
     fwrite(text, 1, len, out);
     first += n;
   }
-  if (out == stdout) fflush(out); else fclose(out);
 }
 
 } // namespace
@@ -213,12 +212,22 @@ int main(int argc, char **argv) {
   if (rc) { fprintf(stderr, "kmer-count: %s (%s)\n", kmc_last_error(nullptr), kmc_strerror(rc)); return 3; }
   Feeder fd;
   feed_fasta(o, ctx, fd);
-  uint64_t n_distinct = 0, n_total = 0;
-  rc = kmc_finish(ctx, &n_distinct, &n_total);
-  if (rc == KMC_E_BADBASE) panic("Unexpected charactor appears in a chunk", kmc_last_error(ctx));                  // main.rs:23
-  if (rc == KMC_E_EMPTY) panic("index out of bounds: the len is 0 but the index is 0", kmc_last_error(ctx));        // main.rs:35
-  if (rc) panic(kmc_strerror(rc), kmc_last_error(ctx));
-  emit(o, ctx, n_distinct);
+  FILE *out = nullptr;
+  // --parts P: the key space in P ascending ranges, one counting pass each (inputs whose keys exceed HBM); the output
+  // is the same text, since the ranges' tables follow each other in key order
+  for (uint32_t part = 0; part < (uint32_t)o.parts; part++) {
+    uint64_t n_distinct = 0, n_total = 0;
+    rc = kmc_finish_part(ctx, part, (uint32_t)o.parts, &n_distinct, &n_total);
+    if (rc == KMC_E_BADBASE) panic("Unexpected charactor appears in a chunk", kmc_last_error(ctx));                  // main.rs:23
+    if (rc == KMC_E_EMPTY) panic("index out of bounds: the len is 0 but the index is 0", kmc_last_error(ctx));        // main.rs:35
+    if (rc) panic(kmc_strerror(rc), kmc_last_error(ctx));
+    if (!out) { // opened after the first count: the reference prints nothing when it panics
+      out = o.out.empty() ? stdout : fopen(o.out.c_str(), "wb");
+      if (!out) panic("cannot open output", o.out);
+    }
+    emit(o, ctx, n_distinct, out);
+  }
+  if (out == stdout) fflush(out); else if (out) fclose(out);
   if (!o.stats.empty()) {
     size_t n = kmc_stats_json(ctx, nullptr, 0);
     std::vector<char> s(n);

@@ -20,7 +20,12 @@ struct ExtractParams {
   uint64_t n_bases;
   uint32_t k;
   uint32_t canonical;
+  // partial count (kmc_finish_part): only keys whose top bits `key >> range_shift` lie in [range_lo, range_lo + range_n)
+  uint32_t range_on, range_shift, range_lo, range_n;
 };
+template <typename P, typename KeyT> __device__ __forceinline__ bool in_key_range(const P &p, const KeyT &key) {
+  return key_shr32(key, p.range_shift) - p.range_lo < p.range_n;
+}
 
 __global__ void mark_breaks_kernel(const uint64_t *__restrict__ rec_off, uint64_t n_recs, uint64_t base_shift,
                                    uint32_t *__restrict__ brk) {
@@ -183,6 +188,14 @@ __global__ void __launch_bounds__(256) extract_compact_kernel(ExtractParams P, u
   for (uint64_t t = warp0; t < n_tiles; t += nwarps) {
     Win<KeyT> W;
     W.template load<FOLD>(P, t * Win<KeyT>::kLanes + lane);
+    if (P.range_on) { // partial count: drop the window starts whose key is outside the range
+      uint32_t m = W.ok;
+      while (m) {
+        uint32_t s = __clz(m);
+        m &= ~(0x80000000u >> s);
+        if (!in_key_range(P, W.key(s, P.k, P.canonical != 0))) W.ok &= ~(0x80000000u >> s);
+      }
+    }
     uint32_t cnt = __popc(W.ok);
     uint32_t inc = cnt;
 #pragma unroll
@@ -210,6 +223,7 @@ struct GapParams {
   const uint32_t *brk;
   uint64_t n_bases;
   uint32_t l_len, r_len, d_min, d_max;
+  uint32_t range_on, range_shift, range_lo, range_n; // as in ExtractParams
 };
 
 // Per-position packed L-mer and R-mer with strict (upper-case ACGT) validity — main.rs:18-23.
@@ -252,31 +266,55 @@ __device__ __forceinline__ uint32_t room_to_record_end(const uint32_t *__restric
   return (uint32_t)lim;
 }
 
-// FILL=false: count keys and check validity.  FILL=true: write keys (compacted, unordered).
+template <typename KeyT> __device__ __forceinline__ KeyT gap_key(uint64_t L, uint64_t R, uint32_t r_len);
+template <> __device__ __forceinline__ uint64_t gap_key<uint64_t>(uint64_t L, uint64_t R, uint32_t r_len) { return (L << (2 * r_len)) | R; }
+template <> __device__ __forceinline__ U128 gap_key<U128>(uint64_t L, uint64_t R, uint32_t r_len) {
+  const uint32_t s = 2 * r_len; // 2..64
+  U128 key;
+  key.lo = (s == 64) ? R : ((L << s) | R);
+  key.hi = (s == 64) ? L : (L >> (64 - s));
+  return key;
+}
+
+// FILL=false: count keys and check validity (every key, whatever the range: main.rs:23,35 see the whole input).
+// FILL=true: write keys (compacted, unordered).  With a key range (partial count) only keys inside it are counted
+// in *cursor / written; *total_all (count pass) is the number of keys before the range filter.
 // err[0] |= 1 on a bad base at chunk offset >= 1, |= 2 when only offset 0 is bad.
 template <typename KeyT, bool FILL>
 __global__ void __launch_bounds__(256) gap_pairs_kernel(GapParams P, const uint64_t *__restrict__ lmer,
                                                         const uint64_t *__restrict__ rmer, const uint8_t *__restrict__ flags,
                                                         KeyT *__restrict__ out, unsigned long long *__restrict__ cursor,
+                                                        unsigned long long *__restrict__ total_all,
                                                         uint32_t *__restrict__ err) {
   uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  uint32_t cnt = 0, room = 0;
+  uint32_t cnt_all = 0, room = 0;
   if (p < P.n_bases) {
     room = room_to_record_end(P.brk, p, P.n_bases, P.d_max);
-    if (room >= P.d_min) cnt = room - P.d_min + 1;
+    if (room >= P.d_min) cnt_all = room - P.d_min + 1;
+  }
+  uint32_t cnt = cnt_all;
+  if (P.range_on && cnt_all) {
+    cnt = 0;
+    const uint64_t L = lmer[p];
+    for (uint32_t d = P.d_min; d <= room; d++) cnt += in_key_range(P, gap_key<KeyT>(L, rmer[p + d - P.r_len], P.r_len));
   }
   const uint32_t lane = lane_id();
-  uint32_t inc = cnt;
+  uint32_t inc = cnt, all = cnt_all;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= (uint32_t)o) inc += nn;
   }
+  if (!FILL) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) all += __shfl_xor_sync(0xffffffffu, all, o);
+    if (lane == 0 && all) atomicAdd(total_all, (unsigned long long)all);
+  }
   uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
   unsigned long long base = 0;
   if (lane == 31 && total) base = atomicAdd(cursor, (unsigned long long)total);
   base = __shfl_sync(0xffffffffu, base, 31);
-  if (!cnt) return;
+  if (!cnt_all) return;
   uint32_t e = 0;
   if (!FILL) {
     uint8_t fl = flags[p];
@@ -289,18 +327,37 @@ __global__ void __launch_bounds__(256) gap_pairs_kernel(GapParams P, const uint6
     uint64_t o = base + (inc - cnt);
     uint64_t L = lmer[p];
     for (uint32_t d = P.d_min; d <= room; d++) {
-      uint64_t R = rmer[p + d - P.r_len];
-      KeyT key;
-      if constexpr (sizeof(KeyT) == 8) {
-        key = (L << (2 * P.r_len)) | R;
-      } else {
-        uint32_t s = 2 * P.r_len; // 2..64
-        key.lo = (s == 64) ? R : ((L << s) | R);
-        key.hi = (s == 64) ? L : (L >> (64 - s));
-      }
-      out[o++] = key;
+      KeyT key = gap_key<KeyT>(L, rmer[p + d - P.r_len], P.r_len);
+      if (!P.range_on || in_key_range(P, key)) out[o++] = key;
     }
   }
+}
+
+// Exact coarse histogram of the lr-gapped keys (partial counts choose their key ranges from it):
+// top `nbits` bits of every key, nbins = 2^nbits <= 4096.
+template <typename KeyT>
+__global__ void __launch_bounds__(256) gap_hist_kernel(GapParams P, const uint64_t *__restrict__ lmer,
+                                                       const uint64_t *__restrict__ rmer, uint32_t shift, uint32_t nbins,
+                                                       unsigned long long *__restrict__ ghist) {
+  extern __shared__ uint32_t sh_hist[];
+  for (uint32_t i = threadIdx.x; i < nbins; i += blockDim.x) sh_hist[i] = 0;
+  __syncthreads();
+  uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (p < P.n_bases) {
+    uint32_t room = room_to_record_end(P.brk, p, P.n_bases, P.d_max);
+    if (room >= P.d_min) {
+      const uint64_t L = lmer[p];
+      if (shift >= 2 * P.r_len) { // the bin depends on the L-mer only
+        atomicAdd(&sh_hist[key_shr32(gap_key<KeyT>(L, 0, P.r_len), shift) & (nbins - 1)], room - P.d_min + 1);
+      } else {
+        for (uint32_t d = P.d_min; d <= room; d++)
+          atomicAdd(&sh_hist[key_shr32(gap_key<KeyT>(L, rmer[p + d - P.r_len], P.r_len), shift) & (nbins - 1)], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < nbins; i += blockDim.x)
+    if (sh_hist[i]) atomicAdd(&ghist[i], (unsigned long long)sh_hist[i]);
 }
 
 } // namespace kmc

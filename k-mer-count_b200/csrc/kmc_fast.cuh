@@ -62,7 +62,8 @@ __device__ __forceinline__ void emit_key(uint64_t *lo, uint64_t *hi, uint64_t i,
 
 struct FastPlan {
   uint32_t kb, b1;          // key bits, level-1 bits
-  uint32_t n_l1, n_fine;
+  uint32_t n_l1, n_fine;    // level-1 buckets [l1_base, l1_base + n_l1) of the 2^b1 exist (all of them unless partial)
+  uint32_t l1_base;
   uint64_t l1_trash, l2_trash;   // key index of the trash areas (>= one tile each) in the two arrays
   const FineDesc *fdesc;    // [n_fine]
   const uint64_t *l1_start; // [n_l1+1] key index in the level-1 array (each start a multiple of 16)
@@ -74,16 +75,28 @@ struct FastPlan {
   uint32_t *fine_cursor;    // [n_fine]
 };
 
-// bucket functions of the level-1 scatter: the top b1 key bits (counting), or the owner part (routing)
-struct PrefixBucket {
+// bucket functions of the level-1 scatter: the top b1 key bits (counting), or the owner part (routing).
+// accept(): does the key take part at all?  RANGE (partial count, kmc_finish_part): only keys whose coarse bin
+// `key >> cshift` lies in [c_lo, c_lo + c_n); level-1 buckets are then numbered from the first one in range (`base`).
+template <bool RANGE>
+struct PrefixBucketT {
   uint32_t b1, bshift;
-  template <typename KeyT> __device__ __forceinline__ uint32_t operator()(const KeyT &key) const { return b1 ? key_shr32(key, bshift) : 0u; }
+  uint32_t base, cshift, c_lo, c_n;
+  template <typename KeyT> __device__ __forceinline__ uint32_t operator()(const KeyT &key) const {
+    const uint32_t v = b1 ? key_shr32(key, bshift) : 0u;
+    return RANGE ? v - base : v;
+  }
+  template <typename KeyT> __device__ __forceinline__ bool accept(const KeyT &key) const {
+    return RANGE ? (key_shr32(key, cshift) - c_lo < c_n) : true;
+  }
 };
+using PrefixBucket = PrefixBucketT<false>;
 struct OwnerBucket {
   uint32_t n_parts;
   template <typename KeyT> __device__ __forceinline__ uint32_t operator()(const KeyT &key) const {
     return owner_of(key_hi(key), key_lo(key), n_parts);
   }
+  template <typename KeyT> __device__ __forceinline__ bool accept(const KeyT &) const { return true; }
 };
 
 // shapes per key width: 128-bit keys take twice the registers and shared memory, so half the keys per tile
@@ -263,7 +276,7 @@ __global__ void __launch_bounds__(kFastThreads, (sizeof(KeyT) == 8 && FastShape<
 #pragma unroll
       for (int s = 0; s < kSPH; s++) {
         key[s] = W.key(half * kSPH + s, P.k, P.canonical != 0);
-        if (ok & (0x80000000u >> (half * kSPH + s))) valid |= 1u << s;
+        if ((ok & (0x80000000u >> (half * kSPH + s))) && bucket.accept(key[s])) valid |= 1u << s;
       }
       scatter_tile_l1<KeyT, kSPH>(pl, S, nb, bucket, key, valid, l1, flags);
     }
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part1_array_kernel(const
   constexpr int kKPT = FastShape<KeyT>::kArrKPT, kTile = arr_tile<KeyT>();
   const uint32_t nb = pl.n_l1;
   PartSmem<KeyT> S(smem_raw, kTile, nb);
-  const PrefixBucket bucket{pl.b1, pl.kb - pl.b1};
+  const PrefixBucketT<true> bucket{pl.b1, pl.kb - pl.b1, pl.l1_base, 0, 0, 0}; // keys are pre-filtered: accept() unused
   const uint64_t n_cta_tiles = (n + kTile - 1) / kTile;
   for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
     for (uint32_t i = threadIdx.x; i < nb; i += kFastThreads) S.hist[i] = 0;

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) hash_count_kernel(ExtractParams P, uint64
     Win<uint64_t> W{};
     W.template load<FOLD>(P, ts * step * Win<uint64_t>::kLanes + lane);
     uint32_t m = W.ok;
-    mine += __popc(m);
+    if (!P.range_on) mine += __popc(m);
     // a lane's k-mers are consecutive windows: merge runs of equal keys before touching the table
     uint64_t prev = 0;
     uint32_t run = 0, claimed = 0;
@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(256) hash_count_kernel(ExtractParams P, uint64
       uint32_t s = __clz(m);
       m &= ~(0x80000000u >> s);
       uint64_t key = W.key(s, P.k, P.canonical != 0);
+      if (P.range_on) { // partial count: keys outside the range do not exist
+        if (!in_key_range(P, key)) continue;
+        mine++;
+      }
       if (run && key == prev) { run++; continue; }
       if (run && !(n_hot && hot_add(H, prev, run))) claimed += hash_add(T, prev, run);
       prev = key; run = 1;

@@ -24,7 +24,7 @@ SYMBOLS = ["kmc_create", "kmc_destroy", "kmc_last_error", "kmc_strerror", "kmc_s
            "kmc_staging", "kmc_submit", "kmc_submit_host", "kmc_submit_device", "kmc_finish", "kmc_read",
            "kmc_table_device", "kmc_digest", "kmc_key_bases", "kmc_route", "kmc_ingest_keys", "kmc_owner_of",
            "kmc_stats_json", "kmc_route_to_peers", "kmc_recv_buffer", "kmc_ipc_export", "kmc_ipc_open",
-           "kmc_ipc_close", "kmc_submit_fasta", "kmc_format"]
+           "kmc_ipc_close", "kmc_submit_fasta", "kmc_format", "kmc_finish_part"]
 
 
 class KmcConfig(C.Structure):
@@ -69,6 +69,7 @@ def load_library(path=None):
     L.kmc_submit_device.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t]
     L.kmc_submit_fasta.argtypes = [vp, vp, C.c_size_t, u64p, u64p]
     L.kmc_finish.argtypes = [vp, u64p, u64p]
+    L.kmc_finish_part.argtypes = [vp, C.c_uint32, C.c_uint32, u64p, u64p]
     L.kmc_read.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp]
     L.kmc_format.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t)]
     L.kmc_table_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
@@ -187,6 +188,14 @@ class KmerCounter:
     def finish(self):
         d, t = C.c_uint64(), C.c_uint64()
         self._ck(self._L.kmc_finish(self._h, C.byref(d), C.byref(t)))
+        self.n_distinct, self.n_total = d.value, t.value
+        return d.value, t.value
+
+    def finish_part(self, part, n_parts):
+        """Count key range `part` of `n_parts` (ascending ranges of about equal population) — kmc_finish_part.
+        The tables of part 0..n_parts-1, read in turn, are the table finish() would have produced."""
+        d, t = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.kmc_finish_part(self._h, part, n_parts, C.byref(d), C.byref(t)))
         self.n_distinct, self.n_total = d.value, t.value
         return d.value, t.value
 
