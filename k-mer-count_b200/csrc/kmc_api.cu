@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -49,7 +50,11 @@ struct Phase {
   std::string name;
   cudaEvent_t a = nullptr, b = nullptr;
   float ms = 0.f;
+  double host_begin = 0, host_end = 0; // host clock (ms) when the phase was opened / closed: finds host-side stalls
 };
+inline double host_now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 struct KernelStat {
   std::string name;
   uint64_t launches = 0;
@@ -92,7 +97,7 @@ struct kmc_ctx {
   DevBuf keys_a, keys_b, block_hist, offsets, sums, scalars, route_keys;
   DevBuf gap_l, gap_r, gap_f;
   DevBuf t_lo, t_hi, t_cnt;
-  DevBuf fast_l1, fast_l2, fast_state, fast_tables, recv_keys;
+  DevBuf fast_l1, fast_l2, fast_state, fast_tables, fast_fdesc, recv_keys;
   DevBuf hash_slots, hash_scalars, hash_hot;
   DevBuf fa_raw, fa_tiles, fa_flags;
   DevBuf fmt_len, fmt_off, fmt_text;
@@ -127,6 +132,7 @@ struct kmc_ctx {
   bool ktiming = false;
   std::vector<Phase> klaunches;
   std::vector<KernelStat> kstats;
+  std::vector<std::pair<const char *, double>> host_marks; // KMC_HOST_PROF: host clock at points between phases
 };
 
 namespace {
@@ -167,7 +173,8 @@ int ensure(kmc_ctx *c, DevBuf &b, size_t bytes) {
   size_t want = std::max<size_t>(bytes, 256);
   // sizes derived from sampled estimates wobble by a fraction of a percent from job to job: leave headroom so that
   // a slightly larger next job does not free and reallocate gigabytes (cudaFree/cudaMalloc stall the host for tens of ms)
-  if (want > ((size_t)16 << 20)) want += want / 8;
+  // (small buffers too: plan tables of a few MB grow by single descriptors from job to job)
+  want += want / 8 + 4096;
   want = (want + 255) & ~size_t(255);
   CK(cudaMalloc(&b.p, want));
   b.cap = want;
@@ -190,11 +197,13 @@ int phase_begin(kmc_ctx *c, const char *name) {
     *e = c->event_pool[c->events_used++];
   }
   CK(cudaEventRecord(ph.a, c->stream));
+  ph.host_begin = host_now_ms();
   c->phases.push_back(ph);
   return KMC_OK;
 }
 int phase_end(kmc_ctx *c) {
   CK(cudaEventRecord(c->phases.back().b, c->stream));
+  c->phases.back().host_end = host_now_ms();
   return KMC_OK;
 }
 int ktime_begin(kmc_ctx *c, const char *name) {
@@ -216,6 +225,7 @@ int ktime_end(kmc_ctx *c) {
   CK(cudaEventRecord(c->klaunches.back().b, c->stream));
   return KMC_OK;
 }
+#define HOST_MARK(name) c->host_marks.emplace_back(name, host_now_ms())
 #define PHASE_BEGIN(name) do { int r_ = phase_begin(c, name); if (r_) return r_; } while (0)
 #define PHASE_END() do { int r_ = phase_end(c); if (r_) return r_; } while (0)
 #define TRY(...) do { int r_ = (__VA_ARGS__); if (r_) return r_; } while (0)
@@ -943,6 +953,7 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
     n_est += v;
   }
   if (n_est < (1u << 18)) return KMC_OK; // small job: the generic path is as fast and simpler
+  HOST_MARK("hist_read");
 
   // ---- plan
   std::vector<uint32_t> e(ncoarse);
@@ -985,13 +996,20 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   uint64_t n_fine = 0;
   for (uint32_t b = 0; b < n_l1; b++) n_fine += 1ull << l1e[b];
   if (n_fine > (1ull << 28)) return KMC_OK;
-  // tables: fdesc | l1_start | l1_cap | l1_tile0 | l1_fine0 | l1_e
+  // Host tables (a few tens of KB): per level-1 bucket l1_start | l1_cap | l1_tile0 | l1_fine0 | l1_e, and per coarse
+  // bin the first fine bucket, its level-2 start and the capacity of its fine buckets.  The per-fine-bucket
+  // descriptors (n_fine x 32 B, megabytes) are expanded from these on the device (plan_expand_kernel): filling and
+  // uploading them from the host cost ~1.2 ms of idle GPU per job.
   auto al16 = [](size_t x) { return (x + 15) & ~size_t(15); };
-  const size_t o_fdesc = 0, o_l1s = o_fdesc + n_fine * sizeof(FineDesc), o_cap = o_l1s + al16((size_t)(n_l1 + 1) * 8),
+  const uint32_t cshift = cb - b1, n_cb = n_l1 << cshift; // coarse bins under the existing level-1 buckets
+  const size_t o_l1s = 0, o_cap = o_l1s + al16((size_t)(n_l1 + 1) * 8),
                o_t0 = o_cap + al16((size_t)n_l1 * 8), o_f0 = o_t0 + al16((size_t)(n_l1 + 1) * 4),
-               o_e = o_f0 + al16((size_t)(n_l1 + 1) * 4), tab_bytes = o_e + al16(n_l1);
+               o_e = o_f0 + al16((size_t)(n_l1 + 1) * 4), o_cs = o_e + al16(n_l1), o_cf = o_cs + al16((size_t)n_cb * 8),
+               o_cc = o_cf + al16((size_t)n_cb * 4), tab_bytes = o_cc + al16((size_t)n_cb * 2);
   c->fast_host.assign(tab_bytes, 0);
-  FineDesc *fdesc = (FineDesc *)(c->fast_host.data() + o_fdesc);
+  uint64_t *cstart = (uint64_t *)(c->fast_host.data() + o_cs);
+  uint32_t *cfine0 = (uint32_t *)(c->fast_host.data() + o_cf);
+  uint16_t *ccap = (uint16_t *)(c->fast_host.data() + o_cc);
   uint64_t *l1s = (uint64_t *)(c->fast_host.data() + o_l1s), *l1cap = (uint64_t *)(c->fast_host.data() + o_cap);
   uint32_t *t0 = (uint32_t *)(c->fast_host.data() + o_t0), *f0 = (uint32_t *)(c->fast_host.data() + o_f0);
   uint8_t *l1ep = c->fast_host.data() + o_e;
@@ -1009,14 +1027,10 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
       double avg = (double)hist[ci] / (double)(1ull << sub_bits);
       uint32_t cp = relax ? (uint32_t)kCap : (uint32_t)(avg * 1.10 + 6.0 * std::sqrt(avg) + 64.0);
       cp = std::min<uint32_t>((cp + 15) & ~15u, kCap);
-      for (uint32_t sub = 0; sub < (1u << sub_bits); sub++) {
-        const uint32_t rem = kb - b1 - l1e[b];
-        fdesc[fb].start = l2_keys; fdesc[fb].cap = (uint16_t)cp; fdesc[fb].rem = (uint8_t)rem;
-        // bucket index within the level-1 bucket = the l1e[b] bits right below the b1 prefix
-        const uint64_t within = (uint64_t)(fb - f0[b]);
-        fdesc[fb].prefix = (kWide || rem >= 64) ? 0 : ((((uint64_t)b_abs << l1e[b]) | within) << rem); // 128-bit keys stay whole
-        l2_keys += cp; fb++;
-      }
+      const uint32_t ci_rel = ci - (l1_base << cshift);
+      cstart[ci_rel] = l2_keys; cfine0[ci_rel] = fb; ccap[ci_rel] = (uint16_t)cp;
+      l2_keys += (uint64_t)cp << sub_bits;
+      fb += 1u << sub_bits;
     }
     uint64_t cap1 = ((uint64_t)((double)nb * 1.03) + 8192 + 15) & ~15ull;
     l1s[b] = l1_keys; l1cap[b] = cap1; t0[b] = (uint32_t)tiles2; l1ep[b] = l1e[b];
@@ -1025,10 +1039,12 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   }
   l1s[n_l1] = l1_keys; t0[n_l1] = (uint32_t)tiles2; f0[n_l1] = fb;
   if (tiles2 > 0x7FFFFFFFull) return KMC_OK;
+  HOST_MARK("planned");
 
   // ---- buffers (each array ends with a trash area of one tile + slack for runs that spill over a bucket end)
   const uint64_t slack = 2 * kMaxTile;
   TRY(ensure(c, c->fast_tables, tab_bytes));
+  TRY(ensure(c, c->fast_fdesc, n_fine * sizeof(FineDesc)));
   TRY(ensure(c, c->fast_l1, (l1_keys + slack) * sizeof(KeyT)));
   // the level-1 array and the table's key column trade places after every job (64-bit keys): size both, or the
   // smaller one would be freed and reallocated on alternate jobs
@@ -1040,19 +1056,24 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   if (off_status + n_fine * 8 + 64 > c->fast_state.cap) {
     TRY(ensure(c, c->fast_state, off_status + n_fine * 8 + 64));
   }
+  HOST_MARK("buffers");
   CK(cudaMemsetAsync(c->fast_state.p, 0, off_status + n_fine * 8, c->stream));
   TRY(h2d_small(c, c->fast_tables.p, c->fast_host.data(), tab_bytes));
+  HOST_MARK("uploaded");
   unsigned char *st = (unsigned char *)c->fast_state.p, *tb = (unsigned char *)c->fast_tables.p;
   FastPlan pl;
   pl.kb = kb; pl.b1 = b1; pl.n_l1 = n_l1; pl.n_fine = (uint32_t)n_fine; pl.l1_base = l1_base;
   pl.l1_trash = l1_keys; pl.l2_trash = l2_keys + slack;
-  pl.fdesc = (const FineDesc *)(tb + o_fdesc);
+  pl.fdesc = (const FineDesc *)c->fast_fdesc.p;
   pl.l1_start = (const uint64_t *)(tb + o_l1s); pl.l1_cap = (const uint64_t *)(tb + o_cap);
   pl.l1_tile0 = (const uint32_t *)(tb + o_t0); pl.l1_fine0 = (const uint32_t *)(tb + o_f0); pl.l1_e = (const uint8_t *)(tb + o_e);
   pl.l1_cursor = (unsigned long long *)(st + off_l1cur); pl.fine_cursor = (uint32_t *)(st + off_fine);
   unsigned int *ticket = (unsigned int *)(st + off_ticket);
   unsigned long long *d_total = (unsigned long long *)(st + off_dtotal);
   unsigned long long *status = (unsigned long long *)(st + off_status);
+  LAUNCH(plan_expand_kernel, n_cb, 128, 0, (FineDesc *)c->fast_fdesc.p, (const uint64_t *)(tb + o_cs), (const uint32_t *)(tb + o_cf),
+         (const uint16_t *)(tb + o_cc), pl.l1_fine0, pl.l1_e, cshift, l1_base, kb, b1, (uint32_t)kWide);
+  c->launches--; // plumbing
 
   // ---- level 1
   PHASE_BEGIN("fast_part1");
@@ -1338,7 +1359,7 @@ void kmc_destroy(kmc_ctx *c) {
   if (c->fmt_host) cudaFreeHost(c->fmt_host);
   for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); if (s.ready) cudaEventDestroy(s.ready); }
   for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
-                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot, &c->fa_raw, &c->fa_tiles, &c->fa_flags, &c->fmt_len, &c->fmt_off, &c->fmt_text})
+                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->fast_fdesc, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot, &c->fa_raw, &c->fa_tiles, &c->fa_flags, &c->fmt_len, &c->fmt_off, &c->fmt_text})
     release(*b);
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1519,6 +1540,9 @@ int kmc_ingest_keys(kmc_ctx *c, const void *d_keys, uint64_t n_keys) {
 }
 
 static int finish_common(kmc_ctx *c, uint64_t *n_distinct, uint64_t *n_total) {
+  const double host_t0 = host_now_ms();
+  const size_t first_phase = c->phases.size();
+  c->host_marks.clear();
   TRY(zero_scalars(c));
   int rc = c->wide ? finish_impl<U128>(c) : finish_impl<uint64_t>(c);
   if (rc) return rc;
@@ -1533,6 +1557,16 @@ static int finish_common(kmc_ctx *c, uint64_t *n_distinct, uint64_t *n_total) {
     for (auto &k : c->kstats) if (k.name == p.name) ks = &k;
     if (!ks) { c->kstats.emplace_back(); ks = &c->kstats.back(); ks->name = p.name; }
     ks->launches++; ks->ms += p.ms;
+  }
+  // development aid: KMC_HOST_PROF=<ms> prints the host-side timeline of a kmc_finish that took longer than that
+  static const double host_prof = getenv("KMC_HOST_PROF") ? atof(getenv("KMC_HOST_PROF")) : -1.0;
+  if (host_prof >= 0 && host_now_ms() - host_t0 > host_prof) {
+    fprintf(stderr, "[kmc host] finish %.2f ms:", host_now_ms() - host_t0);
+    for (size_t i = first_phase; i < c->phases.size(); i++)
+      fprintf(stderr, " %s %.2f..%.2f (gpu %.2f)", c->phases[i].name.c_str(), c->phases[i].host_begin - host_t0,
+              c->phases[i].host_end - host_t0, c->phases[i].ms);
+    for (auto &m : c->host_marks) fprintf(stderr, " [%s %.2f]", m.first, m.second - host_t0);
+    fprintf(stderr, "\n");
   }
   c->finished = true;
   if (n_distinct) *n_distinct = c->n_distinct;

@@ -40,6 +40,7 @@ constexpr int kMaxFinePerL1 = 2048;      // fine buckets under one level-1 bucke
 constexpr int kFinishBins = 8192;        // sub-bins of fast_finish (13 bits)
 constexpr int kSmallBin = 32;            // sub-bins up to this size are ranked by comparison per key
 constexpr int kMaxHard = 64;
+constexpr int kDupList = 32;             // fast_finish: buckets with at most this many duplicate keys skip the run-length encode
 
 constexpr uint32_t kFlagOverflow = 8u;   // err flag bits 1,2,4 are used by kmc_extract / kmc_sort
 constexpr uint32_t kFlagSpin = 16u;
@@ -74,6 +75,27 @@ struct FastPlan {
   unsigned long long *l1_cursor; // [n_l1] keys reserved so far (may exceed the capacity on overflow)
   uint32_t *fine_cursor;    // [n_fine]
 };
+
+// Per-fine-bucket descriptors from the per-coarse-bin plan (one CTA per coarse bin): the fine buckets of coarse bin
+// ci are consecutive, equally sized (cap), and split the bin by the key bits right below the coarse prefix.
+__global__ void __launch_bounds__(128) plan_expand_kernel(FineDesc *__restrict__ fdesc, const uint64_t *__restrict__ cstart,
+                                                          const uint32_t *__restrict__ cfine0, const uint16_t *__restrict__ ccap,
+                                                          const uint32_t *__restrict__ l1_fine0, const uint8_t *__restrict__ l1_e,
+                                                          uint32_t cshift, uint32_t l1_base, uint32_t kb, uint32_t b1, uint32_t wide) {
+  const uint32_t ci = blockIdx.x, b = ci >> cshift;
+  const uint32_t e = l1_e[b], sub_bits = e - cshift, rem = kb - b1 - e, cp = ccap[ci];
+  const uint32_t fine0 = cfine0[ci], within0 = fine0 - l1_fine0[b];
+  const uint64_t start = cstart[ci];
+  for (uint32_t sub = threadIdx.x; sub < (1u << sub_bits); sub += blockDim.x) {
+    FineDesc d{};
+    d.start = start + (uint64_t)sub * cp;
+    // bucket index within the level-1 bucket = the e bits right below the b1 prefix; 128-bit keys stay whole
+    d.prefix = (wide || rem >= 64) ? 0 : ((((uint64_t)(l1_base + b) << e) | (within0 + sub)) << rem);
+    d.cap = (uint16_t)cp;
+    d.rem = (uint8_t)rem;
+    fdesc[fine0 + sub] = d;
+  }
+}
 
 // bucket functions of the level-1 scatter: the top b1 key bits (counting), or the owner part (routing).
 // accept(): does the key take part at all?  RANGE (partial count, kmc_finish_part): only keys whose coarse bin
@@ -439,17 +461,29 @@ template <typename L2T> __host__ __device__ constexpr int fin_cap() { return siz
 template <typename L2T> __host__ __device__ constexpr int fin_kpt() { return fin_cap<L2T>() / kFinThreads; }
 static_assert(fin_kpt<uint32_t>() <= 32 && fin_kpt<uint32_t>() * kFinWarps <= kFinThreads && kFinWordsPT % 4 == 0, "fast_finish shape");
 
+// Deferred write-back (KMC_FINISH_DEFER=1, off by default) keeps two buckets in shared memory (32-bit suffixes
+// only: 2 x 32 KB) and writes a bucket's rows one bucket after its row count was announced, so that the look-back
+// never waits.  Measured on B200 (cfg2): the wait drops from 24 % to 5 % of a CTA's time, but the second buffer
+// costs the third resident CTA per SM and the kernel gets slower (9.3 ms vs 8.3 ms) — the SM is bound by its
+// shared-memory pipe and issue slots, which a waiting CTA does not use; the other two CTAs fill them.
+#ifndef KMC_FINISH_DEFER
+#define KMC_FINISH_DEFER 0
+#endif
+template <typename L2T> __host__ __device__ constexpr int fin_bufs() { return (KMC_FINISH_DEFER && sizeof(L2T) == 4) ? 2 : 1; }
+
 template <typename L2T>
 struct FinishSmem {
-  L2T keys[fin_cap<L2T>()];                // 64 KB (u64, u128) / 32 KB (u32)
+  L2T keys[fin_bufs<L2T>()][fin_cap<L2T>()]; // 32 KB per buffer (u32) / 64 KB (u64, u128)
   uint32_t bins[kFinishBins / 2];          // packed u16 pairs: counts → starts → (after the scatter) ends
   uint16_t hp[kFineCap + 8];               // multi-key sub-bin list, then head position of every run
   uint32_t scan32[40];
   uint32_t rowcnt[fin_kpt<L2T>() * kFinWarps];// heads per (row, warp), then their exclusive scan
   uint32_t hard[kMaxHard];
+  uint16_t dup[fin_bufs<L2T>()][kDupList]; // sorted positions whose key equals the one before (while they are few)
   uint32_t n_hard;
   uint32_t n_multi;
   uint32_t n_dups;
+  uint32_t dups_listed;                    // 0 once a duplicate was counted without being put on dup[]
   uint32_t ticket;
   unsigned long long goff;
 };
@@ -459,8 +493,37 @@ __device__ __forceinline__ uint32_t bin_end(const uint32_t *bins, uint32_t b) { 
 __device__ __forceinline__ uint32_t bin_start(const uint32_t *bins, uint32_t b) { return b ? bin_end(bins, b - 1) : 0u; }
 
 #ifndef KMC_FINISH_MINB32
-#define KMC_FINISH_MINB32 3
+#define KMC_FINISH_MINB32 (KMC_FINISH_DEFER ? 2 : 3)
 #endif
+
+// A sorted bucket whose rows are known up to their output offset: every position is a row except the `m` listed
+// ones (copies of the key before them); a row's index is its position minus the listed positions before it, its
+// count 1 plus the listed positions that follow it directly.
+struct FinPending {
+  FineDesc D;
+  uint32_t f, n, m;
+  bool valid;
+};
+
+template <typename L2T>
+__device__ __forceinline__ void finish_write_rows(const FinPending &P, const L2T *keys, const uint16_t *dup, unsigned long long G,
+                                                  uint64_t *__restrict__ out_lo, uint64_t *__restrict__ out_hi,
+                                                  uint32_t *__restrict__ out_cnt) {
+  const uint32_t m = P.m;
+  for (uint32_t p = threadIdx.x; p < P.n; p += kFinThreads) {
+    uint32_t before = 0, cnt = 1;
+    bool listed = false;
+    for (uint32_t q = 0; q < m; q++) { const uint32_t dq = dup[q]; before += dq < p; listed |= dq == p; }
+    if (listed) continue;
+    for (bool more = m != 0; more;) {
+      more = false;
+      for (uint32_t q = 0; q < m; q++) if (dup[q] == p + cnt) { cnt++; more = true; break; }
+    }
+    emit_key(out_lo, out_hi, G + p - before, P.D, keys[p]);
+    out_cnt[G + p - before] = cnt;
+  }
+}
+
 template <typename L2T>
 __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MINB32 : 2) fast_finish_kernel(FastPlan pl, const L2T *__restrict__ l2,
                                                                        uint64_t *__restrict__ out_lo, uint64_t *__restrict__ out_hi,
@@ -472,10 +535,33 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FinishSmem<L2T> &S = *reinterpret_cast<FinishSmem<L2T> *>(smem_raw);
   constexpr int kFinishKPT = fin_kpt<L2T>();
+  constexpr bool kDefer = fin_bufs<L2T>() == 2;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // optional phase timeline (development aid, env KMC_FINISH_PROF=1): thread 0 adds the cycles between marks
   long long t_prev = prof ? clock64() : 0;
 #define FIN_MARK(k) do { if (prof && tid == 0) { long long t_ = clock64(); atomicAdd(&prof[k], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
+  // Look-back resolve + row write of a bucket whose rows are settled (see KMC_FINISH_DEFER above for the deferred form).
+#define FIN_FLUSH(P, buf)                                                                                   \
+  do {                                                                                                      \
+    if (warp == 0) {                                                                                        \
+      long long lb0 = prof ? clock64() : 0;                                                                 \
+      unsigned long long prefix = lookback_resolve(status, (P).f, (P).n - (P).m, flags);                    \
+      if (prof && tid == 0) atomicAdd(&prof[10], (unsigned long long)(clock64() - lb0));                    \
+      if (lane == 0) {                                                                                      \
+        S.goff = prefix;                                                                                    \
+        if ((P).f + 1 == pl.n_fine) *d_total = prefix + ((P).n - (P).m);                                    \
+      }                                                                                                     \
+    }                                                                                                       \
+    __syncthreads();                                                                                        \
+    FIN_MARK(8);                                                                                            \
+    finish_write_rows<L2T>((P), S.keys[buf], S.dup[buf], S.goff, out_lo, out_hi, out_cnt);                   \
+    __syncthreads();                                                                                        \
+    FIN_MARK(9);                                                                                            \
+  } while (0)
+
+  FinPending pend;
+  pend.valid = false;
+  uint32_t cur = 0; // buffer of the bucket being sorted; a pending bucket sits in the other one
   for (;;) {
     if (tid == 0) S.ticket = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -487,11 +573,12 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
     if (n > D.cap) n = D.cap; // overflow was flagged by fast_part2; the caller discards this result
     const uint32_t sb = D.rem < 13 ? D.rem : 13;
     const uint32_t bshift = D.rem - sb, bmask = (1u << sb) - 1u; // sb == 0 → every key in sub-bin 0
+    L2T *const keys = S.keys[cur];
     {
       uint4 z = make_uint4(0, 0, 0, 0);
       for (uint32_t i = tid; i < kFinishBins / 8; i += kFinThreads) reinterpret_cast<uint4 *>(S.bins)[i] = z;
     }
-    if (tid == 0) { S.n_hard = 0; S.n_multi = 0; S.n_dups = 0; }
+    if (tid == 0) { S.n_hard = 0; S.n_multi = 0; S.n_dups = 0; S.dups_listed = 1; }
     __syncthreads();
     FIN_MARK(1);
     // ---- load (thread t owns positions t, t+512, ...) + count per sub-bin.  The thread that adds the SECOND
@@ -550,7 +637,7 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
         uint32_t b = key_shr32(x[j], bshift) & bmask;
         uint32_t sh = 16 * (b & 1);
         uint32_t p = (atomicAdd(&S.bins[b >> 1], 1u << sh) >> sh) & 0xFFFFu;
-        S.keys[p] = x[j];
+        keys[p] = x[j];
       }
     }
     __syncthreads();
@@ -560,53 +647,74 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
     {
       const uint16_t *end16 = reinterpret_cast<const uint16_t *>(S.bins);
       const uint32_t n_multi = S.n_multi;
-      uint32_t dups = 0; // equal neighbours after sorting = rows that the run-length encode will merge
+      uint32_t dups = 0; // equal neighbours after sorting = rows that merge into the one before
       for (uint32_t q = tid; q < n_multi; q += kFinThreads) {
         const uint32_t b = S.hp[q];
         const uint32_t s0 = b ? end16[b - 1] : 0u, e0 = end16[b];
         if (e0 - s0 > (uint32_t)kSmallBin) {
           // many keys in one sub-bin are almost always copies of one key (input with coverage > 1): a linear check
           // settles those without sorting; only sub-bins with several distinct keys go to the cooperative sort
-          const L2T first = S.keys[s0];
+          const L2T first = keys[s0];
           bool same = true;
-          for (uint32_t i = s0 + 1; i < e0; i++) if (!key_eq(S.keys[i], first)) { same = false; break; }
-          if (same) { dups += e0 - s0 - 1; continue; }
+          for (uint32_t i = s0 + 1; i < e0; i++) if (!key_eq(keys[i], first)) { same = false; break; }
+          if (same) { dups += e0 - s0 - 1; S.dups_listed = 0; continue; }
           uint32_t h = atomicAdd(&S.n_hard, 1u);
           if (h < (uint32_t)kMaxHard) S.hard[h] = b;
           continue;
         }
+        uint32_t here = 0;
         for (uint32_t i = s0 + 1; i < e0; i++) {
-          const L2T v = S.keys[i];
+          const L2T v = keys[i];
           uint32_t jj = i;
-          while (jj > s0 && key_lt(v, S.keys[jj - 1])) { S.keys[jj] = S.keys[jj - 1]; jj--; }
-          S.keys[jj] = v;
-          dups += (jj > s0 && key_eq(S.keys[jj - 1], v));
+          while (jj > s0 && key_lt(v, keys[jj - 1])) { keys[jj] = keys[jj - 1]; jj--; }
+          keys[jj] = v;
+          here += (jj > s0 && key_eq(keys[jj - 1], v));
+        }
+        if (here) { // rare: note where the copies ended up (final positions are known only now)
+          uint32_t q2 = atomicAdd(&S.n_dups, here);
+          for (uint32_t i = s0 + 1; i < e0; i++)
+            if (key_eq(keys[i], keys[i - 1])) { if (q2 < (uint32_t)kDupList) S.dup[cur][q2] = (uint16_t)i; q2++; }
         }
       }
       if (dups) atomicAdd(&S.n_dups, dups);
     }
     __syncthreads();
     FIN_MARK(5);
-    // ---- big sub-bins (duplicates or adversarial input): cooperative rank sort; too many of them → recount
-    // the row count of the bucket is already known unless big sub-bins remain: announce it now, so that by the
-    // time this CTA needs its own offset (after the run-length encode) its predecessors have announced theirs
+    // ---- the row count of the bucket is known now unless big sub-bins remain: announce it to the look-back
     const bool early = S.n_hard == 0;
-    if (early && tid == 0) lookback_publish(status, f, n - S.n_dups);
+    const uint32_t n_dups = S.n_dups;
+    const bool light = early && S.dups_listed && n_dups <= (uint32_t)kDupList;
+    if (early && tid == 0) lookback_publish(status, f, n - n_dups);
+    // ---- few duplicates (the usual case for high-cardinality input): no run-length encode
+    if (light) {
+      FinPending now;
+      now.D = D; now.f = f; now.n = n; now.m = n_dups; now.valid = true;
+      if (kDefer) {
+        if (pend.valid) FIN_FLUSH(pend, cur ^ 1u); // the previous bucket: announced a whole bucket ago
+        pend = now;
+        cur ^= 1u;
+      } else {
+        FIN_FLUSH(now, cur);
+      }
+      continue;
+    }
+    if (kDefer && pend.valid) { FIN_FLUSH(pend, cur ^ 1u); pend.valid = false; }
+    // ---- big sub-bins (duplicates or adversarial input): cooperative rank sort; too many of them → recount
     {
       uint32_t nh = S.n_hard;
       if (nh > (uint32_t)kMaxHard) { if (tid == 0) atomicOr(flags, kFlagOverflow); nh = 0; }
       for (uint32_t h = 0; h < nh; h++) {
         const uint32_t b = S.hard[h];
         const uint32_t s = bin_start(S.bins, b), m = bin_end(S.bins, b) - s;
-        const L2T first = S.keys[s];
+        const L2T first = keys[s];
         int differ = 0;
-        for (uint32_t i = tid; i < m; i += kFinThreads) differ |= !key_eq(S.keys[s + i], first);
+        for (uint32_t i = tid; i < m; i += kFinThreads) differ |= !key_eq(keys[s + i], first);
         if (__syncthreads_or(differ)) {
           for (uint32_t i = tid; i < m; i += kFinThreads) {
-            const L2T v = S.keys[s + i];
+            const L2T v = keys[s + i];
             uint32_t r = 0;
             for (uint32_t q = 0; q < m; q++) {
-              L2T o = S.keys[s + q];
+              L2T o = keys[s + q];
               r += key_lt(o, v) || (key_eq(o, v) && q < i);
             }
             S.hp[i] = (uint16_t)r;
@@ -615,13 +723,13 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
 #pragma unroll
           for (int j = 0; j < kFinishKPT; j++) {
             uint32_t i = j * kFinThreads + tid;
-            if (i < m) x[j] = S.keys[s + i];
+            if (i < m) x[j] = keys[s + i];
           }
           __syncthreads();
 #pragma unroll
           for (int j = 0; j < kFinishKPT; j++) {
             uint32_t i = j * kFinThreads + tid;
-            if (i < m) S.keys[s + S.hp[i]] = x[j];
+            if (i < m) keys[s + S.hp[i]] = x[j];
           }
           __syncthreads();
         }
@@ -636,8 +744,8 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
       uint32_t p = j * kFinThreads + tid;
       bool h = false;
       if ((uint32_t)j < rows && p < n) {
-        x[j] = S.keys[p];
-        h = (p == 0) || !key_eq(S.keys[p - 1], x[j]);
+        x[j] = keys[p];
+        h = (p == 0) || !key_eq(keys[p - 1], x[j]);
       }
       uint32_t bal = (uint32_t)j < rows ? __ballot_sync(0xffffffffu, h) : 0u;
       if (h) heads |= 1u << j;
@@ -652,11 +760,11 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
     }
     __syncthreads();
     FIN_MARK(7);
-    // every thread holds its keys in registers: S.keys can now take the compacted rows.
+    // every thread holds its keys in registers: the key buffer can now take the compacted rows.
     if (warp == 0) {
       long long lb0 = prof ? clock64() : 0;
       if (!early && lane == 0) lookback_publish(status, f, d);
-      if (early && lane == 0 && d != n - S.n_dups) atomicOr(flags, kFlagSpin); // the early count must be the real one
+      if (early && lane == 0 && d != n - n_dups) atomicOr(flags, kFlagSpin); // the early count must be the real one
       unsigned long long prefix = lookback_resolve(status, f, d, flags);
       if (prof && tid == 0) atomicAdd(&prof[10], (unsigned long long)(clock64() - lb0));
       if (lane == 0) {
@@ -671,7 +779,7 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
       const uint32_t bal = __ballot_sync(0xffffffffu, h); // same vote as in the head pass
       if (h) {
         uint32_t u = S.rowcnt[j * kFinWarps + warp] + __popc(bal & ((1u << lane) - 1u));
-        S.keys[u] = x[j];
+        keys[u] = x[j];
         S.hp[u] = (uint16_t)(j * kFinThreads + tid);
       }
     }
@@ -679,13 +787,15 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
     FIN_MARK(8);
     const unsigned long long G = S.goff;
     for (uint32_t i = tid; i < d; i += kFinThreads) {
-      emit_key(out_lo, out_hi, G + i, D, S.keys[i]);
+      emit_key(out_lo, out_hi, G + i, D, keys[i]);
       uint32_t nxt = (i + 1 < d) ? S.hp[i + 1] : n;
       out_cnt[G + i] = nxt - S.hp[i];
     }
     __syncthreads();
     FIN_MARK(9);
   }
+  if (kDefer && pend.valid) FIN_FLUSH(pend, cur ^ 1u);
+#undef FIN_FLUSH
 #undef FIN_MARK
 }
 
