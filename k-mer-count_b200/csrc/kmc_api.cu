@@ -63,6 +63,18 @@ struct KernelStat {
 
 } // namespace
 
+// kmc_dist_plan's result (see there)
+struct DistPlan {
+  bool valid = false, scattered = false;
+  uint32_t world = 0, rank = 0, b1 = 0, n_all = 0; // n_all = 2^b1 level-1 buckets over the whole key space
+  std::vector<uint32_t> own_lo;                    // [world+1] first level-1 bucket of every owner
+  std::vector<uint64_t> s_off, s_cap;              // [n_all] sender view: key offset of MY sub-region in its owner's array, capacity
+  std::vector<uint8_t> l1e;                        // [n_all]
+  std::vector<uint64_t> fine_hist;                 // [ncoarse] global upper estimate (fine-bucket capacities)
+  std::vector<uint64_t> x_cap;                     // [my level-1 buckets x world] owner view: capacity of every sender's sub-region
+  uint64_t l1_keys = 0;                            // keys my level-1 array must hold (sum of x_cap)
+};
+
 struct kmc_ctx {
   kmc_config cfg{};
   int device = 0;
@@ -115,6 +127,10 @@ struct kmc_ctx {
   uint32_t range_lo = 0, range_n = 0;
   std::vector<uint64_t> part_hist; // raw (sampled) counts per coarse bin
   uint32_t part_hist_step = 0;     // sampling step of part_hist; 0 = not computed yet
+
+  // multi-GPU range partition (kmc_dist_*): plan shared by all ranks, this rank's views of it
+  DistPlan dist;
+  DevBuf dist_tables;
 
   // results
   bool finished = false;
@@ -913,6 +929,60 @@ int coarse_hist_gapped(kmc_ctx *c, std::vector<uint64_t> &hist) {
   return KMC_OK;
 }
 
+// Shape of the two-level partition for an (upper-estimate) coarse histogram: how finely every coarse bin is split
+// (2^e[ci] fine buckets of <= target keys), the level-1 width b1, and per level-1 bucket the number of key bits
+// (below the b1 prefix) that select its fine bucket.  Level 1 = the top b1 key bits.  Only the level-1 buckets that
+// meet the coarse range [c_lo, c_hi) exist, numbered from l1_base (all 2^b1 of them unless this is a partial count —
+// which may therefore use more level-1 bits: what is bounded is the number of buckets the scatter kernel ranks in
+// shared memory, kMaxL1).  false: the input does not suit the partitioned path.
+struct PlanShape {
+  uint32_t b1 = 0, l1_base = 0, n_l1 = 0;
+  std::vector<uint32_t> e;   // [ncoarse]
+  std::vector<uint8_t> l1e;  // [n_l1]
+  uint64_t n_fine = 0;
+};
+bool plan_shape(const std::vector<uint64_t> &hist, uint32_t kb, uint32_t c_lo, uint32_t c_hi, bool ranged, int target,
+                PlanShape &P, uint32_t b1_min = 0) {
+  const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb), ncoarse = 1u << cb;
+  P.e.assign(ncoarse, 0);
+  for (uint32_t ci = 0; ci < ncoarse; ci++) {
+    uint32_t ee = 0;
+    while (((hist[ci] + ((1ull << ee) - 1)) >> ee) > (uint64_t)target) ee++;
+    if (ee > kb - cb) return false; // cannot split far enough: too many keys share a prefix (duplicates)
+    P.e[ci] = ee;
+  }
+  uint32_t b1_lo = cb > 6 ? cb - 6 : 0, b1_hi = ranged ? cb : std::min<uint32_t>(cb, 10);
+  uint64_t nf_guess = 0;
+  for (uint32_t ci = c_lo; ci < c_hi; ci++) nf_guess += 1ull << P.e[ci];
+  uint32_t b1 = (uint32_t)std::lround(std::log2(std::sqrt((double)nf_guess) * (double)ncoarse / (double)(c_hi - c_lo)));
+  b1 = std::max(std::max(b1_lo, std::min(b1_min, b1_hi)), std::min(b1, b1_hi));
+  auto l1_span = [&](uint32_t bits, uint32_t *base) { // level-1 buckets met by the coarse range at `bits` level-1 bits
+    *base = c_lo >> (cb - bits);
+    return ((c_hi - 1) >> (cb - bits)) + 1 - *base;
+  };
+  uint32_t l1_base = 0, n_l1 = 0;
+  while (b1 > b1_lo && l1_span(b1, &l1_base) > (uint32_t)kMaxL1) b1--;
+  for (;; b1++) {
+    if (b1 > b1_hi) return false;
+    n_l1 = l1_span(b1, &l1_base);
+    if (n_l1 > (uint32_t)kMaxL1) return false; // too many keys for two levels of this size
+    P.l1e.assign(n_l1, 0);
+    uint32_t mx = 0;
+    for (uint32_t rb = 0; rb < n_l1; rb++) {
+      const uint32_t b = l1_base + rb;
+      uint32_t em = 0;
+      for (uint32_t ci = b << (cb - b1); ci < ((b + 1) << (cb - b1)); ci++) em = std::max(em, P.e[ci]);
+      P.l1e[rb] = (uint8_t)(cb - b1 + em);
+      mx = std::max<uint32_t>(mx, P.l1e[rb]);
+    }
+    if ((1ull << mx) <= (uint64_t)kMaxFinePerL1) break;
+  }
+  P.b1 = b1; P.l1_base = l1_base; P.n_l1 = n_l1;
+  P.n_fine = 0;
+  for (uint32_t b = 0; b < n_l1; b++) P.n_fine += 1ull << P.l1e[b];
+  return P.n_fine <= (1ull << 28);
+}
+
 // ---- partitioned fast path (kmc_fast.cuh) --------------------------------------------------------------------
 // *used = false: the input does not suit it (tiny, duplicate-heavy, or a bucket overflowed); nothing is left
 // behind and the caller counts with the baseline path.
@@ -956,46 +1026,11 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   HOST_MARK("hist_read");
 
   // ---- plan
-  std::vector<uint32_t> e(ncoarse);
-  for (uint32_t ci = 0; ci < ncoarse; ci++) {
-    uint32_t ee = 0;
-    while (((hist[ci] + ((1ull << ee) - 1)) >> ee) > (uint64_t)kTarget) ee++;
-    if (ee > kb - cb) return KMC_OK; // cannot split far enough: too many keys share a prefix (duplicates)
-    e[ci] = ee;
-  }
-  // Level 1 = the top b1 key bits.  Only the level-1 buckets that meet the key range exist, numbered from l1_base
-  // (all 2^b1 of them unless this is a partial count — which may therefore use more level-1 bits: what is bounded
-  // is the number of buckets the scatter kernel ranks in shared memory, kMaxL1).
-  uint32_t b1_lo = cb > 6 ? cb - 6 : 0, b1_hi = ranged ? cb : std::min<uint32_t>(cb, 10);
-  uint64_t nf_guess = 0;
-  for (uint32_t ci = c_lo; ci < c_hi; ci++) nf_guess += 1ull << e[ci];
-  uint32_t b1 = (uint32_t)std::lround(std::log2(std::sqrt((double)nf_guess) * (double)ncoarse / (double)(c_hi - c_lo)));
-  b1 = std::max(b1_lo, std::min(b1, b1_hi));
-  auto l1_span = [&](uint32_t bits, uint32_t *base) { // level-1 buckets met by the coarse range at `bits` level-1 bits
-    *base = c_lo >> (cb - bits);
-    return ((c_hi - 1) >> (cb - bits)) + 1 - *base;
-  };
-  std::vector<uint8_t> l1e;
-  uint32_t l1_base = 0, n_l1 = 0;
-  while (b1 > b1_lo && l1_span(b1, &l1_base) > (uint32_t)kMaxL1) b1--;
-  for (;; b1++) {
-    if (b1 > b1_hi) return KMC_OK;
-    n_l1 = l1_span(b1, &l1_base);
-    if (n_l1 > (uint32_t)kMaxL1) return KMC_OK; // too many keys for two levels of this size
-    l1e.assign(n_l1, 0);
-    uint32_t mx = 0;
-    for (uint32_t rb = 0; rb < n_l1; rb++) {
-      const uint32_t b = l1_base + rb;
-      uint32_t em = 0;
-      for (uint32_t ci = b << (cb - b1); ci < ((b + 1) << (cb - b1)); ci++) em = std::max(em, e[ci]);
-      l1e[rb] = (uint8_t)(cb - b1 + em);
-      mx = std::max<uint32_t>(mx, l1e[rb]);
-    }
-    if ((1ull << mx) <= (uint64_t)kMaxFinePerL1) break;
-  }
-  uint64_t n_fine = 0;
-  for (uint32_t b = 0; b < n_l1; b++) n_fine += 1ull << l1e[b];
-  if (n_fine > (1ull << 28)) return KMC_OK;
+  PlanShape shape;
+  if (!plan_shape(hist, kb, c_lo, c_hi, ranged, kTarget, shape)) return KMC_OK;
+  const uint32_t b1 = shape.b1, l1_base = shape.l1_base, n_l1 = shape.n_l1;
+  const std::vector<uint8_t> &l1e = shape.l1e;
+  const uint64_t n_fine = shape.n_fine;
   // Host tables (a few tens of KB): per level-1 bucket l1_start | l1_cap | l1_tile0 | l1_fine0 | l1_e, and per coarse
   // bin the first fine bucket, its level-2 start and the capacity of its fine buckets.  The per-fine-bucket
   // descriptors (n_fine x 32 B, megabytes) are expanded from these on the device (plan_expand_kernel): filling and
@@ -1187,8 +1222,326 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   return KMC_OK;
 }
 
+// ---- multi-GPU: range partition with the level-1 scatter done by the SENDERS --------------------------
+// Every rank holds a shard of the reads.  Instead of routing keys to owners by hash and letting every owner run the
+// level-1 scatter over what it received (an extra pass over all keys), the ranks agree on ONE plan for the whole key
+// space — from the all-gathered coarse histograms, so every rank computes the same plan by itself — whose level-1
+// buckets are dealt to the owners in consecutive, equally populated runs; each sender's level-1 scatter then stores
+// every key straight into its bucket of its owner's level-1 array over NVLink.  An owner's bucket is made of one
+// sub-region per sender (sized from that sender's histogram), so senders need no shared cursors: each counts its own
+// fills and leaves them in the owner's cursor table at the end.  The owner runs fast_part2 + fast_finish only, and
+// its table is the key range it owns: the ranks' tables, in rank order, are the globally sorted table.
+//
+// Receive buffer of an owner (kmc_recv_buffer, mapped by the peers with CUDA IPC):
+//   [ cursor table: (bucket, sender) -> keys stored, u64, kDistHeader bytes ][ level-1 array ]
+constexpr size_t kDistHeader = (size_t)kMaxL1 * 16 * 8;
+constexpr uint32_t kDistMaxWorld = 16;
+
+__global__ void dist_publish_kernel(const unsigned long long *__restrict__ cursor, const uint64_t *__restrict__ cap,
+                                    const uint32_t *__restrict__ own_lo, const uint64_t *__restrict__ peer_header,
+                                    uint32_t n_all, uint32_t world, uint32_t rank) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_all) return;
+  uint32_t o = 0;
+  while (o + 1 < world && own_lo[o + 1] <= b) o++;
+  unsigned long long v = cursor[b];
+  if (v > cap[b]) v = cap[b]; // overflow was flagged by the scatter; the job is recounted
+  unsigned long long *dst = reinterpret_cast<unsigned long long *>(peer_header[o]) + (size_t)(b - own_lo[o]) * world + rank;
+  *dst = v;
+}
+
+template <typename KeyT>
+int dist_hist_impl(kmc_ctx *c, uint64_t *hist_out, uint32_t *low_cardinality) {
+  const uint32_t ncoarse = 1u << coarse_bits(c);
+  TRY(zero_scalars(c));
+  bool low = c->cfg.strategy == KMC_STRATEGY_HASH;
+  if (c->cfg.strategy == KMC_STRATEGY_AUTO && sizeof(KeyT) == 8) TRY(hash_probe(c, &low));
+  KeyArrays ka;
+  std::vector<uint64_t> hist;
+  uint32_t step = 1;
+  TRY(coarse_hist<KeyT>(c, ka, hist, &step));
+  for (uint32_t i = 0; i < 4096; i++) {
+    double est = i < ncoarse ? (double)hist[i] * step : 0.0;
+    if (step > 1 && i < ncoarse) est += 5.0 * std::sqrt(est * step) + step; // upper estimate, as in finish_fast
+    hist_out[i] = (uint64_t)est;
+  }
+  if (low_cardinality) *low_cardinality = low ? 1u : 0u;
+  return KMC_OK;
+}
+
+template <typename KeyT>
+int dist_plan_impl(kmc_ctx *c, uint32_t world, uint32_t rank, const uint64_t *all_hist, uint64_t *need_bytes) {
+  constexpr bool kWide = sizeof(KeyT) == 16;
+  const int kTarget = kWide ? 3200 : kFineTarget;
+  const uint32_t kb = c->key_bits, cb = coarse_bits(c), ncoarse = 1u << cb;
+  DistPlan &D = c->dist;
+  D.valid = false; D.scattered = false;
+  for (uint32_t o = 0; o < world; o++) need_bytes[o] = 0;
+  std::vector<uint64_t> G(ncoarse, 0);
+  uint64_t n_est = 0;
+  for (uint32_t s = 0; s < world; s++)
+    for (uint32_t ci = 0; ci < ncoarse; ci++) { G[ci] += all_hist[(size_t)s * 4096 + ci]; n_est += all_hist[(size_t)s * 4096 + ci]; }
+  if (n_est < ((uint64_t)world << 20)) return KMC_OK; // small job: not worth a plan
+  PlanShape shape;
+  // at least 64 level-1 buckets per owner, so that owners can be balanced to a few percent
+  uint32_t b1_min = 6;
+  while ((1u << (b1_min - 6)) < world) b1_min++;
+  if (!plan_shape(G, kb, 0, ncoarse, false, kTarget, shape, b1_min)) return KMC_OK;
+  const uint32_t b1 = shape.b1, n_all = 1u << b1, cshift = cb - b1;
+  if (n_all < world) return KMC_OK;
+  // owners: consecutive level-1 buckets, about equal population
+  std::vector<uint64_t> pop(n_all, 0);
+  unsigned __int128 total = 0;
+  for (uint32_t b = 0; b < n_all; b++) {
+    for (uint32_t ci = b << cshift; ci < ((b + 1) << cshift); ci++) pop[b] += G[ci];
+    total += pop[b];
+  }
+  D.own_lo.assign(world + 1, 0);
+  {
+    unsigned __int128 before = 0;
+    uint32_t b = 0;
+    for (uint32_t o = 1; o < world; o++) {
+      const unsigned __int128 want = (total * o + world - 1) / world;
+      while (b < n_all && before < want) before += pop[b++];
+      D.own_lo[o] = b;
+    }
+    D.own_lo[world] = n_all;
+  }
+  // sub-region (bucket, sender): capacity from that sender's own histogram; an owner's array is the concatenation
+  D.s_off.assign(n_all, 0); D.s_cap.assign(n_all, 0);
+  D.x_cap.clear();
+  const uint64_t slack = 2 * kMaxTile;
+  for (uint32_t o = 0; o < world; o++) {
+    uint64_t off = 0;
+    for (uint32_t b = D.own_lo[o]; b < D.own_lo[o + 1]; b++)
+      for (uint32_t s = 0; s < world; s++) {
+        uint64_t nb = 0;
+        for (uint32_t ci = b << cshift; ci < ((b + 1) << cshift); ci++) nb += all_hist[(size_t)s * 4096 + ci];
+        const uint64_t cap1 = ((uint64_t)((double)nb * 1.03) + 4096 + 15) & ~15ull;
+        if (s == rank) { D.s_off[b] = off; D.s_cap[b] = cap1; }
+        if (o == rank) D.x_cap.push_back(cap1);
+        off += cap1;
+      }
+    need_bytes[o] = kDistHeader + (off + slack) * sizeof(KeyT);
+    if (o == rank) D.l1_keys = off;
+  }
+  D.world = world; D.rank = rank; D.b1 = b1; D.n_all = n_all;
+  D.l1e = shape.l1e;
+  D.fine_hist = G;
+  D.valid = true;
+  return KMC_OK;
+}
+
+template <typename KeyT>
+int dist_scatter_impl(kmc_ctx *c, void *const *peer_buf, uint32_t *overflow) {
+  DistPlan &D = c->dist;
+  const uint32_t n_all = D.n_all, world = D.world, kb = c->key_bits;
+  // sender tables: l1_start (absolute address / key size) | l1_cap | own_lo | peer header pointers
+  auto al16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+  const size_t o_s = 0, o_c = o_s + al16((size_t)(n_all + 1) * 8), o_own = o_c + al16((size_t)n_all * 8),
+               o_ph = o_own + al16((size_t)(world + 1) * 4), tab_bytes = o_ph + al16((size_t)world * 8);
+  c->fast_host.assign(tab_bytes, 0);
+  uint64_t *l1s = (uint64_t *)(c->fast_host.data() + o_s), *l1c = (uint64_t *)(c->fast_host.data() + o_c);
+  uint32_t *own = (uint32_t *)(c->fast_host.data() + o_own);
+  uint64_t *ph = (uint64_t *)(c->fast_host.data() + o_ph);
+  for (uint32_t o = 0; o < world; o++) {
+    ph[o] = (uint64_t)(uintptr_t)peer_buf[o];
+    const uint64_t base = ((uint64_t)(uintptr_t)peer_buf[o] + kDistHeader) / sizeof(KeyT);
+    for (uint32_t b = D.own_lo[o]; b < D.own_lo[o + 1]; b++) { l1s[b] = base + D.s_off[b]; l1c[b] = D.s_cap[b]; }
+  }
+  for (uint32_t o = 0; o <= world; o++) own[o] = D.own_lo[o];
+  TRY(ensure(c, c->dist_tables, tab_bytes));
+  TRY(ensure(c, c->route_keys, (size_t)2 * kMaxTile * sizeof(KeyT) + 256)); // trash area for runs that do not fit
+  const size_t off_l1cur = 4096 * 8 + 16;
+  TRY(ensure(c, c->fast_state, off_l1cur + kMaxL1 * 8 + 64));
+  CK(cudaMemsetAsync((unsigned char *)c->fast_state.p + off_l1cur, 0, kMaxL1 * 8, c->stream));
+  TRY(h2d_small(c, c->dist_tables.p, c->fast_host.data(), tab_bytes));
+  unsigned char *tb = (unsigned char *)c->dist_tables.p;
+  FastPlan pl{};
+  pl.kb = kb; pl.b1 = D.b1; pl.n_l1 = n_all; pl.n_fine = 0; pl.l1_base = 0;
+  pl.l1_trash = ((uint64_t)(uintptr_t)c->route_keys.p + sizeof(KeyT) - 1) / sizeof(KeyT);
+  pl.l1_start = (const uint64_t *)(tb + o_s);
+  pl.l1_cap = (const uint64_t *)(tb + o_c);
+  pl.l1_cursor = (unsigned long long *)((unsigned char *)c->fast_state.p + off_l1cur);
+  PHASE_BEGIN("route");
+  {
+    size_t smem = PartSmem<KeyT>::bytes(part1_stage<KeyT>(), n_all);
+    auto fast_scatter_to_owners = fast_part1_kernel<KeyT, true, PrefixBucket>;
+    CK(cudaFuncSetAttribute(fast_scatter_to_owners, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const PrefixBucket bucket{D.b1, kb - D.b1, 0, 0, 0, 0};
+    for (size_t i = 0; i < c->n_segs; i++) {
+      Segment &s = c->segs[i];
+      if (!s.n_bases) continue;
+      TRY(seg_wait(c, s));
+      ExtractParams P = seg_params(c, s);
+      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
+      LAUNCH(fast_scatter_to_owners, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)nullptr, d_err(c));
+    }
+    LAUNCH(dist_publish_kernel, grid_for(n_all, 256), 256, 0, pl.l1_cursor, pl.l1_cap, (const uint32_t *)(tb + o_own),
+           (const uint64_t *)(tb + o_ph), n_all, world, D.rank);
+  }
+  PHASE_END();
+  uint32_t err = 0;
+  TRY(read_scalars(c, nullptr, &err));
+  if (err & kFlagOverflow) TRY(zero_scalars(c));
+  *overflow = (err & kFlagOverflow) ? 1u : 0u;
+  D.scattered = !*overflow;
+  return KMC_OK;
+}
+
+// the owner's half: fast_part2 + fast_finish over what the senders left in the receive buffer
+template <typename KeyT>
+int finish_dist(kmc_ctx *c) {
+  constexpr bool kWide = sizeof(KeyT) == 16;
+  constexpr int kCap = kWide ? 4096 : kFineCap;
+  DistPlan &D = c->dist;
+  const uint32_t kb = c->key_bits, cb = coarse_bits(c), b1 = D.b1, cshift = cb - b1, world = D.world;
+  const uint32_t my_lo = D.own_lo[D.rank], my_n = D.own_lo[D.rank + 1] - my_lo, n_x = my_n * world, n_cb = my_n << cshift;
+  if (!c->recv_keys.p || c->recv_keys.cap < kDistHeader + (D.l1_keys + 2 * kMaxTile) * sizeof(KeyT))
+    return fail(c, KMC_E_ARG, "kmc_finish: the receive buffer is smaller than kmc_dist_plan asked for");
+  auto al16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+  // owner tables: per (bucket, sender) x: start | cap | tile0 | fine0 | e;  per bucket: fine0 | e;  per coarse bin: start | fine0 | cap
+  const size_t o_xs = 0, o_xc = o_xs + al16((size_t)(n_x + 1) * 8), o_xt = o_xc + al16((size_t)n_x * 8),
+               o_xf = o_xt + al16((size_t)(n_x + 1) * 4), o_xe = o_xf + al16((size_t)(n_x + 1) * 4), o_rf = o_xe + al16(n_x),
+               o_re = o_rf + al16((size_t)(my_n + 1) * 4), o_cs = o_re + al16(my_n), o_cf = o_cs + al16((size_t)n_cb * 8),
+               o_cc = o_cf + al16((size_t)n_cb * 4), tab_bytes = o_cc + al16((size_t)n_cb * 2);
+  c->fast_host.assign(tab_bytes, 0);
+  unsigned char *hb = c->fast_host.data();
+  uint64_t *xs = (uint64_t *)(hb + o_xs), *xc = (uint64_t *)(hb + o_xc);
+  uint32_t *xt = (uint32_t *)(hb + o_xt), *xf = (uint32_t *)(hb + o_xf), *rf = (uint32_t *)(hb + o_rf);
+  uint8_t *xe = hb + o_xe, *re = hb + o_re;
+  uint64_t *cstart = (uint64_t *)(hb + o_cs);
+  uint32_t *cfine0 = (uint32_t *)(hb + o_cf);
+  uint16_t *ccap = (uint16_t *)(hb + o_cc);
+  uint64_t l1_keys = 0, l2_keys = 0, tiles2 = 0;
+  uint32_t fb = 0;
+  bool key32 = !kWide;
+  for (uint32_t rb = 0; rb < my_n; rb++) if (kb - b1 - D.l1e[my_lo + rb] > 32) key32 = false;
+  for (uint32_t rb = 0; rb < my_n; rb++) {
+    const uint32_t b = my_lo + rb, e = D.l1e[b], sub_bits = e - cshift;
+    rf[rb] = fb; re[rb] = (uint8_t)e;
+    for (uint32_t s = 0; s < world; s++) {
+      const uint32_t x = rb * world + s;
+      const uint64_t cap1 = D.x_cap[x];
+      xs[x] = l1_keys; xc[x] = cap1; xt[x] = (uint32_t)tiles2; xf[x] = fb; xe[x] = (uint8_t)e;
+      l1_keys += cap1;
+      tiles2 += (cap1 + p2_tile<KeyT>() - 1) / p2_tile<KeyT>();
+    }
+    for (uint32_t ci = b << cshift; ci < ((b + 1) << cshift); ci++) {
+      double avg = (double)D.fine_hist[ci] / (double)(1ull << sub_bits);
+      uint32_t cp = (uint32_t)(avg * 1.10 + 6.0 * std::sqrt(avg) + 64.0);
+      cp = std::min<uint32_t>((cp + 15) & ~15u, kCap);
+      const uint32_t ci_rel = ci - (my_lo << cshift);
+      cstart[ci_rel] = l2_keys; cfine0[ci_rel] = fb; ccap[ci_rel] = (uint16_t)cp;
+      l2_keys += (uint64_t)cp << sub_bits;
+      fb += 1u << sub_bits;
+    }
+  }
+  xs[n_x] = l1_keys; xt[n_x] = (uint32_t)tiles2; xf[n_x] = fb; rf[my_n] = fb;
+  const uint64_t n_fine = fb;
+  if (tiles2 > 0x7FFFFFFFull || n_fine == 0) return fail(c, KMC_E_CAPACITY, "kmc_finish: range-partition plan too large");
+  const uint64_t slack = 2 * kMaxTile;
+  const size_t off_ticket = 4096 * 8, off_dtotal = off_ticket + 8, off_l1cur = off_dtotal + 8, off_fine = off_l1cur + kMaxL1 * 8;
+  const size_t off_status = (off_fine + n_fine * 4 + 15) & ~size_t(15);
+  TRY(ensure(c, c->fast_tables, tab_bytes));
+  TRY(ensure(c, c->fast_fdesc, n_fine * sizeof(FineDesc)));
+  TRY(ensure(c, c->fast_l2, (l2_keys + 2 * slack) * sizeof(KeyT)));
+  TRY(ensure(c, c->t_lo, l1_keys * 8 + 64));
+  if (kWide) TRY(ensure(c, c->t_hi, l1_keys * 8 + 64));
+  TRY(ensure(c, c->t_cnt, l1_keys * 4 + 64));
+  TRY(ensure(c, c->fast_state, off_status + n_fine * 8 + 64));
+  CK(cudaMemsetAsync(c->fast_state.p, 0, off_status + n_fine * 8, c->stream));
+  TRY(h2d_small(c, c->fast_tables.p, c->fast_host.data(), tab_bytes));
+  unsigned char *st = (unsigned char *)c->fast_state.p, *tb = (unsigned char *)c->fast_tables.p;
+  unsigned long long *header = (unsigned long long *)c->recv_keys.p;
+  const KeyT *l1 = (const KeyT *)((unsigned char *)c->recv_keys.p + kDistHeader);
+  FastPlan pl{};
+  pl.kb = kb; pl.b1 = b1; pl.n_l1 = n_x; pl.n_fine = (uint32_t)n_fine; pl.l1_base = my_lo;
+  pl.l1_trash = l1_keys; pl.l2_trash = l2_keys + slack;
+  pl.fdesc = (const FineDesc *)c->fast_fdesc.p;
+  pl.l1_start = (const uint64_t *)(tb + o_xs); pl.l1_cap = (const uint64_t *)(tb + o_xc);
+  pl.l1_tile0 = (const uint32_t *)(tb + o_xt); pl.l1_fine0 = (const uint32_t *)(tb + o_xf); pl.l1_e = tb + o_xe;
+  pl.l1_cursor = header; pl.fine_cursor = (uint32_t *)(st + off_fine);
+  unsigned int *ticket = (unsigned int *)(st + off_ticket);
+  unsigned long long *d_total = (unsigned long long *)(st + off_dtotal);
+  unsigned long long *status = (unsigned long long *)(st + off_status);
+  LAUNCH(plan_expand_kernel, n_cb, 128, 0, (FineDesc *)c->fast_fdesc.p, (const uint64_t *)(tb + o_cs), (const uint32_t *)(tb + o_cf),
+         (const uint16_t *)(tb + o_cc), (const uint32_t *)(tb + o_rf), (const uint8_t *)(tb + o_re), cshift, my_lo, kb, b1, (uint32_t)kWide);
+  c->launches--;
+  PHASE_BEGIN("fast_part2");
+  {
+    size_t smem = PartSmem<KeyT>::bytes(p2_tile<KeyT>(), kMaxFinePerL1);
+    if constexpr (kWide) {
+      auto fast_part2 = fast_part2_kernel<U128, U128>;
+      CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const U128 *)l1, (U128 *)c->fast_l2.p, d_err(c));
+    } else if (key32) {
+      auto fast_part2 = fast_part2_kernel<uint64_t, uint32_t>;
+      CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const uint64_t *)l1, (uint32_t *)c->fast_l2.p, d_err(c));
+    } else {
+      auto fast_part2 = fast_part2_kernel<uint64_t, uint64_t>;
+      CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const uint64_t *)l1, (uint64_t *)c->fast_l2.p, d_err(c));
+    }
+  }
+  PHASE_END();
+  PHASE_BEGIN("fast_finish");
+  {
+    unsigned long long *prof = nullptr;
+    if constexpr (kWide) {
+      size_t fsmem = sizeof(FinishSmem<U128>);
+      auto fast_finish = fast_finish_kernel<U128>;
+      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2), kFinThreads, fsmem, pl, (const U128 *)c->fast_l2.p,
+             (uint64_t *)c->t_lo.p, (uint64_t *)c->t_hi.p, (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
+    } else if (key32) {
+      size_t fsmem = sizeof(FinishSmem<uint32_t>);
+      auto fast_finish = fast_finish_kernel<uint32_t>;
+      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB32), kFinThreads, fsmem, pl,
+             (const uint32_t *)c->fast_l2.p, (uint64_t *)c->t_lo.p, (uint64_t *)nullptr, (uint32_t *)c->t_cnt.p, status, ticket, d_err(c),
+             d_total, prof);
+    } else {
+      size_t fsmem = sizeof(FinishSmem<uint64_t>);
+      auto fast_finish = fast_finish_kernel<uint64_t>;
+      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2), kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p,
+             (uint64_t *)c->t_lo.p, (uint64_t *)nullptr, (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
+    }
+  }
+  PHASE_END();
+  uint64_t d = 0;
+  uint32_t err = 0;
+  TRY(d2h_small(c, &d, d_total, 8));
+  TRY(read_scalars(c, nullptr, &err));
+  if (err & kFlagSpin) return fail(c, KMC_E_CUDA, "fast_finish: look-back did not make progress");
+  if (err & kFlagOverflow) {
+    c->fast_fallbacks++;
+    TRY(zero_scalars(c));
+    return fail(c, KMC_E_CAPACITY, "range-partitioned count: a fine bucket overflowed (recount through kmc_route_to_peers)");
+  }
+  // keys I own = what the senders' cursor table says
+  uint64_t N = 0;
+  {
+    std::vector<unsigned long long> cur(n_x);
+    for (size_t o = 0; o < n_x; o += 4096) { // mailbox-sized pieces
+      size_t m = std::min<size_t>(4096, n_x - o);
+      TRY(d2h_small(c, cur.data() + o, header + o, m * 8));
+    }
+    for (unsigned long long v : cur) N += v;
+  }
+  c->n_total = N; c->n_distinct = d;
+  c->strategy_used = KMC_STRATEGY_SORT;
+  D.scattered = false;
+  return KMC_OK;
+}
+
+
 template <typename KeyT>
 int finish_impl(kmc_ctx *c) {
+  if (c->dist.valid && c->dist.scattered) return finish_dist<KeyT>(c); // keys already sit in my level-1 array
   const uint32_t strat = c->cfg.strategy;
   if (strat != KMC_STRATEGY_SORT_BASELINE) {
     bool used = false;
@@ -1384,6 +1737,7 @@ int kmc_reset(kmc_ctx *c) {
   c->ingested.clear();
   c->finished = false; c->n_total = c->n_distinct = 0;
   c->range_on = false; c->part_hist_step = 0;
+  c->dist.valid = false; c->dist.scattered = false;
   c->phases.clear(); c->klaunches.clear(); c->events_used = 0;
   c->launches_total += c->launches; c->launches = 0; c->h2d_bytes = 0;
   c->staged = false;
@@ -1746,6 +2100,30 @@ int kmc_route_to_peers(kmc_ctx *c, uint32_t n_parts, void *const *d_part_ptr, ui
   if (c->wide) TRY(route_fast<U128>(c, n_parts, nullptr, part_count, &done, d_part_ptr, part_cap_keys));
   else TRY(route_fast<uint64_t>(c, n_parts, nullptr, part_count, &done, d_part_ptr, part_cap_keys));
   return done ? KMC_OK : fail(c, KMC_E_ARG, "kmc_route_to_peers: nothing routed");
+}
+
+int kmc_dist_hist(kmc_ctx *c, uint64_t hist[4096], uint32_t *low_cardinality) {
+  if (!c || !hist) return KMC_E_ARG;
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_dist_hist after kmc_finish");
+  if (c->cfg.mode != KMC_MODE_CONTIGUOUS || !c->ingested.empty())
+    return fail(c, KMC_E_ARG, "kmc_dist_hist: contiguous mode with submitted reads only");
+  CK(cudaSetDevice(c->device));
+  return c->wide ? dist_hist_impl<U128>(c, hist, low_cardinality) : dist_hist_impl<uint64_t>(c, hist, low_cardinality);
+}
+
+int kmc_dist_plan(kmc_ctx *c, uint32_t world, uint32_t rank, const uint64_t *all_hist, uint64_t *need_bytes) {
+  if (!c || !all_hist || !need_bytes) return KMC_E_ARG;
+  if (world < 1 || world > kDistMaxWorld || rank >= world) return fail(c, KMC_E_ARG, "kmc_dist_plan: 1 <= world <= %u, rank < world", kDistMaxWorld);
+  if (c->cfg.mode != KMC_MODE_CONTIGUOUS) return fail(c, KMC_E_ARG, "kmc_dist_plan: contiguous mode only");
+  return c->wide ? dist_plan_impl<U128>(c, world, rank, all_hist, need_bytes) : dist_plan_impl<uint64_t>(c, world, rank, all_hist, need_bytes);
+}
+
+int kmc_dist_scatter(kmc_ctx *c, void *const *d_peer_buf, uint32_t *overflow) {
+  if (!c || !d_peer_buf || !overflow) return KMC_E_ARG;
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_dist_scatter after kmc_finish");
+  if (!c->dist.valid) return fail(c, KMC_E_ARG, "kmc_dist_scatter: no plan (kmc_dist_plan returned need_bytes = 0?)");
+  CK(cudaSetDevice(c->device));
+  return c->wide ? dist_scatter_impl<U128>(c, d_peer_buf, overflow) : dist_scatter_impl<uint64_t>(c, d_peer_buf, overflow);
 }
 
 int kmc_recv_buffer(kmc_ctx *c, uint64_t n_keys, void **d_ptr) {

@@ -1,7 +1,12 @@
-"""Multi-GPU host logic: one process per GPU, reads sharded across ranks, keys routed to their owner
-GPU by hash prefix with one all-to-all.  The exchange is `torch.distributed`
-(NCCL over NVLink on the GPU box; gloo in the CPU tests of the routing arithmetic); everything
-either side of it is libkmc through its C ABI."""
+"""Multi-GPU host logic: one process per GPU, reads sharded across ranks, every key sent to the GPU that owns
+it.  Two partitions of the key space:
+  * range (default for the partitioned counting path): owners hold consecutive key ranges of equal population, chosen
+    from the all-gathered coarse histograms; the senders' scatter kernels store keys straight into their level-1
+    bucket inside the owner's buffer over NVLink, so the exchange IS the first pass of the count;
+  * hash (low-cardinality input, lr-gapped mode, fall-back): owner = hash prefix; keys are stored into per-source
+    regions of the owner's buffer (or exchanged with an NCCL all-to-all), and the owner counts them from scratch.
+`torch.distributed` carries only histograms, counts and the rank barrier (NCCL on the GPU box; gloo in the CPU tests of
+the routing arithmetic); everything either side of it is libkmc through its C ABI."""
 import os
 import sys
 import time
@@ -41,6 +46,7 @@ def kernel_bytes(name, n_keys, n_distinct, n_bases, key_bytes, key_bits):
         "fast_part1": n_bases + n_keys * W,
         "fast_part1_array": 2 * n_keys * W,
         "fast_route": n_bases + n_keys * W,
+        "fast_scatter_to_owners": n_bases + n_keys * W,
         "fast_part2": n_keys * W + n_keys * (4 if key_bits <= 50 else W),
         "fast_finish": n_keys * (4 if key_bits <= 50 else W) + n_distinct * (W + 4),
     }
@@ -87,12 +93,15 @@ class DistCounter:
         self.world, self.rank, self.dist, self.torch = world, rank, dist, torch
         self.key_bits = 2 * self.kc.key_bases
         self._keep = None
-        self._peer = None       # (cap_keys, my recv buffer ptr, [pointer of my region in every rank's recv buffer])
+        self._map = (0, 0, [])  # (bytes of my receive buffer, its pointer, [every rank's receive buffer as mapped here])
         self._opened = []
-        self._peer_bases = None
+        self._t = []
+        self.path = None
         self.n_bases = 0
         self.key_bytes = 8 if self.key_bits <= 64 else 16
         self.use_peer = world > 1 and kw.get("mode", 0) == 0 and os.environ.get("KMC_DIST_EXCHANGE", "peer") == "peer"
+        # KMC_DIST_PARTITION=hash keeps every job on the hash route (owner = hash prefix; owners re-scatter)
+        self.use_range = self.use_peer and strategy in (0, 2) and os.environ.get("KMC_DIST_PARTITION", "range") == "range"
 
     def set_stream(self, ptr):
         self.kc.set_stream(ptr)
@@ -110,50 +119,103 @@ class DistCounter:
         self.n_bases += len(bases)
         self.kc.submit_host(bases, rec_off)
 
-    def _setup_peers(self):
-        """Receive buffer of world regions, one per source rank; map every peer's buffer (CUDA IPC)."""
+    # -- receive buffers: one per rank, mapped by every peer with CUDA IPC; remapped only when one has to grow
+    def _map_buffers(self, my_bytes):
+        """Every rank calls this together (the decision to call it must be the same on all ranks)."""
         torch, dist = self.torch, self.dist
-        dev = torch.device("cuda", torch.cuda.current_device())
-        # one small all-reduce per job: agrees on the region size, and is the point after which nobody is still
-        # reading its receive buffer from the previous job (every rank has returned from its last kmc_finish)
-        nb = torch.tensor([self.n_bases], dtype=torch.int64, device=dev)
-        dist.all_reduce(nb, op=dist.ReduceOp.MAX)
-        cap = (int(int(nb) / self.world * 1.03) + 65536 + 15) // 16 * 16
-        if self._peer is not None and self._peer[0] >= cap:
-            return
         for p in self._opened:
             self.kc.ipc_close(p)
         self._opened = []
         torch.cuda.synchronize()
-        dist.barrier()
-        mine = self.kc.recv_buffer(cap * self.world)
+        dist.barrier()                          # nobody still has the old buffers mapped
+        my_bytes = int(my_bytes * 1.1) + (1 << 20)  # headroom: sizes from sampled estimates wobble from job to job
+        mine = self.kc.recv_buffer(my_bytes // self.key_bytes + 1)
         handles = [None] * self.world
         dist.all_gather_object(handles, self.kc.ipc_export(mine))
-        regions = []
+        bases = []
         for p in range(self.world):
             if p == self.rank:
-                base = mine
+                bases.append(mine)
             else:
-                base = self.kc.ipc_open(handles[p])
-                self._opened.append(base)
-            regions.append(base + self.rank * cap * self.key_bytes)
-        self._peer = (cap, mine, regions)
+                bases.append(self.kc.ipc_open(handles[p]))
+                self._opened.append(bases[-1])
+        self._map = (my_bytes, mine, bases)
+
+    def _setup_peers(self):
+        """Hash route: receive buffer of `world` regions, one per source rank."""
+        torch, dist = self.torch, self.dist
+        dev = torch.device("cuda", torch.cuda.current_device())
+        # one small all-reduce per job: agrees on the region size (and on whether any rank's buffer is too small), and
+        # is the point after which nobody is still reading its receive buffer from the previous job
+        nb = torch.tensor([self.n_bases, -self._map[0]], dtype=torch.int64, device=dev)
+        dist.all_reduce(nb, op=dist.ReduceOp.MAX)
+        nb = nb.tolist()
+        cap = (int(nb[0] / self.world * 1.03) + 65536 + 15) // 16 * 16
+        if -nb[1] < cap * self.world * self.key_bytes:
+            self._map_buffers(cap * self.world * self.key_bytes)
+        _, mine, bases = self._map
+        return cap, mine, [b + self.rank * cap * self.key_bytes for b in bases]
+
+    def _finish_range(self):
+        """Range partition (kmc_dist_*): the senders' scatter kernels store every key straight into its level-1 bucket
+        in its owner's receive buffer; the owners run only the second scatter and the bucket sort.  None = this job does
+        not suit it (every rank comes to the same conclusion) and goes through the hash route instead."""
+        torch, dist = self.torch, self.dist
+        dev = torch.device("cuda", torch.cuda.current_device())
+        hist, low = self.kc.dist_hist()
+        # one all-gather per job: the histograms every rank plans from, plus what decides the fall-backs.  It is also the
+        # point after which nobody is still reading its receive buffer from the previous job.
+        mine = np.concatenate([hist, np.array([int(low), self._map[0]], np.uint64)])
+        send = torch.from_numpy(mine.view(np.int64)).to(dev)
+        allv = torch.empty(self.world * send.numel(), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allv, send)
+        allv = allv.cpu().numpy().view(np.uint64).reshape(self.world, -1)
+        self._mark()
+        if allv[:, 4096].any():
+            return None                          # low-cardinality input somewhere: hash route + hash table
+        need = self.kc.dist_plan(self.world, self.rank, allv[:, :4096])
+        if not need.all():
+            return None
+        if (need > allv[:, 4097]).any():         # some rank's buffer must grow; every rank sees that
+            self._map_buffers(int(need[self.rank]))
+        self._mark()
+        overflow = self.kc.dist_scatter(self._map[2])
+        self._mark()
+        flag = torch.tensor([int(overflow)], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)   # the hand-over point: every rank's scatter kernel is done
+        if int(flag):
+            return None
+        self._mark()
+        out = self.kc.finish()
+        self._mark()
+        return out
+
+    def _mark(self):
+        if _PROF:
+            self.torch.cuda.synchronize()
+            self._t.append(time.perf_counter())
 
     def finish(self):
         if self.world == 1:
             return self.kc.finish()
         torch, dist = self.torch, self.dist
-        t = [time.perf_counter()]
-
-        def mark():
-            if _PROF:
-                torch.cuda.synchronize()
-                t.append(time.perf_counter())
-
+        self._t = [time.perf_counter()]
         dev = torch.device("cuda", torch.cuda.current_device())
+        if self.use_range:
+            out = self._finish_range()
+            if out is not None:
+                self.path = "range"
+                if _PROF:
+                    d = [1e3 * (b - a) for a, b in zip(self._t[:-1], self._t[1:])]
+                    names = ["hist+gather", "plan", "scatter", "barrier", "count"]
+                    print(f"[kmc dist r{self.rank}] " + ", ".join(f"{n} {v:.2f} ms" for n, v in zip(names, d)) +
+                          f" (range partition) phases={self.kc.stats().get('phases_ms')}", file=sys.stderr)
+                return out
+            self._t = [time.perf_counter()]
+        self.path = "hash"
+        mark = self._mark
         if self.use_peer:
-            self._setup_peers()
-            cap, mine, regions = self._peer
+            cap, mine, regions = self._setup_peers()
             mark()
             count = self.kc.route_to_peers(regions, cap)
             mark()
@@ -178,7 +240,7 @@ class DistCounter:
         out = self.kc.finish()
         mark()
         if _PROF:
-            d = [1e3 * (b - a) for a, b in zip(t[:-1], t[1:])]
+            d = [1e3 * (b - a) for a, b in zip(self._t[:-1], self._t[1:])]
             names = ["setup+barrier", "route", "exchange", "count"] if self.use_peer else ["route", "exchange", "count"]
             print(f"[kmc dist r{self.rank}] " + ", ".join(f"{n} {v:.2f} ms" for n, v in zip(names, d)) +
                   f" ({'peer stores' if self.use_peer else 'nccl all-to-all'}) end@{time.time() % 100:.4f} "

@@ -24,7 +24,8 @@ SYMBOLS = ["kmc_create", "kmc_destroy", "kmc_last_error", "kmc_strerror", "kmc_s
            "kmc_staging", "kmc_submit", "kmc_submit_host", "kmc_submit_device", "kmc_finish", "kmc_read",
            "kmc_table_device", "kmc_digest", "kmc_key_bases", "kmc_route", "kmc_ingest_keys", "kmc_owner_of",
            "kmc_stats_json", "kmc_route_to_peers", "kmc_recv_buffer", "kmc_ipc_export", "kmc_ipc_open",
-           "kmc_ipc_close", "kmc_submit_fasta", "kmc_format", "kmc_finish_part"]
+           "kmc_ipc_close", "kmc_submit_fasta", "kmc_format", "kmc_finish_part",
+           "kmc_dist_hist", "kmc_dist_plan", "kmc_dist_scatter"]
 
 
 class KmcConfig(C.Structure):
@@ -80,6 +81,9 @@ def load_library(path=None):
     L.kmc_ingest_keys.argtypes = [vp, vp, C.c_uint64]
     L.kmc_route_to_peers.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.c_uint64, vp]
     L.kmc_recv_buffer.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    L.kmc_dist_hist.argtypes = [vp, vp, C.POINTER(C.c_uint32)]
+    L.kmc_dist_plan.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp]
+    L.kmc_dist_scatter.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint32)]
     L.kmc_ipc_export.argtypes = [vp, vp, C.c_char_p]
     L.kmc_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.kmc_ipc_close.argtypes = [vp, vp]
@@ -244,6 +248,29 @@ class KmerCounter:
         count = np.zeros(n, np.uint64)
         self._ck(self._L.kmc_route_to_peers(self._h, n, arr, part_cap_keys, count.ctypes.data))
         return count
+
+    def dist_hist(self):
+        """→ (uint64[4096] upper-estimate histogram of this rank's keys by their top 12 bits, low_cardinality flag)."""
+        h = np.zeros(4096, np.uint64)
+        low = C.c_uint32()
+        self._ck(self._L.kmc_dist_hist(self._h, h.ctypes.data, C.byref(low)))
+        return h, bool(low.value)
+
+    def dist_plan(self, world, rank, all_hist):
+        """all_hist: (world, 4096) uint64, the same on every rank → bytes every rank's receive buffer must have
+        (all zero: the job does not suit the range partition)."""
+        ah = np.ascontiguousarray(all_hist, dtype=np.uint64)
+        assert ah.shape == (world, 4096)
+        need = np.zeros(world, np.uint64)
+        self._ck(self._L.kmc_dist_plan(self._h, world, rank, ah.ctypes.data, need.ctypes.data))
+        return need
+
+    def dist_scatter(self, peer_bufs):
+        """Level-1 scatter of this rank's keys into the owners' receive buffers → True if a bucket overflowed."""
+        arr = (C.c_void_p * len(peer_bufs))(*[int(p) for p in peer_bufs])
+        ov = C.c_uint32()
+        self._ck(self._L.kmc_dist_scatter(self._h, arr, C.byref(ov)))
+        return bool(ov.value)
 
     def recv_buffer(self, n_keys):
         p = C.c_void_p()
