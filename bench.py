@@ -263,7 +263,13 @@ def main():
         e2e_res = step_e2e()
     barrier()
     e2e_ms_local = 1e3 * (time.perf_counter() - t0) / args.steps
-    assert e2e_res[2] == digest, "e2e and device-resident runs disagree"
+    # whole-job digests (sum over ranks mod 2^64: which rank owns which keys may differ between the two runs)
+    dg = torch.tensor(np.array([digest, e2e_res[2]], np.uint64).view(np.int64), device=dev)
+    if dist is not None:
+        dist.all_reduce(dg, op=dist.ReduceOp.SUM)
+    dg = dg.cpu().numpy().view(np.uint64)
+    assert int(dg[0]) == int(dg[1]), "e2e and device-resident runs disagree"
+    digest_all = int(dg[0])
 
     t = torch.tensor([ms_local, e2e_ms_local], dtype=torch.float64, device=dev)
     cnt = torch.tensor([totals[1], totals[0]], dtype=torch.int64, device=dev)
@@ -314,8 +320,8 @@ def main():
             "config": {"workload": args.workload + ": " + wl["desc"], "k": wl["k"], "canonical": wl["canonical"],
                        "bases_per_gpu": n, "records_per_gpu": n_recs, "seed": seed, "first_mib_sha256": first_mib,
                        "l2": "inputs (>= 1 GB) larger than the 126 MB L2; no explicit flush",
-                       "strategy": kstats[-1].get("strategy_used"), "parallelism": f"hash-partition x{world}"},
-            "n_total": n_total, "n_distinct": n_distinct, "digest_rank0": digest,
+                       "strategy": kstats[-1].get("strategy_used"), "parallelism": f"{getattr(dc, 'path', None) or 'single'}-partition x{world}"},
+            "n_total": n_total, "n_distinct": n_distinct, "digest": digest_all,
             "roofline": roof,
             "e2e": {"value": n_total / (e2e_ms / 1e3) / 1e9, "unit": "Gk/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(n + 8 * (n_recs + 1)), "d2h_bytes_per_step": 8 + 32 + 32,

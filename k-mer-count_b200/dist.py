@@ -1,10 +1,10 @@
 """Multi-GPU host logic: one process per GPU, reads sharded across ranks, every key sent to the GPU that owns
 it.  Two partitions of the key space:
-  * range (default for the partitioned counting path): owners hold consecutive key ranges of equal population, chosen
-    from the all-gathered coarse histograms; the senders' scatter kernels store keys straight into their level-1
-    bucket inside the owner's buffer over NVLink, so the exchange IS the first pass of the count;
-  * hash (low-cardinality input, lr-gapped mode, fall-back): owner = hash prefix; keys are stored into per-source
-    regions of the owner's buffer (or exchanged with an NCCL all-to-all), and the owner counts them from scratch.
+  * hash (default): owner = hash prefix; the routing kernel stores keys into per-source regions of the owner's buffer
+    over NVLink (or they are exchanged with an NCCL all-to-all), and the owner counts what it received;
+  * range (KMC_DIST_PARTITION=range): owners hold consecutive key ranges of equal population, chosen from the
+    all-gathered coarse histograms; the senders' scatter kernels store keys straight into their level-1 bucket inside
+    the owner's buffer, so the exchange IS the first pass of the count and the ranks' tables are globally sorted.
 `torch.distributed` carries only histograms, counts and the rank barrier (NCCL on the GPU box; gloo in the CPU tests of
 the routing arithmetic); everything either side of it is libkmc through its C ABI."""
 import os
@@ -100,8 +100,11 @@ class DistCounter:
         self.n_bases = 0
         self.key_bytes = 8 if self.key_bits <= 64 else 16
         self.use_peer = world > 1 and kw.get("mode", 0) == 0 and os.environ.get("KMC_DIST_EXCHANGE", "peer") == "peer"
-        # KMC_DIST_PARTITION=hash keeps every job on the hash route (owner = hash prefix; owners re-scatter)
-        self.use_range = self.use_peer and strategy in (0, 2) and os.environ.get("KMC_DIST_PARTITION", "range") == "range"
+        # KMC_DIST_PARTITION=range: owners hold key ranges and the senders do the level-1 scatter (see _finish_range).
+        # Measured on B200 x2 it is as fast as the hash route (26.1 vs 26.0 ms/step): the owners skip their level-1
+        # scatter (-4.6 ms), but the senders' NVLink stores now come in runs of ~250 B instead of ~16 KB and reach
+        # 360 instead of 535 GB/s (+3.5 ms), and with more GPUs the runs only get shorter.  Default: hash.
+        self.use_range = self.use_peer and strategy in (0, 2) and os.environ.get("KMC_DIST_PARTITION", "hash") == "range"
 
     def set_stream(self, ptr):
         self.kc.set_stream(ptr)
