@@ -935,6 +935,18 @@ int coarse_hist_gapped(kmc_ctx *c, std::vector<uint64_t> &hist) {
 // meet the coarse range [c_lo, c_hi) exist, numbered from l1_base (all 2^b1 of them unless this is a partial count —
 // which may therefore use more level-1 bits: what is bounded is the number of buckets the scatter kernel ranks in
 // shared memory, kMaxL1).  false: the input does not suit the partitioned path.
+// Capacity of the fine buckets of a coarse bin whose fine buckets expect `avg` keys each: 10 % + 6 sigma of slack,
+// a multiple of kFineAlign (bucket starts are sums of capacities: fast_finish's loads then start on a 128 B line).
+inline uint32_t fine_cap_for(double avg, uint32_t cap_max) {
+  uint32_t cp = (uint32_t)(avg * 1.10 + 6.0 * std::sqrt(avg) + 64.0);
+  return std::min<uint32_t>((cp + (kFineAlign - 1)) & ~(uint32_t)(kFineAlign - 1), cap_max);
+}
+// development knobs (tools/ab.py): KMC_FINE_TARGET_RT = keys aimed at per 64-bit-key fine bucket, KMC_B1 = level-1 bits
+inline int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
 struct PlanShape {
   uint32_t b1 = 0, l1_base = 0, n_l1 = 0;
   std::vector<uint32_t> e;   // [ncoarse]
@@ -956,6 +968,7 @@ bool plan_shape(const std::vector<uint64_t> &hist, uint32_t kb, uint32_t c_lo, u
   for (uint32_t ci = c_lo; ci < c_hi; ci++) nf_guess += 1ull << P.e[ci];
   uint32_t b1 = (uint32_t)std::lround(std::log2(std::sqrt((double)nf_guess) * (double)ncoarse / (double)(c_hi - c_lo)));
   b1 = std::max(std::max(b1_lo, std::min(b1_min, b1_hi)), std::min(b1, b1_hi));
+  if (const int forced = env_int("KMC_B1", 0); forced > 0) b1 = std::max(b1_lo, std::min<uint32_t>((uint32_t)forced, b1_hi));
   auto l1_span = [&](uint32_t bits, uint32_t *base) { // level-1 buckets met by the coarse range at `bits` level-1 bits
     *base = c_lo >> (cb - bits);
     return ((c_hi - 1) >> (cb - bits)) + 1 - *base;
@@ -992,7 +1005,7 @@ template <typename KeyT>
 int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   constexpr bool kWide = sizeof(KeyT) == 16;
   constexpr int kCap = kWide ? 4096 : kFineCap;
-  const int kTarget = (kWide ? 3200 : kFineTarget) >> relax;
+  const int kTarget = (kWide ? 3200 : std::min(env_int("KMC_FINE_TARGET_RT", kFineTarget), kFineTarget)) >> relax;
   *used = false;
   const uint32_t kb = c->key_bits;
   const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb);
@@ -1060,8 +1073,7 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
     for (uint32_t ci = b_abs << (cb - b1); ci < ((b_abs + 1) << (cb - b1)); ci++) {
       nb += hist[ci];
       double avg = (double)hist[ci] / (double)(1ull << sub_bits);
-      uint32_t cp = relax ? (uint32_t)kCap : (uint32_t)(avg * 1.10 + 6.0 * std::sqrt(avg) + 64.0);
-      cp = std::min<uint32_t>((cp + 15) & ~15u, kCap);
+      const uint32_t cp = relax ? (uint32_t)kCap : fine_cap_for(avg, kCap);
       const uint32_t ci_rel = ci - (l1_base << cshift);
       cstart[ci_rel] = l2_keys; cfine0[ci_rel] = fb; ccap[ci_rel] = (uint16_t)cp;
       l2_keys += (uint64_t)cp << sub_bits;
@@ -1430,8 +1442,7 @@ int finish_dist(kmc_ctx *c) {
     }
     for (uint32_t ci = b << cshift; ci < ((b + 1) << cshift); ci++) {
       double avg = (double)D.fine_hist[ci] / (double)(1ull << sub_bits);
-      uint32_t cp = (uint32_t)(avg * 1.10 + 6.0 * std::sqrt(avg) + 64.0);
-      cp = std::min<uint32_t>((cp + 15) & ~15u, kCap);
+      const uint32_t cp = fine_cap_for(avg, kCap);
       const uint32_t ci_rel = ci - (my_lo << cshift);
       cstart[ci_rel] = l2_keys; cfine0[ci_rel] = fb; ccap[ci_rel] = (uint16_t)cp;
       l2_keys += (uint64_t)cp << sub_bits;

@@ -32,12 +32,45 @@ constexpr int kFastThreads = 512;
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kCoarseBitsMax = 12;
 constexpr int kHistSampleMax = 16;       // fast_hist looks at every step-th tile, step <= 16
-constexpr int kFineTarget = 6400;        // aimed keys per fine bucket
-constexpr int kFineCap = 8192;           // smem capacity of fast_finish (keys)
+// Shape of a fine bucket (compile-time so that tools/ab.py can build variants side by side):
+//   KMC_FINE_CAP    keys fast_finish can hold in shared memory (a multiple of kFinThreads)
+//   KMC_FINE_TARGET keys the plan aims at per fine bucket; the plan halves buckets until they hold at most this
+//                   many, so the real fill is between TARGET/2 and TARGET.  Capacity must cover TARGET * 1.10 + 6 sigma + 64.
+//   KMC_FINISH_BITS log2 of the sub-bins of fast_finish's counting sort
+//   KMC_FINE_ALIGN  fine-bucket starts are multiples of this many level-2 elements (32 x 4 B = one 128 B line)
+//   KMC_ALIGNED_ROWS fast_finish shifts its row loop by the output offset so that every warp store covers whole lines
+#ifndef KMC_FINE_CAP
+#define KMC_FINE_CAP 9216
+#endif
+#ifndef KMC_FINE_TARGET
+#define KMC_FINE_TARGET 7800
+#endif
+#ifndef KMC_FINISH_BITS
+#define KMC_FINISH_BITS 13
+#endif
+#ifndef KMC_FINE_ALIGN
+#define KMC_FINE_ALIGN 32
+#endif
+#ifndef KMC_ALIGNED_ROWS
+#define KMC_ALIGNED_ROWS 1
+#endif
+#ifndef KMC_P2_PSEARCH
+#define KMC_P2_PSEARCH 1   // fast_part2 finds its level-1 bucket with all threads at once
+#endif
+#ifndef KMC_LB_SLEEP
+#define KMC_LB_SLEEP 0      // look-back: nanoseconds to sleep between polls of a predecessor that has not published yet
+#endif
+#ifndef KMC_FIN_SEGROWS
+#define KMC_FIN_SEGROWS 1  // fast_finish: rows between two listed duplicates are written by a plain shifted copy loop
+#endif
+constexpr int kFineTarget = KMC_FINE_TARGET; // aimed keys per fine bucket
+constexpr int kFineCap = KMC_FINE_CAP;       // smem capacity of fast_finish (keys)
+constexpr int kFineAlign = KMC_FINE_ALIGN;
 constexpr int kMaxTile = 16384;           // largest tile of any partition kernel (sizes the trash areas)
 constexpr int kMaxL1 = 1024;             // level-1 buckets (smem histogram size in fast_part1)
 constexpr int kMaxFinePerL1 = 2048;      // fine buckets under one level-1 bucket (smem histogram in fast_part2)
-constexpr int kFinishBins = 8192;        // sub-bins of fast_finish (13 bits)
+constexpr int kFinishBits = KMC_FINISH_BITS;
+constexpr int kFinishBins = 1 << kFinishBits; // sub-bins of fast_finish
 constexpr int kSmallBin = 32;            // sub-bins up to this size are ranked by comparison per key
 constexpr int kMaxHard = 64;
 constexpr int kDupList = 32;             // fast_finish: buckets with at most this many duplicate keys skip the run-length encode
@@ -48,7 +81,7 @@ constexpr uint32_t kFlagSpin = 16u;
 struct __align__(16) FineDesc { // one per fine bucket
   uint64_t start;   // element index in the level-2 array
   uint64_t prefix;  // the key bits above `rem`, in place (key = prefix | low bits)
-  uint16_t cap;     // capacity (multiple of 16, <= kFineCap)
+  uint16_t cap;     // capacity (multiple of kFineAlign, <= kFineCap)
   uint8_t rem;      // key bits below the bucket prefix
   uint8_t pad[13];
 };
@@ -339,7 +372,13 @@ __global__ void __launch_bounds__(kFastThreads, 2) fast_part2_kernel(FastPlan pl
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_b;
   constexpr int kKPT = FastShape<KeyT>::kP2KPT, kTile = p2_tile<KeyT>();
-  // which level-1 bucket owns this tile: last b with l1_tile0[b] <= tile
+  // which level-1 bucket owns this tile: the b with l1_tile0[b] <= tile < l1_tile0[b+1] (every bucket has at least
+  // one tile).  All threads look at once — a binary search by one thread is ten dependent L2 round trips, a
+  // quarter of this CTA's life (12.8 % of the kernel's stall samples in profiles/r01).
+#if KMC_P2_PSEARCH
+  for (uint32_t i = threadIdx.x; i < pl.n_l1; i += kFastThreads)
+    if (pl.l1_tile0[i] <= blockIdx.x && blockIdx.x < pl.l1_tile0[i + 1]) s_b = i;
+#else
   if (threadIdx.x == 0) {
     uint32_t lo = 0, hi = pl.n_l1;
     while (hi - lo > 1) {
@@ -348,6 +387,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) fast_part2_kernel(FastPlan pl
     }
     s_b = lo;
   }
+#endif
   __syncthreads();
   const uint32_t b = s_b;
   unsigned long long n_b = pl.l1_cursor[b];
@@ -434,6 +474,7 @@ __device__ __forceinline__ unsigned long long lookback_resolve(unsigned long lon
       uint32_t spins = 0;
       while (((v = ld_status(&status[idx])) >> 62) == 0) {
         if (++spins > (1u << 24)) { atomicOr(flags, kFlagSpin); v = kIncl; break; }
+        if (KMC_LB_SLEEP) __nanosleep(KMC_LB_SLEEP);
       }
     }
     uint32_t incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
@@ -505,12 +546,60 @@ struct FinPending {
   bool valid;
 };
 
+// one warp: sort the m <= 32 listed positions ascending, in place (they are distinct: rank = how many are smaller)
+__device__ __forceinline__ void sort_dup_list(uint16_t *dup, uint32_t m) {
+  const uint32_t lane = lane_id();
+  const uint32_t v = lane < m ? (uint32_t)dup[lane] : 0xFFFFFFFFu;
+  uint32_t r = 0;
+#pragma unroll
+  for (int j = 0; j < 32; j++) r += __shfl_sync(0xffffffffu, v, j) < v;
+  __syncwarp();
+  if (lane < m) dup[r] = (uint16_t)v;
+}
+
+#if KMC_FIN_SEGROWS
+// `dup` sorted ascending.  The positions between two listed ones form a segment whose rows all sit the same distance
+// below their position (the number of listed positions before them): m + 1 plain copy loops, no per-row search.
+// A segment's last position is followed by a listed one — it is the row the copies merge into, and its count is
+// written by the fix-up at the end (1 + length of the run of listed positions that follows).
+template <typename L2T>
+__device__ __forceinline__ void finish_write_rows(const FinPending &P, const L2T *keys, const uint16_t *dup, unsigned long long G,
+                                                  uint64_t *__restrict__ out_lo, uint64_t *__restrict__ out_hi,
+                                                  uint32_t *__restrict__ out_cnt) {
+  const uint32_t m = P.m, n = P.n, tid = threadIdx.x;
+  for (uint32_t s = 0; s <= m; s++) {
+    const uint32_t lo = s ? (uint32_t)dup[s - 1] + 1u : 0u, hi = s < m ? (uint32_t)dup[s] : n;
+    const unsigned long long base = G - s; // row of position p = base + p
+    // lane l of every warp writes rows with index % 32 == l: whole 128 B lines per warp store
+    const uint32_t a = KMC_ALIGNED_ROWS ? (uint32_t)((base + lo) & 31u) : 0u;
+    for (uint32_t q = tid; q < hi - lo + a; q += kFinThreads) {
+      if (q < a) continue;
+      const uint32_t p = lo + q - a;
+      emit_key(out_lo, out_hi, base + p, P.D, keys[p]);
+      if (s == m || p + 1 != hi) out_cnt[base + p] = 1u;
+    }
+  }
+  if (tid < m) {
+    const uint32_t d = dup[tid];
+    if (tid == 0 || (uint32_t)dup[tid - 1] + 1u != d) { // first of a run of copies: the row is position d - 1
+      uint32_t run = 1;
+      while (tid + run < m && (uint32_t)dup[tid + run] == d + run) run++;
+      out_cnt[G + (d - 1u) - tid] = 1u + run;
+    }
+  }
+}
+#else
 template <typename L2T>
 __device__ __forceinline__ void finish_write_rows(const FinPending &P, const L2T *keys, const uint16_t *dup, unsigned long long G,
                                                   uint64_t *__restrict__ out_lo, uint64_t *__restrict__ out_hi,
                                                   uint32_t *__restrict__ out_cnt) {
   const uint32_t m = P.m;
-  for (uint32_t p = threadIdx.x; p < P.n; p += kFinThreads) {
+  // lane l of every warp writes row G + p with (G + p) % 32 == l: each warp store covers whole 128 B lines (an
+  // unaligned 256 B store is three L2 requests instead of two, and the kernel's stores run near the request ceiling)
+  const uint32_t a = KMC_ALIGNED_ROWS ? (uint32_t)(G & 31u) : 0u;
+  for (uint32_t q = threadIdx.x; q < P.n + a; q += kFinThreads) {
+    if (q < a) continue;
+    const uint32_t p = q - a;
     uint32_t before = 0, cnt = 1;
     bool listed = false;
     for (uint32_t q = 0; q < m; q++) { const uint32_t dq = dup[q]; before += dq < p; listed |= dq == p; }
@@ -523,6 +612,7 @@ __device__ __forceinline__ void finish_write_rows(const FinPending &P, const L2T
     out_cnt[G + p - before] = cnt;
   }
 }
+#endif
 
 template <typename L2T>
 __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MINB32 : 2) fast_finish_kernel(FastPlan pl, const L2T *__restrict__ l2,
@@ -551,6 +641,8 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
         S.goff = prefix;                                                                                    \
         if ((P).f + 1 == pl.n_fine) *d_total = prefix + ((P).n - (P).m);                                    \
       }                                                                                                     \
+    } else if (KMC_FIN_SEGROWS && warp == 1 && (P).m > 1) {                                                 \
+      sort_dup_list(S.dup[buf], (P).m);                                                                     \
     }                                                                                                       \
     __syncthreads();                                                                                        \
     FIN_MARK(8);                                                                                            \
@@ -571,7 +663,7 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
     const FineDesc D = pl.fdesc[f];
     uint32_t n = pl.fine_cursor[f];
     if (n > D.cap) n = D.cap; // overflow was flagged by fast_part2; the caller discards this result
-    const uint32_t sb = D.rem < 13 ? D.rem : 13;
+    const uint32_t sb = D.rem < (uint32_t)kFinishBits ? D.rem : (uint32_t)kFinishBits;
     const uint32_t bshift = D.rem - sb, bmask = (1u << sb) - 1u; // sb == 0 → every key in sub-bin 0
     L2T *const keys = S.keys[cur];
     {
@@ -786,7 +878,10 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
     __syncthreads();
     FIN_MARK(8);
     const unsigned long long G = S.goff;
-    for (uint32_t i = tid; i < d; i += kFinThreads) {
+    const uint32_t a = KMC_ALIGNED_ROWS ? (uint32_t)(G & 31u) : 0u; // whole-line warp stores, as in finish_write_rows
+    for (uint32_t q = tid; q < d + a; q += kFinThreads) {
+      if (q < a) continue;
+      const uint32_t i = q - a;
       emit_key(out_lo, out_hi, G + i, D, keys[i]);
       uint32_t nxt = (i + 1 < d) ? S.hp[i + 1] : n;
       out_cnt[G + i] = nxt - S.hp[i];

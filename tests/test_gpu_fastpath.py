@@ -233,3 +233,45 @@ def test_fast_path_with_coverage_duplicates(kmc, orc):
         assert_tables_equal(got, want)
         assert st["strategy_used"] == 2, st   # possibly after one retry with half-full buckets
         assert float(want.count.mean()) > 20
+
+
+@pytest.mark.parametrize("k,canonical,n", [(15, True, 4_000_000), (14, False, 5_000_000), (16, True, 6_000_000),
+                                           (16, False, 29_000_000)])
+def test_fast_path_few_duplicates_per_bucket(kmc, orc, k, canonical, n):
+    """Key spaces only ~100-1000x larger than the input: every fine bucket holds a handful to a few dozen keys that
+    occur twice — the case fast_finish settles without a run-length encode (sorted list of duplicate positions,
+    rows between two of them written by shifted copy loops, counts of the merged rows fixed up afterwards)."""
+    rng = np.random.default_rng(100 + k)
+    bases = ACGT[rng.integers(0, 4, n)]
+    off = np.arange(0, n + 1, 400, dtype=np.uint64)
+    want = orc.contiguous_mt(bases, off, k, canonical)
+    dup_frac = 1.0 - want.n_distinct / want.n_total
+    assert 2e-4 < dup_frac < 0.05, dup_frac
+    got, st, dig = _count(kmc, bases, off, k, canonical, strategy=2)
+    assert_tables_equal(got, want)
+    assert dig == want.digest()
+    assert st["strategy_used"] == 2 and st["fast_fallbacks"] == 0, st
+
+
+def test_fast_path_duplicate_runs(kmc, orc):
+    """Keys that occur three and four times among otherwise distinct keys: runs of consecutive listed positions
+    (a row followed by two or three copies), and copies that are neighbours of other rows' copies."""
+    rng = np.random.default_rng(77)
+    k = 21
+    filler = ACGT[rng.integers(0, 4, 3_000_000)]
+    picks = [ACGT[rng.integers(0, 4, k)] for _ in range(3000)]
+    # neighbours in key order: same first 20 bases, last base differs — their copies sit side by side after sorting
+    twins = []
+    for p in picks[:500]:
+        q = p.copy()
+        q[-1] = ACGT[(int(np.searchsorted(ACGT, p[-1])) + 1) % 4]
+        twins.append(q)
+    recs = picks * 3 + picks[:1000] + twins * 2
+    bases = np.concatenate(recs + [filler])
+    off = np.concatenate([np.arange(0, (len(recs) + 1) * k, k), [len(bases)]]).astype(np.uint64)
+    want = orc.contiguous_mt(bases, off, k, False)
+    assert int(want.count.max()) >= 4
+    got, st, dig = _count(kmc, bases, off, k, False, strategy=2)
+    assert_tables_equal(got, want)
+    assert dig == want.digest()
+    assert st["strategy_used"] == 2 and st["fast_fallbacks"] == 0, st
