@@ -502,13 +502,14 @@ template <typename L2T> __host__ __device__ constexpr int fin_cap() { return siz
 template <typename L2T> __host__ __device__ constexpr int fin_kpt() { return fin_cap<L2T>() / kFinThreads; }
 static_assert(fin_kpt<uint32_t>() <= 32 && fin_kpt<uint32_t>() * kFinWarps <= kFinThreads && kFinWordsPT % 4 == 0, "fast_finish shape");
 
-// Deferred write-back (KMC_FINISH_DEFER=1, off by default) keeps two buckets in shared memory (32-bit suffixes
-// only: 2 x 32 KB) and writes a bucket's rows one bucket after its row count was announced, so that the look-back
-// never waits.  Measured on B200 (cfg2): the wait drops from 24 % to 5 % of a CTA's time, but the second buffer
-// costs the third resident CTA per SM and the kernel gets slower (9.3 ms vs 8.3 ms) — the SM is bound by its
-// shared-memory pipe and issue slots, which a waiting CTA does not use; the other two CTAs fill them.
+// Deferred write-back (KMC_FINISH_DEFER, 32-bit suffixes only) keeps two buckets in shared memory (2 x 36 KB) and
+// writes a bucket's rows one bucket after its row count was announced, so that the look-back hardly ever waits.
+// The second buffer costs the third resident CTA per SM.  Measured on B200 (cfg2, 1e9 bases, k=21): before buckets
+// with few duplicates skipped the run-length encode it lost (9.3 vs 8.3 ms: the SM was bound by its shared-memory
+// pipe and issue slots, which a waiting CTA does not use); with that light path it wins, 6.59 vs 6.99 ms — what is
+// left per bucket is short enough that the look-back convoy (25 % of the stall samples) is the larger loss.
 #ifndef KMC_FINISH_DEFER
-#define KMC_FINISH_DEFER 0
+#define KMC_FINISH_DEFER 1
 #endif
 template <typename L2T> __host__ __device__ constexpr int fin_bufs() { return (KMC_FINISH_DEFER && sizeof(L2T) == 4) ? 2 : 1; }
 
