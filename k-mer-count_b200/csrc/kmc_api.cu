@@ -1004,8 +1004,8 @@ bool plan_shape(const std::vector<uint64_t> &hist, uint32_t kb, uint32_t c_lo, u
 template <typename KeyT>
 int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   constexpr bool kWide = sizeof(KeyT) == 16;
-  constexpr int kCap = kWide ? 4096 : kFineCap;
-  const int kTarget = (kWide ? 3200 : std::min(env_int("KMC_FINE_TARGET_RT", kFineTarget), kFineTarget)) >> relax;
+  int kCap = kWide ? 4096 : kFineCap;
+  int kTarget = (kWide ? 3200 : std::min(env_int("KMC_FINE_TARGET_RT", kFineTarget), kFineTarget)) >> relax;
   *used = false;
   const uint32_t kb = c->key_bits;
   const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb);
@@ -1041,6 +1041,16 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   // ---- plan
   PlanShape shape;
   if (!plan_shape(hist, kb, c_lo, c_hi, ranged, kTarget, shape)) return KMC_OK;
+  if (!kWide && (kFineCap64 != kFineCap || kFineTarget64 != kFineTarget)) {
+    // buckets that leave more than 32 key bits are sorted as 64-bit elements, whose bucket shape is smaller: plan again
+    bool wide_elems = false;
+    for (uint32_t b = 0; b < shape.n_l1; b++) if (kb - shape.b1 - shape.l1e[b] > 32) wide_elems = true;
+    if (wide_elems) {
+      kCap = kFineCap64;
+      kTarget = std::min(kTarget, kFineTarget64 >> relax);
+      if (!plan_shape(hist, kb, c_lo, c_hi, ranged, kTarget, shape)) return KMC_OK;
+    }
+  }
   const uint32_t b1 = shape.b1, l1_base = shape.l1_base, n_l1 = shape.n_l1;
   const std::vector<uint8_t> &l1e = shape.l1e;
   const uint64_t n_fine = shape.n_fine;
@@ -1148,6 +1158,15 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps,
                                                    (uint64_t)kNumSMsB200 * ((sizeof(KeyT) == 8 && FastShape<KeyT>::kHalves == 2) ? 2 : 1));
+      if constexpr (KMC_PART1_WIDE && sizeof(KeyT) == 8) {
+        if (!ranged) {
+          auto fast_part1_wide = fast_part1_wide_kernel<true, PrefixBucket>;
+          CK(cudaFuncSetAttribute(fast_part1_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          LAUNCH(fast_part1_wide, std::min<uint32_t>(grid, (uint32_t)kNumSMsB200), kWideThreads, smem, P, tiles, pl, bucket,
+                 (uint64_t *)c->fast_l1.p, d_err(c));
+          continue;
+        }
+      }
       if (ranged) LAUNCH(fast_part1_ranged, grid, kFastThreads, smem, P, tiles, pl, bucket_ranged, (KeyT *)c->fast_l1.p, d_err(c));
       else LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->fast_l1.p, d_err(c));
     }
@@ -1197,7 +1216,7 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
       size_t fsmem = sizeof(FinishSmem<uint64_t>);
       auto fast_finish = fast_finish_kernel<uint64_t>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2);
+      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB64);
       LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
              (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
     }
@@ -1284,7 +1303,7 @@ int dist_hist_impl(kmc_ctx *c, uint64_t *hist_out, uint32_t *low_cardinality) {
 template <typename KeyT>
 int dist_plan_impl(kmc_ctx *c, uint32_t world, uint32_t rank, const uint64_t *all_hist, uint64_t *need_bytes) {
   constexpr bool kWide = sizeof(KeyT) == 16;
-  const int kTarget = kWide ? 3200 : kFineTarget;
+  const int kTarget = kWide ? 3200 : kFineTarget64; // <= kFineTarget: fits whichever element width the owners end up with
   const uint32_t kb = c->key_bits, cb = coarse_bits(c), ncoarse = 1u << cb;
   DistPlan &D = c->dist;
   D.valid = false; D.scattered = false;
@@ -1406,7 +1425,7 @@ int dist_scatter_impl(kmc_ctx *c, void *const *peer_buf, uint32_t *overflow) {
 template <typename KeyT>
 int finish_dist(kmc_ctx *c) {
   constexpr bool kWide = sizeof(KeyT) == 16;
-  constexpr int kCap = kWide ? 4096 : kFineCap;
+  constexpr int kCap = kWide ? 4096 : kFineCap64; // <= kFineCap
   DistPlan &D = c->dist;
   const uint32_t kb = c->key_bits, cb = coarse_bits(c), b1 = D.b1, cshift = cb - b1, world = D.world;
   const uint32_t my_lo = D.own_lo[D.rank], my_n = D.own_lo[D.rank + 1] - my_lo, n_x = my_n * world, n_cb = my_n << cshift;
@@ -1518,7 +1537,7 @@ int finish_dist(kmc_ctx *c) {
       size_t fsmem = sizeof(FinishSmem<uint64_t>);
       auto fast_finish = fast_finish_kernel<uint64_t>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2), kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p,
+      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB64), kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p,
              (uint64_t *)c->t_lo.p, (uint64_t *)nullptr, (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
     }
   }

@@ -65,6 +65,20 @@ constexpr int kHistSampleMax = 16;       // fast_hist looks at every step-th til
 #endif
 constexpr int kFineTarget = KMC_FINE_TARGET; // aimed keys per fine bucket
 constexpr int kFineCap = KMC_FINE_CAP;       // smem capacity of fast_finish (keys)
+// 64-bit level-2 elements (buckets that leave more than 32 key bits, e.g. k=31) may get their own, smaller shape:
+// two 72 KB CTAs fit an SM, three 44 KB ones would too (experiment; by default the same shape as 32-bit suffixes)
+#ifndef KMC_FINE_CAP64
+#define KMC_FINE_CAP64 KMC_FINE_CAP
+#endif
+#ifndef KMC_FINE_TARGET64
+#define KMC_FINE_TARGET64 KMC_FINE_TARGET
+#endif
+#ifndef KMC_FINISH_MINB64
+#define KMC_FINISH_MINB64 2
+#endif
+constexpr int kFineTarget64 = KMC_FINE_TARGET64;
+constexpr int kFineCap64 = KMC_FINE_CAP64;
+static_assert(kFineCap64 <= kFineCap && kFineTarget64 <= kFineTarget, "the 64-bit bucket shape may only be smaller");
 constexpr int kFineAlign = KMC_FINE_ALIGN;
 constexpr int kMaxTile = 16384;           // largest tile of any partition kernel (sizes the trash areas)
 constexpr int kMaxL1 = 1024;             // level-1 buckets (smem histogram size in fast_part1)
@@ -241,7 +255,8 @@ struct PartSmem {
   }
 };
 
-// exclusive scan of hist[0..nb) into loc[0..nb); nb <= kFastThreads * 4.  Returns the total.
+// exclusive scan of hist[0..nb) into loc[0..nb); nb <= THREADS * 4.  Returns the total.
+template <int THREADS = kFastThreads>
 __device__ __forceinline__ uint32_t scan_bins(const uint32_t *hist, uint32_t *loc, uint32_t nb, uint32_t *scratch) {
   uint32_t v[4], s = 0;
 #pragma unroll
@@ -251,7 +266,7 @@ __device__ __forceinline__ uint32_t scan_bins(const uint32_t *hist, uint32_t *lo
     s += v[j];
   }
   uint32_t total;
-  uint32_t ex = block_excl_scan<uint32_t, kFastThreads>(s, scratch, total);
+  uint32_t ex = block_excl_scan<uint32_t, THREADS>(s, scratch, total);
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     uint32_t b = threadIdx.x * 4 + j;
@@ -263,9 +278,9 @@ __device__ __forceinline__ uint32_t scan_bins(const uint32_t *hist, uint32_t *lo
 }
 
 // reserve room for the tile's run of every level-1 bucket; runs that do not fit go to the trash area
-template <typename KeyT>
+template <typename KeyT, int THREADS = kFastThreads>
 __device__ __forceinline__ void reserve_l1(const FastPlan &pl, PartSmem<KeyT> &S, uint32_t nb, uint32_t *flags) {
-  for (uint32_t b = threadIdx.x; b < nb; b += kFastThreads) {
+  for (uint32_t b = threadIdx.x; b < nb; b += THREADS) {
     uint32_t c = S.hist[b];
     if (c) {
       unsigned long long g = atomicAdd(&pl.l1_cursor[b], (unsigned long long)c);
@@ -281,7 +296,7 @@ __device__ __forceinline__ void reserve_l1(const FastPlan &pl, PartSmem<KeyT> &S
 
 // rank (smem atomics) → scan → reserve → stage in bucket order → write runs: the common back end of the
 // level-1 scatters.  key[]/valid describe this thread's NK keys.
-template <typename KeyT, int NK, typename BucketFn>
+template <typename KeyT, int NK, typename BucketFn, int THREADS = kFastThreads>
 __device__ __forceinline__ void scatter_tile_l1(const FastPlan &pl, PartSmem<KeyT> &S, uint32_t nb, const BucketFn &bucket,
                                                 const KeyT (&key)[NK], uint32_t valid, KeyT *__restrict__ l1, uint32_t *flags) {
   uint32_t rank[NK / 2]; // two 16-bit ranks per word
@@ -292,14 +307,14 @@ __device__ __forceinline__ void scatter_tile_l1(const FastPlan &pl, PartSmem<Key
     if (s & 1) rank[s >> 1] |= r << 16; else rank[s >> 1] = r;
   }
   __syncthreads();
-  uint32_t total = scan_bins(S.hist, S.loc, nb, S.scan);
-  reserve_l1(pl, S, nb, flags);
+  uint32_t total = scan_bins<THREADS>(S.hist, S.loc, nb, S.scan);
+  reserve_l1<KeyT, THREADS>(pl, S, nb, flags);
   __syncthreads();
 #pragma unroll
   for (int s = 0; s < NK; s++)
     if (valid & (1u << s)) S.stage[S.loc[bucket(key[s])] + ((rank[s >> 1] >> (16 * (s & 1))) & 0xFFFFu)] = key[s];
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < total; i += kFastThreads) {
+  for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
     KeyT k = S.stage[i];
     l1[S.gdelta[bucket(k)] + i] = k;
   }
@@ -335,6 +350,41 @@ __global__ void __launch_bounds__(kFastThreads, (sizeof(KeyT) == 8 && FastShape<
       }
       scatter_tile_l1<KeyT, kSPH>(pl, S, nb, bucket, key, valid, l1, flags);
     }
+  }
+}
+
+// Experimental (KMC_PART1_WIDE, off): the same tile with twice the warps.  fast_part1_kernel holds all 32 window
+// starts of a lane in one thread — 126 registers, one 16-warp CTA per SM, 25 % of the SM's warp slots, and every
+// __syncthreads phase exposes its latency.  Here warps w and w + 16 load the same 32-base chunks and take 16 starts
+// each (64 registers, 32 warps per SM); tile, staging and run lengths are unchanged.  64-bit keys only.
+#ifndef KMC_PART1_WIDE
+#define KMC_PART1_WIDE 0
+#endif
+constexpr int kWideThreads = 2 * kFastThreads;
+template <bool FOLD, typename BucketFn>
+__global__ void __launch_bounds__(kWideThreads, 1) fast_part1_wide_kernel(ExtractParams P, uint64_t n_tiles, FastPlan pl, BucketFn bucket,
+                                                                           uint64_t *__restrict__ l1, uint32_t *__restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kSPT = 16; // window starts per thread
+  const uint32_t nb = pl.n_l1;
+  PartSmem<uint64_t> S(smem_raw, part1_stage<uint64_t>(), nb);
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, tw = warp & (kFastWarps - 1), half = warp / kFastWarps;
+  const uint64_t n_cta_tiles = (n_tiles + kFastWarps - 1) / kFastWarps;
+  for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
+    const uint64_t t = ct * kFastWarps + tw;
+    Win<uint64_t> W{};
+    W.template load<FOLD>(P, t * Win<uint64_t>::kLanes + lane);
+    const uint32_t ok = t < n_tiles ? W.ok : 0u;
+    for (uint32_t i = threadIdx.x; i < nb; i += kWideThreads) S.hist[i] = 0;
+    __syncthreads();
+    uint64_t key[kSPT];
+    uint32_t valid = 0;
+#pragma unroll
+    for (int s = 0; s < kSPT; s++) {
+      key[s] = W.key(half * kSPT + s, P.k, P.canonical != 0);
+      if ((ok & (0x80000000u >> (half * kSPT + s))) && bucket.accept(key[s])) valid |= 1u << s;
+    }
+    scatter_tile_l1<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags);
   }
 }
 
@@ -498,7 +548,7 @@ constexpr int kFinWarps = kFinThreads / 32;
 constexpr int kFinWordsPT = kFinishBins / 2 / kFinThreads; // packed bin words per thread in the scan (8 at 512 threads)
 // keys per fine bucket that fast_finish can hold: 8192 32/64-bit elements, 4096 128-bit keys (64 KB either way
 // for the widest; 32 KB for 32-bit suffixes)
-template <typename L2T> __host__ __device__ constexpr int fin_cap() { return sizeof(L2T) == 16 ? 4096 : kFineCap; }
+template <typename L2T> __host__ __device__ constexpr int fin_cap() { return sizeof(L2T) == 16 ? 4096 : sizeof(L2T) == 8 ? kFineCap64 : kFineCap; }
 template <typename L2T> __host__ __device__ constexpr int fin_kpt() { return fin_cap<L2T>() / kFinThreads; }
 static_assert(fin_kpt<uint32_t>() <= 32 && fin_kpt<uint32_t>() * kFinWarps <= kFinThreads && kFinWordsPT % 4 == 0, "fast_finish shape");
 
@@ -517,7 +567,7 @@ template <typename L2T>
 struct FinishSmem {
   L2T keys[fin_bufs<L2T>()][fin_cap<L2T>()]; // 32 KB per buffer (u32) / 64 KB (u64, u128)
   uint32_t bins[kFinishBins / 2];          // packed u16 pairs: counts → starts → (after the scatter) ends
-  uint16_t hp[kFineCap + 8];               // multi-key sub-bin list, then head position of every run
+  uint16_t hp[(sizeof(L2T) == 8 ? kFineCap64 : kFineCap) + 8]; // multi-key sub-bin list, then head position of every run
   uint32_t scan32[40];
   uint32_t rowcnt[fin_kpt<L2T>() * kFinWarps];// heads per (row, warp), then their exclusive scan
   uint32_t hard[kMaxHard];
@@ -616,7 +666,7 @@ __device__ __forceinline__ void finish_write_rows(const FinPending &P, const L2T
 #endif
 
 template <typename L2T>
-__global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MINB32 : 2) fast_finish_kernel(FastPlan pl, const L2T *__restrict__ l2,
+__global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MINB32 : sizeof(L2T) == 8 ? KMC_FINISH_MINB64 : 2) fast_finish_kernel(FastPlan pl, const L2T *__restrict__ l2,
                                                                        uint64_t *__restrict__ out_lo, uint64_t *__restrict__ out_hi,
                                                                        uint32_t *__restrict__ out_cnt,
                                                                        unsigned long long *__restrict__ status,
