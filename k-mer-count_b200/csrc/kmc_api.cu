@@ -637,6 +637,10 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
                void *const *part_ptr = nullptr, uint64_t peer_cap = 0) {
   *done = false;
   if (!part_ptr && (c->total_bases < (1u << 18) || n_parts > (uint32_t)kMaxL1)) return KMC_OK;
+  if (OwnerBucket::kBulkStores && n_parts > (uint32_t)kBulkMaxBuckets) {
+    if (part_ptr) return fail(c, KMC_E_ARG, "kmc_route_to_peers: at most %d parts in this build", kBulkMaxBuckets);
+    return KMC_OK;
+  }
   const uint64_t cap = part_ptr ? peer_cap : (((uint64_t)((double)c->total_bases / n_parts * 1.03) + 65536 + 15) & ~15ull);
   const uint64_t total = part_ptr ? 0 : cap * n_parts;
   TRY(ensure(c, c->route_keys, (total + 2 * kMaxTile) * sizeof(KeyT)));
@@ -659,7 +663,7 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
   pl.l1_cursor = (unsigned long long *)((unsigned char *)c->fast_state.p + off_l1cur);
   PHASE_BEGIN("route");
   {
-    size_t smem = PartSmem<KeyT>::bytes(part1_stage<KeyT>(), n_parts);
+    size_t smem = PartSmem<KeyT>::bytes(part1_stage_for<KeyT, OwnerBucket>(), n_parts);
     auto fast_route = fast_part1_kernel<KeyT, true, OwnerBucket>;
     CK(cudaFuncSetAttribute(fast_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const OwnerBucket bucket{n_parts};
@@ -670,7 +674,13 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
       ExtractParams P = seg_params(c, s);
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
-      LAUNCH(fast_route, grid, kFastThreads, smem, P, tiles, pl, bucket, dst, d_err(c));
+      if constexpr (KMC_PART1_WIDE && sizeof(KeyT) == 8) {
+        auto wide = fast_part1_wide_kernel<true, OwnerBucket>;
+        CK(cudaFuncSetAttribute(wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(wide, grid, kWideThreads, smem, P, tiles, pl, bucket, (uint64_t *)dst, d_err(c));
+      } else {
+        LAUNCH(fast_route, grid, kFastThreads, smem, P, tiles, pl, bucket, dst, d_err(c));
+      }
     }
   }
   PHASE_END();
@@ -1407,7 +1417,13 @@ int dist_scatter_impl(kmc_ctx *c, void *const *peer_buf, uint32_t *overflow) {
       ExtractParams P = seg_params(c, s);
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
-      LAUNCH(fast_scatter_to_owners, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)nullptr, d_err(c));
+      if constexpr (KMC_PART1_WIDE && sizeof(KeyT) == 8) {
+        auto wide = fast_part1_wide_kernel<true, PrefixBucket>;
+        CK(cudaFuncSetAttribute(wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(wide, grid, kWideThreads, smem, P, tiles, pl, bucket, (uint64_t *)nullptr, d_err(c));
+      } else {
+        LAUNCH(fast_scatter_to_owners, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)nullptr, d_err(c));
+      }
     }
     LAUNCH(dist_publish_kernel, grid_for(n_all, 256), 256, 0, pl.l1_cursor, pl.l1_cap, (const uint32_t *)(tb + o_own),
            (const uint64_t *)(tb + o_ph), n_all, world, D.rank);

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(128) plan_expand_kernel(FineDesc *__restrict__
 // `key >> cshift` lies in [c_lo, c_lo + c_n); level-1 buckets are then numbered from the first one in range (`base`).
 template <bool RANGE>
 struct PrefixBucketT {
+  static constexpr bool kBulkStores = false;
   uint32_t b1, bshift;
   uint32_t base, cshift, c_lo, c_n;
   template <typename KeyT> __device__ __forceinline__ uint32_t operator()(const KeyT &key) const {
@@ -160,7 +161,17 @@ struct PrefixBucketT {
   }
 };
 using PrefixBucket = PrefixBucketT<false>;
+// Experimental (KMC_ROUTE_TMA, off): the routing kernel's runs — a few thousand keys per owner and tile, contiguous
+// in the staging area — leave shared memory as ONE bulk async copy each (cp.async.bulk, the TMA unit) instead of
+// ~60 warp stores: fewer instructions and larger NVLink write bursts (peer stores from SM threads measured
+// ~530 GB/s per direction at 2 and at 8 GPUs, well under the link's 900).
+#ifndef KMC_ROUTE_TMA
+#define KMC_ROUTE_TMA 0
+#endif
+constexpr int kBulkMaxBuckets = 32;   // bulk stores only for this few buckets (owners), planned by one thread
+constexpr int kBulkPadKeys = 64;      // extra staging slots: one alignment slot per bucket
 struct OwnerBucket {
+  static constexpr bool kBulkStores = KMC_ROUTE_TMA != 0;
   uint32_t n_parts;
   template <typename KeyT> __device__ __forceinline__ uint32_t operator()(const KeyT &key) const {
     return owner_of(key_hi(key), key_lo(key), n_parts);
@@ -186,6 +197,9 @@ template <> struct FastShape<U128> {
   static constexpr int kP2KPT = 8;
 };
 template <typename KeyT> __host__ __device__ constexpr int part1_stage() { return kFastWarps * FastShape<KeyT>::kLanes * (32 / FastShape<KeyT>::kHalves); }
+template <typename KeyT, typename BucketFn> __host__ __device__ constexpr int part1_stage_for() {
+  return part1_stage<KeyT>() + (BucketFn::kBulkStores ? kBulkPadKeys : 0);
+}
 template <typename KeyT> __host__ __device__ constexpr int arr_tile() { return kFastThreads * FastShape<KeyT>::kArrKPT; }
 template <typename KeyT> __host__ __device__ constexpr int p2_tile() { return kFastThreads * FastShape<KeyT>::kP2KPT; }
 
@@ -321,6 +335,68 @@ __device__ __forceinline__ void scatter_tile_l1(const FastPlan &pl, PartSmem<Key
   __syncthreads();
 }
 
+// The same with bulk stores (few buckets only: nb <= kBulkMaxBuckets).  A bulk copy needs 16-byte aligned source and
+// destination: room is reserved FIRST, so that every bucket's run can start in the staging area at a slot with the
+// same 16-byte phase as its destination (one padding slot where they differ); a run's unaligned head and tail key
+// (8-byte keys) go by ordinary stores.
+template <typename KeyT, int NK, typename BucketFn, int THREADS = kFastThreads>
+__device__ __forceinline__ void scatter_tile_bulk(const FastPlan &pl, PartSmem<KeyT> &S, uint32_t nb, const BucketFn &bucket,
+                                                  const KeyT (&key)[NK], uint32_t valid, KeyT *__restrict__ l1, uint32_t *flags) {
+  constexpr uint32_t kPer16 = 16 / sizeof(KeyT); // keys per 16 bytes: 2 or 1
+  uint32_t rank[NK / 2];
+#pragma unroll
+  for (int s = 0; s < NK; s++) {
+    uint32_t r = 0;
+    if (valid & (1u << s)) r = atomicAdd(&S.hist[bucket(key[s])], 1u);
+    if (s & 1) rank[s >> 1] |= r << 16; else rank[s >> 1] = r;
+  }
+  __syncthreads();
+  // reserve: gdelta[b] = destination key index of the run (absolute, not a delta here)
+  if (threadIdx.x < nb) {
+    const uint32_t b = threadIdx.x, c = S.hist[b];
+    unsigned long long dst = pl.l1_trash;
+    if (c) {
+      unsigned long long g = atomicAdd(&pl.l1_cursor[b], (unsigned long long)c);
+      if (g + c > pl.l1_cap[b]) atomicOr(flags, kFlagOverflow);
+      else dst = pl.l1_start[b] + g;
+    }
+    S.gdelta[b] = dst;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { // staging offsets: runs back to back, each starting in its destination's 16-byte phase
+    uint32_t pos = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+      if (kPer16 == 2 && ((pos ^ (uint32_t)S.gdelta[b]) & 1u)) pos++;
+      S.loc[b] = pos;
+      pos += S.hist[b];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < NK; s++)
+    if (valid & (1u << s)) S.stage[S.loc[bucket(key[s])] + ((rank[s >> 1] >> (16 * (s & 1))) & 0xFFFFu)] = key[s];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the staged keys are read by the async proxy next
+  __syncthreads();
+  if (threadIdx.x < nb) {
+    const uint32_t b = threadIdx.x;
+    uint32_t n = S.hist[b];
+    const KeyT *src = S.stage + S.loc[b];
+    KeyT *dst = l1 + S.gdelta[b];
+    if (kPer16 == 2) {
+      if (n && (S.gdelta[b] & 1ull)) { *dst = *src; dst++; src++; n--; } // head key up to the 16-byte boundary
+      if (n & 1u) { dst[n - 1] = src[n - 1]; n--; }                       // odd tail key
+    }
+    if (n) {
+      const uint32_t bytes = n * (uint32_t)sizeof(KeyT);
+      const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(src);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(saddr), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the staging area may be overwritten afterwards
+  }
+  __syncthreads();
+}
+
 // Level-1 scatter, extraction front end.  One CTA tile = 16 warp tiles (u64: all 32 starts of every lane,
 // <= 15872 keys; u128: 16 starts at a time, two tiles per load).
 template <typename KeyT, bool FOLD, typename BucketFn>
@@ -329,7 +405,7 @@ __global__ void __launch_bounds__(kFastThreads, (sizeof(KeyT) == 8 && FastShape<
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kHalves = FastShape<KeyT>::kHalves, kSPH = 32 / kHalves;
   const uint32_t nb = pl.n_l1;
-  PartSmem<KeyT> S(smem_raw, part1_stage<KeyT>(), nb);
+  PartSmem<KeyT> S(smem_raw, part1_stage_for<KeyT, BucketFn>(), nb);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   const uint64_t n_cta_tiles = (n_tiles + kFastWarps - 1) / kFastWarps;
   for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
@@ -348,7 +424,8 @@ __global__ void __launch_bounds__(kFastThreads, (sizeof(KeyT) == 8 && FastShape<
         key[s] = W.key(half * kSPH + s, P.k, P.canonical != 0);
         if ((ok & (0x80000000u >> (half * kSPH + s))) && bucket.accept(key[s])) valid |= 1u << s;
       }
-      scatter_tile_l1<KeyT, kSPH>(pl, S, nb, bucket, key, valid, l1, flags);
+      if constexpr (BucketFn::kBulkStores) scatter_tile_bulk<KeyT, kSPH>(pl, S, nb, bucket, key, valid, l1, flags);
+      else scatter_tile_l1<KeyT, kSPH>(pl, S, nb, bucket, key, valid, l1, flags);
     }
   }
 }
@@ -367,7 +444,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) fast_part1_wide_kernel(Extrac
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kSPT = 16; // window starts per thread
   const uint32_t nb = pl.n_l1;
-  PartSmem<uint64_t> S(smem_raw, part1_stage<uint64_t>(), nb);
+  PartSmem<uint64_t> S(smem_raw, part1_stage_for<uint64_t, BucketFn>(), nb);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, tw = warp & (kFastWarps - 1), half = warp / kFastWarps;
   const uint64_t n_cta_tiles = (n_tiles + kFastWarps - 1) / kFastWarps;
   for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
@@ -384,7 +461,8 @@ __global__ void __launch_bounds__(kWideThreads, 1) fast_part1_wide_kernel(Extrac
       key[s] = W.key(half * kSPT + s, P.k, P.canonical != 0);
       if ((ok & (0x80000000u >> (half * kSPT + s))) && bucket.accept(key[s])) valid |= 1u << s;
     }
-    scatter_tile_l1<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags);
+    if constexpr (BucketFn::kBulkStores) scatter_tile_bulk<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags);
+    else scatter_tile_l1<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags);
   }
 }
 
