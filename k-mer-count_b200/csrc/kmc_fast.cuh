@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(kFastThreads, (sizeof(KeyT) == 8 && FastShape<
       else scatter_tile_l1<KeyT, kSPH>(pl, S, nb, bucket, key, valid, l1, flags);
     }
   }
+  if constexpr (BucketFn::kBulkStores) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // writes landed, not only read
 }
 
 // Experimental (KMC_PART1_WIDE, off): the same tile with twice the warps.  fast_part1_kernel holds all 32 window
@@ -464,6 +465,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) fast_part1_wide_kernel(Extrac
     if constexpr (BucketFn::kBulkStores) scatter_tile_bulk<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags);
     else scatter_tile_l1<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags);
   }
+  if constexpr (BucketFn::kBulkStores) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // Level-1 scatter, key-array front end (ingested keys of the multi-GPU path, lr-gapped keys).
