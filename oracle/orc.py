@@ -29,8 +29,11 @@ class _Table(C.Structure):
 
 
 def build():
-    """Compile oracle/liborc.so (gcc, seconds)."""
-    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+    """Compile oracle/liborc.so (gcc, seconds).  Serialised with a file lock: several test workers may call it."""
+    import fcntl
+    with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        subprocess.run(["make", "-s", "-C", _HERE], check=True)
 
 
 _lib = None
