@@ -88,6 +88,40 @@ __device__ __forceinline__ void load_chunk(const uint8_t *__restrict__ bases, ui
   }
 }
 
+// The 32 bytes of a chunk (and its record-start word) fetched ahead of use: issued before a phase that does not
+// need them (the write-out of the previous tile in fast_part1, KMC_PART1_PREFETCH) and packed afterwards, so the
+// loads' latency is not exposed.  Only the common case — 16-byte aligned, fully inside the segment — is prefetched;
+// ok == 0 means "load as usual".
+struct ChunkPrefetch {
+  uint4 a, b;
+  uint32_t brk, ok;
+};
+__device__ __forceinline__ ChunkPrefetch prefetch_chunk(const ExtractParams &P, uint64_t chunk) {
+  ChunkPrefetch r;
+  r.a = r.b = make_uint4(0u, 0u, 0u, 0u);
+  r.brk = 0u; r.ok = 0u;
+  const uint64_t pos = chunk * 32;
+  if (pos + 32 <= P.n_bases && ((uintptr_t)(P.bases + pos) & 15) == 0) {
+    r.a = ld_stream16(P.bases + pos);
+    r.b = ld_stream16(P.bases + pos + 16);
+    r.brk = P.brk ? P.brk[chunk] : 0u;
+    r.ok = 1u;
+  }
+  return r;
+}
+template <bool FOLD>
+__device__ __forceinline__ void pack_chunk(const uint4 &a, const uint4 &b, uint64_t &codes, uint32_t &valid) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  codes = 0; valid = 0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    uint32_t c, v;
+    pack4<FOLD>(w[q], c, v);
+    codes = (codes << 8) | c;
+    valid = (valid << 4) | v;
+  }
+}
+
 // ---- per-lane window state -----------------------------------------------------------------------
 // K64 : k <= 32, window = 2 chunks (64 positions), 31 productive lanes
 // K128: k <= 64, window = 3 chunks (96 positions), 30 productive lanes
@@ -98,10 +132,13 @@ template <> struct Win<uint64_t> {
   uint64_t w0, w1;
   uint32_t ok; // start s (0..31) valid <-> bit (31 - s)
   template <bool FOLD>
-  __device__ __forceinline__ void load(const ExtractParams &P, uint64_t chunk) {
+  __device__ __forceinline__ void load(const ExtractParams &P, uint64_t chunk, const ChunkPrefetch *pf = nullptr) {
     uint64_t pos = chunk * 32;
     uint64_t c = 0; uint32_t v = 0, b = 0;
-    if (pos < P.n_bases) {
+    if (pf && pf->ok) { // the bytes were fetched ahead (prefetch_chunk of this very chunk)
+      pack_chunk<FOLD>(pf->a, pf->b, c, v);
+      b = pf->brk;
+    } else if (pos < P.n_bases) {
       load_chunk<FOLD>(P.bases, pos, P.n_bases, c, v);
       b = P.brk ? P.brk[chunk] : 0u;
     }

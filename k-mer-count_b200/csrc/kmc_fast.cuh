@@ -60,6 +60,9 @@ constexpr int kHistSampleMax = 16;       // fast_hist looks at every step-th til
 #ifndef KMC_LB_SLEEP
 #define KMC_LB_SLEEP 0      // look-back: nanoseconds to sleep between polls of a predecessor that has not published yet
 #endif
+#ifndef KMC_PART1_PREFETCH
+#define KMC_PART1_PREFETCH 0  // fast_part1: request the next tile's bases before writing the current tile out
+#endif
 #ifndef KMC_FIN_SEGROWS
 #define KMC_FIN_SEGROWS 1  // fast_finish: rows between two listed duplicates are written by a plain shifted copy loop
 #endif
@@ -310,9 +313,13 @@ __device__ __forceinline__ void reserve_l1(const FastPlan &pl, PartSmem<KeyT> &S
 
 // rank (smem atomics) → scan → reserve → stage in bucket order → write runs: the common back end of the
 // level-1 scatters.  key[]/valid describe this thread's NK keys.
-template <typename KeyT, int NK, typename BucketFn, int THREADS = kFastThreads>
+struct NoMid { __device__ __forceinline__ void operator()() const {} };
+// `mid` runs between staging and write-out: the caller's keys are dead by then (KMC_PART1_PREFETCH issues the next
+// tile's loads there).
+template <typename KeyT, int NK, typename BucketFn, int THREADS = kFastThreads, typename Mid = NoMid>
 __device__ __forceinline__ void scatter_tile_l1(const FastPlan &pl, PartSmem<KeyT> &S, uint32_t nb, const BucketFn &bucket,
-                                                const KeyT (&key)[NK], uint32_t valid, KeyT *__restrict__ l1, uint32_t *flags) {
+                                                const KeyT (&key)[NK], uint32_t valid, KeyT *__restrict__ l1, uint32_t *flags,
+                                                const Mid &mid = Mid()) {
   uint32_t rank[NK / 2]; // two 16-bit ranks per word
 #pragma unroll
   for (int s = 0; s < NK; s++) {
@@ -327,6 +334,7 @@ __device__ __forceinline__ void scatter_tile_l1(const FastPlan &pl, PartSmem<Key
 #pragma unroll
   for (int s = 0; s < NK; s++)
     if (valid & (1u << s)) S.stage[S.loc[bucket(key[s])] + ((rank[s >> 1] >> (16 * (s & 1))) & 0xFFFFu)] = key[s];
+  mid();
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
     KeyT k = S.stage[i];
@@ -408,10 +416,16 @@ __global__ void __launch_bounds__(kFastThreads, (sizeof(KeyT) == 8 && FastShape<
   PartSmem<KeyT> S(smem_raw, part1_stage_for<KeyT, BucketFn>(), nb);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   const uint64_t n_cta_tiles = (n_tiles + kFastWarps - 1) / kFastWarps;
+  // KMC_PART1_PREFETCH (experimental, off): the next tile's 32 bytes per lane are requested right after this tile's
+  // keys were staged, so they travel while the staged keys are written out, instead of after it
+  constexpr bool kPrefetch = KMC_PART1_PREFETCH && kHalves == 1 && !BucketFn::kBulkStores;
+  ChunkPrefetch pf;
+  pf.ok = 0u;
   for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
     uint64_t t = ct * kFastWarps + warp;
     Win<KeyT> W{};
-    W.template load<FOLD>(P, t * Win<KeyT>::kLanes + lane);
+    if constexpr (kPrefetch) W.template load<FOLD>(P, t * Win<KeyT>::kLanes + lane, &pf);
+    else W.template load<FOLD>(P, t * Win<KeyT>::kLanes + lane);
     const uint32_t ok = t < n_tiles ? W.ok : 0u;
 #pragma unroll 1
     for (int half = 0; half < kHalves; half++) {
@@ -425,7 +439,14 @@ __global__ void __launch_bounds__(kFastThreads, (sizeof(KeyT) == 8 && FastShape<
         if ((ok & (0x80000000u >> (half * kSPH + s))) && bucket.accept(key[s])) valid |= 1u << s;
       }
       if constexpr (BucketFn::kBulkStores) scatter_tile_bulk<KeyT, kSPH>(pl, S, nb, bucket, key, valid, l1, flags);
-      else scatter_tile_l1<KeyT, kSPH>(pl, S, nb, bucket, key, valid, l1, flags);
+      else if constexpr (kPrefetch) {
+        const uint64_t ct_next = ct + gridDim.x;
+        auto mid = [&]() {
+          pf.ok = 0u;
+          if (ct_next < n_cta_tiles) pf = prefetch_chunk(P, (ct_next * kFastWarps + warp) * Win<KeyT>::kLanes + lane);
+        };
+        scatter_tile_l1<KeyT, kSPH, BucketFn, kFastThreads>(pl, S, nb, bucket, key, valid, l1, flags, mid);
+      } else scatter_tile_l1<KeyT, kSPH>(pl, S, nb, bucket, key, valid, l1, flags);
     }
   }
   if constexpr (BucketFn::kBulkStores) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // writes landed, not only read
@@ -448,10 +469,14 @@ __global__ void __launch_bounds__(kWideThreads, 1) fast_part1_wide_kernel(Extrac
   PartSmem<uint64_t> S(smem_raw, part1_stage_for<uint64_t, BucketFn>(), nb);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, tw = warp & (kFastWarps - 1), half = warp / kFastWarps;
   const uint64_t n_cta_tiles = (n_tiles + kFastWarps - 1) / kFastWarps;
+  constexpr bool kPrefetch = KMC_PART1_PREFETCH && !BucketFn::kBulkStores;
+  ChunkPrefetch pf;
+  pf.ok = 0u;
   for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
     const uint64_t t = ct * kFastWarps + tw;
     Win<uint64_t> W{};
-    W.template load<FOLD>(P, t * Win<uint64_t>::kLanes + lane);
+    if constexpr (kPrefetch) W.template load<FOLD>(P, t * Win<uint64_t>::kLanes + lane, &pf);
+    else W.template load<FOLD>(P, t * Win<uint64_t>::kLanes + lane);
     const uint32_t ok = t < n_tiles ? W.ok : 0u;
     for (uint32_t i = threadIdx.x; i < nb; i += kWideThreads) S.hist[i] = 0;
     __syncthreads();
@@ -463,7 +488,14 @@ __global__ void __launch_bounds__(kWideThreads, 1) fast_part1_wide_kernel(Extrac
       if ((ok & (0x80000000u >> (half * kSPT + s))) && bucket.accept(key[s])) valid |= 1u << s;
     }
     if constexpr (BucketFn::kBulkStores) scatter_tile_bulk<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags);
-    else scatter_tile_l1<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags);
+    else if constexpr (kPrefetch) {
+      const uint64_t ct_next = ct + gridDim.x;
+      auto mid = [&]() {
+        pf.ok = 0u;
+        if (ct_next < n_cta_tiles) pf = prefetch_chunk(P, (ct_next * kFastWarps + tw) * Win<uint64_t>::kLanes + lane);
+      };
+      scatter_tile_l1<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags, mid);
+    } else scatter_tile_l1<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags);
   }
   if constexpr (BucketFn::kBulkStores) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
