@@ -1146,11 +1146,12 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   PHASE_BEGIN("fast_part1");
   if (from_array) {
     size_t smem = PartSmem<KeyT>::bytes(arr_tile<KeyT>(), n_l1);
-    auto fast_part1_array = fast_part1_array_kernel<KeyT>;
+    constexpr int kArrThreads = (KMC_PART1_WIDE && sizeof(KeyT) == 8) ? 2 * kFastThreads : kFastThreads;
+    auto fast_part1_array = fast_part1_array_kernel<KeyT, kArrThreads>;
     CK(cudaFuncSetAttribute(fast_part1_array, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (auto &a : arrays) {
       uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, arr_tile<KeyT>()), (uint64_t)kNumSMsB200);
-      LAUNCH(fast_part1_array, grid, kFastThreads, smem, (const KeyT *)a.first, a.second, pl, (KeyT *)c->fast_l1.p, d_err(c));
+      LAUNCH(fast_part1_array, grid, kArrThreads, smem, (const KeyT *)a.first, a.second, pl, (KeyT *)c->fast_l1.p, d_err(c));
     }
   } else {
     size_t smem = PartSmem<KeyT>::bytes(part1_stage<KeyT>(), n_l1);

@@ -501,18 +501,19 @@ __global__ void __launch_bounds__(kWideThreads, 1) fast_part1_wide_kernel(Extrac
 }
 
 // Level-1 scatter, key-array front end (ingested keys of the multi-GPU path, lr-gapped keys).
-template <typename KeyT>
-__global__ void __launch_bounds__(kFastThreads, 1) fast_part1_array_kernel(const KeyT *__restrict__ keys, uint64_t n,
-                                                                            FastPlan pl, KeyT *__restrict__ l1,
-                                                                            uint32_t *__restrict__ flags) {
+// THREADS = 2 * kFastThreads (KMC_PART1_WIDE, 64-bit keys): the same tile with half the keys per thread, twice the warps.
+template <typename KeyT, int THREADS = kFastThreads>
+__global__ void __launch_bounds__(THREADS, 1) fast_part1_array_kernel(const KeyT *__restrict__ keys, uint64_t n,
+                                                                       FastPlan pl, KeyT *__restrict__ l1,
+                                                                       uint32_t *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int kKPT = FastShape<KeyT>::kArrKPT, kTile = arr_tile<KeyT>();
+  constexpr int kTile = arr_tile<KeyT>(), kKPT = kTile / THREADS;
   const uint32_t nb = pl.n_l1;
   PartSmem<KeyT> S(smem_raw, kTile, nb);
   const PrefixBucketT<true> bucket{pl.b1, pl.kb - pl.b1, pl.l1_base, 0, 0, 0}; // keys are pre-filtered: accept() unused
   const uint64_t n_cta_tiles = (n + kTile - 1) / kTile;
   for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
-    for (uint32_t i = threadIdx.x; i < nb; i += kFastThreads) S.hist[i] = 0;
+    for (uint32_t i = threadIdx.x; i < nb; i += THREADS) S.hist[i] = 0;
     __syncthreads();
     const uint64_t base = ct * kTile;
     const uint32_t cnt = (uint32_t)((n - base < (uint64_t)kTile) ? n - base : kTile);
@@ -520,10 +521,10 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part1_array_kernel(const
     uint32_t valid = 0;
 #pragma unroll
     for (int j = 0; j < kKPT; j++) {
-      uint32_t idx = j * kFastThreads + threadIdx.x;
+      uint32_t idx = j * THREADS + threadIdx.x;
       if (idx < cnt) { key[j] = keys[base + idx]; valid |= 1u << j; } else key[j] = KeyT{};
     }
-    scatter_tile_l1<KeyT, kKPT>(pl, S, nb, bucket, key, valid, l1, flags);
+    scatter_tile_l1<KeyT, kKPT, PrefixBucketT<true>, THREADS>(pl, S, nb, bucket, key, valid, l1, flags);
   }
 }
 
