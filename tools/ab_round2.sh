@@ -16,6 +16,7 @@ cat <<'MSG'
 
 # 1 GPU: step time, per-phase times and digest equality of every variant (k = 21, 31, 19), ~40 s of box time
 gpurun --timeout 240 -- 'python tools/ab.py --k 21,31,19 ab_libs/cur.so ab_libs/wide.so ab_libs/pf.so ab_libs/wide_pf.so ab_libs/cap64.so ab_libs/wide_cap64.so > gpurun_out/ab_r2.jsonl 2> gpurun_out/ab_r2.err; tail -n 3 gpurun_out/ab_r2.err'
+python tools/ab_report.py gpurun_out/ab_r2.jsonl
 
 # 1 GPU: the routing kernel with bulk stores against the oracle (kmc_route goes through the same kernel)
 gpurun --timeout 300 -- 'KMC_LIB=$PWD/ab_libs/tma.so python -m pytest tests/test_gpu_parity.py tests/test_gpu_fastpath.py -x -q -m gpu -k "route or dist or key_array" > gpurun_out/tma_tests.log 2>&1; tail -n 3 gpurun_out/tma_tests.log'
