@@ -186,6 +186,21 @@ int kmc_ipc_close(kmc_ctx *ctx, void *d_peer_ptr);
 /* Hand the ctx keys it owns (device pointer, same layout as kmc_route's output; referenced until
  * kmc_finish).  kmc_finish then counts the ingested keys instead of extracting from the input.    */
 int kmc_ingest_keys(kmc_ctx *ctx, const void *d_keys, uint64_t n_keys);
+/* ---- multi-GPU, low-cardinality input: count locally, exchange rows ("(key,count) pairs after local
+ * combine when cardinality is low") -------------------------------------------------------------------------------
+ * When every rank's input has few distinct keys (BASELINE.json config 5: reads from a small repetitive genome), routing
+ * every key occurrence to its owner moves gigabytes to merge what fits in megabytes.  Instead each rank counts its own
+ * shard (kmc_finish), groups the rows of its table by owner with kmc_table_route, the rows are exchanged (one small
+ * all-to-all of keys and one of counts), and every owner merges what it received:
+ *   kmc_submit* → kmc_finish → kmc_table_route(n_parts) → [all-to-all] → kmc_reset → kmc_ingest_pairs* → kmc_finish
+ * kmc_table_route: part p's rows are the part_count[p] entries from index part_begin[p] of *d_keys (keys) and
+ *   *d_counts (counts, 64-bit): library-owned device arrays, valid until the next kmc_table_route or kmc_destroy.
+ * kmc_ingest_pairs: rows this ctx owns (device pointers, referenced until kmc_finish).  kmc_finish then leaves the
+ *   sorted table in which equal keys' counts have been added up; n_total = the sum of all counts.  Cannot be mixed
+ *   with submitted input or kmc_ingest_keys.  Both calls: keys of <= 64 bits only.                                */
+int kmc_table_route(kmc_ctx *ctx, uint32_t n_parts, uint64_t *part_begin, uint64_t *part_count, const uint64_t **d_keys,
+                    const uint64_t **d_counts);
+int kmc_ingest_pairs(kmc_ctx *ctx, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n_rows);
 /* owner part of a key, host-side (the same function the device uses).                            */
 uint32_t kmc_owner_of(uint64_t key_hi, uint64_t key_lo, uint32_t n_parts);
 

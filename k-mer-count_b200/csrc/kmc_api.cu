@@ -104,6 +104,10 @@ struct kmc_ctx {
 
   // ingested keys (multi-GPU)
   std::vector<std::pair<const void *, uint64_t>> ingested;
+  // ingested (key, count) rows (multi-GPU, locally combined counts): keys, counts, rows
+  struct PairArray { const uint64_t *keys; const uint64_t *counts; uint64_t n; };
+  std::vector<PairArray> ingested_pairs;
+  DevBuf pair_rows, pair_state; // kmc_table_route: rows grouped by owner; per-part population / cursors
 
   // work buffers (grow-only, reused across kmc_reset)
   DevBuf keys_a, keys_b, block_hist, offsets, sums, scalars, route_keys;
@@ -832,6 +836,63 @@ int finish_hash(kmc_ctx *c, uint32_t log2_slots, uint64_t limit, bool *used) {
   c->n_total = n_total; c->n_distinct = rows;
   c->strategy_used = KMC_STRATEGY_HASH;
   *used = true;
+  return KMC_OK;
+}
+
+// (key, count) rows handed over with kmc_ingest_pairs: merge them through the hash table (equal keys add up), then
+// the same compaction / sort / look-up as finish_hash.  Kept apart from finish_hash on purpose: that one is the measured
+// single-GPU path.
+int finish_pairs(kmc_ctx *c) {
+  uint64_t rows_in = 0;
+  for (auto &a : c->ingested_pairs) rows_in += a.n;
+  uint32_t lg = 10;
+  while (lg < 33 && (1ull << lg) < 2 * rows_in + 2) lg++; // load factor <= 1/2 even if every row is a distinct key
+  const uint64_t slots = 1ull << lg;
+  TRY(ensure(c, c->hash_slots, slots * sizeof(HashSlot)));
+  TRY(ensure(c, c->hash_scalars, 64));
+  PHASE_BEGIN("hash_count");
+  LAUNCH(hash_init_kernel, std::min<uint32_t>(grid_for(slots, 256), kNumSMsB200 * 16), 256, 0, (HashSlot *)c->hash_slots.p, slots);
+  CK(cudaMemsetAsync(c->hash_scalars.p, 0, 64, c->stream));
+  HashTable T;
+  T.slots = (HashSlot *)c->hash_slots.p;
+  T.mask = slots - 1; T.shift = 64 - lg;
+  T.n_used = (unsigned long long *)c->hash_scalars.p; T.n_total = T.n_used + 1; T.n_ones = T.n_used + 2;
+  T.limit = slots; T.flags = d_err(c);
+  for (auto &a : c->ingested_pairs)
+    if (a.n) LAUNCH(hash_count_pairs_kernel, std::min<uint32_t>(grid_for(a.n, 1024), kNumSMsB200 * 8), 256, 0, a.keys, a.counts, a.n, T);
+  PHASE_END();
+  uint32_t err = 0;
+  TRY(read_scalars(c, nullptr, &err));
+  if (err & kFlagHashFull) return fail(c, KMC_E_CAPACITY, "kmc_finish: the merge table filled up (internal sizing error)");
+  unsigned long long sc[3];
+  TRY(d2h_small(c, sc, c->hash_scalars.p, sizeof sc));
+  const uint64_t d = sc[0], n_total = sc[1], n_ones = sc[2];
+  if (n_ones > 0xFFFFFFFFull) return fail(c, KMC_E_COUNT_OVERFLOW, "a k-mer occurs more than 2^32-1 times");
+  PHASE_BEGIN("hash_sort");
+  TRY(ensure(c, c->t_lo, (d + 2) * 8));
+  TRY(ensure(c, c->keys_b, (d + 2) * 8));
+  TRY(ensure(c, c->t_cnt, (d + 2) * 4));
+  uint64_t *dense = (uint64_t *)c->t_lo.p, *scratch = (uint64_t *)c->keys_b.p, *sorted = nullptr;
+  if (d) {
+    CK(cudaMemsetAsync(d_cursor(c), 0, 8, c->stream));
+    LAUNCH(hash_compact_kernel, std::min<uint32_t>(grid_for(T.mask + 1, 256), kNumSMsB200 * 16), 256, 0, T, dense, d_cursor(c));
+    TRY(radix_sort<uint64_t>(c, dense, scratch, d, c->key_bits, &sorted));
+    if (sorted != dense) CK(cudaMemcpyAsync(dense, sorted, d * 8, cudaMemcpyDeviceToDevice, c->stream));
+    LAUNCH(hash_lookup_kernel, std::min<uint32_t>(grid_for(d, 256), kNumSMsB200 * 16), 256, 0, T, (const uint64_t *)dense, d,
+           (uint32_t *)c->t_cnt.p);
+  }
+  uint64_t rows = d;
+  if (n_ones) { // the all-ones key (k = 32) sorts last
+    uint64_t k1 = kHashEmpty;
+    uint32_t c1 = (uint32_t)n_ones;
+    CK(cudaMemcpyAsync(dense + d, &k1, 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync((uint32_t *)c->t_cnt.p + d, &c1, 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    rows++;
+  }
+  PHASE_END();
+  c->n_total = n_total; c->n_distinct = rows;
+  c->strategy_used = KMC_STRATEGY_HASH;
   return KMC_OK;
 }
 
@@ -1759,7 +1820,8 @@ void kmc_destroy(kmc_ctx *c) {
   if (c->fmt_host) cudaFreeHost(c->fmt_host);
   for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); if (s.ready) cudaEventDestroy(s.ready); }
   for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
-                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->fast_fdesc, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot, &c->fa_raw, &c->fa_tiles, &c->fa_flags, &c->fmt_len, &c->fmt_off, &c->fmt_text})
+                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->fast_fdesc, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot, &c->fa_raw, &c->fa_tiles, &c->fa_flags, &c->fmt_len, &c->fmt_off, &c->fmt_text, &c->pair_rows, &c->pair_state,
+                    &c->dist_tables})
     release(*b);
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1782,6 +1844,7 @@ int kmc_reset(kmc_ctx *c) {
   if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
   c->n_segs = 0; c->total_bases = c->total_recs = 0;
   c->ingested.clear();
+  c->ingested_pairs.clear();
   c->finished = false; c->n_total = c->n_distinct = 0;
   c->range_on = false; c->part_hist_step = 0;
   c->dist.valid = false; c->dist.scattered = false;
@@ -1940,12 +2003,54 @@ int kmc_ingest_keys(kmc_ctx *c, const void *d_keys, uint64_t n_keys) {
   return KMC_OK;
 }
 
+int kmc_ingest_pairs(kmc_ctx *c, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n_rows) {
+  if (!c || ((!d_keys || !d_counts) && n_rows)) return KMC_E_ARG;
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_ingest_pairs after kmc_finish (call kmc_reset first)");
+  if (c->wide) return fail(c, KMC_E_ARG, "kmc_ingest_pairs: 64-bit keys only");
+  if (c->n_segs || !c->ingested.empty()) return fail(c, KMC_E_ARG, "kmc_ingest_pairs cannot be mixed with submitted input or ingested keys");
+  c->ingested_pairs.push_back({d_keys, d_counts, n_rows});
+  return KMC_OK;
+}
+
+int kmc_table_route(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *part_count, const uint64_t **d_keys,
+                    const uint64_t **d_counts) {
+  if (!c || !part_begin || !part_count || !d_keys || !d_counts) return KMC_E_ARG;
+  if (!c->finished) return fail(c, KMC_E_ARG, "kmc_table_route before kmc_finish");
+  if (c->wide) return fail(c, KMC_E_ARG, "kmc_table_route: 64-bit keys only");
+  if (n_parts < 1 || n_parts > 1024) return fail(c, KMC_E_ARG, "kmc_table_route: n_parts must be 1..1024");
+  CK(cudaSetDevice(c->device));
+  const uint64_t rows = c->n_distinct;
+  TRY(ensure(c, c->pair_rows, 2 * (rows + 2) * 8));
+  TRY(ensure(c, c->pair_state, 1024 * 8));
+  uint64_t *out_keys = (uint64_t *)c->pair_rows.p, *out_counts = out_keys + (rows + 2);
+  unsigned long long *state = (unsigned long long *)c->pair_state.p;
+  std::vector<unsigned long long> h(n_parts, 0);
+  if (rows) {
+    CK(cudaMemsetAsync(state, 0, (size_t)n_parts * 8, c->stream));
+    const uint32_t grid = std::min<uint32_t>(grid_for(rows, 1024), kNumSMsB200 * 8);
+    LAUNCH(table_owner_hist_kernel, grid, 256, 0, (const uint64_t *)c->t_lo.p, rows, n_parts, state);
+    TRY(d2h_small(c, h.data(), state, (size_t)n_parts * 8));
+    std::vector<unsigned long long> begin(n_parts, 0);
+    for (uint32_t p = 1; p < n_parts; p++) begin[p] = begin[p - 1] + h[p - 1];
+    TRY(h2d_small(c, state, begin.data(), (size_t)n_parts * 8));
+    LAUNCH(table_owner_scatter_kernel, grid, 256, 0, (const uint64_t *)c->t_lo.p, (const uint32_t *)c->t_cnt.p, rows, n_parts, state,
+           out_keys, out_counts);
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  uint64_t b = 0;
+  for (uint32_t p = 0; p < n_parts; p++) { part_begin[p] = b; part_count[p] = h[p]; b += h[p]; }
+  *d_keys = out_keys; *d_counts = out_counts;
+  return KMC_OK;
+}
+
 static int finish_common(kmc_ctx *c, uint64_t *n_distinct, uint64_t *n_total) {
   const double host_t0 = host_now_ms();
   const size_t first_phase = c->phases.size();
   c->host_marks.clear();
+  if (!c->ingested_pairs.empty() && (c->n_segs || !c->ingested.empty()))
+    return fail(c, KMC_E_ARG, "kmc_finish: (key, count) rows cannot be mixed with submitted input or ingested keys");
   TRY(zero_scalars(c));
-  int rc = c->wide ? finish_impl<U128>(c) : finish_impl<uint64_t>(c);
+  int rc = !c->ingested_pairs.empty() ? finish_pairs(c) : c->wide ? finish_impl<U128>(c) : finish_impl<uint64_t>(c);
   if (rc) return rc;
   uint32_t err = 0;
   TRY(read_scalars(c, nullptr, &err));

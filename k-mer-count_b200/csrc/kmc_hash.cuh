@@ -197,6 +197,54 @@ __global__ void __launch_bounds__(256) hash_count_array_kernel(const uint64_t *_
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(T.n_total, mine);
 }
 
+// (key, count) rows front end: the merge step of the multi-GPU "count locally, exchange rows" route for
+// low-cardinality input — equal keys from different ranks add up in the table.
+__global__ void __launch_bounds__(256) hash_count_pairs_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ counts,
+                                                                uint64_t n, HashTable T) {
+  unsigned long long mine = 0;
+  for (uint64_t base = blockIdx.x * 1024ull; base < n; base += gridDim.x * 1024ull) { // block-uniform: the lanes stay together
+    uint32_t claimed = 0;
+    for (uint32_t j = threadIdx.x; j < 1024; j += 256)
+      if (base + j < n) {
+        const unsigned long long cnt = counts[base + j];
+        if (cnt) {
+          // a row's count fits 32 bits (it comes from a table); the slot's running sum is 64-bit
+          claimed += hash_add(T, keys[base + j], (uint32_t)(cnt > 0xFFFFFFFFull ? 0xFFFFFFFFull : cnt));
+          if (cnt > 0xFFFFFFFFull) atomicOr(T.flags, 4u);
+          mine += cnt;
+        }
+      }
+    hash_report(T, claimed);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(T.n_total, mine);
+}
+
+// rows of a finished table (64-bit keys) grouped by owner part: population per part, then a scatter with one cursor
+// per part (order inside a part does not matter — the owner merges through its hash table)
+__global__ void __launch_bounds__(256) table_owner_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t n_parts,
+                                                                unsigned long long *__restrict__ hist) {
+  __shared__ uint32_t sh[1024];
+  for (uint32_t i = threadIdx.x; i < n_parts; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    atomicAdd(&sh[owner_of(0ull, keys[i], n_parts)], 1u);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n_parts; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+__global__ void __launch_bounds__(256) table_owner_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ counts,
+                                                                   uint64_t n, uint32_t n_parts, unsigned long long *__restrict__ cursor,
+                                                                   uint64_t *__restrict__ out_keys, uint64_t *__restrict__ out_counts) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = keys[i];
+    const unsigned long long pos = atomicAdd(&cursor[owner_of(0ull, key, n_parts)], 1ull);
+    out_keys[pos] = key;
+    out_counts[pos] = counts[i];
+  }
+}
+
 // occupied slots → dense key array (unordered); *cursor ends at the number of distinct keys
 __global__ void __launch_bounds__(256) hash_compact_kernel(HashTable T, uint64_t *__restrict__ out,
                                                             unsigned long long *__restrict__ cursor) {

@@ -25,6 +25,14 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 2}
 
 
+def _view(torch, ptr, n_words, dev):
+    """int64 tensor over `n_words` words at `ptr` — device memory, or (CPU tests of the host logic) host memory."""
+    if dev.type == "cuda":
+        return torch.as_tensor(_DevArray(ptr, n_words), device=dev)
+    import ctypes
+    return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_int64 * n_words).from_address(ptr)))
+
+
 def split_sizes(part_count, words):
     """int64 elements per destination, from kmc_route's part counts (a key is `words` int64s)."""
     return (np.asarray(part_count, dtype=np.int64) * words).tolist()
@@ -80,6 +88,29 @@ def exchange(torch, dist, send_parts):
     return recv, recv_sizes
 
 
+def finish_combined(kc, torch, dist, world, dev, keep):
+    """Low-cardinality input on several GPUs ("(key,count) pairs after local combine"): every rank counts
+    its own shard, the rows of its table are grouped by owner (kmc_table_route) and exchanged — two small all-to-alls
+    instead of one of every key occurrence — and every owner merges the rows it received (kmc_ingest_pairs + kmc_finish:
+    equal keys' counts add up).  `kc` is a KmerCounter (or, in the CPU tests of this orchestration, a stand-in with the
+    same four methods); `keep` receives the tensors the ctx references until its finish returns."""
+    kc.finish()                                            # this rank's shard, counted on its own
+    begin, count, kptr, cptr = kc.table_route(world)
+    rows = int((begin + count).max()) if len(begin) else 0
+    if rows:
+        keys, cnts = _view(torch, kptr, rows, dev), _view(torch, cptr, rows, dev)
+    else:
+        keys = cnts = torch.empty(0, dtype=torch.int64, device=dev)
+    parts_k = [keys[int(b):int(b) + int(n)] for b, n in zip(begin, count)]
+    parts_c = [cnts[int(b):int(b) + int(n)] for b, n in zip(begin, count)]
+    recv_k, _ = exchange(torch, dist, parts_k)
+    recv_c, _ = exchange(torch, dist, parts_c)
+    keep.extend([recv_k, recv_c])
+    kc.reset()                                             # drops the shard's input and table, keeps the buffers
+    kc.ingest_pairs(recv_k.data_ptr(), recv_c.data_ptr(), recv_k.numel())
+    return kc.finish()
+
+
 class DistCounter:
     """KmerCounter that, when world > 1, routes keys to their owner ranks before counting.
 
@@ -105,6 +136,10 @@ class DistCounter:
         # scatter (-4.6 ms), but the senders' NVLink stores now come in runs of ~250 B instead of ~16 KB and reach
         # 360 instead of 535 GB/s (+3.5 ms), and with more GPUs the runs only get shorter.  Default: hash.
         self.use_range = self.use_peer and strategy in (0, 2) and os.environ.get("KMC_DIST_PARTITION", "hash") == "range"
+        # KMC_DIST_COMBINE=1 (opt-in until it has been measured on a multi-GPU box): when every rank's input is
+        # low-cardinality — the hash strategy's case — count locally and exchange table rows (finish_combined)
+        self.use_combine = (world > 1 and kw.get("mode", 0) == 0 and self.key_bytes == 8 and strategy in (0, 1)
+                            and os.environ.get("KMC_DIST_COMBINE", "0") == "1")
 
     def set_stream(self, ptr):
         self.kc.set_stream(ptr)
@@ -204,6 +239,15 @@ class DistCounter:
         torch, dist = self.torch, self.dist
         self._t = [time.perf_counter()]
         dev = torch.device("cuda", torch.cuda.current_device())
+        if self.use_combine:
+            # the cardinality probe of the AUTO strategy, on this rank's shard; the route is taken only if every rank agrees
+            _, low = self.kc.dist_hist()
+            flag = torch.tensor([int(low)], dtype=torch.int64, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag):
+                self.path = "combine"
+                self._keep = []
+                return finish_combined(self.kc, torch, dist, self.world, dev, self._keep)
         if self.use_range:
             out = self._finish_range()
             if out is not None:

@@ -25,7 +25,7 @@ SYMBOLS = ["kmc_create", "kmc_destroy", "kmc_last_error", "kmc_strerror", "kmc_s
            "kmc_table_device", "kmc_digest", "kmc_key_bases", "kmc_route", "kmc_ingest_keys", "kmc_owner_of",
            "kmc_stats_json", "kmc_route_to_peers", "kmc_recv_buffer", "kmc_ipc_export", "kmc_ipc_open",
            "kmc_ipc_close", "kmc_submit_fasta", "kmc_format", "kmc_finish_part",
-           "kmc_dist_hist", "kmc_dist_plan", "kmc_dist_scatter"]
+           "kmc_dist_hist", "kmc_dist_plan", "kmc_dist_scatter", "kmc_table_route", "kmc_ingest_pairs"]
 
 
 class KmcConfig(C.Structure):
@@ -87,6 +87,8 @@ def load_library(path=None):
     L.kmc_ipc_export.argtypes = [vp, vp, C.c_char_p]
     L.kmc_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.kmc_ipc_close.argtypes = [vp, vp]
+    L.kmc_table_route.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(vp), C.POINTER(vp)]
+    L.kmc_ingest_pairs.argtypes = [vp, vp, vp, C.c_uint64]
     L.kmc_owner_of.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
     L.kmc_owner_of.restype = C.c_uint32
     L.kmc_stats_json.argtypes = [vp, C.c_char_p, C.c_size_t]
@@ -292,6 +294,19 @@ class KmerCounter:
 
     def ingest_keys(self, d_keys_ptr, n_keys):
         self._ck(self._L.kmc_ingest_keys(self._h, C.c_void_p(d_keys_ptr), n_keys))
+
+    # -- multi-GPU, low-cardinality input: locally combined (key, count) rows
+    def table_route(self, n_parts):
+        """Rows of the finished table grouped by owner part → (part_begin, part_count, device pointer of the keys,
+        device pointer of the 64-bit counts)."""
+        begin, count = np.zeros(n_parts, np.uint64), np.zeros(n_parts, np.uint64)
+        keys, counts = C.c_void_p(), C.c_void_p()
+        self._ck(self._L.kmc_table_route(self._h, n_parts, begin.ctypes.data, count.ctypes.data, C.byref(keys), C.byref(counts)))
+        return begin, count, keys.value, counts.value
+
+    def ingest_pairs(self, d_keys_ptr, d_counts_ptr, n_rows):
+        """(key, count) rows this context owns; finish() merges them (equal keys add up) into the sorted table."""
+        self._ck(self._L.kmc_ingest_pairs(self._h, C.c_void_p(d_keys_ptr), C.c_void_p(d_counts_ptr), n_rows))
 
 
 def count_kmers(bases, rec_off, k, canonical=True, strategy=STRATEGY_AUTO, device=-1):

@@ -67,3 +67,84 @@ def test_split_sizes():
     from kmer_count_b200.dist import split_sizes
     assert split_sizes(np.array([3, 0, 7], np.uint64), 1) == [3, 0, 7]
     assert split_sizes(np.array([3, 0, 7], np.uint64), 2) == [6, 0, 14]
+
+
+class _FakeCounter:
+    """numpy stand-in for KmerCounter's four calls used by finish_combined (host memory instead of HBM): lets the
+    orchestration — who sends which rows where, and that the owners end up with summed counts — run on CPU ranks."""
+
+    def __init__(self, lib, occurrences):
+        self.L, self.occ = lib, occurrences
+        self.pairs, self.table, self.keep = [], None, []
+
+    def finish(self):
+        if self.pairs:
+            k = np.concatenate([p[0] for p in self.pairs])
+            c = np.concatenate([p[1] for p in self.pairs])
+            keys, inv = np.unique(k, return_inverse=True)
+            counts = np.bincount(inv, weights=c.astype(np.float64), minlength=len(keys)).astype(np.uint64)
+        else:
+            keys, counts = np.unique(self.occ, return_counts=True)
+            counts = counts.astype(np.uint64)
+        self.table = (keys.astype(np.uint64), counts)
+        return len(keys), int(counts.sum())
+
+    def table_route(self, world):
+        keys, counts = self.table
+        owner = np.array([self.L.kmc_owner_of(0, int(k), world) for k in keys], dtype=np.int64)
+        order = np.argsort(owner, kind="stable")
+        ko, co = np.ascontiguousarray(keys[order]), np.ascontiguousarray(counts[order])
+        self.keep = [ko, co]
+        count = np.bincount(owner, minlength=world).astype(np.uint64)
+        begin = (np.cumsum(count) - count).astype(np.uint64)
+        return begin, count, ko.ctypes.data, co.ctypes.data
+
+    def reset(self):
+        self.occ, self.pairs, self.table = np.zeros(0, np.uint64), [], None
+
+    def ingest_pairs(self, kptr, cptr, n):
+        import ctypes
+        rd = lambda p: np.ctypeslib.as_array((ctypes.c_uint64 * n).from_address(p)).copy() if n else np.zeros(0, np.uint64)
+        self.pairs.append((rd(kptr), rd(cptr)))
+
+
+def _combine_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import kmer_count_b200 as K
+    from kmer_count_b200.dist import finish_combined
+    L = K.load_library()
+    pool = np.random.default_rng(7).integers(0, 1 << 62, 3000, dtype=np.uint64)       # the same pool on every rank
+    occ = pool[np.random.default_rng(50 + rank).integers(0, len(pool), 40000 + 1000 * rank)]
+    kc = _FakeCounter(L, occ)
+    keep = []
+    d, t = finish_combined(kc, torch, dist, world, torch.device("cpu"), keep)
+    keys, counts = kc.table
+    owned = all(L.kmc_owner_of(0, int(k), world) == rank for k in keys)
+    q.put((rank, owned, d, t, keys.tolist(), counts.tolist(), occ.tolist()))
+    dist.destroy_process_group()
+
+
+def test_finish_combined_merges_local_tables():
+    """Low-cardinality route: local tables → rows to owners → owners hold disjoint key sets with globally summed counts."""
+    import kmer_count_b200 as K
+    K.build()
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_combine_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res)
+    want_k, want_c = np.unique(np.concatenate([np.array(r[6], np.uint64) for r in res]), return_counts=True)
+    got = {}
+    for r in res:
+        assert r[2] == len(r[4]) and r[3] == sum(r[5])
+        for k, c in zip(r[4], r[5]):
+            assert k not in got
+            got[k] = c
+    assert got == dict(zip(want_k.tolist(), want_c.tolist()))

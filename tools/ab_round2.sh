@@ -21,6 +21,9 @@ python tools/ab_report.py gpurun_out/ab_r2.jsonl
 # 1 GPU: the routing kernel with bulk stores against the oracle (kmc_route goes through the same kernel)
 gpurun --timeout 300 -- 'KMC_LIB=$PWD/ab_libs/tma.so python -m pytest tests/test_gpu_parity.py tests/test_gpu_fastpath.py -x -q -m gpu -k "route or dist or key_array" > gpurun_out/tma_tests.log 2>&1; tail -n 3 gpurun_out/tma_tests.log'
 
+# 1 GPU: the low-cardinality multi-GPU route (kmc_table_route + kmc_ingest_pairs) with emulated ranks, vs the oracle
+gpurun --timeout 200 -- 'python tools/check_combine.py 3 31 && python tools/check_combine.py 2 21 && python tools/check_combine.py 4 32'
+
 # 2 GPUs: routing pass with and without bulk stores (phases_ms.route in the JSON line)
 gpurun --gpus 2 --timeout 200 -- 'for v in cur tma; do KMC_LIB=$PWD/ab_libs/$v.so python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu > gpurun_out/n2_$v.json 2> gpurun_out/n2_$v.err; done'
 MSG
