@@ -57,3 +57,13 @@ def test_owner_function_is_balanced(kmc):
         counts[L.kmc_owner_of(0, i * 2654435761 % (1 << 42), 8)] += 1
     assert counts.min() > 400 and counts.max() < 600
     assert all(L.kmc_owner_of(i, i, 1) == 0 for i in range(10))
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/kmc.h must compile as C99 (and as C++) on its own — no C++ or torch types."""
+    import subprocess
+    hdr = os.path.join(REPO, "include", "kmc.h")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                ["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
