@@ -641,10 +641,6 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
                void *const *part_ptr = nullptr, uint64_t peer_cap = 0) {
   *done = false;
   if (!part_ptr && (c->total_bases < (1u << 18) || n_parts > (uint32_t)kMaxL1)) return KMC_OK;
-  if (OwnerBucket::kBulkStores && n_parts > (uint32_t)kBulkMaxBuckets) {
-    if (part_ptr) return fail(c, KMC_E_ARG, "kmc_route_to_peers: at most %d parts in this build", kBulkMaxBuckets);
-    return KMC_OK;
-  }
   const uint64_t cap = part_ptr ? peer_cap : (((uint64_t)((double)c->total_bases / n_parts * 1.03) + 65536 + 15) & ~15ull);
   const uint64_t total = part_ptr ? 0 : cap * n_parts;
   TRY(ensure(c, c->route_keys, (total + 2 * kMaxTile) * sizeof(KeyT)));
@@ -667,7 +663,7 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
   pl.l1_cursor = (unsigned long long *)((unsigned char *)c->fast_state.p + off_l1cur);
   PHASE_BEGIN("route");
   {
-    size_t smem = PartSmem<KeyT>::bytes(part1_stage_for<KeyT, OwnerBucket>(), n_parts);
+    size_t smem = L1Smem<KeyT>::bytes(part1_stage<KeyT>(), n_parts);
     auto fast_route = fast_part1_kernel<KeyT, true, OwnerBucket>;
     CK(cudaFuncSetAttribute(fast_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const OwnerBucket bucket{n_parts};
@@ -678,13 +674,7 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
       ExtractParams P = seg_params(c, s);
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
-      if constexpr (KMC_PART1_WIDE && sizeof(KeyT) == 8) {
-        auto wide = fast_part1_wide_kernel<true, OwnerBucket>;
-        CK(cudaFuncSetAttribute(wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LAUNCH(wide, grid, kWideThreads, smem, P, tiles, pl, bucket, (uint64_t *)dst, d_err(c));
-      } else {
-        LAUNCH(fast_route, grid, kFastThreads, smem, P, tiles, pl, bucket, dst, d_err(c));
-      }
+      LAUNCH(fast_route, grid, kFastThreads, smem, P, tiles, pl, bucket, dst, d_err(c));
     }
   }
   PHASE_END();
@@ -1206,39 +1196,29 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   // ---- level 1
   PHASE_BEGIN("fast_part1");
   if (from_array) {
-    size_t smem = PartSmem<KeyT>::bytes(arr_tile<KeyT>(), n_l1);
-    constexpr int kArrThreads = (KMC_PART1_WIDE && sizeof(KeyT) == 8) ? 2 * kFastThreads : kFastThreads;
-    auto fast_part1_array = fast_part1_array_kernel<KeyT, kArrThreads>;
+    size_t smem = L1Smem<KeyT>::bytes(arr_tile<KeyT>(), n_l1);
+    constexpr int kArrThreads = kFastThreads;
+    auto fast_part1_array = fast_part1_array_kernel<KeyT>;
     CK(cudaFuncSetAttribute(fast_part1_array, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (auto &a : arrays) {
       uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, arr_tile<KeyT>()), (uint64_t)kNumSMsB200);
       LAUNCH(fast_part1_array, grid, kArrThreads, smem, (const KeyT *)a.first, a.second, pl, (KeyT *)c->fast_l1.p, d_err(c));
     }
   } else {
-    size_t smem = PartSmem<KeyT>::bytes(part1_stage<KeyT>(), n_l1);
+    size_t smem = L1Smem<KeyT>::bytes(part1_stage<KeyT>(), n_l1);
     auto fast_part1 = fast_part1_kernel<KeyT, true, PrefixBucket>;
     auto fast_part1_ranged = fast_part1_kernel<KeyT, true, PrefixBucketT<true>>;
     if (ranged) CK(cudaFuncSetAttribute(fast_part1_ranged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else CK(cudaFuncSetAttribute(fast_part1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const PrefixBucket bucket{b1, kb - b1, 0, 0, 0, 0};
-    const PrefixBucketT<true> bucket_ranged{b1, kb - b1, l1_base, kb - cb, c_lo, c_hi - c_lo};
+    const PrefixBucket bucket = make_prefix_bucket<false>(kb, b1);
+    const PrefixBucketT<true> bucket_ranged = make_prefix_bucket<true>(kb, b1, l1_base, kb - cb, c_lo, c_hi - c_lo);
     for (size_t i = 0; i < c->n_segs; i++) {
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
       TRY(seg_wait(c, s));
       ExtractParams P = seg_params(c, s);
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps,
-                                                   (uint64_t)kNumSMsB200 * ((sizeof(KeyT) == 8 && FastShape<KeyT>::kHalves == 2) ? 2 : 1));
-      if constexpr (KMC_PART1_WIDE && sizeof(KeyT) == 8) {
-        if (!ranged) {
-          auto fast_part1_wide = fast_part1_wide_kernel<true, PrefixBucket>;
-          CK(cudaFuncSetAttribute(fast_part1_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          LAUNCH(fast_part1_wide, std::min<uint32_t>(grid, (uint32_t)kNumSMsB200), kWideThreads, smem, P, tiles, pl, bucket,
-                 (uint64_t *)c->fast_l1.p, d_err(c));
-          continue;
-        }
-      }
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
       if (ranged) LAUNCH(fast_part1_ranged, grid, kFastThreads, smem, P, tiles, pl, bucket_ranged, (KeyT *)c->fast_l1.p, d_err(c));
       else LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->fast_l1.p, d_err(c));
     }
@@ -1468,10 +1448,10 @@ int dist_scatter_impl(kmc_ctx *c, void *const *peer_buf, uint32_t *overflow) {
   pl.l1_cursor = (unsigned long long *)((unsigned char *)c->fast_state.p + off_l1cur);
   PHASE_BEGIN("route");
   {
-    size_t smem = PartSmem<KeyT>::bytes(part1_stage<KeyT>(), n_all);
+    size_t smem = L1Smem<KeyT>::bytes(part1_stage<KeyT>(), n_all);
     auto fast_scatter_to_owners = fast_part1_kernel<KeyT, true, PrefixBucket>;
     CK(cudaFuncSetAttribute(fast_scatter_to_owners, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const PrefixBucket bucket{D.b1, kb - D.b1, 0, 0, 0, 0};
+    const PrefixBucket bucket = make_prefix_bucket<false>(kb, D.b1);
     for (size_t i = 0; i < c->n_segs; i++) {
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
@@ -1479,13 +1459,7 @@ int dist_scatter_impl(kmc_ctx *c, void *const *peer_buf, uint32_t *overflow) {
       ExtractParams P = seg_params(c, s);
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
-      if constexpr (KMC_PART1_WIDE && sizeof(KeyT) == 8) {
-        auto wide = fast_part1_wide_kernel<true, PrefixBucket>;
-        CK(cudaFuncSetAttribute(wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LAUNCH(wide, grid, kWideThreads, smem, P, tiles, pl, bucket, (uint64_t *)nullptr, d_err(c));
-      } else {
-        LAUNCH(fast_scatter_to_owners, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)nullptr, d_err(c));
-      }
+      LAUNCH(fast_scatter_to_owners, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)nullptr, d_err(c));
     }
     LAUNCH(dist_publish_kernel, grid_for(n_all, 256), 256, 0, pl.l1_cursor, pl.l1_cap, (const uint32_t *)(tb + o_own),
            (const uint64_t *)(tb + o_ph), n_all, world, D.rank);
@@ -1649,7 +1623,9 @@ int finish_dist(kmc_ctx *c) {
 
 template <typename KeyT>
 int finish_impl(kmc_ctx *c) {
-  if (c->dist.valid && c->dist.scattered) return finish_dist<KeyT>(c); // keys already sit in my level-1 array
+  // keys already sit in my level-1 array — unless the job went on through the hash route afterwards (a peer's scatter
+  // overflowed: every rank recounts, and the hash route's peer stores have overwritten the receive buffer)
+  if (c->ingested.empty() && c->dist.valid && c->dist.scattered) return finish_dist<KeyT>(c);
   const uint32_t strat = c->cfg.strategy;
   if (strat != KMC_STRATEGY_SORT_BASELINE) {
     bool used = false;
@@ -1999,6 +1975,7 @@ int kmc_submit_device(kmc_ctx *c, const uint8_t *d_bases, const uint64_t *d_rec_
 int kmc_ingest_keys(kmc_ctx *c, const void *d_keys, uint64_t n_keys) {
   if (!c || (!d_keys && n_keys)) return KMC_E_ARG;
   if (c->finished) return fail(c, KMC_E_ARG, "kmc_ingest_keys after kmc_finish");
+  c->dist.valid = false; c->dist.scattered = false; // a range-partition scatter of this job, if any, is abandoned
   c->ingested.emplace_back(d_keys, n_keys);
   return KMC_OK;
 }
@@ -2220,6 +2197,7 @@ int kmc_route(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *part
   if (!c || !part_begin || !part_count || !d_keys) return KMC_E_ARG;
   if (n_parts < 1 || n_parts > kRadix) return fail(c, KMC_E_ARG, "n_parts must be 1..%d", kRadix);
   if (c->finished) return fail(c, KMC_E_ARG, "kmc_route after kmc_finish");
+  c->dist.valid = false; c->dist.scattered = false;
   CK(cudaSetDevice(c->device));
   TRY(zero_scalars(c));
   bool done = false;
@@ -2244,6 +2222,7 @@ int kmc_route_to_peers(kmc_ctx *c, uint32_t n_parts, void *const *d_part_ptr, ui
   if (c->cfg.mode != KMC_MODE_CONTIGUOUS)
     return fail(c, KMC_E_ARG, "kmc_route_to_peers handles contiguous mode; use kmc_route + an all-to-all for lr-gapped keys");
   if (c->finished) return fail(c, KMC_E_ARG, "kmc_route_to_peers after kmc_finish");
+  c->dist.valid = false; c->dist.scattered = false;
   for (uint32_t p = 0; p < n_parts; p++)
     if (!d_part_ptr[p] || ((uintptr_t)d_part_ptr[p] & 127)) return fail(c, KMC_E_ARG, "part pointers must be 128-byte aligned device pointers");
   CK(cudaSetDevice(c->device));

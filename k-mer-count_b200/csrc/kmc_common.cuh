@@ -76,7 +76,11 @@ __host__ __device__ __forceinline__ uint32_t owner_of(uint64_t hi, uint64_t lo, 
   uint64_t m = (lo ^ (hi * 0xD6E8FEB86659FD93ULL)) * 0x9E3779B97F4A7C15ULL;
   m ^= m >> 29;
   m *= 0xBF58476D1CE4E5B9ULL;
+#ifdef __CUDA_ARCH__
+  return __umulhi((uint32_t)(m >> 32), n_parts);
+#else
   return (uint32_t)(((m >> 32) * (uint64_t)n_parts) >> 32);
+#endif
 }
 
 // ---- ASCII → 2-bit ---------------------------------------------------------------------------------
@@ -95,30 +99,6 @@ __device__ __forceinline__ void pack4(uint32_t x, uint32_t &codes, uint32_t &val
   uint32_t t = ((y >> 1) ^ (y >> 2)) & 0x03030303u;
   codes = (t * 0x40100401u) >> 24;                       // c0<<6 | c1<<4 | c2<<2 | c3
   valid = (((v & 0x01010101u) * 0x08040201u) >> 24) & 0xFu; // v0<<3 | v1<<2 | v2<<1 | v3
-}
-
-// 64-bit left shift that brings in the top of `b` (s in 0..63)
-__device__ __forceinline__ uint64_t shl_pair(uint64_t a, uint64_t b, uint32_t s) {
-  return (a << s) | ((b >> 1) >> (63 - s));
-}
-
-// reverse complement of a k-mer held in the low 2k bits (k <= 32)
-__device__ __forceinline__ uint64_t revcomp64(uint64_t x, uint32_t k) {
-  uint64_t y = __brevll(x);
-  y = ((y & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((y & 0x5555555555555555ULL) << 1);
-  return (~y) >> (64 - 2 * k);
-}
-// reverse complement of a k-mer held in the low 2k bits of (hi:lo), 32 < k <= 64
-__device__ __forceinline__ U128 revcomp128(const U128 &x, uint32_t k) {
-  uint64_t a = __brevll(x.lo), b = __brevll(x.hi);
-  a = ~(((a & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((a & 0x5555555555555555ULL) << 1)); // becomes the new hi
-  b = ~(((b & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((b & 0x5555555555555555ULL) << 1)); // becomes the new lo
-  // (a:b) >> (128 - 2k)
-  uint32_t s = 128 - 2 * k; // 0..62
-  U128 r;
-  if (s == 0) { r.hi = a; r.lo = b; }
-  else { r.lo = (b >> s) | (a << (64 - s)); r.hi = a >> s; }
-  return r;
 }
 
 // bit p (position p <-> bit 63-p) of the result is set iff bits p..p+len-1 of x are all set

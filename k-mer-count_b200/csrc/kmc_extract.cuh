@@ -127,10 +127,32 @@ __device__ __forceinline__ void pack_chunk(const uint4 &a, const uint4 &b, uint6
 // K128: k <= 64, window = 3 chunks (96 positions), 30 productive lanes
 template <typename KeyT> struct Win;
 
+// Key arithmetic.  A lane's window is 2 (3) packed words; everything that does not depend on the window start is
+// done once per lane in prep(): the window shifted so that every forward k-mer ends on a word boundary, and the
+// reverse complement of the WHOLE window (bit reversal + pair swap + complement of four / six 32-bit words).  The
+// k-mer at start s is then a funnel shift of two adjacent 32-bit words per output word — forward: the high words of
+// (A << 2s); reverse complement: the low words of (R >> 2s) — plus the 2k-bit mask and a compare.  With s a
+// compile-time constant (the unrolled loops of the partition kernels) that is 4 + 4 + 4 instructions per 64-bit key
+// instead of the ~30 of shifting, reversing and re-aligning every k-mer on its own.
+__device__ __forceinline__ uint32_t rc16(uint32_t x) { // reverse complement of the 16 bases of a word
+  const uint32_t y = __brev(x);
+  return ~(((y & 0xAAAAAAAAu) >> 1) | ((y & 0x55555555u) << 1));
+}
+
 template <> struct Win<uint64_t> {
   static constexpr int kLanes = 31;
-  uint64_t w0, w1;
+  uint32_t a0, a1, a2, a3; // (w0:w1) >> (64 - 2k), a3 most significant
+  uint32_t r0, r1, r2, r3; // reverse complement of the 64-base window, r3 most significant
+  uint32_t mlo, mhi;       // mask of the low 2k bits
   uint32_t ok; // start s (0..31) valid <-> bit (31 - s)
+  __device__ __forceinline__ void prep(uint64_t w0, uint64_t w1, uint32_t k) {
+    const uint32_t sh = 64 - 2 * k; // 0..62
+    const uint64_t hi = w0 >> sh, lo = sh ? ((w1 >> sh) | (w0 << (64 - sh))) : w1;
+    a3 = (uint32_t)(hi >> 32); a2 = (uint32_t)hi; a1 = (uint32_t)(lo >> 32); a0 = (uint32_t)lo;
+    r3 = rc16((uint32_t)w1); r2 = rc16((uint32_t)(w1 >> 32)); r1 = rc16((uint32_t)w0); r0 = rc16((uint32_t)(w0 >> 32));
+    const uint64_t m = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    mlo = (uint32_t)m; mhi = (uint32_t)(m >> 32);
+  }
   template <bool FOLD>
   __device__ __forceinline__ void load(const ExtractParams &P, uint64_t chunk, const ChunkPrefetch *pf = nullptr) {
     uint64_t pos = chunk * 32;
@@ -142,19 +164,25 @@ template <> struct Win<uint64_t> {
       load_chunk<FOLD>(P.bases, pos, P.n_bases, c, v);
       b = P.brk ? P.brk[chunk] : 0u;
     }
-    w0 = c;
-    w1 = __shfl_down_sync(0xffffffffu, c, 1);
+    const uint64_t w1 = __shfl_down_sync(0xffffffffu, c, 1);
     uint32_t v1 = __shfl_down_sync(0xffffffffu, v, 1), b1 = __shfl_down_sync(0xffffffffu, b, 1);
     uint64_t E = ((uint64_t)v << 32) | v1;
     uint64_t NB = ~(((uint64_t)b << 32) | b1);
     uint64_t g = run_and64(E, P.k);
     if (P.k > 1) g &= run_and64(NB, P.k - 1) << 1;
     ok = (lane_id() < kLanes) ? (uint32_t)(g >> 32) : 0u;
+    prep(c, w1, P.k);
   }
-  __device__ __forceinline__ uint64_t key(uint32_t s, uint32_t k, bool canonical) const {
-    uint64_t f = shl_pair(w0, w1, 2 * s) >> (64 - 2 * k);
+  __device__ __forceinline__ uint64_t key(uint32_t s, uint32_t, bool canonical) const {
+    const uint32_t c = 2 * s, cc = c & 31u;
+    const bool up = c >= 32u;
+    const uint32_t ft = up ? a2 : a3, fm = up ? a1 : a2, fb = up ? a0 : a1;
+    const uint32_t fh = __funnelshift_l(fm, ft, cc) & mhi, fl = __funnelshift_l(fb, fm, cc) & mlo;
+    uint64_t f = ((uint64_t)fh << 32) | fl;
     if (canonical) {
-      uint64_t r = revcomp64(f, k);
+      const uint32_t rb = up ? r1 : r0, rm = up ? r2 : r1, rt = up ? r3 : r2;
+      const uint32_t rl = __funnelshift_r(rb, rm, cc) & mlo, rh = __funnelshift_r(rm, rt, cc) & mhi;
+      const uint64_t r = ((uint64_t)rh << 32) | rl;
       f = r < f ? r : f;
     }
     return f;
@@ -171,8 +199,21 @@ __device__ __forceinline__ unsigned __int128 run_and128(unsigned __int128 x, uin
 
 template <> struct Win<U128> {
   static constexpr int kLanes = 30;
-  uint64_t w0, w1, w2;
+  uint32_t a[6];  // (w0:w1:w2) >> (128 - 2k), a[5] most significant
+  uint32_t r[6];  // reverse complement of the 96-base window, r[5] most significant
+  uint32_t mh0, mh1; // mask of key bits 64..2k-1 (the low 64 bits are always part of the key: k > 32)
   uint32_t ok;
+  __device__ __forceinline__ void prep(uint64_t w0, uint64_t w1, uint64_t w2, uint32_t k) {
+    const uint32_t sh = 128 - 2 * k; // k in 33..64 → 0..62
+    uint64_t x2 = w0, x1 = w1, x0 = w2;
+    if (sh) { x0 = (x0 >> sh) | (x1 << (64 - sh)); x1 = (x1 >> sh) | (x2 << (64 - sh)); x2 >>= sh; }
+    a[5] = (uint32_t)(x2 >> 32); a[4] = (uint32_t)x2; a[3] = (uint32_t)(x1 >> 32); a[2] = (uint32_t)x1;
+    a[1] = (uint32_t)(x0 >> 32); a[0] = (uint32_t)x0;
+    r[5] = rc16((uint32_t)w2); r[4] = rc16((uint32_t)(w2 >> 32)); r[3] = rc16((uint32_t)w1); r[2] = rc16((uint32_t)(w1 >> 32));
+    r[1] = rc16((uint32_t)w0); r[0] = rc16((uint32_t)(w0 >> 32));
+    const uint64_t m = k >= 64 ? ~0ull : ((1ull << (2 * k - 64)) - 1ull);
+    mh0 = (uint32_t)m; mh1 = (uint32_t)(m >> 32);
+  }
   template <bool FOLD>
   __device__ __forceinline__ void load(const ExtractParams &P, uint64_t chunk) {
     uint64_t pos = chunk * 32;
@@ -181,9 +222,8 @@ template <> struct Win<U128> {
       load_chunk<FOLD>(P.bases, pos, P.n_bases, c, v);
       b = P.brk ? P.brk[chunk] : 0u;
     }
-    w0 = c;
-    w1 = __shfl_down_sync(0xffffffffu, c, 1);
-    w2 = __shfl_down_sync(0xffffffffu, c, 2);
+    const uint64_t w1 = __shfl_down_sync(0xffffffffu, c, 1);
+    const uint64_t w2 = __shfl_down_sync(0xffffffffu, c, 2);
     uint32_t v1 = __shfl_down_sync(0xffffffffu, v, 1), v2 = __shfl_down_sync(0xffffffffu, v, 2);
     uint32_t b1 = __shfl_down_sync(0xffffffffu, b, 1), b2 = __shfl_down_sync(0xffffffffu, b, 2);
     typedef unsigned __int128 u128;
@@ -192,18 +232,34 @@ template <> struct Win<U128> {
     u128 g = run_and128(E, P.k);
     if (P.k > 1) g &= run_and128(NB, P.k - 1) << 1;
     ok = (lane_id() < kLanes) ? (uint32_t)(g >> 96) : 0u;
+    prep(c, w1, w2, P.k);
   }
-  __device__ __forceinline__ U128 key(uint32_t s, uint32_t k, bool canonical) const {
-    uint64_t a = shl_pair(w0, w1, 2 * s), b = shl_pair(w1, w2, 2 * s);
-    uint32_t sh = 128 - 2 * k; // k in 33..64 → 0..62
-    U128 f;
-    if (sh == 0) { f.hi = a; f.lo = b; }
-    else { f.hi = a >> sh; f.lo = (b >> sh) | (a << (64 - sh)); }
-    if (canonical) {
-      U128 r = revcomp128(f, k);
-      if (key_lt(r, f)) f = r;
+  __device__ __forceinline__ U128 key(uint32_t s, uint32_t, bool canonical) const {
+    const uint32_t c = 2 * s, cc = c & 31u;
+    const bool up = c >= 32u;
+    // forward: the four high words of (A << 2s)
+    uint32_t f[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t hi = up ? a[j + 1] : a[j + 2], lo = up ? a[j] : a[j + 1];
+      f[j] = __funnelshift_l(lo, hi, cc);
     }
-    return f;
+    U128 fk;
+    fk.lo = ((uint64_t)f[1] << 32) | f[0];
+    fk.hi = ((uint64_t)(f[3] & mh1) << 32) | (f[2] & mh0);
+    if (canonical) {
+      uint32_t q[4]; // the four low words of (R >> 2s)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t lo = up ? r[j + 1] : r[j], hi = up ? r[j + 2] : r[j + 1];
+        q[j] = __funnelshift_r(lo, hi, cc);
+      }
+      U128 rk;
+      rk.lo = ((uint64_t)q[1] << 32) | q[0];
+      rk.hi = ((uint64_t)(q[3] & mh1) << 32) | (q[2] & mh0);
+      if (key_lt(rk, fk)) fk = rk;
+    }
+    return fk;
   }
 };
 

@@ -60,9 +60,12 @@ constexpr int kHistSampleMax = 16;       // fast_hist looks at every step-th til
 #ifndef KMC_LB_SLEEP
 #define KMC_LB_SLEEP 0      // look-back: nanoseconds to sleep between polls of a predecessor that has not published yet
 #endif
-#ifndef KMC_PART1_PREFETCH
-#define KMC_PART1_PREFETCH 0  // fast_part1: request the next tile's bases before writing the current tile out
+#ifndef KMC_L1_NO_TMA
+#define KMC_L1_NO_TMA 0
 #endif
+#ifndef KMC_PART1_PREFETCH
+#define KMC_PART1_PREFETCH 1  // fast_part1: request the next tile's bases before writing the current tile out
+#endif                        // (measured on B200, profiles/r02_ab_prepared_variants.jsonl: 5.67 -> 5.28 ms at 1e9 bases)
 #ifndef KMC_FIN_SEGROWS
 #define KMC_FIN_SEGROWS 1  // fast_finish: rows between two listed duplicates are written by a plain shifted copy loop
 #endif
@@ -150,13 +153,13 @@ __global__ void __launch_bounds__(128) plan_expand_kernel(FineDesc *__restrict__
 // bucket functions of the level-1 scatter: the top b1 key bits (counting), or the owner part (routing).
 // accept(): does the key take part at all?  RANGE (partial count, kmc_finish_part): only keys whose coarse bin
 // `key >> cshift` lies in [c_lo, c_lo + c_n); level-1 buckets are then numbered from the first one in range (`base`).
+// bshift < key bits and bmask = all ones, or (b1 == 0: a single bucket) bshift = 0 and bmask = 0 — no branch per key.
 template <bool RANGE>
 struct PrefixBucketT {
-  static constexpr bool kBulkStores = false;
-  uint32_t b1, bshift;
+  uint32_t bshift, bmask;
   uint32_t base, cshift, c_lo, c_n;
   template <typename KeyT> __device__ __forceinline__ uint32_t operator()(const KeyT &key) const {
-    const uint32_t v = b1 ? key_shr32(key, bshift) : 0u;
+    const uint32_t v = key_shr32(key, bshift) & bmask;
     return RANGE ? v - base : v;
   }
   template <typename KeyT> __device__ __forceinline__ bool accept(const KeyT &key) const {
@@ -164,17 +167,11 @@ struct PrefixBucketT {
   }
 };
 using PrefixBucket = PrefixBucketT<false>;
-// Experimental (KMC_ROUTE_TMA, off): the routing kernel's runs — a few thousand keys per owner and tile, contiguous
-// in the staging area — leave shared memory as ONE bulk async copy each (cp.async.bulk, the TMA unit) instead of
-// ~60 warp stores: fewer instructions and larger NVLink write bursts (peer stores from SM threads measured
-// ~530 GB/s per direction at 2 and at 8 GPUs, well under the link's 900).
-#ifndef KMC_ROUTE_TMA
-#define KMC_ROUTE_TMA 0
-#endif
-constexpr int kBulkMaxBuckets = 32;   // bulk stores only for this few buckets (owners), planned by one thread
-constexpr int kBulkPadKeys = 64;      // extra staging slots: one alignment slot per bucket
+template <bool RANGE>
+inline PrefixBucketT<RANGE> make_prefix_bucket(uint32_t kb, uint32_t b1, uint32_t base = 0, uint32_t cshift = 0, uint32_t c_lo = 0, uint32_t c_n = 0) {
+  return PrefixBucketT<RANGE>{b1 ? kb - b1 : 0u, b1 ? 0xFFFFFFFFu : 0u, base, cshift, c_lo, c_n};
+}
 struct OwnerBucket {
-  static constexpr bool kBulkStores = KMC_ROUTE_TMA != 0;
   uint32_t n_parts;
   template <typename KeyT> __device__ __forceinline__ uint32_t operator()(const KeyT &key) const {
     return owner_of(key_hi(key), key_lo(key), n_parts);
@@ -184,11 +181,8 @@ struct OwnerBucket {
 
 // shapes per key width: 128-bit keys take twice the registers and shared memory, so half the keys per tile
 template <typename KeyT> struct FastShape;
-#ifndef KMC_PART1_HALVES64
-#define KMC_PART1_HALVES64 1
-#endif
 template <> struct FastShape<uint64_t> {
-  static constexpr int kHalves = KMC_PART1_HALVES64;     // fast_part1: all 32 window starts of a lane in one tile
+  static constexpr int kHalves = 1;                      // fast_part1: all 32 window starts of a lane in one tile
   static constexpr int kLanes = 31;
   static constexpr int kArrKPT = 32;                     // fast_part1_array keys per thread
   static constexpr int kP2KPT = 16;                      // fast_part2 keys per thread
@@ -199,10 +193,9 @@ template <> struct FastShape<U128> {
   static constexpr int kArrKPT = 16;
   static constexpr int kP2KPT = 8;
 };
-template <typename KeyT> __host__ __device__ constexpr int part1_stage() { return kFastWarps * FastShape<KeyT>::kLanes * (32 / FastShape<KeyT>::kHalves); }
-template <typename KeyT, typename BucketFn> __host__ __device__ constexpr int part1_stage_for() {
-  return part1_stage<KeyT>() + (BucketFn::kBulkStores ? kBulkPadKeys : 0);
-}
+// staging slots of a fast_part1 tile: every thread's window starts, taking part or not (the load-only lanes' starts
+// and other non-keys are staged too, behind the runs: no branch per key)
+template <typename KeyT> __host__ __device__ constexpr int part1_stage() { return kFastThreads * (32 / FastShape<KeyT>::kHalves); }
 template <typename KeyT> __host__ __device__ constexpr int arr_tile() { return kFastThreads * FastShape<KeyT>::kArrKPT; }
 template <typename KeyT> __host__ __device__ constexpr int p2_tile() { return kFastThreads * FastShape<KeyT>::kP2KPT; }
 
@@ -255,7 +248,7 @@ __global__ void __launch_bounds__(256) fast_hist_array_kernel(const KeyT *__rest
 }
 
 // ------------------------------------------------------------------------------------------------ part1 / part2
-// Shared-memory layout of the partition kernels (dynamic smem):
+// Shared-memory layout of fast_part2 (dynamic smem):
 //   stage[STAGE] keys | gdelta[NB] u64 | hist[NB] u32 | loc[NB] u32 | scan scratch
 template <typename KeyT>
 struct PartSmem {
@@ -290,135 +283,149 @@ __device__ __forceinline__ uint32_t scan_bins(const uint32_t *hist, uint32_t *lo
     if (b < nb) loc[b] = ex;
     ex += v[j];
   }
-  __syncthreads(); // loc[] is read next by other threads (bucket b is reserved by thread b, not by its writer b/4)
+  __syncthreads(); // loc[] is read next by other threads
   return total;
 }
 
-// reserve room for the tile's run of every level-1 bucket; runs that do not fit go to the trash area
-template <typename KeyT, int THREADS = kFastThreads>
-__device__ __forceinline__ void reserve_l1(const FastPlan &pl, PartSmem<KeyT> &S, uint32_t nb, uint32_t *flags) {
-  for (uint32_t b = threadIdx.x; b < nb; b += THREADS) {
-    uint32_t c = S.hist[b];
-    if (c) {
-      unsigned long long g = atomicAdd(&pl.l1_cursor[b], (unsigned long long)c);
-      if (g + c > pl.l1_cap[b]) {
-        atomicOr(flags, kFlagOverflow);
-        S.gdelta[b] = pl.l1_trash - S.loc[b];
-      } else {
-        S.gdelta[b] = pl.l1_start[b] + g - S.loc[b];
+// ---- level-1 scatter: rank → reserve → stage → one TMA bulk store per bucket run ----------------------------------
+// The common back end of fast_part1 / fast_part1_array / the routing kernels.  A CTA tile's keys are ranked inside
+// their bucket with shared-memory atomics, room for every bucket's run is reserved with one global atomic per
+// bucket, the keys are staged in shared memory in bucket order, and every run then leaves as ONE cp.async.bulk
+// (shared → global, the TMA unit; SASS: UBLKCP) issued by the thread that owns the bucket — instead of a loop in
+// which every thread looks up its key's bucket again and stores 8 bytes (13 instructions per key, a third of the
+// kernel).  The copies of tile t drain while tile t+1 is loaded, extracted and ranked: only the staging area is
+// shared between consecutive tiles, and it is not touched before `wait_group.read` of the previous tile's copies.
+//
+// A bulk copy needs 16-byte aligned source, destination and size.  128-bit keys always are.  64-bit keys: a run starts
+// in the staging area at a slot of the same parity as its destination index (every non-empty bucket gets its count
+// rounded up to even plus room for that shift — at most two extra slots per bucket), and a run's unaligned first /
+// last key goes by an ordinary 8-byte store.
+//
+// Keys that do not take part (`valid` bit clear) are ranked in a dummy bucket `nb` and staged behind all the runs:
+// no branch per key anywhere.
+template <typename KeyT> __host__ __device__ constexpr uint32_t l1_stage_pad(uint32_t nb) { return sizeof(KeyT) == 8 ? 2 * nb : 0; }
+template <typename KeyT>
+struct L1Smem { // stage[STAGE + pad] keys | gdst[NB] u64 | hist[NB+1] u32 | loc[NB+1] u32 | cnt[NB] u32 | scan scratch
+  KeyT *stage; unsigned long long *gdst; uint32_t *hist; uint32_t *loc; uint32_t *cnt; uint32_t *scan;
+  static __host__ __device__ uint32_t nb4(uint32_t nb) { return (nb + 4) & ~3u; }
+  __device__ L1Smem(unsigned char *base, uint32_t stage_keys, uint32_t nb) {
+    stage = (KeyT *)base;
+    gdst = (unsigned long long *)(stage + stage_keys + l1_stage_pad<KeyT>(nb));
+    hist = (uint32_t *)(gdst + nb4(nb));
+    loc = hist + nb4(nb);
+    cnt = loc + nb4(nb);
+    scan = cnt + nb4(nb);
+  }
+  static __host__ __device__ size_t bytes(uint32_t stage_keys, uint32_t nb) {
+    return (size_t)(stage_keys + l1_stage_pad<KeyT>(nb)) * sizeof(KeyT) + (size_t)nb4(nb) * 20 + 64 * 4;
+  }
+};
+__device__ __forceinline__ void bulk_store_s2g(void *dst, const void *src_smem, uint32_t bytes) {
+  const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(src_smem);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+struct NoMid { __device__ __forceinline__ void operator()() const {} };
+// `mid` runs between staging and write-out: the caller's keys are dead by then (fast_part1 issues the next tile's
+// loads there).  S.hist[0..nb] must be zero on entry and is zero again on exit.  nb <= 2 * kFastThreads.
+// keyf(s), s < NK: the thread's s-th key.  It is called twice per key (count, stage): a functor that computes the key
+// from the packed window again (12 instructions) costs less than keeping NK keys in registers across the phases
+// (fast_part1 at 128 registers spilled 35 of them: 4.5 GB of local-memory traffic per 1e9 bases).
+template <typename KeyT, int NK, typename BucketFn, typename KeyFn, typename Mid = NoMid>
+__device__ __forceinline__ void scatter_tile_l1(const FastPlan &pl, L1Smem<KeyT> &S, uint32_t nb, const BucketFn &bucket,
+                                                const KeyFn &keyf, uint32_t valid, KeyT *__restrict__ l1, uint32_t *flags,
+                                                const Mid &mid = Mid()) {
+  constexpr bool kPhase = sizeof(KeyT) == 8; // two keys per 16 bytes: staging parity must match the destination's
+  // count per bucket (results unused: nothing to wait for, no rank to keep — a second atomic hands out the slots)
+#pragma unroll
+  for (int s = 0; s < NK; s++) atomicAdd(&S.hist[(valid & (1u << s)) ? bucket(keyf(s)) : nb], 1u);
+  __syncthreads();
+  // thread t owns buckets 2t and 2t+1: count, reserve (the global atomics fly during the scan), staging slot.  What
+  // the write-out needs later (count, destination, slot) waits in shared memory, not in registers: the staging loop
+  // below holds all of the thread's keys and ranks.
+  {
+    uint32_t cnt[2], sz[2];
+    unsigned long long g[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const uint32_t b = 2 * threadIdx.x + j;
+      cnt[j] = b < nb ? S.hist[b] : 0u;
+      g[j] = 0;
+      if (b < nb) { S.hist[b] = 0; S.cnt[b] = cnt[j]; }
+      if (cnt[j]) g[j] = atomicAdd(&pl.l1_cursor[b], (unsigned long long)cnt[j]);
+      sz[j] = cnt[j] ? (kPhase ? ((cnt[j] + 2u) & ~1u) : cnt[j]) : 0u;
+    }
+    if (threadIdx.x == 0) S.hist[nb] = 0;
+    uint32_t total;
+    uint32_t pos = block_excl_scan<uint32_t, kFastThreads>(sz[0] + sz[1], S.scan, total);
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const uint32_t b = 2 * threadIdx.x + j;
+      if (cnt[j]) {
+        unsigned long long dst;
+        if (g[j] + cnt[j] > pl.l1_cap[b]) { atomicOr(flags, kFlagOverflow); dst = pl.l1_trash; } // the caller recounts
+        else dst = pl.l1_start[b] + g[j];
+        S.gdst[b] = dst;
+        S.loc[b] = pos + (kPhase ? (uint32_t)(dst & 1ull) : 0u);
+        pos += sz[j];
       }
     }
+    if (threadIdx.x == 0) S.loc[nb] = total; // the dummy bucket: behind every run
   }
-}
-
-// rank (smem atomics) → scan → reserve → stage in bucket order → write runs: the common back end of the
-// level-1 scatters.  key[]/valid describe this thread's NK keys.
-struct NoMid { __device__ __forceinline__ void operator()() const {} };
-// `mid` runs between staging and write-out: the caller's keys are dead by then (KMC_PART1_PREFETCH issues the next
-// tile's loads there).
-template <typename KeyT, int NK, typename BucketFn, int THREADS = kFastThreads, typename Mid = NoMid>
-__device__ __forceinline__ void scatter_tile_l1(const FastPlan &pl, PartSmem<KeyT> &S, uint32_t nb, const BucketFn &bucket,
-                                                const KeyT (&key)[NK], uint32_t valid, KeyT *__restrict__ l1, uint32_t *flags,
-                                                const Mid &mid = Mid()) {
-  uint32_t rank[NK / 2]; // two 16-bit ranks per word
+  bulk_wait_read(); // the previous tile's copies have read the staging area
+  __syncthreads();
+  // slot of a key = atomic increment of its bucket's cursor (loc[b] ends as the END of run b)
 #pragma unroll
   for (int s = 0; s < NK; s++) {
-    uint32_t r = 0;
-    if (valid & (1u << s)) r = atomicAdd(&S.hist[bucket(key[s])], 1u);
-    if (s & 1) rank[s >> 1] |= r << 16; else rank[s >> 1] = r;
+    const KeyT k = keyf(s);
+    S.stage[atomicAdd(&S.loc[(valid & (1u << s)) ? bucket(k) : nb], 1u)] = k;
   }
-  __syncthreads();
-  uint32_t total = scan_bins<THREADS>(S.hist, S.loc, nb, S.scan);
-  reserve_l1<KeyT, THREADS>(pl, S, nb, flags);
-  __syncthreads();
-#pragma unroll
-  for (int s = 0; s < NK; s++)
-    if (valid & (1u << s)) S.stage[S.loc[bucket(key[s])] + ((rank[s >> 1] >> (16 * (s & 1))) & 0xFFFFu)] = key[s];
   mid();
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
-    KeyT k = S.stage[i];
-    l1[S.gdelta[bucket(k)] + i] = k;
-  }
-  __syncthreads();
-}
-
-// The same with bulk stores (few buckets only: nb <= kBulkMaxBuckets).  A bulk copy needs 16-byte aligned source and
-// destination: room is reserved FIRST, so that every bucket's run can start in the staging area at a slot with the
-// same 16-byte phase as its destination (one padding slot where they differ); a run's unaligned head and tail key
-// (8-byte keys) go by ordinary stores.
-template <typename KeyT, int NK, typename BucketFn, int THREADS = kFastThreads>
-__device__ __forceinline__ void scatter_tile_bulk(const FastPlan &pl, PartSmem<KeyT> &S, uint32_t nb, const BucketFn &bucket,
-                                                  const KeyT (&key)[NK], uint32_t valid, KeyT *__restrict__ l1, uint32_t *flags) {
-  constexpr uint32_t kPer16 = 16 / sizeof(KeyT); // keys per 16 bytes: 2 or 1
-  uint32_t rank[NK / 2];
-#pragma unroll
-  for (int s = 0; s < NK; s++) {
-    uint32_t r = 0;
-    if (valid & (1u << s)) r = atomicAdd(&S.hist[bucket(key[s])], 1u);
-    if (s & 1) rank[s >> 1] |= r << 16; else rank[s >> 1] = r;
-  }
-  __syncthreads();
-  // reserve: gdelta[b] = destination key index of the run (absolute, not a delta here)
-  if (threadIdx.x < nb) {
-    const uint32_t b = threadIdx.x, c = S.hist[b];
-    unsigned long long dst = pl.l1_trash;
-    if (c) {
-      unsigned long long g = atomicAdd(&pl.l1_cursor[b], (unsigned long long)c);
-      if (g + c > pl.l1_cap[b]) atomicOr(flags, kFlagOverflow);
-      else dst = pl.l1_start[b] + g;
-    }
-    S.gdelta[b] = dst;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) { // staging offsets: runs back to back, each starting in its destination's 16-byte phase
-    uint32_t pos = 0;
-    for (uint32_t b = 0; b < nb; b++) {
-      if (kPer16 == 2 && ((pos ^ (uint32_t)S.gdelta[b]) & 1u)) pos++;
-      S.loc[b] = pos;
-      pos += S.hist[b];
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int s = 0; s < NK; s++)
-    if (valid & (1u << s)) S.stage[S.loc[bucket(key[s])] + ((rank[s >> 1] >> (16 * (s & 1))) & 0xFFFFu)] = key[s];
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the staged keys are read by the async proxy next
   __syncthreads();
-  if (threadIdx.x < nb) {
-    const uint32_t b = threadIdx.x;
-    uint32_t n = S.hist[b];
-    const KeyT *src = S.stage + S.loc[b];
-    KeyT *dst = l1 + S.gdelta[b];
-    if (kPer16 == 2) {
-      if (n && (S.gdelta[b] & 1ull)) { *dst = *src; dst++; src++; n--; } // head key up to the 16-byte boundary
-      if (n & 1u) { dst[n - 1] = src[n - 1]; n--; }                       // odd tail key
-    }
+#pragma unroll 1
+  for (uint32_t b = threadIdx.x; b < nb; b += kFastThreads) {
+    uint32_t n = S.cnt[b];
     if (n) {
-      const uint32_t bytes = n * (uint32_t)sizeof(KeyT);
-      const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(src);
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(saddr), "r"(bytes) : "memory");
+      const unsigned long long dst = S.gdst[b];
+      const KeyT *src = S.stage + (S.loc[b] - n); // loc[b] is the end of the run by now
+      KeyT *d = l1 + dst;
+      if (kPhase) {
+        if (dst & 1ull) { *d = *src; d++; src++; n--; } // head key up to the 16-byte boundary
+        if (n & 1u) { d[n - 1] = src[n - 1]; n--; }      // odd tail key
+      }
+#if KMC_L1_NO_TMA // debugging aid: the same runs by plain stores
+      for (uint32_t i = 0; i < n; i++) d[i] = src[i];
+#else
+      if (n) bulk_store_s2g(d, src, n * (uint32_t)sizeof(KeyT));
+#endif
     }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the staging area may be overwritten afterwards
   }
+  bulk_commit();
+}
+__device__ __forceinline__ void l1_smem_init(uint32_t *hist, uint32_t nb) {
+  for (uint32_t i = threadIdx.x; i <= nb; i += blockDim.x) hist[i] = 0;
   __syncthreads();
 }
 
 // Level-1 scatter, extraction front end.  One CTA tile = 16 warp tiles (u64: all 32 starts of every lane,
 // <= 15872 keys; u128: 16 starts at a time, two tiles per load).
 template <typename KeyT, bool FOLD, typename BucketFn>
-__global__ void __launch_bounds__(kFastThreads, (sizeof(KeyT) == 8 && FastShape<KeyT>::kHalves == 2) ? 2 : 1) fast_part1_kernel(ExtractParams P, uint64_t n_tiles, FastPlan pl, BucketFn bucket,
+__global__ void __launch_bounds__(kFastThreads, 1) fast_part1_kernel(ExtractParams P, uint64_t n_tiles, FastPlan pl, BucketFn bucket,
                                                                       KeyT *__restrict__ l1, uint32_t *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kHalves = FastShape<KeyT>::kHalves, kSPH = 32 / kHalves;
   const uint32_t nb = pl.n_l1;
-  PartSmem<KeyT> S(smem_raw, part1_stage_for<KeyT, BucketFn>(), nb);
+  L1Smem<KeyT> S(smem_raw, part1_stage<KeyT>(), nb);
+  l1_smem_init(S.hist, nb);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   const uint64_t n_cta_tiles = (n_tiles + kFastWarps - 1) / kFastWarps;
-  // KMC_PART1_PREFETCH (experimental, off): the next tile's 32 bytes per lane are requested right after this tile's
-  // keys were staged, so they travel while the staged keys are written out, instead of after it
-  constexpr bool kPrefetch = KMC_PART1_PREFETCH && kHalves == 1 && !BucketFn::kBulkStores;
+  // KMC_PART1_PREFETCH: the next tile's 32 bytes per lane are requested right after this tile's keys were staged, so
+  // they travel while the staged keys are written out, instead of after it
+  constexpr bool kPrefetch = KMC_PART1_PREFETCH && kHalves == 1;
   ChunkPrefetch pf;
   pf.ok = 0u;
   for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
@@ -429,103 +436,51 @@ __global__ void __launch_bounds__(kFastThreads, (sizeof(KeyT) == 8 && FastShape<
     const uint32_t ok = t < n_tiles ? W.ok : 0u;
 #pragma unroll 1
     for (int half = 0; half < kHalves; half++) {
-      for (uint32_t i = threadIdx.x; i < nb; i += kFastThreads) S.hist[i] = 0;
-      __syncthreads();
-      KeyT key[kSPH];
+      const bool canonical = P.canonical != 0;
+      auto keyf = [&](int s) { return W.key(half * kSPH + s, P.k, canonical); };
       uint32_t valid = 0;
 #pragma unroll
-      for (int s = 0; s < kSPH; s++) {
-        key[s] = W.key(half * kSPH + s, P.k, P.canonical != 0);
-        if ((ok & (0x80000000u >> (half * kSPH + s))) && bucket.accept(key[s])) valid |= 1u << s;
-      }
-      if constexpr (BucketFn::kBulkStores) scatter_tile_bulk<KeyT, kSPH>(pl, S, nb, bucket, key, valid, l1, flags);
-      else if constexpr (kPrefetch) {
+      for (int s = 0; s < kSPH; s++)
+        if ((ok & (0x80000000u >> (half * kSPH + s))) && bucket.accept(keyf(s))) valid |= 1u << s;
+      if constexpr (kPrefetch) {
         const uint64_t ct_next = ct + gridDim.x;
         auto mid = [&]() {
           pf.ok = 0u;
           if (ct_next < n_cta_tiles) pf = prefetch_chunk(P, (ct_next * kFastWarps + warp) * Win<KeyT>::kLanes + lane);
         };
-        scatter_tile_l1<KeyT, kSPH, BucketFn, kFastThreads>(pl, S, nb, bucket, key, valid, l1, flags, mid);
-      } else scatter_tile_l1<KeyT, kSPH>(pl, S, nb, bucket, key, valid, l1, flags);
+        scatter_tile_l1<KeyT, kSPH>(pl, S, nb, bucket, keyf, valid, l1, flags, mid);
+      } else scatter_tile_l1<KeyT, kSPH>(pl, S, nb, bucket, keyf, valid, l1, flags);
     }
   }
-  if constexpr (BucketFn::kBulkStores) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // writes landed, not only read
-}
-
-// Experimental (KMC_PART1_WIDE, off): the same tile with twice the warps.  fast_part1_kernel holds all 32 window
-// starts of a lane in one thread — 126 registers, one 16-warp CTA per SM, 25 % of the SM's warp slots, and every
-// __syncthreads phase exposes its latency.  Here warps w and w + 16 load the same 32-base chunks and take 16 starts
-// each (64 registers, 32 warps per SM); tile, staging and run lengths are unchanged.  64-bit keys only.
-#ifndef KMC_PART1_WIDE
-#define KMC_PART1_WIDE 0
-#endif
-constexpr int kWideThreads = 2 * kFastThreads;
-template <bool FOLD, typename BucketFn>
-__global__ void __launch_bounds__(kWideThreads, 1) fast_part1_wide_kernel(ExtractParams P, uint64_t n_tiles, FastPlan pl, BucketFn bucket,
-                                                                           uint64_t *__restrict__ l1, uint32_t *__restrict__ flags) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int kSPT = 16; // window starts per thread
-  const uint32_t nb = pl.n_l1;
-  PartSmem<uint64_t> S(smem_raw, part1_stage_for<uint64_t, BucketFn>(), nb);
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, tw = warp & (kFastWarps - 1), half = warp / kFastWarps;
-  const uint64_t n_cta_tiles = (n_tiles + kFastWarps - 1) / kFastWarps;
-  constexpr bool kPrefetch = KMC_PART1_PREFETCH && !BucketFn::kBulkStores;
-  ChunkPrefetch pf;
-  pf.ok = 0u;
-  for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
-    const uint64_t t = ct * kFastWarps + tw;
-    Win<uint64_t> W{};
-    if constexpr (kPrefetch) W.template load<FOLD>(P, t * Win<uint64_t>::kLanes + lane, &pf);
-    else W.template load<FOLD>(P, t * Win<uint64_t>::kLanes + lane);
-    const uint32_t ok = t < n_tiles ? W.ok : 0u;
-    for (uint32_t i = threadIdx.x; i < nb; i += kWideThreads) S.hist[i] = 0;
-    __syncthreads();
-    uint64_t key[kSPT];
-    uint32_t valid = 0;
-#pragma unroll
-    for (int s = 0; s < kSPT; s++) {
-      key[s] = W.key(half * kSPT + s, P.k, P.canonical != 0);
-      if ((ok & (0x80000000u >> (half * kSPT + s))) && bucket.accept(key[s])) valid |= 1u << s;
-    }
-    if constexpr (BucketFn::kBulkStores) scatter_tile_bulk<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags);
-    else if constexpr (kPrefetch) {
-      const uint64_t ct_next = ct + gridDim.x;
-      auto mid = [&]() {
-        pf.ok = 0u;
-        if (ct_next < n_cta_tiles) pf = prefetch_chunk(P, (ct_next * kFastWarps + tw) * Win<uint64_t>::kLanes + lane);
-      };
-      scatter_tile_l1<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags, mid);
-    } else scatter_tile_l1<uint64_t, kSPT, BucketFn, kWideThreads>(pl, S, nb, bucket, key, valid, l1, flags);
-  }
-  if constexpr (BucketFn::kBulkStores) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  bulk_wait_all(); // the last copies have landed, not only left shared memory
 }
 
 // Level-1 scatter, key-array front end (ingested keys of the multi-GPU path, lr-gapped keys).
-// THREADS = 2 * kFastThreads (KMC_PART1_WIDE, 64-bit keys): the same tile with half the keys per thread, twice the warps.
-template <typename KeyT, int THREADS = kFastThreads>
-__global__ void __launch_bounds__(THREADS, 1) fast_part1_array_kernel(const KeyT *__restrict__ keys, uint64_t n,
-                                                                       FastPlan pl, KeyT *__restrict__ l1,
-                                                                       uint32_t *__restrict__ flags) {
+template <typename KeyT>
+__global__ void __launch_bounds__(kFastThreads, 1) fast_part1_array_kernel(const KeyT *__restrict__ keys, uint64_t n,
+                                                                            FastPlan pl, KeyT *__restrict__ l1,
+                                                                            uint32_t *__restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int kTile = arr_tile<KeyT>(), kKPT = kTile / THREADS;
+  constexpr int kTile = arr_tile<KeyT>(), kKPT = kTile / kFastThreads;
   const uint32_t nb = pl.n_l1;
-  PartSmem<KeyT> S(smem_raw, kTile, nb);
-  const PrefixBucketT<true> bucket{pl.b1, pl.kb - pl.b1, pl.l1_base, 0, 0, 0}; // keys are pre-filtered: accept() unused
+  L1Smem<KeyT> S(smem_raw, kTile, nb);
+  l1_smem_init(S.hist, nb);
+  const PrefixBucketT<true> bucket{pl.b1 ? pl.kb - pl.b1 : 0u, pl.b1 ? 0xFFFFFFFFu : 0u, pl.l1_base, 0, 0, 0}; // keys are pre-filtered: accept() unused
   const uint64_t n_cta_tiles = (n + kTile - 1) / kTile;
   for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
-    for (uint32_t i = threadIdx.x; i < nb; i += THREADS) S.hist[i] = 0;
-    __syncthreads();
     const uint64_t base = ct * kTile;
     const uint32_t cnt = (uint32_t)((n - base < (uint64_t)kTile) ? n - base : kTile);
     KeyT key[kKPT];
     uint32_t valid = 0;
 #pragma unroll
     for (int j = 0; j < kKPT; j++) {
-      uint32_t idx = j * THREADS + threadIdx.x;
+      uint32_t idx = j * kFastThreads + threadIdx.x;
       if (idx < cnt) { key[j] = keys[base + idx]; valid |= 1u << j; } else key[j] = KeyT{};
     }
-    scatter_tile_l1<KeyT, kKPT, PrefixBucketT<true>, THREADS>(pl, S, nb, bucket, key, valid, l1, flags);
+    auto keyf = [&](int j) { return key[j]; };
+    scatter_tile_l1<KeyT, kKPT>(pl, S, nb, bucket, keyf, valid, l1, flags);
   }
+  bulk_wait_all();
 }
 
 // One CTA per tile of p2_tile<KeyT>() keys of one level-1 bucket → its 2^e fine buckets (the next e key bits).

@@ -113,6 +113,8 @@ __device__ __forceinline__ void hot_build(HotDict &H, const uint64_t *__restrict
 }
 // true: the key is hot and was counted in shared memory
 __device__ __forceinline__ bool hot_add(HotDict &H, uint64_t key, uint32_t inc) {
+  // the all-ones key (k = 32, poly-T, non-canonical) is the dictionary's empty marker: never hot, hash_add counts it in n_ones
+  if (key == kHashEmpty) return false;
   uint32_t s = hot_slot(key);
   for (;;) {
     uint64_t cur = H.key[s];
