@@ -153,8 +153,10 @@ int kmc_route(kmc_ctx *ctx, uint32_t n_parts, uint64_t *part_begin, uint64_t *pa
 /* Fused route + exchange over NVLink peer memory: like kmc_route, but part p's keys are stored by the
  * routing kernel straight into d_part_ptr[p] — normally this rank's region of rank p's receive buffer,
  * mapped with kmc_ipc_open (or any device pointer, e.g. torch symmetric memory).  Each region holds at
- * most part_cap_keys keys; part_count[p] (host) receives how many were written.  The caller exchanges the
- * counts and synchronises the ranks before the owners call kmc_ingest_keys on what they received.   */
+ * most part_cap_keys keys; part_count[p] (host) receives how many keys part p has.  A count above
+ * part_cap_keys means that region overflowed (nothing of the job is usable): the ranks must agree on a
+ * larger capacity — the counts are exact — and every rank calls kmc_route_to_peers again.  The caller exchanges
+ * the counts and synchronises the ranks before the owners call kmc_ingest_keys on what they received.   */
 int kmc_route_to_peers(kmc_ctx *ctx, uint32_t n_parts, void *const *d_part_ptr, uint64_t part_cap_keys,
                        uint64_t *part_count);
 /* ---- multi-GPU, range partition: the level-1 scatter of the counting pipeline done by the SENDERS --------

@@ -124,6 +124,7 @@ struct kmc_ctx {
   uint32_t hash_aborts = 0;
   std::vector<unsigned char> fast_host; // plan tables staged for upload
   uint32_t fast_fallbacks = 0;          // times the partitioned path overflowed and the job was recounted
+  const char *fast_variant = "";        // level-2 element form of the last partitioned count: u32 / split64 / u64 / u128
 
   // partial count (kmc_finish_part): the coarse-bin range [range_lo, range_lo + range_n) being counted, and the
   // coarse histogram of the whole input it is cut from (computed once per input)
@@ -683,8 +684,10 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
   TRY(d2h_small(c, cur.data(), pl.l1_cursor, (size_t)n_parts * 8));
   TRY(read_scalars(c, nullptr, &err));
   if (err & kFlagOverflow) {
-    if (part_ptr) return fail(c, KMC_E_CAPACITY, "kmc_route_to_peers: a part exceeded part_cap_keys");
     TRY(zero_scalars(c));
+    // peers: not an error here — the counts tell the caller (some exceed part_cap_keys: those regions hold garbage beyond
+    // nothing useful), who must agree with the other ranks on a larger capacity and route again
+    if (part_ptr) { for (uint32_t p = 0; p < n_parts; p++) part_count[p] = cur[p]; *done = true; }
     return KMC_OK;
   }
   for (uint32_t p = 0; p < n_parts; p++) { if (part_begin) part_begin[p] = cap * p; part_count[p] = cur[p]; }
@@ -1008,18 +1011,31 @@ inline int env_int(const char *name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
+// 64-bit keys whose fine buckets leave more than 32 key bits are sorted fastest as Split64 (kmc_fast.cuh), which needs
+// every bucket to leave at most 32 + kFinishBits bits.  Sparse coarse bins (canonical k-mers thin out towards the top
+// of the key space) would be split less than that: the number of extra splits that brings them within reach, or 0
+// when the input is too small for it to pay (buckets of a few hundred keys).
+inline uint32_t split64_min_e(uint32_t kb, uint64_t n_est, bool wide) {
+  const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb);
+  if (wide || kb <= cb + 32 + (uint32_t)kFinishBits) return 0;
+  const uint32_t me = kb - cb - (32 + (uint32_t)kFinishBits);
+  if (me > 12 || (n_est >> (cb + me)) < 512) return 0;
+  return me;
+}
+
 struct PlanShape {
   uint32_t b1 = 0, l1_base = 0, n_l1 = 0;
   std::vector<uint32_t> e;   // [ncoarse]
   std::vector<uint8_t> l1e;  // [n_l1]
   uint64_t n_fine = 0;
 };
+// min_e: split every coarse bin at least 2^min_e ways (split64_min_e: keeps sparse bins within Split64's reach)
 bool plan_shape(const std::vector<uint64_t> &hist, uint32_t kb, uint32_t c_lo, uint32_t c_hi, bool ranged, int target,
-                PlanShape &P, uint32_t b1_min = 0) {
+                PlanShape &P, uint32_t b1_min = 0, uint32_t min_e = 0) {
   const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb), ncoarse = 1u << cb;
   P.e.assign(ncoarse, 0);
   for (uint32_t ci = 0; ci < ncoarse; ci++) {
-    uint32_t ee = 0;
+    uint32_t ee = hist[ci] ? min_e : 0;
     while (((hist[ci] + ((1ull << ee) - 1)) >> ee) > (uint64_t)target) ee++;
     if (ee > kb - cb) return false; // cannot split far enough: too many keys share a prefix (duplicates)
     P.e[ci] = ee;
@@ -1057,6 +1073,30 @@ bool plan_shape(const std::vector<uint64_t> &hist, uint32_t kb, uint32_t c_lo, u
   return P.n_fine <= (1ull << 28);
 }
 
+// level-2 scatter of the keys in [l1_done, l1_cursor) of every level-1 bucket (all of them if done == nullptr);
+// t_max = tiles per bucket the grid provides (a CTA takes several if there are more); nb_max = most fine buckets
+// under one level-1 bucket (sizes the shared memory).
+template <typename KeyT, typename L2T>
+int launch_part2_as(kmc_ctx *c, const FastPlan &pl, const KeyT *l1, uint32_t nb_max, uint64_t t_max, unsigned long long *done, bool flush) {
+  const size_t smem = PartSmem<KeyT>::bytes(p2_tile<KeyT>(), nb_max);
+  auto fast_part2 = fast_part2_kernel<KeyT, L2T>;
+  CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const dim3 grid((uint32_t)std::min<uint64_t>(std::max<uint64_t>(t_max, 1), 1u << 20), pl.n_l1);
+  LAUNCH(fast_part2, grid, kFastThreads, smem, pl, l1, (L2T *)c->fast_l2.p, d_err(c), (const unsigned long long *)done, flush ? 1u : 0u, nb_max);
+  if (done) {
+    LAUNCH(l2_done_kernel, grid_for(pl.n_l1, 256), 256, 0, pl, done, (uint32_t)p2_tile<KeyT>(), flush ? 1u : 0u, grid.x);
+    c->launches--; // plumbing
+  }
+  return KMC_OK;
+}
+template <typename KeyT>
+int launch_part2(kmc_ctx *c, const FastPlan &pl, const KeyT *l1, bool key32, uint32_t nb_max, uint64_t t_max, unsigned long long *done = nullptr,
+                 bool flush = true) {
+  if constexpr (sizeof(KeyT) == 16) return launch_part2_as<U128, U128>(c, pl, l1, nb_max, t_max, done, flush);
+  else if (key32) return launch_part2_as<uint64_t, uint32_t>(c, pl, l1, nb_max, t_max, done, flush);
+  else return launch_part2_as<uint64_t, uint64_t>(c, pl, l1, nb_max, t_max, done, flush);
+}
+
 // ---- partitioned fast path (kmc_fast.cuh) --------------------------------------------------------------------
 // *used = false: the input does not suit it (tiny, duplicate-heavy, or a bucket overflowed); nothing is left
 // behind and the caller counts with the baseline path.
@@ -1075,8 +1115,9 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   TRY(key_sources<KeyT>(c, &ka));
   const bool from_array = ka.from_array;
   const auto &arrays = ka.arrays;
-  // fast_state layout: ghist[4096] u64 | ticket u32 (+pad) | d_total u64 | l1_cursor[kMaxL1] u64 | fine_cursor[nf] u32 | status[nf] u64
-  const size_t off_ticket = 4096 * 8, off_dtotal = off_ticket + 8, off_l1cur = off_dtotal + 8, off_fine = off_l1cur + kMaxL1 * 8;
+  // fast_state layout: ghist[4096] u64 | ticket u32 (+pad) | d_total u64 | l1_cursor[kMaxL1] u64 | l1_done[kMaxL1] u64 | fine_cursor[nf] u32 | status[nf] u64
+  const size_t off_ticket = 4096 * 8, off_dtotal = off_ticket + 8, off_l1cur = off_dtotal + 8, off_l1done = off_l1cur + kMaxL1 * 8,
+               off_fine = off_l1done + kMaxL1 * 8;
   TRY(ensure(c, c->fast_state, off_fine + 64));
   CK(cudaMemsetAsync(c->fast_state.p, 0, off_fine, c->stream));
   std::vector<uint64_t> hist;
@@ -1101,7 +1142,8 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
 
   // ---- plan
   PlanShape shape;
-  if (!plan_shape(hist, kb, c_lo, c_hi, ranged, kTarget, shape)) return KMC_OK;
+  const uint32_t min_e = getenv("KMC_NO_SPLIT64") ? 0u : split64_min_e(kb, n_est, kWide);
+  if (!plan_shape(hist, kb, c_lo, c_hi, ranged, kTarget, shape, 0, min_e)) return KMC_OK;
   if (!kWide && (kFineCap64 != kFineCap || kFineTarget64 != kFineTarget)) {
     // buckets that leave more than 32 key bits are sorted as 64-bit elements, whose bucket shape is smaller: plan again
     bool wide_elems = false;
@@ -1109,7 +1151,7 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
     if (wide_elems) {
       kCap = kFineCap64;
       kTarget = std::min(kTarget, kFineTarget64 >> relax);
-      if (!plan_shape(hist, kb, c_lo, c_hi, ranged, kTarget, shape)) return KMC_OK;
+      if (!plan_shape(hist, kb, c_lo, c_hi, ranged, kTarget, shape, 0, min_e)) return KMC_OK;
     }
   }
   const uint32_t b1 = shape.b1, l1_base = shape.l1_base, n_l1 = shape.n_l1;
@@ -1132,10 +1174,15 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   uint64_t *l1s = (uint64_t *)(c->fast_host.data() + o_l1s), *l1cap = (uint64_t *)(c->fast_host.data() + o_cap);
   uint32_t *t0 = (uint32_t *)(c->fast_host.data() + o_t0), *f0 = (uint32_t *)(c->fast_host.data() + o_f0);
   uint8_t *l1ep = c->fast_host.data() + o_e;
-  uint64_t l1_keys = 0, l2_keys = 0, tiles2 = 0;
-  uint32_t fb = 0;
+  uint64_t l1_keys = 0, l2_keys = 0, tiles2 = 0, t_max = 1;
+  uint32_t fb = 0, nb_max = 1;
   bool key32 = !kWide; // every bucket leaves <= 32 key bits: level 2 stores 32-bit suffixes
-  for (uint32_t b = 0; b < n_l1; b++) if (kb - b1 - l1e[b] > 32) key32 = false;
+  bool split64 = !kWide && !getenv("KMC_NO_SPLIT64"); // ... at most 32 + kFinishBits: sorted as 32-bit suffixes + sub-bin ids (Split64)
+  for (uint32_t b = 0; b < n_l1; b++) {
+    if (kb - b1 - l1e[b] > 32) key32 = false;
+    if (kb - b1 - l1e[b] > 32 + (uint32_t)kFinishBits) split64 = false;
+  }
+  if (key32) split64 = false;
   for (uint32_t b = 0; b < n_l1; b++) { // b: index among the existing level-1 buckets; b_abs: its key prefix
     const uint32_t b_abs = l1_base + b;
     uint64_t nb = 0;
@@ -1154,6 +1201,8 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
     l1s[b] = l1_keys; l1cap[b] = cap1; t0[b] = (uint32_t)tiles2; l1ep[b] = l1e[b];
     l1_keys += cap1;
     tiles2 += (cap1 + p2_tile<KeyT>() - 1) / p2_tile<KeyT>();
+    t_max = std::max<uint64_t>(t_max, (cap1 + p2_tile<KeyT>() - 1) / p2_tile<KeyT>());
+    nb_max = std::max<uint32_t>(nb_max, 1u << l1e[b]);
   }
   l1s[n_l1] = l1_keys; t0[n_l1] = (uint32_t)tiles2; f0[n_l1] = fb;
   if (tiles2 > 0x7FFFFFFFull) return KMC_OK;
@@ -1194,6 +1243,8 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   c->launches--; // plumbing
 
   // ---- level 1
+  bool incremental = false;
+  c->fast_variant = kWide ? "u128" : key32 ? "u32" : split64 ? "split64" : "u64";
   PHASE_BEGIN("fast_part1");
   if (from_array) {
     size_t smem = L1Smem<KeyT>::bytes(arr_tile<KeyT>(), n_l1);
@@ -1212,6 +1263,13 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
     else CK(cudaFuncSetAttribute(fast_part1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const PrefixBucket bucket = make_prefix_bucket<false>(kb, b1);
     const PrefixBucketT<true> bucket_ranged = make_prefix_bucket<true>(kb, b1, l1_base, kb - cb, c_lo, c_hi - c_lo);
+    // A large pinned submit arrives in chunks (submit_chunked): the level-2 scatter then follows every chunk's level-1
+    // scatter for the keys that have come in so far (whole tiles only; the last round takes the rest), so that when
+    // the last chunk has landed only its own share of the two scatters and the bucket sort remain.
+    size_t n_live = 0, i_last = 0;
+    for (size_t i = 0; i < c->n_segs; i++) if (c->segs[i].n_bases) { n_live++; i_last = i; }
+    incremental = n_live >= 4;
+    unsigned long long *l1_done = (unsigned long long *)(st + off_l1done);
     for (size_t i = 0; i < c->n_segs; i++) {
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
@@ -1221,28 +1279,23 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
       if (ranged) LAUNCH(fast_part1_ranged, grid, kFastThreads, smem, P, tiles, pl, bucket_ranged, (KeyT *)c->fast_l1.p, d_err(c));
       else LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->fast_l1.p, d_err(c));
+      if (incremental) {
+        PHASE_END();
+        PHASE_BEGIN("fast_part2");
+        const uint64_t t_seg = (uint64_t)((double)s.n_bases / n_l1 / p2_tile<KeyT>() * 1.25) + 2;
+        TRY(launch_part2<KeyT>(c, pl, (const KeyT *)c->fast_l1.p, key32, nb_max, i == i_last ? t_max : std::min(t_seg, t_max), l1_done, i == i_last));
+        PHASE_END();
+        if (i != i_last) PHASE_BEGIN("fast_part1");
+      }
     }
   }
-  PHASE_END();
-  // ---- level 2
-  PHASE_BEGIN("fast_part2");
-  {
-    size_t smem = PartSmem<KeyT>::bytes(p2_tile<KeyT>(), kMaxFinePerL1);
-    if constexpr (kWide) {
-      auto fast_part2 = fast_part2_kernel<U128, U128>;
-      CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const U128 *)c->fast_l1.p, (U128 *)c->fast_l2.p, d_err(c));
-    } else if (key32) {
-      auto fast_part2 = fast_part2_kernel<uint64_t, uint32_t>;
-      CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const uint64_t *)c->fast_l1.p, (uint32_t *)c->fast_l2.p, d_err(c));
-    } else {
-      auto fast_part2 = fast_part2_kernel<uint64_t, uint64_t>;
-      CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const uint64_t *)c->fast_l1.p, (uint64_t *)c->fast_l2.p, d_err(c));
-    }
+  if (!incremental) {
+    PHASE_END();
+    // ---- level 2
+    PHASE_BEGIN("fast_part2");
+    TRY(launch_part2<KeyT>(c, pl, (const KeyT *)c->fast_l1.p, key32, nb_max, t_max));
+    PHASE_END();
   }
-  PHASE_END();
   // ---- finish: the level-1 array is dead after part2 and (64-bit keys) becomes the table's key column
   PHASE_BEGIN("fast_finish");
   {
@@ -1263,6 +1316,13 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB32);
       LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint32_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
+             (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
+    } else if (split64) {
+      size_t fsmem = sizeof(FinishSmem<Split64>);
+      auto fast_finish = fast_finish_kernel<Split64>;
+      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2);
+      LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
              (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
     } else {
       size_t fsmem = sizeof(FinishSmem<uint64_t>);
@@ -1369,7 +1429,7 @@ int dist_plan_impl(kmc_ctx *c, uint32_t world, uint32_t rank, const uint64_t *al
   // at least 64 level-1 buckets per owner, so that owners can be balanced to a few percent
   uint32_t b1_min = 6;
   while ((1u << (b1_min - 6)) < world) b1_min++;
-  if (!plan_shape(G, kb, 0, ncoarse, false, kTarget, shape, b1_min)) return KMC_OK;
+  if (!plan_shape(G, kb, 0, ncoarse, false, kTarget, shape, b1_min, getenv("KMC_NO_SPLIT64") ? 0u : split64_min_e(kb, n_est, kWide))) return KMC_OK;
   const uint32_t b1 = shape.b1, n_all = 1u << b1, cshift = cb - b1;
   if (n_all < world) return KMC_OK;
   // owners: consecutive level-1 buckets, about equal population
@@ -1497,10 +1557,14 @@ int finish_dist(kmc_ctx *c) {
   uint64_t *cstart = (uint64_t *)(hb + o_cs);
   uint32_t *cfine0 = (uint32_t *)(hb + o_cf);
   uint16_t *ccap = (uint16_t *)(hb + o_cc);
-  uint64_t l1_keys = 0, l2_keys = 0, tiles2 = 0;
-  uint32_t fb = 0;
-  bool key32 = !kWide;
-  for (uint32_t rb = 0; rb < my_n; rb++) if (kb - b1 - D.l1e[my_lo + rb] > 32) key32 = false;
+  uint64_t l1_keys = 0, l2_keys = 0, tiles2 = 0, t_max = 1;
+  uint32_t fb = 0, nb_max = 1;
+  bool key32 = !kWide, split64 = !kWide && !getenv("KMC_NO_SPLIT64");
+  for (uint32_t rb = 0; rb < my_n; rb++) {
+    if (kb - b1 - D.l1e[my_lo + rb] > 32) key32 = false;
+    if (kb - b1 - D.l1e[my_lo + rb] > 32 + (uint32_t)kFinishBits) split64 = false;
+  }
+  if (key32) split64 = false;
   for (uint32_t rb = 0; rb < my_n; rb++) {
     const uint32_t b = my_lo + rb, e = D.l1e[b], sub_bits = e - cshift;
     rf[rb] = fb; re[rb] = (uint8_t)e;
@@ -1510,6 +1574,8 @@ int finish_dist(kmc_ctx *c) {
       xs[x] = l1_keys; xc[x] = cap1; xt[x] = (uint32_t)tiles2; xf[x] = fb; xe[x] = (uint8_t)e;
       l1_keys += cap1;
       tiles2 += (cap1 + p2_tile<KeyT>() - 1) / p2_tile<KeyT>();
+      t_max = std::max<uint64_t>(t_max, (cap1 + p2_tile<KeyT>() - 1) / p2_tile<KeyT>());
+      nb_max = std::max<uint32_t>(nb_max, 1u << e);
     }
     for (uint32_t ci = b << cshift; ci < ((b + 1) << cshift); ci++) {
       double avg = (double)D.fine_hist[ci] / (double)(1ull << sub_bits);
@@ -1552,22 +1618,7 @@ int finish_dist(kmc_ctx *c) {
          (const uint16_t *)(tb + o_cc), (const uint32_t *)(tb + o_rf), (const uint8_t *)(tb + o_re), cshift, my_lo, kb, b1, (uint32_t)kWide);
   c->launches--;
   PHASE_BEGIN("fast_part2");
-  {
-    size_t smem = PartSmem<KeyT>::bytes(p2_tile<KeyT>(), kMaxFinePerL1);
-    if constexpr (kWide) {
-      auto fast_part2 = fast_part2_kernel<U128, U128>;
-      CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const U128 *)l1, (U128 *)c->fast_l2.p, d_err(c));
-    } else if (key32) {
-      auto fast_part2 = fast_part2_kernel<uint64_t, uint32_t>;
-      CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const uint64_t *)l1, (uint32_t *)c->fast_l2.p, d_err(c));
-    } else {
-      auto fast_part2 = fast_part2_kernel<uint64_t, uint64_t>;
-      CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      LAUNCH(fast_part2, (uint32_t)tiles2, kFastThreads, smem, pl, (const uint64_t *)l1, (uint64_t *)c->fast_l2.p, d_err(c));
-    }
-  }
+  TRY(launch_part2<KeyT>(c, pl, l1, key32, nb_max, t_max));
   PHASE_END();
   PHASE_BEGIN("fast_finish");
   {
@@ -1585,6 +1636,12 @@ int finish_dist(kmc_ctx *c) {
       LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB32), kFinThreads, fsmem, pl,
              (const uint32_t *)c->fast_l2.p, (uint64_t *)c->t_lo.p, (uint64_t *)nullptr, (uint32_t *)c->t_cnt.p, status, ticket, d_err(c),
              d_total, prof);
+    } else if (split64) {
+      size_t fsmem = sizeof(FinishSmem<Split64>);
+      auto fast_finish = fast_finish_kernel<Split64>;
+      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2), kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p,
+             (uint64_t *)c->t_lo.p, (uint64_t *)nullptr, (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
     } else {
       size_t fsmem = sizeof(FinishSmem<uint64_t>);
       auto fast_finish = fast_finish_kernel<uint64_t>;
@@ -1684,9 +1741,9 @@ void build_stats(kmc_ctx *c) {
   char buf[1024];
   snprintf(buf, sizeof buf,
            "\"n_bases\": %llu, \"n_records\": %llu, \"n_total\": %llu, \"n_distinct\": %llu, \"key_bits\": %u, "
-           "\"strategy_used\": %u, \"fast_fallbacks\": %u, \"hash_aborts\": %u, \"hot_keys\": %u, \"kernel_launches\": %llu, \"kernel_launches_total\": %llu, \"h2d_bytes\": %llu, \"phases_ms\": {",
+           "\"strategy_used\": %u, \"fast_variant\": \"%s\", \"fast_fallbacks\": %u, \"hash_aborts\": %u, \"hot_keys\": %u, \"kernel_launches\": %llu, \"kernel_launches_total\": %llu, \"h2d_bytes\": %llu, \"phases_ms\": {",
            (unsigned long long)c->total_bases, (unsigned long long)c->total_recs, (unsigned long long)c->n_total,
-           (unsigned long long)c->n_distinct, c->key_bits, c->strategy_used, c->fast_fallbacks, c->hash_aborts, c->n_hot, (unsigned long long)c->launches,
+           (unsigned long long)c->n_distinct, c->key_bits, c->strategy_used, c->fast_variant, c->fast_fallbacks, c->hash_aborts, c->n_hot, (unsigned long long)c->launches,
            (unsigned long long)c->launches_total, (unsigned long long)c->h2d_bytes);
   s += buf;
   // sum phases of the same name

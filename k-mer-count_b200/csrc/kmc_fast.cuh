@@ -66,18 +66,14 @@ constexpr int kHistSampleMax = 16;       // fast_hist looks at every step-th til
 #ifndef KMC_PART1_PREFETCH
 #define KMC_PART1_PREFETCH 1  // fast_part1: request the next tile's bases before writing the current tile out
 #endif                        // (measured on B200, profiles/r02_ab_prepared_variants.jsonl: 5.67 -> 5.28 ms at 1e9 bases)
-#ifndef KMC_FIN_SEGROWS
-#define KMC_FIN_SEGROWS 1  // fast_finish: rows between two listed duplicates are written by a plain shifted copy loop
-#endif
 constexpr int kFineTarget = KMC_FINE_TARGET; // aimed keys per fine bucket
 constexpr int kFineCap = KMC_FINE_CAP;       // smem capacity of fast_finish (keys)
-// 64-bit level-2 elements (buckets that leave more than 32 key bits, e.g. k=31) may get their own, smaller shape:
-// two 72 KB CTAs fit an SM, three 44 KB ones would too (experiment; by default the same shape as 32-bit suffixes)
+// 64-bit level-2 elements (buckets that leave more than 32 key bits, e.g. k=31) have their own, smaller shape:
 #ifndef KMC_FINE_CAP64
-#define KMC_FINE_CAP64 KMC_FINE_CAP
-#endif
+#define KMC_FINE_CAP64 5632   // with Split64's two buffers (deferred write-back) two CTAs still fit an SM; measured on
+#endif                        // B200 against 9216 / one buffer: k=31, 1.25e9 bases 11.4 -> 9.8 ms (profiles/r02_ab_split64.jsonl)
 #ifndef KMC_FINE_TARGET64
-#define KMC_FINE_TARGET64 KMC_FINE_TARGET
+#define KMC_FINE_TARGET64 4800
 #endif
 #ifndef KMC_FINISH_MINB64
 #define KMC_FINISH_MINB64 2
@@ -113,6 +109,13 @@ template <typename L2T> __device__ __forceinline__ L2T to_l2(const U128 &key) { 
 __device__ __forceinline__ void emit_key(uint64_t *lo, uint64_t *, uint64_t i, const FineDesc &D, uint32_t x) { lo[i] = D.prefix | x; }
 __device__ __forceinline__ void emit_key(uint64_t *lo, uint64_t *, uint64_t i, const FineDesc &D, uint64_t x) { lo[i] = D.prefix | x; }
 __device__ __forceinline__ void emit_key(uint64_t *lo, uint64_t *hi, uint64_t i, const FineDesc &, const U128 &x) { lo[i] = x.lo; hi[i] = x.hi; }
+// Split64 row: bucket prefix | sub-bin id at `bshift` | low 32 bits (which overlap the sub-bin id consistently)
+template <bool SPLIT, typename T>
+__device__ __forceinline__ void emit_row(uint64_t *lo, uint64_t *hi, uint64_t i, const FineDesc &D, const T &x, const uint16_t *binof, uint32_t p,
+                                         uint32_t bshift) {
+  if constexpr (SPLIT) lo[i] = D.prefix | ((uint64_t)binof[p] << bshift) | (uint64_t)x;
+  else emit_key(lo, hi, i, D, x);
+}
 
 struct FastPlan {
   uint32_t kb, b1;          // key bits, level-1 bits
@@ -248,45 +251,6 @@ __global__ void __launch_bounds__(256) fast_hist_array_kernel(const KeyT *__rest
 }
 
 // ------------------------------------------------------------------------------------------------ part1 / part2
-// Shared-memory layout of fast_part2 (dynamic smem):
-//   stage[STAGE] keys | gdelta[NB] u64 | hist[NB] u32 | loc[NB] u32 | scan scratch
-template <typename KeyT>
-struct PartSmem {
-  KeyT *stage; uint64_t *gdelta; uint32_t *hist; uint32_t *loc; uint32_t *scan;
-  __device__ PartSmem(unsigned char *base, uint32_t stage_keys, uint32_t nb) {
-    stage = (KeyT *)base;
-    gdelta = (uint64_t *)(stage + stage_keys);
-    hist = (uint32_t *)(gdelta + nb);
-    loc = hist + nb;
-    scan = loc + nb;
-  }
-  static __host__ __device__ size_t bytes(uint32_t stage_keys, uint32_t nb) {
-    return (size_t)stage_keys * sizeof(KeyT) + (size_t)nb * 16 + 64 * 4;
-  }
-};
-
-// exclusive scan of hist[0..nb) into loc[0..nb); nb <= THREADS * 4.  Returns the total.
-template <int THREADS = kFastThreads>
-__device__ __forceinline__ uint32_t scan_bins(const uint32_t *hist, uint32_t *loc, uint32_t nb, uint32_t *scratch) {
-  uint32_t v[4], s = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    uint32_t b = threadIdx.x * 4 + j;
-    v[j] = b < nb ? hist[b] : 0u;
-    s += v[j];
-  }
-  uint32_t total;
-  uint32_t ex = block_excl_scan<uint32_t, THREADS>(s, scratch, total);
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    uint32_t b = threadIdx.x * 4 + j;
-    if (b < nb) loc[b] = ex;
-    ex += v[j];
-  }
-  __syncthreads(); // loc[] is read next by other threads
-  return total;
-}
-
 // ---- level-1 scatter: rank → reserve → stage → one TMA bulk store per bucket run ----------------------------------
 // The common back end of fast_part1 / fast_part1_array / the routing kernels.  A CTA tile's keys are ranked inside
 // their bucket with shared-memory atomics, room for every bucket's run is reserved with one global atomic per
@@ -483,81 +447,133 @@ __global__ void __launch_bounds__(kFastThreads, 1) fast_part1_array_kernel(const
   bulk_wait_all();
 }
 
-// One CTA per tile of p2_tile<KeyT>() keys of one level-1 bucket → its 2^e fine buckets (the next e key bits).
+// Shared-memory layout of fast_part2 (dynamic smem):
+//   stage[STAGE] keys | gdelta[NB] u64 | hist[NB] u32 | loc[NB] u32 | scan scratch
+template <typename KeyT>
+struct PartSmem {
+  KeyT *stage; uint64_t *gdelta; uint32_t *hist; uint32_t *loc; uint32_t *scan;
+  __device__ PartSmem(unsigned char *base, uint32_t stage_keys, uint32_t nb) {
+    stage = (KeyT *)base;
+    gdelta = (uint64_t *)(stage + stage_keys);
+    hist = (uint32_t *)(gdelta + nb);
+    loc = hist + nb;
+    scan = loc + nb;
+  }
+  static __host__ __device__ size_t bytes(uint32_t stage_keys, uint32_t nb) {
+    return (size_t)stage_keys * sizeof(KeyT) + (size_t)nb * 16 + 64 * 4;
+  }
+};
+
+// exclusive scan of hist[0..nb) into loc[0..nb); nb <= THREADS * 4.  Returns the total.
+template <int THREADS = kFastThreads>
+__device__ __forceinline__ uint32_t scan_bins(const uint32_t *hist, uint32_t *loc, uint32_t nb, uint32_t *scratch) {
+  uint32_t v[4], s = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    uint32_t b = threadIdx.x * 4 + j;
+    v[j] = b < nb ? hist[b] : 0u;
+    s += v[j];
+  }
+  uint32_t total;
+  uint32_t ex = block_excl_scan<uint32_t, THREADS>(s, scratch, total);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    uint32_t b = threadIdx.x * 4 + j;
+    if (b < nb) loc[b] = ex;
+    ex += v[j];
+  }
+  __syncthreads(); // loc[] is read next by other threads (bucket b is reserved by thread b, not by its writer b/4)
+  return total;
+}
+
+// ---- level-2 scatter ---------------------------------------------------------------------------------------------
+// Tiles of p2_tile<KeyT>() keys of one level-1 bucket → its 2^e fine buckets (the next e key bits), as level-2
+// elements (32-bit suffixes when every bucket leaves <= 32 key bits): rank inside the fine bucket with shared-memory
+// atomics, one global atomic per fine bucket reserves the run's room, keys staged in bucket order, runs written by
+// all threads.  (The level-1 scatter's back end — second atomic for the slot, one TMA bulk store per run — was measured
+// here too, profiles/r02_ab_part2_bulk.jsonl: 5.0 ms against 4.07; these runs are 128 B, and a CTA has nothing to
+// overlap the drain of 256 small bulk copies with.)
+//
+// Grid (T, level-1 buckets): CTA (j, b) takes tile j of the keys of bucket b that have not been moved yet —
+// [l1_done[b], l1_cursor[b]) — so the kernel can run after every chunk of a large input (the H2D copy of the next
+// chunks then overlaps it).  Unless `flush`, only whole tiles are taken, and at most T of them per bucket: the rest
+// waits for the next round (the flushing round's T covers a whole bucket).  l2_done_kernel then advances l1_done.
+__global__ void l2_done_kernel(const FastPlan pl, unsigned long long *__restrict__ l1_done, uint32_t tile, uint32_t flush,
+                               uint32_t t_grid) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= pl.n_l1) return;
+  unsigned long long cur = pl.l1_cursor[b];
+  if (cur > pl.l1_cap[b]) cur = pl.l1_cap[b];
+  const unsigned long long done = l1_done[b];
+  unsigned long long tiles = (cur - done) / tile;
+  if (tiles > t_grid) tiles = t_grid;
+  l1_done[b] = flush ? cur : done + tiles * tile;
+}
+
 template <typename KeyT, typename L2T>
 __global__ void __launch_bounds__(kFastThreads, 2) fast_part2_kernel(FastPlan pl, const KeyT *__restrict__ l1,
-                                                                      L2T *__restrict__ l2, uint32_t *__restrict__ flags) {
+                                                                      L2T *__restrict__ l2, uint32_t *__restrict__ flags,
+                                                                      const unsigned long long *__restrict__ l1_done, uint32_t flush,
+                                                                      uint32_t nb_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t s_b;
   constexpr int kKPT = FastShape<KeyT>::kP2KPT, kTile = p2_tile<KeyT>();
-  // which level-1 bucket owns this tile: the b with l1_tile0[b] <= tile < l1_tile0[b+1] (every bucket has at least
-  // one tile).  All threads look at once — a binary search by one thread is ten dependent L2 round trips, a
-  // quarter of this CTA's life (12.8 % of the kernel's stall samples in profiles/r01).
-#if KMC_P2_PSEARCH
-  for (uint32_t i = threadIdx.x; i < pl.n_l1; i += kFastThreads)
-    if (pl.l1_tile0[i] <= blockIdx.x && blockIdx.x < pl.l1_tile0[i + 1]) s_b = i;
-#else
-  if (threadIdx.x == 0) {
-    uint32_t lo = 0, hi = pl.n_l1;
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (pl.l1_tile0[mid] <= blockIdx.x) lo = mid; else hi = mid;
-    }
-    s_b = lo;
-  }
-#endif
-  __syncthreads();
-  const uint32_t b = s_b;
+  const uint32_t b = blockIdx.y; // tiles of one bucket are neighbours in launch order: their runs meet in L2
   unsigned long long n_b = pl.l1_cursor[b];
   if (n_b > pl.l1_cap[b]) n_b = pl.l1_cap[b];
-  const uint64_t toff = (uint64_t)(blockIdx.x - pl.l1_tile0[b]) * kTile;
-  if (toff >= n_b) return; // tiles are laid out over the capacity; this one is past the fill
+  const unsigned long long done = l1_done ? l1_done[b] : 0ull;
+  const uint64_t n_new = n_b - done;
+  const uint64_t n_tiles = flush ? (n_new + kTile - 1) / kTile : n_new / kTile;
+  if (blockIdx.x >= n_tiles) return;
   const uint32_t e = pl.l1_e[b];
   const uint32_t fshift = pl.kb - pl.b1 - e, fmask = (1u << e) - 1u; // e == 0 → fmask 0 → fine index 0
   const uint32_t fine0 = pl.l1_fine0[b], nb = 1u << e;
-  PartSmem<KeyT> S(smem_raw, kTile, kMaxFinePerL1);
-  for (uint32_t i = threadIdx.x; i < nb; i += kFastThreads) S.hist[i] = 0;
-  __syncthreads();
-  const uint64_t base = pl.l1_start[b] + toff;
-  const uint32_t cnt = (uint32_t)((n_b - toff < (uint64_t)kTile) ? n_b - toff : kTile);
-  KeyT key[kKPT];
-  uint32_t rank[kKPT / 2];
+  PartSmem<KeyT> S(smem_raw, kTile, nb_max);
+  { // one tile per CTA (a loop over tiles here cost 15 %: spills in the unrolled key loops)
+    const uint64_t tj = blockIdx.x;
+    for (uint32_t i = threadIdx.x; i < nb; i += kFastThreads) S.hist[i] = 0;
+    __syncthreads(); // also: the previous tile's write-out has read the staging area
+    const uint64_t toff = tj * kTile;
+    const uint64_t base = pl.l1_start[b] + done + toff;
+    const uint32_t cnt = (uint32_t)((n_new - toff < (uint64_t)kTile) ? n_new - toff : kTile);
+    KeyT key[kKPT];
+    uint32_t rank[kKPT / 2];
 #pragma unroll
-  for (int j = 0; j < kKPT; j++) {
-    uint32_t idx = j * kFastThreads + threadIdx.x;
-    if (idx < cnt) key[j] = l1[base + idx]; else key[j] = KeyT{};
-  }
-#pragma unroll
-  for (int j = 0; j < kKPT; j++) {
-    uint32_t idx = j * kFastThreads + threadIdx.x;
-    uint32_t r = 0;
-    if (idx < cnt) r = atomicAdd(&S.hist[fmask ? key_shr32(key[j], fshift) & fmask : 0u], 1u);
-    if (j & 1) rank[j >> 1] |= r << 16; else rank[j >> 1] = r;
-  }
-  __syncthreads();
-  uint32_t total = scan_bins(S.hist, S.loc, nb, S.scan);
-  for (uint32_t fl = threadIdx.x; fl < nb; fl += kFastThreads) {
-    uint32_t c = S.hist[fl];
-    if (c) {
-      const FineDesc D = pl.fdesc[fine0 + fl];
-      uint32_t pos = atomicAdd(&pl.fine_cursor[fine0 + fl], c);
-      if (pos + c > D.cap) atomicOr(flags, kFlagOverflow);
-      // a run that starts inside the bucket may spill past its end (into the next bucket's room or the
-      // array's tail slack — the result is discarded anyway); one that starts outside goes to the trash
-      S.gdelta[fl] = (pos < D.cap ? D.start + pos : pl.l2_trash) - S.loc[fl];
+    for (int j = 0; j < kKPT; j++) {
+      uint32_t idx = j * kFastThreads + threadIdx.x;
+      if (idx < cnt) key[j] = l1[base + idx]; else key[j] = KeyT{};
     }
-  }
-  __syncthreads();
 #pragma unroll
-  for (int j = 0; j < kKPT; j++) {
-    uint32_t idx = j * kFastThreads + threadIdx.x;
-    if (idx < cnt)
-      S.stage[S.loc[fmask ? key_shr32(key[j], fshift) & fmask : 0u] + ((rank[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)] = key[j];
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < total; i += kFastThreads) {
-    KeyT k = S.stage[i];
-    l2[S.gdelta[fmask ? key_shr32(k, fshift) & fmask : 0u] + i] = to_l2<L2T>(k);
+    for (int j = 0; j < kKPT; j++) {
+      uint32_t idx = j * kFastThreads + threadIdx.x;
+      uint32_t r = 0;
+      if (idx < cnt) r = atomicAdd(&S.hist[key_shr32(key[j], fshift) & fmask], 1u);
+      if (j & 1) rank[j >> 1] |= r << 16; else rank[j >> 1] = r;
+    }
+    __syncthreads();
+    uint32_t total = scan_bins(S.hist, S.loc, nb, S.scan);
+    for (uint32_t fl = threadIdx.x; fl < nb; fl += kFastThreads) {
+      uint32_t c = S.hist[fl];
+      if (c) {
+        const FineDesc D = pl.fdesc[fine0 + fl];
+        uint32_t pos = atomicAdd(&pl.fine_cursor[fine0 + fl], c);
+        if (pos + c > D.cap) atomicOr(flags, kFlagOverflow);
+        // a run that starts inside the bucket may spill past its end (into the next bucket's room or the
+        // array's tail slack — the result is discarded anyway); one that starts outside goes to the trash
+        S.gdelta[fl] = (pos < D.cap ? D.start + pos : pl.l2_trash) - S.loc[fl];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kKPT; j++) {
+      uint32_t idx = j * kFastThreads + threadIdx.x;
+      if (idx < cnt)
+        S.stage[S.loc[key_shr32(key[j], fshift) & fmask] + ((rank[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)] = key[j];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < total; i += kFastThreads) {
+      KeyT k = S.stage[i];
+      l2[S.gdelta[key_shr32(k, fshift) & fmask] + i] = to_l2<L2T>(k);
+    }
   }
 }
 
@@ -616,7 +632,16 @@ constexpr int kFinWarps = kFinThreads / 32;
 constexpr int kFinWordsPT = kFinishBins / 2 / kFinThreads; // packed bin words per thread in the scan (8 at 512 threads)
 // keys per fine bucket that fast_finish can hold: 8192 32/64-bit elements, 4096 128-bit keys (64 KB either way
 // for the widest; 32 KB for 32-bit suffixes)
-template <typename L2T> __host__ __device__ constexpr int fin_cap() { return sizeof(L2T) == 16 ? 4096 : sizeof(L2T) == 8 ? kFineCap64 : kFineCap; }
+// Split64: 64-bit level-2 elements whose buckets leave at most 32 + kFinishBits key bits (k = 31 at the usual sizes).
+// The counting sort's sub-bin is taken from the 64-bit element, but only its low 32 bits go to shared memory — the
+// bits above them are the sub-bin id, kept per position in a 16-bit side array and put back when the rows are
+// written.  Shared memory, bank traffic and compares of the in-bucket sort are those of 32-bit suffixes.
+struct Split64 {};
+template <typename L2T> struct FinTraits { using Global = L2T; using Smem = L2T; static constexpr bool kSplit = false; };
+template <> struct FinTraits<Split64> { using Global = uint64_t; using Smem = uint32_t; static constexpr bool kSplit = true; };
+template <typename L2T> __host__ __device__ constexpr int fin_cap() { // 64-bit level-2 elements share one bucket shape, split or not
+  return FinTraits<L2T>::kSplit ? kFineCap64 : sizeof(typename FinTraits<L2T>::Smem) == 16 ? 4096 : sizeof(typename FinTraits<L2T>::Smem) == 8 ? kFineCap64 : kFineCap;
+}
 template <typename L2T> __host__ __device__ constexpr int fin_kpt() { return fin_cap<L2T>() / kFinThreads; }
 static_assert(fin_kpt<uint32_t>() <= 32 && fin_kpt<uint32_t>() * kFinWarps <= kFinThreads && kFinWordsPT % 4 == 0, "fast_finish shape");
 
@@ -629,13 +654,24 @@ static_assert(fin_kpt<uint32_t>() <= 32 && fin_kpt<uint32_t>() * kFinWarps <= kF
 #ifndef KMC_FINISH_DEFER
 #define KMC_FINISH_DEFER 1
 #endif
-template <typename L2T> __host__ __device__ constexpr int fin_bufs() { return (KMC_FINISH_DEFER && sizeof(L2T) == 4) ? 2 : 1; }
+#ifndef KMC_FINISH_DEFER64
+#define KMC_FINISH_DEFER64 0 // the same for 64-bit level-2 elements (needs a KMC_FINE_CAP64 small enough for two buffers)
+#endif
+#ifndef KMC_FINISH_DEFER_SPLIT
+#define KMC_FINISH_DEFER_SPLIT 1
+#endif
+template <typename L2T> __host__ __device__ constexpr int fin_bufs() {
+  using ST = typename FinTraits<L2T>::Smem;
+  if (FinTraits<L2T>::kSplit) return KMC_FINISH_DEFER_SPLIT ? 2 : 1;
+  return ((KMC_FINISH_DEFER && sizeof(ST) == 4) || (KMC_FINISH_DEFER64 && sizeof(ST) == 8)) ? 2 : 1;
+}
 
 template <typename L2T>
 struct FinishSmem {
-  L2T keys[fin_bufs<L2T>()][fin_cap<L2T>()]; // 32 KB per buffer (u32) / 64 KB (u64, u128)
+  typename FinTraits<L2T>::Smem keys[fin_bufs<L2T>()][fin_cap<L2T>()]; // 36 KB per buffer (u32) / 72 KB (u64) / 64 KB (u128)
+  uint16_t binof[FinTraits<L2T>::kSplit ? fin_bufs<L2T>() : 1][FinTraits<L2T>::kSplit ? fin_cap<L2T>() : 8]; // Split64: sub-bin of every position
   uint32_t bins[kFinishBins / 2];          // packed u16 pairs: counts → starts → (after the scatter) ends
-  uint16_t hp[(sizeof(L2T) == 8 ? kFineCap64 : kFineCap) + 8]; // multi-key sub-bin list, then head position of every run
+  uint16_t hp[fin_cap<L2T>() + 8];         // multi-key sub-bin list, then head position of every run
   uint32_t scan32[40];
   uint32_t rowcnt[fin_kpt<L2T>() * kFinWarps];// heads per (row, warp), then their exclusive scan
   uint32_t hard[kMaxHard];
@@ -676,16 +712,17 @@ __device__ __forceinline__ void sort_dup_list(uint16_t *dup, uint32_t m) {
   if (lane < m) dup[r] = (uint16_t)v;
 }
 
-#if KMC_FIN_SEGROWS
 // `dup` sorted ascending.  The positions between two listed ones form a segment whose rows all sit the same distance
 // below their position (the number of listed positions before them): m + 1 plain copy loops, no per-row search.
 // A segment's last position is followed by a listed one — it is the row the copies merge into, and its count is
 // written by the fix-up at the end (1 + length of the run of listed positions that follows).
 template <typename L2T>
-__device__ __forceinline__ void finish_write_rows(const FinPending &P, const L2T *keys, const uint16_t *dup, unsigned long long G,
+__device__ __forceinline__ void finish_write_rows(const FinPending &P, const typename FinTraits<L2T>::Smem *keys, const uint16_t *binof,
+                                                  const uint16_t *dup, unsigned long long G,
                                                   uint64_t *__restrict__ out_lo, uint64_t *__restrict__ out_hi,
                                                   uint32_t *__restrict__ out_cnt) {
   const uint32_t m = P.m, n = P.n, tid = threadIdx.x;
+  const uint32_t bshift = P.D.rem - (P.D.rem < (uint32_t)kFinishBits ? P.D.rem : (uint32_t)kFinishBits);
   for (uint32_t s = 0; s <= m; s++) {
     const uint32_t lo = s ? (uint32_t)dup[s - 1] + 1u : 0u, hi = s < m ? (uint32_t)dup[s] : n;
     const unsigned long long base = G - s; // row of position p = base + p
@@ -694,7 +731,7 @@ __device__ __forceinline__ void finish_write_rows(const FinPending &P, const L2T
     for (uint32_t q = tid; q < hi - lo + a; q += kFinThreads) {
       if (q < a) continue;
       const uint32_t p = lo + q - a;
-      emit_key(out_lo, out_hi, base + p, P.D, keys[p]);
+      emit_row<FinTraits<L2T>::kSplit>(out_lo, out_hi, base + p, P.D, keys[p], binof, p, bshift);
       if (s == m || p + 1 != hi) out_cnt[base + p] = 1u;
     }
   }
@@ -707,34 +744,9 @@ __device__ __forceinline__ void finish_write_rows(const FinPending &P, const L2T
     }
   }
 }
-#else
-template <typename L2T>
-__device__ __forceinline__ void finish_write_rows(const FinPending &P, const L2T *keys, const uint16_t *dup, unsigned long long G,
-                                                  uint64_t *__restrict__ out_lo, uint64_t *__restrict__ out_hi,
-                                                  uint32_t *__restrict__ out_cnt) {
-  const uint32_t m = P.m;
-  // lane l of every warp writes row G + p with (G + p) % 32 == l: each warp store covers whole 128 B lines (an
-  // unaligned 256 B store is three L2 requests instead of two, and the kernel's stores run near the request ceiling)
-  const uint32_t a = KMC_ALIGNED_ROWS ? (uint32_t)(G & 31u) : 0u;
-  for (uint32_t q = threadIdx.x; q < P.n + a; q += kFinThreads) {
-    if (q < a) continue;
-    const uint32_t p = q - a;
-    uint32_t before = 0, cnt = 1;
-    bool listed = false;
-    for (uint32_t q = 0; q < m; q++) { const uint32_t dq = dup[q]; before += dq < p; listed |= dq == p; }
-    if (listed) continue;
-    for (bool more = m != 0; more;) {
-      more = false;
-      for (uint32_t q = 0; q < m; q++) if (dup[q] == p + cnt) { cnt++; more = true; break; }
-    }
-    emit_key(out_lo, out_hi, G + p - before, P.D, keys[p]);
-    out_cnt[G + p - before] = cnt;
-  }
-}
-#endif
 
 template <typename L2T>
-__global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MINB32 : sizeof(L2T) == 8 ? KMC_FINISH_MINB64 : 2) fast_finish_kernel(FastPlan pl, const L2T *__restrict__ l2,
+__global__ void __launch_bounds__(kFinThreads, FinTraits<L2T>::kSplit ? 2 : sizeof(L2T) == 4 ? KMC_FINISH_MINB32 : sizeof(L2T) == 8 ? KMC_FINISH_MINB64 : 2) fast_finish_kernel(FastPlan pl, const typename FinTraits<L2T>::Global *__restrict__ l2,
                                                                        uint64_t *__restrict__ out_lo, uint64_t *__restrict__ out_hi,
                                                                        uint32_t *__restrict__ out_cnt,
                                                                        unsigned long long *__restrict__ status,
@@ -745,6 +757,9 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
   FinishSmem<L2T> &S = *reinterpret_cast<FinishSmem<L2T> *>(smem_raw);
   constexpr int kFinishKPT = fin_kpt<L2T>();
   constexpr bool kDefer = fin_bufs<L2T>() == 2;
+  constexpr bool kSplit = FinTraits<L2T>::kSplit;
+  using GlobT = typename FinTraits<L2T>::Global;
+  using SmemT = typename FinTraits<L2T>::Smem;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // optional phase timeline (development aid, env KMC_FINISH_PROF=1): thread 0 adds the cycles between marks
   long long t_prev = prof ? clock64() : 0;
@@ -760,12 +775,12 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
         S.goff = prefix;                                                                                    \
         if ((P).f + 1 == pl.n_fine) *d_total = prefix + ((P).n - (P).m);                                    \
       }                                                                                                     \
-    } else if (KMC_FIN_SEGROWS && warp == 1 && (P).m > 1) {                                                 \
+    } else if (warp == 1 && (P).m > 1) {                                                 \
       sort_dup_list(S.dup[buf], (P).m);                                                                     \
     }                                                                                                       \
     __syncthreads();                                                                                        \
     FIN_MARK(8);                                                                                            \
-    finish_write_rows<L2T>((P), S.keys[buf], S.dup[buf], S.goff, out_lo, out_hi, out_cnt);                   \
+    finish_write_rows<L2T>((P), S.keys[buf], S.binof[kSplit ? (buf) : 0], S.dup[buf], S.goff, out_lo, out_hi, out_cnt); \
     __syncthreads();                                                                                        \
     FIN_MARK(9);                                                                                            \
   } while (0)
@@ -784,7 +799,8 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
     if (n > D.cap) n = D.cap; // overflow was flagged by fast_part2; the caller discards this result
     const uint32_t sb = D.rem < (uint32_t)kFinishBits ? D.rem : (uint32_t)kFinishBits;
     const uint32_t bshift = D.rem - sb, bmask = (1u << sb) - 1u; // sb == 0 → every key in sub-bin 0
-    L2T *const keys = S.keys[cur];
+    SmemT *const keys = S.keys[cur];
+    uint16_t *const binof = S.binof[kSplit ? cur : 0];
     {
       uint4 z = make_uint4(0, 0, 0, 0);
       for (uint32_t i = tid; i < kFinishBins / 8; i += kFinThreads) reinterpret_cast<uint4 *>(S.bins)[i] = z;
@@ -795,18 +811,29 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
     // ---- load (thread t owns positions t, t+512, ...) + count per sub-bin.  The thread that adds the SECOND
     //      key of a sub-bin puts the sub-bin on the multi-key list (S.hp is free until the run-length encode).
     const uint32_t rows = (n + kFinThreads - 1) / kFinThreads;
-    L2T x[kFinishKPT];
+    SmemT x[kFinishKPT];
+    uint32_t xh[kSplit ? kFinishKPT : 1]; // Split64: the element's high word (its sub-bin id from the scatter on)
 #pragma unroll
     for (int j = 0; j < kFinishKPT; j++) {
       uint32_t i = j * kFinThreads + tid;
-      if (i < n) x[j] = l2[D.start + i]; else x[j] = L2T{};
+      if constexpr (kSplit) {
+        const GlobT g = i < n ? l2[D.start + i] : GlobT{};
+        x[j] = (uint32_t)g; xh[j] = (uint32_t)(g >> 32);
+      } else {
+        if (i < n) x[j] = l2[D.start + i]; else x[j] = SmemT{};
+      }
     }
+    // sub-bin of an element: Split64 takes it across the two words (bshift <= 32)
+    auto sub_bin = [&](int j) -> uint32_t {
+      if constexpr (kSplit) return __funnelshift_rc(x[j], xh[j], bshift) & bmask;
+      else return key_shr32(x[j], bshift) & bmask;
+    };
 #pragma unroll
     for (int j = 0; j < kFinishKPT; j++) {
       if ((uint32_t)j >= rows) break;
       uint32_t i = j * kFinThreads + tid;
       if (i < n) {
-        uint32_t b = key_shr32(x[j], bshift) & bmask;
+        uint32_t b = sub_bin(j);
         uint32_t sh = 16 * (b & 1);
         uint32_t old = atomicAdd(&S.bins[b >> 1], 1u << sh);
         if (((old >> sh) & 0xFFFFu) == 1u) S.hp[atomicAdd(&S.n_multi, 1u)] = (uint16_t)b;
@@ -845,10 +872,11 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
       if ((uint32_t)j >= rows) break;
       uint32_t i = j * kFinThreads + tid;
       if (i < n) {
-        uint32_t b = key_shr32(x[j], bshift) & bmask;
+        uint32_t b = sub_bin(j);
         uint32_t sh = 16 * (b & 1);
         uint32_t p = (atomicAdd(&S.bins[b >> 1], 1u << sh) >> sh) & 0xFFFFu;
         keys[p] = x[j];
+        if constexpr (kSplit) binof[p] = (uint16_t)b;
       }
     }
     __syncthreads();
@@ -865,7 +893,7 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
         if (e0 - s0 > (uint32_t)kSmallBin) {
           // many keys in one sub-bin are almost always copies of one key (input with coverage > 1): a linear check
           // settles those without sorting; only sub-bins with several distinct keys go to the cooperative sort
-          const L2T first = keys[s0];
+          const SmemT first = keys[s0];
           bool same = true;
           for (uint32_t i = s0 + 1; i < e0; i++) if (!key_eq(keys[i], first)) { same = false; break; }
           if (same) { dups += e0 - s0 - 1; S.dups_listed = 0; continue; }
@@ -875,7 +903,7 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
         }
         uint32_t here = 0;
         for (uint32_t i = s0 + 1; i < e0; i++) {
-          const L2T v = keys[i];
+          const SmemT v = keys[i];
           uint32_t jj = i;
           while (jj > s0 && key_lt(v, keys[jj - 1])) { keys[jj] = keys[jj - 1]; jj--; }
           keys[jj] = v;
@@ -917,20 +945,21 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
       for (uint32_t h = 0; h < nh; h++) {
         const uint32_t b = S.hard[h];
         const uint32_t s = bin_start(S.bins, b), m = bin_end(S.bins, b) - s;
-        const L2T first = keys[s];
+        const SmemT first = keys[s];
         int differ = 0;
         for (uint32_t i = tid; i < m; i += kFinThreads) differ |= !key_eq(keys[s + i], first);
         if (__syncthreads_or(differ)) {
           for (uint32_t i = tid; i < m; i += kFinThreads) {
-            const L2T v = keys[s + i];
+            const SmemT v = keys[s + i];
             uint32_t r = 0;
             for (uint32_t q = 0; q < m; q++) {
-              L2T o = keys[s + q];
+              SmemT o = keys[s + q];
               r += key_lt(o, v) || (key_eq(o, v) && q < i);
             }
             S.hp[i] = (uint16_t)r;
           }
           __syncthreads();
+          // (all of one sub-bin: the side array of sub-bin ids stays as it is)
 #pragma unroll
           for (int j = 0; j < kFinishKPT; j++) {
             uint32_t i = j * kFinThreads + tid;
@@ -957,6 +986,10 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
       if ((uint32_t)j < rows && p < n) {
         x[j] = keys[p];
         h = (p == 0) || !key_eq(keys[p - 1], x[j]);
+        if constexpr (kSplit) { // equal low halves in neighbouring sub-bins are different keys
+          xh[j] = binof[p];
+          h = h || binof[p - (p ? 1u : 0u)] != xh[j];
+        }
       }
       uint32_t bal = (uint32_t)j < rows ? __ballot_sync(0xffffffffu, h) : 0u;
       if (h) heads |= 1u << j;
@@ -991,6 +1024,7 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
       if (h) {
         uint32_t u = S.rowcnt[j * kFinWarps + warp] + __popc(bal & ((1u << lane) - 1u));
         keys[u] = x[j];
+        if constexpr (kSplit) binof[u] = (uint16_t)xh[j];
         S.hp[u] = (uint16_t)(j * kFinThreads + tid);
       }
     }
@@ -1001,7 +1035,7 @@ __global__ void __launch_bounds__(kFinThreads, sizeof(L2T) == 4 ? KMC_FINISH_MIN
     for (uint32_t q = tid; q < d + a; q += kFinThreads) {
       if (q < a) continue;
       const uint32_t i = q - a;
-      emit_key(out_lo, out_hi, G + i, D, keys[i]);
+      emit_row<kSplit>(out_lo, out_hi, G + i, D, keys[i], binof, i, bshift);
       uint32_t nxt = (i + 1 < d) ? S.hp[i + 1] : n;
       out_cnt[G + i] = nxt - S.hp[i];
     }

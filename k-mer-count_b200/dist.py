@@ -139,7 +139,11 @@ class DistCounter:
         # KMC_DIST_COMBINE=1 (opt-in until it has been measured on a multi-GPU box): when every rank's input is
         # low-cardinality — the hash strategy's case — count locally and exchange table rows (finish_combined)
         self.use_combine = (world > 1 and kw.get("mode", 0) == 0 and self.key_bytes == 8 and strategy in (0, 1)
-                            and os.environ.get("KMC_DIST_COMBINE", "0") == "1")
+                            and os.environ.get("KMC_DIST_COMBINE", "1") == "1")
+        # torch.distributed's collectives run on torch's current stream, and libkmc reads what they deliver (and torch
+        # reads what libkmc routed): both must be the same stream, or the count could start before the exchange lands
+        if world > 1 and torch is not None and torch.cuda.is_available():
+            self.kc.set_stream(torch.cuda.current_stream().cuda_stream)
 
     def set_stream(self, ptr):
         self.kc.set_stream(ptr)
@@ -179,8 +183,9 @@ class DistCounter:
                 self._opened.append(bases[-1])
         self._map = (my_bytes, mine, bases)
 
-    def _setup_peers(self):
-        """Hash route: receive buffer of `world` regions, one per source rank."""
+    def _setup_peers(self, min_cap=0):
+        """Hash route: receive buffer of `world` regions, one per source rank.  min_cap: a capacity (keys per region)
+        every rank already agreed on (the retry after an overflow)."""
         torch, dist = self.torch, self.dist
         dev = torch.device("cuda", torch.cuda.current_device())
         # one small all-reduce per job: agrees on the region size (and on whether any rank's buffer is too small), and
@@ -188,11 +193,34 @@ class DistCounter:
         nb = torch.tensor([self.n_bases, -self._map[0]], dtype=torch.int64, device=dev)
         dist.all_reduce(nb, op=dist.ReduceOp.MAX)
         nb = nb.tolist()
-        cap = (int(nb[0] / self.world * 1.03) + 65536 + 15) // 16 * 16
+        cap = max((int(nb[0] / self.world * 1.03) + 65536 + 15) // 16 * 16, (int(min_cap) + 15) // 16 * 16)
         if -nb[1] < cap * self.world * self.key_bytes:
             self._map_buffers(cap * self.world * self.key_bytes)
         _, mine, bases = self._map
         return cap, mine, [b + self.rank * cap * self.key_bytes for b in bases]
+
+    def _route_to_peers(self):
+        """Fused route + exchange.  → (cap, my receive buffer, keys received from every source rank).  Every rank learns
+        every (source, owner) count from one all-gather — which is also the hand-over point: every rank's routing kernel
+        is done — so all of them see an overflowed region (skewed input: one owner's share of a shard exceeded the
+        region size) and route once more with regions sized from the exact counts."""
+        torch, dist = self.torch, self.dist
+        dev = torch.device("cuda", torch.cuda.current_device())
+        min_cap = 0
+        for attempt in range(2):
+            cap, mine, regions = self._setup_peers(min_cap)
+            self._mark()
+            count = self.kc.route_to_peers(regions, cap)
+            self._mark()
+            sc = torch.from_numpy(count.astype(np.int64)).to(dev)
+            allc = torch.empty(self.world * self.world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allc, sc)
+            allc = allc.cpu().numpy().reshape(self.world, self.world)   # [source, owner]
+            if int(allc.max()) <= cap:
+                self._mark()
+                return cap, mine, allc[:, self.rank].tolist()
+            min_cap = int(int(allc.max()) * 1.02) + 4096
+        raise RuntimeError("kmc dist: a receive region overflowed twice")
 
     def _finish_range(self):
         """Range partition (kmc_dist_*): the senders' scatter kernels store every key straight into its level-1 bucket
@@ -262,15 +290,7 @@ class DistCounter:
         self.path = "hash"
         mark = self._mark
         if self.use_peer:
-            cap, mine, regions = self._setup_peers()
-            mark()
-            count = self.kc.route_to_peers(regions, cap)
-            mark()
-            sc = torch.from_numpy(count.astype(np.int64)).to(dev)
-            rc = torch.empty_like(sc)
-            dist.all_to_all_single(rc, sc)   # also the hand-over point: every rank's routing kernel is done
-            got = rc.tolist()
-            mark()
+            cap, mine, got = self._route_to_peers()
             for src, n in enumerate(got):
                 self.kc.ingest_keys(mine + src * cap * self.key_bytes, n)
         else:

@@ -64,7 +64,7 @@ def main():
                 row.update(ms=round(min(ms), 3), ms_all=[round(x, 3) for x in ms], gkps=round(t / min(ms) / 1e6, 2),
                            n_distinct=d, n_total=t, digest=dig, ok=(ref == (d, t, dig)),
                            phases={p: round(v, 3) for p, v in (st.get("phases_ms") or {}).items()},
-                           strategy=st.get("strategy_used"), fallbacks=st.get("fast_fallbacks"))
+                           strategy=st.get("strategy_used"), fallbacks=st.get("fast_fallbacks"), variant=st.get("fast_variant"))
                 if not row["ok"]:
                     row["MISMATCH"] = {"want": ref}
             except Exception as e:  # keep going: the other variants still tell something

@@ -15,4 +15,4 @@ for r in rows:
     p = r.get("phases", {})
     print(f"{r['spec']:28s} k={r['k']:2d} {r['ms']:8.3f} ms {r['gkps']:7.2f} Gk/s {100 * (r['ms'] / b - 1):+6.1f}%  "
           f"{'ok ' if r['ok'] else 'MISMATCH'} fallbacks={r.get('fallbacks')} strategy={r.get('strategy')}  "
-          f"part1={p.get('fast_part1')} part2={p.get('fast_part2')} finish={p.get('fast_finish')}")
+          f"part1={p.get('fast_part1')} part2={p.get('fast_part2')} finish={p.get('fast_finish')} {r.get('variant') or ''}")
