@@ -206,6 +206,21 @@ int kmc_ingest_pairs(kmc_ctx *ctx, const uint64_t *d_keys, const uint64_t *d_cou
 /* owner part of a key, host-side (the same function the device uses).                            */
 uint32_t kmc_owner_of(uint64_t key_hi, uint64_t key_lo, uint32_t n_parts);
 
+/* ---- synthetic input on the device (random_fasta_generator.py:5-15) ----------
+ * The reference's generator prints 200 unseeded 400-base records and takes no arguments.  These are its
+ * seeded, scalable stand-in: every byte is a pure function of (seed, stream, index) through Philox4x32-10
+ * (csrc/kmc_gen.cuh), so any window of a stream can be produced in any order, and the host twin
+ * (k-mer-count_b200/gen.py, tools/gen_fasta.py) produces the same bytes.  All pointers are device memory.
+ * kmc_gen_bases: upper-case ACGT, bases [first, first + n) of stream `seed` → d_out[0..n).
+ * kmc_gen_nruns: lays that seed's N runs (1e-4 starts per base, geometric length of mean 50) over
+ *   d_bases[0..n) = bases [first, first + n).
+ * kmc_gen_reads: reads [first_read, first_read + n_reads) of read_len bases, each from a uniform position
+ *   and strand of d_genome[0..genome_len) → d_out[0 .. n_reads * read_len).                           */
+int kmc_gen_bases(kmc_ctx *ctx, uint64_t seed, uint64_t first, uint64_t n, uint8_t *d_out);
+int kmc_gen_nruns(kmc_ctx *ctx, uint64_t seed, uint64_t first, uint64_t n, uint8_t *d_bases);
+int kmc_gen_reads(kmc_ctx *ctx, uint64_t seed, const uint8_t *d_genome, uint64_t genome_len, uint32_t read_len,
+                  uint64_t first_read, uint64_t n_reads, uint8_t *d_out);
+
 /* ---- introspection ------------------------------------------------------------------------------
  * JSON object: per-phase device times (CUDA events on the ctx stream), kernel-launch count, chosen
  * strategy, sizes.  Returns bytes needed (incl. NUL); writes at most cap.                          */

@@ -21,6 +21,7 @@
 #include "kmc_hash.cuh"
 #include "kmc_fasta.cuh"
 #include "kmc_format.cuh"
+#include "kmc_gen.cuh"
 #include <cmath>
 
 using namespace kmc;
@@ -2345,6 +2346,33 @@ int kmc_ipc_close(kmc_ctx *c, void *d_peer_ptr) {
   if (!c || !d_peer_ptr) return KMC_E_ARG;
   CK(cudaSetDevice(c->device));
   CK(cudaIpcCloseMemHandle(d_peer_ptr));
+  return KMC_OK;
+}
+
+int kmc_gen_bases(kmc_ctx *c, uint64_t seed, uint64_t first, uint64_t n, uint8_t *d_out) {
+  if (!c || (!d_out && n)) return KMC_E_ARG;
+  if (!n) return KMC_OK;
+  CK(cudaSetDevice(c->device));
+  LAUNCH(gen_bases_kernel, (uint32_t)std::min<uint64_t>(grid_for(n / 16 + 2, 256), (uint64_t)kNumSMsB200 * 16), 256, 0, seed, first, n, d_out);
+  return KMC_OK;
+}
+
+int kmc_gen_nruns(kmc_ctx *c, uint64_t seed, uint64_t first, uint64_t n, uint8_t *d_bases) {
+  if (!c || (!d_bases && n)) return KMC_E_ARG;
+  if (!n) return KMC_OK;
+  CK(cudaSetDevice(c->device));
+  LAUNCH(gen_nruns_kernel, (uint32_t)std::min<uint64_t>(grid_for(n / kGenNBlock + 2, 256), (uint64_t)kNumSMsB200 * 16), 256, 0, seed, first, n, d_bases);
+  return KMC_OK;
+}
+
+int kmc_gen_reads(kmc_ctx *c, uint64_t seed, const uint8_t *d_genome, uint64_t genome_len, uint32_t read_len, uint64_t first_read,
+                  uint64_t n_reads, uint8_t *d_out) {
+  if (!c || !d_genome || (!d_out && n_reads)) return KMC_E_ARG;
+  if (read_len < 1 || genome_len < read_len) return fail(c, KMC_E_ARG, "kmc_gen_reads: need 1 <= read_len <= genome_len");
+  if (!n_reads) return KMC_OK;
+  CK(cudaSetDevice(c->device));
+  LAUNCH(gen_reads_kernel, (uint32_t)std::min<uint64_t>(grid_for(n_reads * read_len, 1024), (uint64_t)kNumSMsB200 * 16), 256, 0, seed, d_genome,
+         genome_len, read_len, first_read, n_reads, d_out);
   return KMC_OK;
 }
 

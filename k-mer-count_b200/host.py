@@ -25,7 +25,8 @@ SYMBOLS = ["kmc_create", "kmc_destroy", "kmc_last_error", "kmc_strerror", "kmc_s
            "kmc_table_device", "kmc_digest", "kmc_key_bases", "kmc_route", "kmc_ingest_keys", "kmc_owner_of",
            "kmc_stats_json", "kmc_route_to_peers", "kmc_recv_buffer", "kmc_ipc_export", "kmc_ipc_open",
            "kmc_ipc_close", "kmc_submit_fasta", "kmc_format", "kmc_finish_part",
-           "kmc_dist_hist", "kmc_dist_plan", "kmc_dist_scatter", "kmc_table_route", "kmc_ingest_pairs"]
+           "kmc_dist_hist", "kmc_dist_plan", "kmc_dist_scatter", "kmc_table_route", "kmc_ingest_pairs",
+           "kmc_gen_bases", "kmc_gen_nruns", "kmc_gen_reads"]
 
 
 class KmcConfig(C.Structure):
@@ -89,6 +90,9 @@ def load_library(path=None):
     L.kmc_ipc_close.argtypes = [vp, vp]
     L.kmc_table_route.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(vp), C.POINTER(vp)]
     L.kmc_ingest_pairs.argtypes = [vp, vp, vp, C.c_uint64]
+    L.kmc_gen_bases.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
+    L.kmc_gen_nruns.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
+    L.kmc_gen_reads.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, vp]
     L.kmc_owner_of.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
     L.kmc_owner_of.restype = C.c_uint32
     L.kmc_stats_json.argtypes = [vp, C.c_char_p, C.c_size_t]
@@ -303,6 +307,17 @@ class KmerCounter:
         keys, counts = C.c_void_p(), C.c_void_p()
         self._ck(self._L.kmc_table_route(self._h, n_parts, begin.ctypes.data, count.ctypes.data, C.byref(keys), C.byref(counts)))
         return begin, count, keys.value, counts.value
+
+    # -- synthetic input on the device (csrc/kmc_gen.cuh; host twin: gen.py)
+    def gen_bases(self, seed, first, n, d_out_ptr):
+        self._ck(self._L.kmc_gen_bases(self._h, seed, first, n, C.c_void_p(d_out_ptr)))
+
+    def gen_nruns(self, seed, first, n, d_bases_ptr):
+        self._ck(self._L.kmc_gen_nruns(self._h, seed, first, n, C.c_void_p(d_bases_ptr)))
+
+    def gen_reads(self, seed, d_genome_ptr, genome_len, read_len, first_read, n_reads, d_out_ptr):
+        self._ck(self._L.kmc_gen_reads(self._h, seed, C.c_void_p(d_genome_ptr), genome_len, read_len, first_read, n_reads,
+                                       C.c_void_p(d_out_ptr)))
 
     def ingest_pairs(self, d_keys_ptr, d_counts_ptr, n_rows):
         """(key, count) rows this context owns; finish() merges them (equal keys add up) into the sorted table."""

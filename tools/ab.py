@@ -18,7 +18,6 @@ import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import kmer_count_b200 as K  # noqa: E402
-from bench import synth  # noqa: E402
 
 host = sys.modules["kmer_count_b200.host"]
 
@@ -32,7 +31,11 @@ def main():
     a = ap.parse_args()
     os.environ["KMC_KERNEL_TIMING"] = "1"
     n = int(a.bases)
-    bases, off = synth(torch, n, 400, 2, torch.device("cuda", 0))
+    # bench.py's cfg2 input: bases of generator stream 2, 400-base records
+    bases = torch.empty(n, dtype=torch.uint8, device="cuda")
+    off = torch.unique(torch.arange(0, n + 400, 400, dtype=torch.int64, device="cuda").clamp(max=n))
+    with K.KmerCounter(k=21) as g:
+        g.gen_bases(2, 0, n, bases.data_ptr())
     n_recs = off.numel() - 1
     torch.cuda.synchronize()
     want = {}
