@@ -449,6 +449,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line (rank 0): whatever libraries print there (NCCL's version banner, ...) is sent
+    # to stderr instead, and the line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libkmc has no CPU fallback")
     torch.cuda.set_device(local)
@@ -500,7 +505,8 @@ def main():
             out["k31"]["unit"] = "Gk/s"
             out["cfg1"] = run_cfg1(torch, np, K, args.steps, args.warmup, args.no_cpu) if world == 1 else None
     if rank == 0:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 

@@ -16,6 +16,7 @@
  *     kmc_create → kmc_submit_device* → kmc_finish → kmc_table_device / kmc_read
  * Multi-GPU (one process per GPU):
  *     kmc_submit* → kmc_route_to_peers(n_parts)   [keys stored into the owners' buffers over NVLink]
+ *     (pipelined: kmc_dist_hist → kmc_owner_begin → { kmc_route_to_peers_part(c) → hand-over → kmc_owner_feed* }* → kmc_finish)
  *                 → [counts exchanged, ranks synchronised] → kmc_ingest_keys* → kmc_finish
  *   or, with the exchange done by the host (NCCL all-to-all):
  *     kmc_submit* → kmc_route(n_parts) → [all-to-all of the routed keys] → kmc_ingest_keys* → kmc_finish
@@ -159,6 +160,23 @@ int kmc_route(kmc_ctx *ctx, uint32_t n_parts, uint64_t *part_begin, uint64_t *pa
  * the counts and synchronises the ranks before the owners call kmc_ingest_keys on what they received.   */
 int kmc_route_to_peers(kmc_ctx *ctx, uint32_t n_parts, void *const *d_part_ptr, uint64_t part_cap_keys,
                        uint64_t *part_count);
+/* The same in chunks, so that the exchange overlaps the owners' counting (streaming owner, below): chunk `chunk` of
+ * `n_chunks` equal slices of the input; part_count receives the CUMULATIVE counts after this chunk (region p holds
+ * keys [0, part_count[p]) of this rank; the previous call's counts say where the new ones start).  max_ctas > 0:
+ * the routing kernel takes at most that many SMs and leaves the rest to the owner's kernels running beside it.     */
+int kmc_route_to_peers_part(kmc_ctx *ctx, uint32_t n_parts, void *const *d_part_ptr, uint64_t part_cap_keys,
+                            uint64_t *part_count, uint32_t chunk, uint32_t n_chunks, uint32_t max_ctas);
+/* Streaming owner: count the keys the ranks route here while they are still routing.
+ *   kmc_owner_begin(global_hist, n_owners)  plan the partitioned count for this owner's share — 1 / n_owners of every
+ *       bin of global_hist, the sum of all ranks' kmc_dist_hist histograms (the owner function is a hash).
+ *       *streaming = 0: declined (small job, strategy, keys that do not suit the path): route as usual, then
+ *       kmc_ingest_keys + kmc_finish.
+ *   kmc_owner_feed(d_keys, n)  after every chunk's hand-over: the keys that have just arrived in one sender's region.
+ *       Asynchronous (a second stream, beside the next chunk's routing kernel); the memory is referenced until
+ *       kmc_finish returns.
+ *   kmc_finish  the rest of the count.  Falls back to a recount of everything fed if a bucket overflowed.          */
+int kmc_owner_begin(kmc_ctx *ctx, const uint64_t global_hist[4096], uint32_t n_owners, uint32_t *streaming);
+int kmc_owner_feed(kmc_ctx *ctx, const void *d_keys, uint64_t n_keys);
 /* ---- multi-GPU, range partition: the level-1 scatter of the counting pipeline done by the SENDERS --------
  * For high-cardinality input the hash route above costs an extra pass: owners re-scatter what they received.
  * Here the ranks agree on one plan for the whole key space and every sender's scatter kernel stores each key

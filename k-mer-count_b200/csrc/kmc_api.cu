@@ -115,6 +115,7 @@ struct kmc_ctx {
   DevBuf gap_l, gap_r, gap_f;
   DevBuf t_lo, t_hi, t_cnt;
   DevBuf fast_l1, fast_l2, fast_state, fast_tables, fast_fdesc, recv_keys;
+  DevBuf route_state, route_tables;     // routing pass (sender role): part cursors and table
   DevBuf hash_slots, hash_scalars, hash_hot;
   DevBuf fa_raw, fa_tiles, fa_flags;
   DevBuf fmt_len, fmt_off, fmt_text;
@@ -136,6 +137,11 @@ struct kmc_ctx {
 
   // multi-GPU range partition (kmc_dist_*): plan shared by all ranks, this rank's views of it
   DistPlan dist;
+  void *job_box = nullptr;                // the partitioned count in progress (a FastJob, defined with the fast path)
+  // streaming owner (kmc_owner_*): keys fed to the partitioned count while the other ranks are still routing
+  cudaStream_t owner_stream = nullptr;
+  bool owner_on = false;
+  std::vector<std::pair<const void *, uint64_t>> owner_fed; // what was fed, for a recount should the count not suit the path
   DevBuf dist_tables;
 
   // results
@@ -259,6 +265,7 @@ unsigned long long *d_cursor(kmc_ctx *c) { return (unsigned long long *)c->scala
 unsigned long long *d_digest(kmc_ctx *c) { return (unsigned long long *)c->scalars.p + 1; }
 uint32_t *d_err(kmc_ctx *c) { return (uint32_t *)((unsigned long long *)c->scalars.p + 2); }
 unsigned long long *d_total_all(kmc_ctx *c) { return (unsigned long long *)c->scalars.p + 3; }
+uint32_t *d_route_err(kmc_ctx *c) { return (uint32_t *)((unsigned long long *)c->scalars.p + 4); } // flags of a routing pass
 
 // Small device→host reads go through a pinned, device-mapped mailbox written by a kernel, not through the copy
 // engines: a cudaMemcpy D2H queues behind the 64 MB H2D chunks of a large submit and would stall the compute
@@ -634,60 +641,75 @@ int route_impl(kmc_ctx *c, uint32_t n_parts, uint64_t *part_off) {
   return KMC_OK;
 }
 
-// fast routing for 64-bit keys: the level-1 scatter of kmc_fast.cuh with bucket = owner part.  Each part gets
+// fast routing: the level-1 scatter of kmc_fast.cuh with bucket = owner part.  Each part gets
 // a region sized from the upper bound (one key per base) with slack; *done = false → use the generic route.
 // part_ptr == nullptr: the parts are regions of c->route_keys (kmc_route).  Otherwise part p is stored at
 // part_ptr[p] — a peer's memory over NVLink (kmc_route_to_peers); positions are then absolute addresses / 8.
+// chunk / n_chunks: route only that slice of the input's CTA tiles (the cursors carry on from chunk to chunk, the
+// counts returned are cumulative): the owners work on chunk c while chunk c + 1 is on the links.  The routing pass has
+// its own cursor / table buffers and its own flag word — an owner's count may be running in this ctx beside it.
+// max_ctas: at most that many CTAs (one per SM), leaving the other SMs to the owner's kernels; 0 = all.
 template <typename KeyT>
 int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *part_count, bool *done,
-               void *const *part_ptr = nullptr, uint64_t peer_cap = 0) {
+               void *const *part_ptr = nullptr, uint64_t peer_cap = 0, uint32_t chunk = 0, uint32_t n_chunks = 1, uint32_t max_ctas = 0) {
   *done = false;
   if (!part_ptr && (c->total_bases < (1u << 18) || n_parts > (uint32_t)kMaxL1)) return KMC_OK;
   const uint64_t cap = part_ptr ? peer_cap : (((uint64_t)((double)c->total_bases / n_parts * 1.03) + 65536 + 15) & ~15ull);
   const uint64_t total = part_ptr ? 0 : cap * n_parts;
   TRY(ensure(c, c->route_keys, (total + 2 * kMaxTile) * sizeof(KeyT)));
   const size_t o_start = 0, o_cap = o_start + ((size_t)(n_parts + 1) * 8 + 15) / 16 * 16, tab_bytes = o_cap + (size_t)n_parts * 8;
-  c->fast_host.assign(tab_bytes, 0);
-  uint64_t *l1s = (uint64_t *)(c->fast_host.data() + o_start), *l1c = (uint64_t *)(c->fast_host.data() + o_cap);
-  for (uint32_t p = 0; p <= n_parts; p++) l1s[p] = part_ptr ? (p < n_parts ? (uint64_t)(uintptr_t)part_ptr[p] / sizeof(KeyT) : 0) : cap * p;
-  for (uint32_t p = 0; p < n_parts; p++) l1c[p] = cap;
-  TRY(ensure(c, c->fast_tables, tab_bytes));
-  TRY(ensure(c, c->fast_state, 4096 * 8 + 16 + kMaxL1 * 8 + 64));
-  const size_t off_l1cur = 4096 * 8 + 16;
-  CK(cudaMemsetAsync((unsigned char *)c->fast_state.p + off_l1cur, 0, kMaxL1 * 8, c->stream));
-  TRY(h2d_small(c, c->fast_tables.p, c->fast_host.data(), tab_bytes));
+  TRY(ensure(c, c->route_tables, tab_bytes));
+  TRY(ensure(c, c->route_state, kMaxL1 * 8 + 64));
+  if (chunk == 0) {
+    std::vector<unsigned char> host(tab_bytes, 0);
+    uint64_t *l1s = (uint64_t *)(host.data() + o_start), *l1c = (uint64_t *)(host.data() + o_cap);
+    for (uint32_t p = 0; p <= n_parts; p++) l1s[p] = part_ptr ? (p < n_parts ? (uint64_t)(uintptr_t)part_ptr[p] / sizeof(KeyT) : 0) : cap * p;
+    for (uint32_t p = 0; p < n_parts; p++) l1c[p] = cap;
+    CK(cudaMemsetAsync(c->route_state.p, 0, kMaxL1 * 8, c->stream));
+    CK(cudaMemsetAsync(d_route_err(c), 0, 8, c->stream));
+    TRY(h2d_small(c, c->route_tables.p, host.data(), tab_bytes));
+  }
   FastPlan pl{};
   pl.kb = c->key_bits; pl.b1 = 0; pl.n_l1 = n_parts; pl.n_fine = 0;
   pl.l1_trash = part_ptr ? (uint64_t)(uintptr_t)c->route_keys.p / sizeof(KeyT) : total;
   KeyT *dst = part_ptr ? (KeyT *)nullptr : (KeyT *)c->route_keys.p;
-  pl.l1_start = (const uint64_t *)((unsigned char *)c->fast_tables.p + o_start);
-  pl.l1_cap = (const uint64_t *)((unsigned char *)c->fast_tables.p + o_cap);
-  pl.l1_cursor = (unsigned long long *)((unsigned char *)c->fast_state.p + off_l1cur);
+  pl.l1_start = (const uint64_t *)((unsigned char *)c->route_tables.p + o_start);
+  pl.l1_cap = (const uint64_t *)((unsigned char *)c->route_tables.p + o_cap);
+  pl.l1_cursor = (unsigned long long *)c->route_state.p;
+  // this chunk's share of the CTA tiles of all segments, in segment order
+  uint64_t all_ct = 0;
+  for (size_t i = 0; i < c->n_segs; i++)
+    if (c->segs[i].n_bases) all_ct += (num_warp_tiles(c->segs[i].n_bases, win_lanes<KeyT>()) + kFastWarps - 1) / kFastWarps;
+  const uint64_t g0 = all_ct * chunk / n_chunks, g1 = all_ct * (chunk + 1) / n_chunks;
   PHASE_BEGIN("route");
   {
     size_t smem = L1Smem<KeyT>::bytes(part1_stage<KeyT>(), n_parts);
     auto fast_route = fast_part1_kernel<KeyT, true, OwnerBucket>;
     CK(cudaFuncSetAttribute(fast_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const OwnerBucket bucket{n_parts};
+    uint64_t seg0 = 0;
     for (size_t i = 0; i < c->n_segs; i++) {
       Segment &s = c->segs[i];
       if (!s.n_bases) continue;
+      const uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>()), n_ct = (tiles + kFastWarps - 1) / kFastWarps;
+      const uint64_t lo = std::max(g0, seg0), hi = std::min(g1, seg0 + n_ct);
+      seg0 += n_ct;
+      if (hi <= lo) continue;
       TRY(seg_wait(c, s));
       ExtractParams P = seg_params(c, s);
-      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
-      LAUNCH(fast_route, grid, kFastThreads, smem, P, tiles, pl, bucket, dst, d_err(c));
+      uint32_t grid = (uint32_t)std::min<uint64_t>(hi - lo, (uint64_t)(max_ctas ? std::min<uint32_t>(max_ctas, kNumSMsB200) : kNumSMsB200));
+      LAUNCH(fast_route, grid, kFastThreads, smem, P, tiles, pl, bucket, dst, d_route_err(c), lo - (seg0 - n_ct), hi - (seg0 - n_ct));
     }
   }
   PHASE_END();
   std::vector<unsigned long long> cur(n_parts);
-  uint32_t err = 0;
-  TRY(d2h_small(c, cur.data(), pl.l1_cursor, (size_t)n_parts * 8));
-  TRY(read_scalars(c, nullptr, &err));
-  if (err & kFlagOverflow) {
-    TRY(zero_scalars(c));
-    // peers: not an error here — the counts tell the caller (some exceed part_cap_keys: those regions hold garbage beyond
-    // nothing useful), who must agree with the other ranks on a larger capacity and route again
+  unsigned long long rerr = 0;
+  TRY(d2h_small(c, cur.data(), pl.l1_cursor, (size_t)n_parts * 8, 0));
+  TRY(d2h_small(c, &rerr, d_route_err(c), 8, 8192));
+  if ((uint32_t)rerr & kFlagOverflow) {
+    CK(cudaMemsetAsync(d_route_err(c), 0, 8, c->stream));
+    // peers: not an error here — the counts tell the caller (some exceed part_cap_keys), who must agree with the other
+    // ranks on a larger capacity and route again
     if (part_ptr) { for (uint32_t p = 0; p < n_parts; p++) part_count[p] = cur[p]; *done = true; }
     return KMC_OK;
   }
@@ -1098,49 +1120,47 @@ int launch_part2(kmc_ctx *c, const FastPlan &pl, const KeyT *l1, bool key32, uin
   else return launch_part2_as<uint64_t, uint64_t>(c, pl, l1, nb_max, t_max, done, flush);
 }
 
+constexpr uint64_t kFastMinKeys = 1u << 18, kFastMinKeysGapped = 1u << 23;
+
+struct FastJob {   // one partitioned count in progress: the plan, and what the later stages need of it
+  bool active = false;
+  FastPlan pl{};
+  bool key32 = false, split64 = false, ranged = false;
+  uint32_t nb_max = 1, c_lo = 0, c_hi = 0;
+  uint64_t t_max = 1, n_fine = 0, fed = 0;
+  unsigned int *ticket = nullptr;
+  unsigned long long *d_total = nullptr, *status = nullptr, *l1_done = nullptr;
+};
+FastJob &job_of(kmc_ctx *c) {
+  if (!c->job_box) c->job_box = new FastJob();
+  return *static_cast<FastJob *>(c->job_box);
+}
+
 // ---- partitioned fast path (kmc_fast.cuh) --------------------------------------------------------------------
-// *used = false: the input does not suit it (tiny, duplicate-heavy, or a bucket overflowed); nothing is left
+// Three stages, so that keys can be fed while they arrive (chunks of a pinned submit; chunks routed by the other ranks):
+//   fast_begin  plan from an upper-estimate coarse histogram, buffers, tables            → *ok
+//   fast_feed_* level-1 scatter of a segment / a key array (+ the level-2 scatter of what has come in so far)
+//   fast_end    (rest of the) level-2 scatter, bucket sort, totals                      → *used
+// *ok / *used = false: the input does not suit the path (tiny, duplicate-heavy, or a bucket overflowed); nothing is left
 // behind and the caller counts with the baseline path.
 // relax = 1: aim at half-full buckets (retry after an overflow: input whose keys come in many copies spreads
 // less evenly than the plan's Poisson slack assumes).
 template <typename KeyT>
-int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
+int fast_begin(kmc_ctx *c, std::vector<uint64_t> &hist, uint64_t n_est, int relax, bool *ok) {
   constexpr bool kWide = sizeof(KeyT) == 16;
   int kCap = kWide ? 4096 : kFineCap;
   int kTarget = (kWide ? 3200 : std::min(env_int("KMC_FINE_TARGET_RT", kFineTarget), kFineTarget)) >> relax;
-  *used = false;
+  *ok = false;
+  FastJob &J = job_of(c);
+  J.active = false;
   const uint32_t kb = c->key_bits;
   const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb);
   const uint32_t ncoarse = 1u << cb;
-  KeyArrays ka;
-  TRY(key_sources<KeyT>(c, &ka));
-  const bool from_array = ka.from_array;
-  const auto &arrays = ka.arrays;
+  const bool ranged = c->range_on;
+  const uint32_t c_lo = ranged ? c->range_lo : 0u, c_hi = ranged ? c->range_lo + c->range_n : ncoarse;
   // fast_state layout: ghist[4096] u64 | ticket u32 (+pad) | d_total u64 | l1_cursor[kMaxL1] u64 | l1_done[kMaxL1] u64 | fine_cursor[nf] u32 | status[nf] u64
   const size_t off_ticket = 4096 * 8, off_dtotal = off_ticket + 8, off_l1cur = off_dtotal + 8, off_l1done = off_l1cur + kMaxL1 * 8,
                off_fine = off_l1done + kMaxL1 * 8;
-  TRY(ensure(c, c->fast_state, off_fine + 64));
-  CK(cudaMemsetAsync(c->fast_state.p, 0, off_fine, c->stream));
-  std::vector<uint64_t> hist;
-  uint32_t step = 1;
-  if (c->range_on && c->part_hist_step) { hist = c->part_hist; step = c->part_hist_step; } // partial count: computed once per input
-  else TRY(coarse_hist<KeyT>(c, ka, hist, &step));
-  // a partial count sees only the coarse bins of its key range
-  const bool ranged = c->range_on;
-  const uint32_t c_lo = ranged ? c->range_lo : 0u, c_hi = ranged ? c->range_lo + c->range_n : ncoarse;
-  if (ranged) for (uint32_t ci = 0; ci < ncoarse; ci++) if (ci < c_lo || ci >= c_hi) hist[ci] = 0;
-  if (c_hi <= c_lo) return KMC_OK; // empty range: the generic path returns the empty table
-  // the histogram is a 1-in-step sample: scale it to an upper estimate (+5 sigma of the sampling noise)
-  uint64_t n_est = 0;
-  for (uint64_t &v : hist) {
-    double est = (double)v * step;
-    if (step > 1) est += 5.0 * std::sqrt(est * step) + step;
-    v = (uint64_t)est;
-    n_est += v;
-  }
-  if (n_est < (1u << 18)) return KMC_OK; // small job: the generic path is as fast and simpler
-  HOST_MARK("hist_read");
-
   // ---- plan
   PlanShape shape;
   const uint32_t min_e = getenv("KMC_NO_SPLIT64") ? 0u : split64_min_e(kb, n_est, kWide);
@@ -1229,74 +1249,67 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   TRY(h2d_small(c, c->fast_tables.p, c->fast_host.data(), tab_bytes));
   HOST_MARK("uploaded");
   unsigned char *st = (unsigned char *)c->fast_state.p, *tb = (unsigned char *)c->fast_tables.p;
-  FastPlan pl;
+  FastPlan &pl = J.pl;
+  pl = FastPlan{};
   pl.kb = kb; pl.b1 = b1; pl.n_l1 = n_l1; pl.n_fine = (uint32_t)n_fine; pl.l1_base = l1_base;
   pl.l1_trash = l1_keys; pl.l2_trash = l2_keys + slack;
   pl.fdesc = (const FineDesc *)c->fast_fdesc.p;
   pl.l1_start = (const uint64_t *)(tb + o_l1s); pl.l1_cap = (const uint64_t *)(tb + o_cap);
   pl.l1_tile0 = (const uint32_t *)(tb + o_t0); pl.l1_fine0 = (const uint32_t *)(tb + o_f0); pl.l1_e = (const uint8_t *)(tb + o_e);
   pl.l1_cursor = (unsigned long long *)(st + off_l1cur); pl.fine_cursor = (uint32_t *)(st + off_fine);
-  unsigned int *ticket = (unsigned int *)(st + off_ticket);
-  unsigned long long *d_total = (unsigned long long *)(st + off_dtotal);
-  unsigned long long *status = (unsigned long long *)(st + off_status);
+  J.ticket = (unsigned int *)(st + off_ticket);
+  J.d_total = (unsigned long long *)(st + off_dtotal);
+  J.status = (unsigned long long *)(st + off_status);
+  J.l1_done = (unsigned long long *)(st + off_l1done);
   LAUNCH(plan_expand_kernel, n_cb, 128, 0, (FineDesc *)c->fast_fdesc.p, (const uint64_t *)(tb + o_cs), (const uint32_t *)(tb + o_cf),
          (const uint16_t *)(tb + o_cc), pl.l1_fine0, pl.l1_e, cshift, l1_base, kb, b1, (uint32_t)kWide);
   c->launches--; // plumbing
 
-  // ---- level 1
-  bool incremental = false;
+
+  J.key32 = key32; J.split64 = split64; J.ranged = ranged; J.nb_max = nb_max; J.c_lo = c_lo; J.c_hi = c_hi;
+  J.t_max = t_max; J.n_fine = n_fine; J.fed = 0;
+  J.active = true;
   c->fast_variant = kWide ? "u128" : key32 ? "u32" : split64 ? "split64" : "u64";
+  *ok = true;
+  return KMC_OK;
+}
+
+// level-1 scatter of a key array; incremental: follow it with the level-2 scatter of the whole tiles that have come in
+template <typename KeyT>
+int fast_feed_array(kmc_ctx *c, const void *keys, uint64_t n, bool incremental) {
+  FastJob &J = job_of(c);
+  if (!n) return KMC_OK;
+  const size_t smem = L1Smem<KeyT>::bytes(arr_tile<KeyT>(), J.pl.n_l1);
+  auto fast_part1_array = fast_part1_array_kernel<KeyT>;
+  CK(cudaFuncSetAttribute(fast_part1_array, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PHASE_BEGIN("fast_part1");
-  if (from_array) {
-    size_t smem = L1Smem<KeyT>::bytes(arr_tile<KeyT>(), n_l1);
-    constexpr int kArrThreads = kFastThreads;
-    auto fast_part1_array = fast_part1_array_kernel<KeyT>;
-    CK(cudaFuncSetAttribute(fast_part1_array, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (auto &a : arrays) {
-      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, arr_tile<KeyT>()), (uint64_t)kNumSMsB200);
-      LAUNCH(fast_part1_array, grid, kArrThreads, smem, (const KeyT *)a.first, a.second, pl, (KeyT *)c->fast_l1.p, d_err(c));
-    }
-  } else {
-    size_t smem = L1Smem<KeyT>::bytes(part1_stage<KeyT>(), n_l1);
-    auto fast_part1 = fast_part1_kernel<KeyT, true, PrefixBucket>;
-    auto fast_part1_ranged = fast_part1_kernel<KeyT, true, PrefixBucketT<true>>;
-    if (ranged) CK(cudaFuncSetAttribute(fast_part1_ranged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else CK(cudaFuncSetAttribute(fast_part1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const PrefixBucket bucket = make_prefix_bucket<false>(kb, b1);
-    const PrefixBucketT<true> bucket_ranged = make_prefix_bucket<true>(kb, b1, l1_base, kb - cb, c_lo, c_hi - c_lo);
-    // A large pinned submit arrives in chunks (submit_chunked): the level-2 scatter then follows every chunk's level-1
-    // scatter for the keys that have come in so far (whole tiles only; the last round takes the rest), so that when
-    // the last chunk has landed only its own share of the two scatters and the bucket sort remain.
-    size_t n_live = 0, i_last = 0;
-    for (size_t i = 0; i < c->n_segs; i++) if (c->segs[i].n_bases) { n_live++; i_last = i; }
-    incremental = n_live >= 4;
-    unsigned long long *l1_done = (unsigned long long *)(st + off_l1done);
-    for (size_t i = 0; i < c->n_segs; i++) {
-      Segment &s = c->segs[i];
-      if (!s.n_bases) continue;
-      TRY(seg_wait(c, s));
-      ExtractParams P = seg_params(c, s);
-      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
-      if (ranged) LAUNCH(fast_part1_ranged, grid, kFastThreads, smem, P, tiles, pl, bucket_ranged, (KeyT *)c->fast_l1.p, d_err(c));
-      else LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->fast_l1.p, d_err(c));
-      if (incremental) {
-        PHASE_END();
-        PHASE_BEGIN("fast_part2");
-        const uint64_t t_seg = (uint64_t)((double)s.n_bases / n_l1 / p2_tile<KeyT>() * 1.25) + 2;
-        TRY(launch_part2<KeyT>(c, pl, (const KeyT *)c->fast_l1.p, key32, nb_max, i == i_last ? t_max : std::min(t_seg, t_max), l1_done, i == i_last));
-        PHASE_END();
-        if (i != i_last) PHASE_BEGIN("fast_part1");
-      }
-    }
-  }
-  if (!incremental) {
-    PHASE_END();
-    // ---- level 2
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(n, arr_tile<KeyT>()), (uint64_t)kNumSMsB200);
+  LAUNCH(fast_part1_array, grid, kFastThreads, smem, (const KeyT *)keys, n, J.pl, (KeyT *)c->fast_l1.p, d_err(c));
+  PHASE_END();
+  J.fed += n;
+  if (incremental) {
     PHASE_BEGIN("fast_part2");
-    TRY(launch_part2<KeyT>(c, pl, (const KeyT *)c->fast_l1.p, key32, nb_max, t_max));
+    const uint64_t t_arr = (uint64_t)((double)n / J.pl.n_l1 / p2_tile<KeyT>() * 1.25) + 2;
+    TRY(launch_part2<KeyT>(c, J.pl, (const KeyT *)c->fast_l1.p, J.key32, J.nb_max, std::min(t_arr, J.t_max), J.l1_done, false));
     PHASE_END();
   }
+  return KMC_OK;
+}
+
+template <typename KeyT>
+int fast_end(kmc_ctx *c, bool incremental, bool *used) {
+  constexpr bool kWide = sizeof(KeyT) == 16;
+  FastJob &J = job_of(c);
+  *used = false;
+  J.active = false;
+  const FastPlan &pl = J.pl;
+  const bool key32 = J.key32, split64 = J.split64;
+  const uint64_t n_fine = J.n_fine;
+  const uint32_t n_l1 = pl.n_l1;
+  // ---- level 2 (all of it, or what the incremental rounds have left)
+  PHASE_BEGIN("fast_part2");
+  TRY(launch_part2<KeyT>(c, pl, (const KeyT *)c->fast_l1.p, key32, J.nb_max, J.t_max, incremental ? J.l1_done : nullptr, true));
+  PHASE_END();
   // ---- finish: the level-1 array is dead after part2 and (64-bit keys) becomes the table's key column
   PHASE_BEGIN("fast_finish");
   {
@@ -1310,28 +1323,28 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2);
       LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const U128 *)c->fast_l2.p, (uint64_t *)c->t_lo.p, (uint64_t *)c->t_hi.p,
-             (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
+             (uint32_t *)c->t_cnt.p, J.status, J.ticket, d_err(c), J.d_total, prof);
     } else if (key32) {
       size_t fsmem = sizeof(FinishSmem<uint32_t>);
       auto fast_finish = fast_finish_kernel<uint32_t>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB32);
       LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint32_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
-             (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
+             (uint32_t *)c->t_cnt.p, J.status, J.ticket, d_err(c), J.d_total, prof);
     } else if (split64) {
       size_t fsmem = sizeof(FinishSmem<Split64>);
       auto fast_finish = fast_finish_kernel<Split64>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2);
       LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
-             (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
+             (uint32_t *)c->t_cnt.p, J.status, J.ticket, d_err(c), J.d_total, prof);
     } else {
       size_t fsmem = sizeof(FinishSmem<uint64_t>);
       auto fast_finish = fast_finish_kernel<uint64_t>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB64);
       LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
-             (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
+             (uint32_t *)c->t_cnt.p, J.status, J.ticket, d_err(c), J.d_total, prof);
     }
     if (want_prof) {
       unsigned long long h[16];
@@ -1348,7 +1361,7 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   uint64_t d = 0;
   uint32_t err = 0;
   std::vector<unsigned long long> cur(n_l1);
-  TRY(d2h_small(c, &d, d_total, 8));
+  TRY(d2h_small(c, &d, J.d_total, 8));
   TRY(d2h_small(c, cur.data(), pl.l1_cursor, (size_t)n_l1 * 8));
   TRY(read_scalars(c, nullptr, &err));
   if (err & kFlagSpin) return fail(c, KMC_E_CUDA, "fast_finish: look-back did not make progress");
@@ -1357,6 +1370,7 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
     TRY(zero_scalars(c));
     return KMC_OK; // recount with the data-independent path
   }
+
   uint64_t N = 0;
   for (unsigned long long v : cur) N += v;
   if (!kWide) std::swap(c->t_lo, c->fast_l1);
@@ -1364,6 +1378,88 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   c->strategy_used = KMC_STRATEGY_SORT;
   *used = true;
   return KMC_OK;
+}
+
+template <typename KeyT>
+int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
+  *used = false;
+  const uint32_t kb = c->key_bits;
+  const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb);
+  const uint32_t ncoarse = 1u << cb;
+  KeyArrays ka;
+  TRY(key_sources<KeyT>(c, &ka));
+  TRY(ensure(c, c->fast_state, 4096 * 8 + 64));
+  std::vector<uint64_t> hist;
+  uint32_t step = 1;
+  if (c->range_on && c->part_hist_step) { hist = c->part_hist; step = c->part_hist_step; } // partial count: computed once per input
+  else TRY(coarse_hist<KeyT>(c, ka, hist, &step));
+  // a partial count sees only the coarse bins of its key range
+  const bool ranged = c->range_on;
+  const uint32_t c_lo = ranged ? c->range_lo : 0u, c_hi = ranged ? c->range_lo + c->range_n : ncoarse;
+  if (ranged) for (uint32_t ci = 0; ci < ncoarse; ci++) if (ci < c_lo || ci >= c_hi) hist[ci] = 0;
+  if (c_hi <= c_lo) return KMC_OK; // empty range: the generic path returns the empty table
+  // the histogram is a 1-in-step sample: scale it to an upper estimate (+5 sigma of the sampling noise)
+  uint64_t n_est = 0;
+  for (uint64_t &v : hist) {
+    double est = (double)v * step;
+    if (step > 1) est += 5.0 * std::sqrt(est * step) + step;
+    v = (uint64_t)est;
+    n_est += v;
+  }
+  // small job: the generic path is as fast (a few passes over a few MB) and does not care what the keys look like.
+  // lr-gapped keys come in groups of up to d_max - d_min + 1 that share their L-mer, 2 * l_len bits; when the input is
+  // repetitive as well (the reference's own fixture: 3.55 M keys, 54-bit prefixes shared by the thousand) no prefix
+  // partition can separate them, so such jobs take the generic path up to a larger size.
+  if (n_est < (c->cfg.mode == KMC_MODE_LR_GAPPED ? kFastMinKeysGapped : kFastMinKeys)) return KMC_OK;
+  HOST_MARK("hist_read");
+  bool ok = false;
+  TRY(fast_begin<KeyT>(c, hist, n_est, relax, &ok));
+  if (!ok) return KMC_OK;
+  FastJob &J = job_of(c);
+  const FastPlan &pl = J.pl;
+  const uint32_t b1 = pl.b1, l1_base = pl.l1_base, n_l1 = pl.n_l1;
+
+  // ---- level 1
+  bool incremental = false;
+  if (ka.from_array) {
+    for (auto &a : ka.arrays) TRY(fast_feed_array<KeyT>(c, a.first, a.second, false));
+  } else {
+    PHASE_BEGIN("fast_part1");
+    size_t smem = L1Smem<KeyT>::bytes(part1_stage<KeyT>(), n_l1);
+    auto fast_part1 = fast_part1_kernel<KeyT, true, PrefixBucket>;
+    auto fast_part1_ranged = fast_part1_kernel<KeyT, true, PrefixBucketT<true>>;
+    if (ranged) CK(cudaFuncSetAttribute(fast_part1_ranged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CK(cudaFuncSetAttribute(fast_part1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const PrefixBucket bucket = make_prefix_bucket<false>(kb, b1);
+    const PrefixBucketT<true> bucket_ranged = make_prefix_bucket<true>(kb, b1, l1_base, kb - cb, c_lo, c_hi - c_lo);
+    // A large pinned submit arrives in chunks (submit_chunked): the level-2 scatter then follows every chunk's level-1
+    // scatter for the keys that have come in so far (whole tiles only; fast_end takes the rest), so that when
+    // the last chunk has landed only its own share of the two scatters and the bucket sort remain.
+    size_t n_live = 0, i_last = 0;
+    for (size_t i = 0; i < c->n_segs; i++) if (c->segs[i].n_bases) { n_live++; i_last = i; }
+    incremental = n_live >= 4;
+    for (size_t i = 0; i < c->n_segs; i++) {
+      Segment &s = c->segs[i];
+      if (!s.n_bases) continue;
+      TRY(seg_wait(c, s));
+      ExtractParams P = seg_params(c, s);
+      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
+      const uint64_t n_ct = (tiles + kFastWarps - 1) / kFastWarps;
+      if (ranged) LAUNCH(fast_part1_ranged, grid, kFastThreads, smem, P, tiles, pl, bucket_ranged, (KeyT *)c->fast_l1.p, d_err(c), (uint64_t)0, n_ct);
+      else LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->fast_l1.p, d_err(c), (uint64_t)0, n_ct);
+      if (incremental && i != i_last) {
+        PHASE_END();
+        PHASE_BEGIN("fast_part2");
+        const uint64_t t_seg = (uint64_t)((double)s.n_bases / n_l1 / p2_tile<KeyT>() * 1.25) + 2;
+        TRY(launch_part2<KeyT>(c, pl, (const KeyT *)c->fast_l1.p, J.key32, J.nb_max, std::min(t_seg, J.t_max), J.l1_done, false));
+        PHASE_END();
+        PHASE_BEGIN("fast_part1");
+      }
+    }
+    PHASE_END();
+  }
+  return fast_end<KeyT>(c, incremental, used);
 }
 
 // ---- multi-GPU: range partition with the level-1 scatter done by the SENDERS --------------------------
@@ -1520,7 +1616,8 @@ int dist_scatter_impl(kmc_ctx *c, void *const *peer_buf, uint32_t *overflow) {
       ExtractParams P = seg_params(c, s);
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
       uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
-      LAUNCH(fast_scatter_to_owners, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)nullptr, d_err(c));
+      LAUNCH(fast_scatter_to_owners, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)nullptr, d_err(c), (uint64_t)0,
+             (tiles + kFastWarps - 1) / kFastWarps);
     }
     LAUNCH(dist_publish_kernel, grid_for(n_all, 256), 256, 0, pl.l1_cursor, pl.l1_cap, (const uint32_t *)(tb + o_own),
            (const uint64_t *)(tb + o_ph), n_all, world, D.rank);
@@ -1678,6 +1775,76 @@ int finish_dist(kmc_ctx *c) {
   return KMC_OK;
 }
 
+
+// ---- streaming owner (multi-GPU): count what the other ranks route here WHILE they are still routing ------
+// The routing pass is cut into chunks (kmc_route_to_peers_part); after every chunk the ranks agree on the counts and
+// each owner feeds the keys that have just arrived to its partitioned count — level-1 scatter and the whole tiles of
+// the level-2 scatter — on a second stream, beside the routing kernel of the next chunk (which leaves it some SMs).
+// kmc_finish then only has the rest of the level-2 scatter and the bucket sort left.
+struct StreamSwap {   // the owner's kernels run on c->owner_stream: every helper launches on c->stream
+  kmc_ctx *c; cudaStream_t saved;
+  StreamSwap(kmc_ctx *c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
+  ~StreamSwap() { c->stream = saved; }
+};
+
+template <typename KeyT>
+int owner_begin_impl(kmc_ctx *c, const uint64_t *global_hist, uint32_t n_owners, uint32_t *streaming) {
+  *streaming = 0;
+  const uint32_t ncoarse = 1u << coarse_bits(c);
+  // this owner's share of every coarse bin: the owner function is a hash, so 1 / n_owners of it, Poisson-distributed
+  std::vector<uint64_t> hist(ncoarse);
+  uint64_t n_est = 0;
+  for (uint32_t ci = 0; ci < ncoarse; ci++) {
+    const double m = (double)global_hist[ci] / n_owners;
+    hist[ci] = (uint64_t)(m * 1.02 + 6.0 * std::sqrt(m) + 64.0);
+    n_est += hist[ci];
+  }
+  if (n_est < (1u << 22)) return KMC_OK; // small job: not worth the choreography
+  if (!c->owner_stream) CK(cudaStreamCreateWithFlags(&c->owner_stream, cudaStreamNonBlocking));
+  CK(cudaStreamSynchronize(c->stream)); // buffers the plan touches may still be read by the previous job's tail
+  StreamSwap sw(c, c->owner_stream);
+  TRY(zero_scalars(c));
+  bool ok = false;
+  TRY(fast_begin<KeyT>(c, hist, n_est, 0, &ok));
+  if (!ok) return KMC_OK;
+  c->owner_on = true;
+  c->owner_fed.clear();
+  *streaming = 1;
+  return KMC_OK;
+}
+
+template <typename KeyT>
+int owner_feed_impl(kmc_ctx *c, const void *d_keys, uint64_t n) {
+  if (!n) return KMC_OK;
+  c->owner_fed.emplace_back(d_keys, n);
+  StreamSwap sw(c, c->owner_stream);
+  return fast_feed_array<KeyT>(c, d_keys, n, true);
+}
+
+template <typename KeyT>
+int finish_impl(kmc_ctx *c);
+
+template <typename KeyT>
+int owner_finish(kmc_ctx *c) {
+  bool used = false;
+  {
+    StreamSwap sw(c, c->owner_stream);
+    TRY(fast_end<KeyT>(c, true, &used));
+  }
+  c->owner_on = false;
+  if (used) return KMC_OK;
+  // the count did not suit the partitioned path (a bucket overflowed): recount what was fed, any way that works
+  CK(cudaStreamSynchronize(c->owner_stream));
+  c->ingested.clear();
+  for (auto &e : c->owner_fed) {
+    if (!c->ingested.empty() && (const char *)c->ingested.back().first + c->ingested.back().second * sizeof(KeyT) == (const char *)e.first)
+      c->ingested.back().second += e.second;       // chunks of one region are adjacent
+    else c->ingested.push_back(e);
+  }
+  c->owner_fed.clear();
+  TRY(zero_scalars(c));
+  return finish_impl<KeyT>(c);
+}
 
 template <typename KeyT>
 int finish_impl(kmc_ctx *c) {
@@ -1855,10 +2022,12 @@ void kmc_destroy(kmc_ctx *c) {
   for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); if (s.ready) cudaEventDestroy(s.ready); }
   for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
                     &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->fast_fdesc, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot, &c->fa_raw, &c->fa_tiles, &c->fa_flags, &c->fmt_len, &c->fmt_off, &c->fmt_text, &c->pair_rows, &c->pair_state,
-                    &c->dist_tables})
+                    &c->dist_tables, &c->route_state, &c->route_tables})
     release(*b);
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
+  if (c->owner_stream) cudaStreamDestroy(c->owner_stream);
+  delete static_cast<FastJob *>(c->job_box);
   delete c;
 }
 
@@ -1876,6 +2045,8 @@ int kmc_reset(kmc_ctx *c) {
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
   if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
+  if (c->owner_stream) CK(cudaStreamSynchronize(c->owner_stream));
+  c->owner_on = false; c->owner_fed.clear();
   c->n_segs = 0; c->total_bases = c->total_recs = 0;
   c->ingested.clear();
   c->ingested_pairs.clear();
@@ -2084,8 +2255,13 @@ static int finish_common(kmc_ctx *c, uint64_t *n_distinct, uint64_t *n_total) {
   c->host_marks.clear();
   if (!c->ingested_pairs.empty() && (c->n_segs || !c->ingested.empty()))
     return fail(c, KMC_E_ARG, "kmc_finish: (key, count) rows cannot be mixed with submitted input or ingested keys");
-  TRY(zero_scalars(c));
-  int rc = !c->ingested_pairs.empty() ? finish_pairs(c) : c->wide ? finish_impl<U128>(c) : finish_impl<uint64_t>(c);
+  int rc;
+  if (c->owner_on) {
+    rc = c->wide ? owner_finish<U128>(c) : owner_finish<uint64_t>(c);
+  } else {
+    TRY(zero_scalars(c));
+    rc = !c->ingested_pairs.empty() ? finish_pairs(c) : c->wide ? finish_impl<U128>(c) : finish_impl<uint64_t>(c);
+  }
   if (rc) return rc;
   uint32_t err = 0;
   TRY(read_scalars(c, nullptr, &err));
@@ -2289,6 +2465,44 @@ int kmc_route_to_peers(kmc_ctx *c, uint32_t n_parts, void *const *d_part_ptr, ui
   if (c->wide) TRY(route_fast<U128>(c, n_parts, nullptr, part_count, &done, d_part_ptr, part_cap_keys));
   else TRY(route_fast<uint64_t>(c, n_parts, nullptr, part_count, &done, d_part_ptr, part_cap_keys));
   return done ? KMC_OK : fail(c, KMC_E_ARG, "kmc_route_to_peers: nothing routed");
+}
+
+int kmc_route_to_peers_part(kmc_ctx *c, uint32_t n_parts, void *const *d_part_ptr, uint64_t part_cap_keys, uint64_t *part_count,
+                            uint32_t chunk, uint32_t n_chunks, uint32_t max_ctas) {
+  if (!c || !d_part_ptr || !part_count) return KMC_E_ARG;
+  if (n_parts < 1 || n_parts > kRadix) return fail(c, KMC_E_ARG, "n_parts must be 1..%d", kRadix);
+  if (n_chunks < 1 || chunk >= n_chunks) return fail(c, KMC_E_ARG, "kmc_route_to_peers_part: need chunk < n_chunks");
+  if (c->cfg.mode != KMC_MODE_CONTIGUOUS)
+    return fail(c, KMC_E_ARG, "kmc_route_to_peers handles contiguous mode; use kmc_route + an all-to-all for lr-gapped keys");
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_route_to_peers after kmc_finish");
+  c->dist.valid = false; c->dist.scattered = false;
+  for (uint32_t p = 0; p < n_parts; p++)
+    if (!d_part_ptr[p] || ((uintptr_t)d_part_ptr[p] & 127)) return fail(c, KMC_E_ARG, "part pointers must be 128-byte aligned device pointers");
+  CK(cudaSetDevice(c->device));
+  if (!c->owner_on && chunk == 0) TRY(zero_scalars(c));
+  else TRY(ensure(c, c->scalars, 64));
+  bool done = false;
+  if (c->wide) TRY(route_fast<U128>(c, n_parts, nullptr, part_count, &done, d_part_ptr, part_cap_keys, chunk, n_chunks, max_ctas));
+  else TRY(route_fast<uint64_t>(c, n_parts, nullptr, part_count, &done, d_part_ptr, part_cap_keys, chunk, n_chunks, max_ctas));
+  return done ? KMC_OK : fail(c, KMC_E_ARG, "kmc_route_to_peers: nothing routed");
+}
+
+int kmc_owner_begin(kmc_ctx *c, const uint64_t global_hist[4096], uint32_t n_owners, uint32_t *streaming) {
+  if (!c || !global_hist || !streaming || !n_owners) return KMC_E_ARG;
+  *streaming = 0;
+  if (c->finished) return fail(c, KMC_E_ARG, "kmc_owner_begin after kmc_finish");
+  if (c->cfg.mode != KMC_MODE_CONTIGUOUS || !c->ingested.empty() || !c->ingested_pairs.empty())
+    return fail(c, KMC_E_ARG, "kmc_owner_begin: contiguous mode, before any kmc_ingest_*");
+  if (c->cfg.strategy != KMC_STRATEGY_AUTO && c->cfg.strategy != KMC_STRATEGY_SORT) return KMC_OK; // not the partitioned path's job
+  CK(cudaSetDevice(c->device));
+  return c->wide ? owner_begin_impl<U128>(c, global_hist, n_owners, streaming) : owner_begin_impl<uint64_t>(c, global_hist, n_owners, streaming);
+}
+
+int kmc_owner_feed(kmc_ctx *c, const void *d_keys, uint64_t n_keys) {
+  if (!c || (!d_keys && n_keys)) return KMC_E_ARG;
+  if (!c->owner_on) return fail(c, KMC_E_ARG, "kmc_owner_feed without a successful kmc_owner_begin");
+  CK(cudaSetDevice(c->device));
+  return c->wide ? owner_feed_impl<U128>(c, d_keys, n_keys) : owner_feed_impl<uint64_t>(c, d_keys, n_keys);
 }
 
 int kmc_dist_hist(kmc_ctx *c, uint64_t hist[4096], uint32_t *low_cardinality) {

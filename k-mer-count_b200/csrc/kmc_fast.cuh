@@ -89,6 +89,7 @@ constexpr int kFinishBits = KMC_FINISH_BITS;
 constexpr int kFinishBins = 1 << kFinishBits; // sub-bins of fast_finish
 constexpr int kSmallBin = 32;            // sub-bins up to this size are ranked by comparison per key
 constexpr int kMaxHard = 64;
+constexpr int kMaxHardKeys = 1024;     // largest multi-key sub-bin fast_finish sorts by ranking (quadratic)
 constexpr int kDupList = 32;             // fast_finish: buckets with at most this many duplicate keys skip the run-length encode
 
 constexpr uint32_t kFlagOverflow = 8u;   // err flag bits 1,2,4 are used by kmc_extract / kmc_sort
@@ -379,20 +380,23 @@ __device__ __forceinline__ void l1_smem_init(uint32_t *hist, uint32_t nb) {
 // <= 15872 keys; u128: 16 starts at a time, two tiles per load).
 template <typename KeyT, bool FOLD, typename BucketFn>
 __global__ void __launch_bounds__(kFastThreads, 1) fast_part1_kernel(ExtractParams P, uint64_t n_tiles, FastPlan pl, BucketFn bucket,
-                                                                      KeyT *__restrict__ l1, uint32_t *__restrict__ flags) {
+                                                                      KeyT *__restrict__ l1, uint32_t *__restrict__ flags,
+                                                                      uint64_t ct_begin, uint64_t ct_end) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kHalves = FastShape<KeyT>::kHalves, kSPH = 32 / kHalves;
   const uint32_t nb = pl.n_l1;
   L1Smem<KeyT> S(smem_raw, part1_stage<KeyT>(), nb);
   l1_smem_init(S.hist, nb);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  const uint64_t n_cta_tiles = (n_tiles + kFastWarps - 1) / kFastWarps;
+  // CTA tiles [ct_begin, ct_end) of the segment's (n_tiles + 15) / 16: all of them, or one chunk of a routing pass that
+  // the owners' work on the previous chunk overlaps
+  const uint64_t n_cta_tiles = ct_end;
   // KMC_PART1_PREFETCH: the next tile's 32 bytes per lane are requested right after this tile's keys were staged, so
   // they travel while the staged keys are written out, instead of after it
   constexpr bool kPrefetch = KMC_PART1_PREFETCH && kHalves == 1;
   ChunkPrefetch pf;
   pf.ok = 0u;
-  for (uint64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
+  for (uint64_t ct = ct_begin + blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
     uint64_t t = ct * kFastWarps + warp;
     Win<KeyT> W{};
     if constexpr (kPrefetch) W.template load<FOLD>(P, t * Win<KeyT>::kLanes + lane, &pf);
@@ -785,6 +789,9 @@ __global__ void __launch_bounds__(kFinThreads, FinTraits<L2T>::kSplit ? 2 : size
     FIN_MARK(9);                                                                                            \
   } while (0)
 
+  // a bucket of an earlier pass overflowed (input the plan did not fit): the caller recounts with the generic path
+  // whatever happens here, so do nothing.  (Every CTA sees the same flag: it was set before this kernel started.)
+  if (*reinterpret_cast<volatile uint32_t *>(flags) & kFlagOverflow) return;
   FinPending pend;
   pend.valid = false;
   uint32_t cur = 0; // buffer of the bucket being sorted; a pending bucket sits in the other one
@@ -945,6 +952,9 @@ __global__ void __launch_bounds__(kFinThreads, FinTraits<L2T>::kSplit ? 2 : size
       for (uint32_t h = 0; h < nh; h++) {
         const uint32_t b = S.hard[h];
         const uint32_t s = bin_start(S.bins, b), m = bin_end(S.bins, b) - s;
+        // the rank sort below is quadratic: a sub-bin of a thousand different keys (keys sharing a prefix longer than
+        // bucket + sub-bin bits, e.g. lr-gapped keys of a repetitive input) is not what this path is for → recount
+        if (m > (uint32_t)kMaxHardKeys) { if (tid == 0) atomicOr(flags, kFlagOverflow); continue; }
         const SmemT first = keys[s];
         int differ = 0;
         for (uint32_t i = tid; i < m; i += kFinThreads) differ |= !key_eq(keys[s + i], first);

@@ -199,27 +199,47 @@ class DistCounter:
         _, mine, bases = self._map
         return cap, mine, [b + self.rank * cap * self.key_bytes for b in bases]
 
-    def _route_to_peers(self):
-        """Fused route + exchange.  → (cap, my receive buffer, keys received from every source rank).  Every rank learns
-        every (source, owner) count from one all-gather — which is also the hand-over point: every rank's routing kernel
-        is done — so all of them see an overflowed region (skewed input: one owner's share of a shard exceeded the
-        region size) and route once more with regions sized from the exact counts."""
+    def _route_to_peers(self, global_hist=None):
+        """Fused route + exchange, in chunks; the owner side counts chunk c while chunk c + 1 is on the links (streaming
+        owner, kmc_owner_*) when `global_hist` — the sum of all ranks' kmc_dist_hist histograms — is given and the job
+        suits the partitioned path.  → (streaming, cap, my receive buffer, keys received from every source rank).
+        After every chunk one all-gather tells every rank every (source, owner) count; it is also the hand-over point:
+        every rank's routing kernel of that chunk is done.  All ranks therefore see an overflowed region (skewed input:
+        one owner's share of a shard exceeded the region size) and start over with regions sized from the counts."""
         torch, dist = self.torch, self.dist
         dev = torch.device("cuda", torch.cuda.current_device())
+        n_chunks = int(os.environ.get("KMC_DIST_CHUNKS", "8")) if self.n_bases >= (1 << 26) else 1
+        pipeline = global_hist is not None and os.environ.get("KMC_DIST_PIPELINE", "1") == "1"
+        # SMs the routing kernel may take while an owner's kernels run beside it: the route is bound by the links, not by
+        # the SMs, once most keys leave the GPU
+        route_sms = int(os.environ.get("KMC_ROUTE_SMS", "0")) or (112 if self.world <= 2 else 88)
         min_cap = 0
         for attempt in range(2):
             cap, mine, regions = self._setup_peers(min_cap)
+            streaming = pipeline and n_chunks > 1 and self.kc.owner_begin(global_hist, self.world)
             self._mark()
-            count = self.kc.route_to_peers(regions, cap)
-            self._mark()
-            sc = torch.from_numpy(count.astype(np.int64)).to(dev)
-            allc = torch.empty(self.world * self.world, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(allc, sc)
-            allc = allc.cpu().numpy().reshape(self.world, self.world)   # [source, owner]
-            if int(allc.max()) <= cap:
+            prev = np.zeros(self.world, np.int64)
+            worst = 0
+            for c in range(n_chunks):
+                count = self.kc.route_to_peers_part(regions, cap, c, n_chunks, route_sms if streaming else 0)
+                sc = torch.from_numpy(count.astype(np.int64)).to(dev)
+                allc = torch.empty(self.world * self.world, dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(allc, sc)
+                allc = allc.cpu().numpy().reshape(self.world, self.world)   # [source, owner], cumulative
+                worst = int(allc.max())
+                if worst > cap:
+                    break
+                got = allc[:, self.rank]
+                if streaming:
+                    for src in range(self.world):
+                        if got[src] > prev[src]:
+                            self.kc.owner_feed(mine + (src * cap + int(prev[src])) * self.key_bytes, int(got[src] - prev[src]))
+                prev = got.copy()
+            if worst <= cap:
                 self._mark()
-                return cap, mine, allc[:, self.rank].tolist()
-            min_cap = int(int(allc.max()) * 1.02) + 4096
+                return streaming, cap, mine, prev.tolist()
+            # a region overflowed: the counts of the chunks so far give its rate — size the regions from that, with room
+            min_cap = int(worst * n_chunks / (c + 1) * 1.05) + 4096
         raise RuntimeError("kmc dist: a receive region overflowed twice")
 
     def _finish_range(self):
@@ -267,32 +287,41 @@ class DistCounter:
         torch, dist = self.torch, self.dist
         self._t = [time.perf_counter()]
         dev = torch.device("cuda", torch.cuda.current_device())
-        if self.use_combine:
-            # the cardinality probe of the AUTO strategy, on this rank's shard; the route is taken only if every rank agrees
-            _, low = self.kc.dist_hist()
-            flag = torch.tensor([int(low)], dtype=torch.int64, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag):
+        global_hist = None
+        if self.use_peer:
+            # one all-gather per job: every rank's sampled coarse histogram (the owners plan their counts from the sum)
+            # and its cardinality probe (the combine route is taken only if every rank's shard is low-cardinality)
+            hist, low = self.kc.dist_hist()
+            mine = np.concatenate([hist, np.array([int(low)], np.uint64)])
+            send = torch.from_numpy(mine.view(np.int64)).to(dev)
+            allv = torch.empty(self.world * send.numel(), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allv, send)
+            allv = allv.cpu().numpy().view(np.uint64).reshape(self.world, -1)
+            self._mark()
+            if self.use_combine and allv[:, 4096].all():
                 self.path = "combine"
                 self._keep = []
                 return finish_combined(self.kc, torch, dist, self.world, dev, self._keep)
+            global_hist = allv[:, :4096].sum(axis=0)
         if self.use_range:
             out = self._finish_range()
             if out is not None:
                 self.path = "range"
                 if _PROF:
                     d = [1e3 * (b - a) for a, b in zip(self._t[:-1], self._t[1:])]
-                    names = ["hist+gather", "plan", "scatter", "barrier", "count"]
-                    print(f"[kmc dist r{self.rank}] " + ", ".join(f"{n} {v:.2f} ms" for n, v in zip(names, d)) +
-                          f" (range partition) phases={self.kc.stats().get('phases_ms')}", file=sys.stderr)
+                    print(f"[kmc dist r{self.rank}] " + ", ".join(f"{v:.2f}" for v in d) +
+                          f" ms (range partition) phases={self.kc.stats().get('phases_ms')}", file=sys.stderr)
                 return out
             self._t = [time.perf_counter()]
         self.path = "hash"
         mark = self._mark
         if self.use_peer:
-            cap, mine, got = self._route_to_peers()
-            for src, n in enumerate(got):
-                self.kc.ingest_keys(mine + src * cap * self.key_bytes, n)
+            streaming, cap, mine, got = self._route_to_peers(global_hist)
+            if streaming:
+                self.path = "hash-pipelined"
+            else:
+                for src, n in enumerate(got):
+                    self.kc.ingest_keys(mine + src * cap * self.key_bytes, n)
         else:
             begin, count, ptr, key_bytes = self.kc.route(self.world)
             mark()
@@ -308,9 +337,8 @@ class DistCounter:
         mark()
         if _PROF:
             d = [1e3 * (b - a) for a, b in zip(self._t[:-1], self._t[1:])]
-            names = ["setup+barrier", "route", "exchange", "count"] if self.use_peer else ["route", "exchange", "count"]
-            print(f"[kmc dist r{self.rank}] " + ", ".join(f"{n} {v:.2f} ms" for n, v in zip(names, d)) +
-                  f" ({'peer stores' if self.use_peer else 'nccl all-to-all'}) end@{time.time() % 100:.4f} "
+            print(f"[kmc dist r{self.rank}] " + ", ".join(f"{v:.2f}" for v in d) +
+                  f" ms ({self.path}; {'peer stores' if self.use_peer else 'nccl all-to-all'}) end@{time.time() % 100:.4f} "
                   f"strategy={self.kc.stats().get('strategy_used')} fallbacks={self.kc.stats().get('fast_fallbacks')} "
                   f"phases={self.kc.stats().get('phases_ms')}", file=sys.stderr)
         return out

@@ -26,7 +26,7 @@ SYMBOLS = ["kmc_create", "kmc_destroy", "kmc_last_error", "kmc_strerror", "kmc_s
            "kmc_stats_json", "kmc_route_to_peers", "kmc_recv_buffer", "kmc_ipc_export", "kmc_ipc_open",
            "kmc_ipc_close", "kmc_submit_fasta", "kmc_format", "kmc_finish_part",
            "kmc_dist_hist", "kmc_dist_plan", "kmc_dist_scatter", "kmc_table_route", "kmc_ingest_pairs",
-           "kmc_gen_bases", "kmc_gen_nruns", "kmc_gen_reads"]
+           "kmc_gen_bases", "kmc_gen_nruns", "kmc_gen_reads", "kmc_route_to_peers_part", "kmc_owner_begin", "kmc_owner_feed"]
 
 
 class KmcConfig(C.Structure):
@@ -90,6 +90,9 @@ def load_library(path=None):
     L.kmc_ipc_close.argtypes = [vp, vp]
     L.kmc_table_route.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(vp), C.POINTER(vp)]
     L.kmc_ingest_pairs.argtypes = [vp, vp, vp, C.c_uint64]
+    L.kmc_route_to_peers_part.argtypes = [vp, C.c_uint32, vp, C.c_uint64, vp, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.kmc_owner_begin.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.kmc_owner_feed.argtypes = [vp, vp, C.c_uint64]
     L.kmc_gen_bases.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
     L.kmc_gen_nruns.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
     L.kmc_gen_reads.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, vp]
@@ -254,6 +257,24 @@ class KmerCounter:
         count = np.zeros(n, np.uint64)
         self._ck(self._L.kmc_route_to_peers(self._h, n, arr, part_cap_keys, count.ctypes.data))
         return count
+
+    def route_to_peers_part(self, part_ptrs, part_cap_keys, chunk, n_chunks, max_ctas=0):
+        """Chunk `chunk` of `n_chunks` of the routing pass.  → cumulative part_count."""
+        n = len(part_ptrs)
+        arr = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in part_ptrs])
+        count = np.zeros(n, np.uint64)
+        self._ck(self._L.kmc_route_to_peers_part(self._h, n, arr, part_cap_keys, count.ctypes.data, chunk, n_chunks, max_ctas))
+        return count
+
+    def owner_begin(self, global_hist, n_owners):
+        """Plan the streaming count of this owner's share of `global_hist` (uint64[4096]).  → False: declined."""
+        h = np.ascontiguousarray(global_hist, np.uint64)
+        on = C.c_uint32()
+        self._ck(self._L.kmc_owner_begin(self._h, h.ctypes.data, n_owners, C.byref(on)))
+        return bool(on.value)
+
+    def owner_feed(self, d_keys_ptr, n_keys):
+        self._ck(self._L.kmc_owner_feed(self._h, C.c_void_p(d_keys_ptr), n_keys))
 
     def dist_hist(self):
         """→ (uint64[4096] upper-estimate histogram of this rank's keys by their top 12 bits, low_cardinality flag)."""

@@ -46,13 +46,15 @@ def test_fast_path_matches_oracle(kmc, orc, k, canonical, n):
     assert_tables_equal(base, want)
 
 
-def test_fast_path_big_sub_bins(kmc, orc):
-    """5000 distinct k-mers that share their first 13 bases land in one sub-bin of one bucket: the
-    cooperative rank sort of fast_finish; plus a block of 3000 identical k-mers (all-equal shortcut)."""
+@pytest.mark.parametrize("n_special,strategy_want", [(900, 2), (5000, 3)])
+def test_fast_path_big_sub_bins(kmc, orc, n_special, strategy_want):
+    """Distinct k-mers that share their first 13 bases land in one sub-bin of one bucket: up to kMaxHardKeys (1024) of
+    them are sorted by fast_finish's cooperative rank sort (quadratic), more make the job fall back to the generic path;
+    plus a block of 3000 identical k-mers (all-equal shortcut).  Exact either way."""
     rng = np.random.default_rng(5)
     k = 21
     prefix = ACGT[rng.integers(0, 4, 13)]
-    special = [np.concatenate([prefix, ACGT[rng.integers(0, 4, 8)]]) for _ in range(5000)]
+    special = [np.concatenate([prefix, ACGT[rng.integers(0, 4, 8)]]) for _ in range(n_special)]
     same = [ACGT[rng.integers(0, 4, 21)]] * 3000
     filler = ACGT[rng.integers(0, 4, 600_000)]
     recs = special + same
@@ -61,7 +63,7 @@ def test_fast_path_big_sub_bins(kmc, orc):
     want = orc.contiguous_mt(bases, off, k, False)
     got, st, _ = _count(kmc, bases, off, k, False, strategy=2)
     assert_tables_equal(got, want)
-    assert st["strategy_used"] == 2, st
+    assert st["strategy_used"] == strategy_want, st
     auto, _, _ = _count(kmc, bases, off, k, False)
     assert_tables_equal(auto, want)
 

@@ -52,7 +52,7 @@ def main():
         dict(name="hash-peer k31", k=31, seed=31, n=n),
         dict(name="hash-peer k63 ragged+N", k=63, seed=63, n=n, ragged=True),
         dict(name="range k31", k=31, seed=32, n=n, env={"KMC_DIST_PARTITION": "range"}),
-        dict(name="nccl-route k21", k=21, seed=22, n=n // 4, env={"KMC_DIST_EXCHANGE": "nccl"}),
+        dict(name="nccl-route k21", k=21, seed=22, n=n // 4, strategy=2, env={"KMC_DIST_EXCHANGE": "nccl"}),
         dict(name="combine k31 low-cardinality", k=31, seed=51, n=n, genome=300_000),
         dict(name="lr-gapped 27+27", mode=1, seed=71, n=60_000),
         dict(name="skewed shard (region overflow)", k=21, seed=81, n=n // 2, skew=True),
@@ -63,7 +63,7 @@ def main():
             os.environ[k_] = v
         mode = case.get("mode", 0)
         kw = dict(mode=1) if mode else {}
-        dc = DistCounter(k=case.get("k", 31), canonical=(mode == 0), strategy=0, device=local, world=world, rank=rank, dist=dist,
+        dc = DistCounter(k=case.get("k", 31), canonical=(mode == 0), strategy=case.get("strategy", 0), device=local, world=world, rank=rank, dist=dist,
                          torch=torch, **kw)
         b, o = shard(case, rank, case["n"])
         if case.get("skew") and rank == 0:                 # rank 0's shard is ONE k-mer over and over: its owner's region overflows
