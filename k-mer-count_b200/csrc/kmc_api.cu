@@ -4,6 +4,7 @@
 #include "../../include/kmc.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: phases show up as ranges in Nsight Systems / ncu --nvtx
 
 #include <algorithm>
 #include <chrono>
@@ -79,6 +80,7 @@ struct DistPlan {
 struct kmc_ctx {
   kmc_config cfg{};
   int device = 0;
+  uint32_t n_sms = 148;   // multiProcessorCount of the device (kmc_create); grids are sized in multiples of it
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;
@@ -225,12 +227,14 @@ int phase_begin(kmc_ctx *c, const char *name) {
     *e = c->event_pool[c->events_used++];
   }
   CK(cudaEventRecord(ph.a, c->stream));
+  nvtxRangePushA(name);
   ph.host_begin = host_now_ms();
   c->phases.push_back(ph);
   return KMC_OK;
 }
 int phase_end(kmc_ctx *c) {
   CK(cudaEventRecord(c->phases.back().b, c->stream));
+  nvtxRangePop();
   c->phases.back().host_end = host_now_ms();
   return KMC_OK;
 }
@@ -307,7 +311,7 @@ int h2d_small(kmc_ctx *c, void *d_dst, const void *src, size_t bytes) {
     CK(cudaStreamSynchronize(c->stream)); // the previous upload kernel may still be reading the box
   }
   memcpy(c->upbox, src, bytes);
-  LAUNCH(upload_kernel, (uint32_t)std::min<size_t>(std::max<size_t>(1, need / 16 / 256), (size_t)kNumSMsB200 * 4), 256, 0,
+  LAUNCH(upload_kernel, (uint32_t)std::min<size_t>(std::max<size_t>(1, need / 16 / 256), (size_t)c->n_sms * 4), 256, 0,
          (const uint4 *)c->upbox_dev, (uint4 *)d_dst, (uint64_t)(need / 16));
   c->launches--;
   return KMC_OK;
@@ -544,7 +548,7 @@ int extract_all(kmc_ctx *c, uint64_t *n_keys) {
     TRY(seg_wait(c, s));
     ExtractParams P = seg_params(c, s);
     uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
-    uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + 7) / 8, (uint64_t)kNumSMsB200 * 16);
+    uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + 7) / 8, (uint64_t)c->n_sms * 16);
     auto extract_compact = extract_compact_kernel<KeyT, true>;
     LAUNCH(extract_compact, grid, 256, 0, P, tiles, (KeyT *)c->keys_a.p, d_cursor(c));
   }
@@ -697,7 +701,7 @@ int route_fast(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t *par
       if (hi <= lo) continue;
       TRY(seg_wait(c, s));
       ExtractParams P = seg_params(c, s);
-      uint32_t grid = (uint32_t)std::min<uint64_t>(hi - lo, (uint64_t)(max_ctas ? std::min<uint32_t>(max_ctas, kNumSMsB200) : kNumSMsB200));
+      uint32_t grid = (uint32_t)std::min<uint64_t>(hi - lo, (uint64_t)(max_ctas ? std::min<uint32_t>(max_ctas, c->n_sms) : c->n_sms));
       LAUNCH(fast_route, grid, kFastThreads, smem, P, tiles, pl, bucket, dst, d_route_err(c), lo - (seg0 - n_ct), hi - (seg0 - n_ct));
     }
   }
@@ -769,12 +773,12 @@ int hash_run(kmc_ctx *c, const KeyArrays &ka, uint32_t log2_slots, uint64_t limi
   // the table size, or a high-cardinality input would swamp the table before anybody notices
   // (the real run's table is sized from the probe, so only the probe itself — step > 1 or forced — is throttled)
   const uint64_t max_warps = std::max<uint64_t>(64, (1ull << log2_slots) / 4 / 992);
-  const uint32_t max_ctas = throttle ? (uint32_t)std::min<uint64_t>((uint64_t)kNumSMsB200 * 8, std::max<uint64_t>(8, max_warps / 8))
-                                     : (uint32_t)kNumSMsB200 * 8;
+  const uint32_t max_ctas = throttle ? (uint32_t)std::min<uint64_t>((uint64_t)c->n_sms * 8, std::max<uint64_t>(8, max_warps / 8))
+                                     : (uint32_t)c->n_sms * 8;
   const uint64_t slots = 1ull << log2_slots;
   TRY(ensure(c, c->hash_slots, slots * sizeof(HashSlot)));
   TRY(ensure(c, c->hash_scalars, 64));
-  LAUNCH(hash_init_kernel, std::min<uint32_t>(grid_for(slots, 256), kNumSMsB200 * 16), 256, 0, (HashSlot *)c->hash_slots.p, slots);
+  LAUNCH(hash_init_kernel, std::min<uint32_t>(grid_for(slots, 256), c->n_sms * 16), 256, 0, (HashSlot *)c->hash_slots.p, slots);
   CK(cudaMemsetAsync(c->hash_scalars.p, 0, 64, c->stream));
   HashTable T;
   T.slots = (HashSlot *)c->hash_slots.p;
@@ -833,10 +837,10 @@ int finish_hash(kmc_ctx *c, uint32_t log2_slots, uint64_t limit, bool *used) {
   dense = (uint64_t *)c->t_lo.p; scratch = (uint64_t *)c->keys_b.p;
   if (d) {
     CK(cudaMemsetAsync(d_cursor(c), 0, 8, c->stream));
-    LAUNCH(hash_compact_kernel, std::min<uint32_t>(grid_for(T.mask + 1, 256), kNumSMsB200 * 16), 256, 0, T, dense, d_cursor(c));
+    LAUNCH(hash_compact_kernel, std::min<uint32_t>(grid_for(T.mask + 1, 256), c->n_sms * 16), 256, 0, T, dense, d_cursor(c));
     TRY(radix_sort<uint64_t>(c, dense, scratch, d, c->key_bits, &sorted));
     if (sorted != dense) CK(cudaMemcpyAsync(dense, sorted, d * 8, cudaMemcpyDeviceToDevice, c->stream));
-    LAUNCH(hash_lookup_kernel, std::min<uint32_t>(grid_for(d, 256), kNumSMsB200 * 16), 256, 0, T, (const uint64_t *)dense, d,
+    LAUNCH(hash_lookup_kernel, std::min<uint32_t>(grid_for(d, 256), c->n_sms * 16), 256, 0, T, (const uint64_t *)dense, d,
            (uint32_t *)c->t_cnt.p);
   }
   uint64_t rows = d;
@@ -867,7 +871,7 @@ int finish_pairs(kmc_ctx *c) {
   TRY(ensure(c, c->hash_slots, slots * sizeof(HashSlot)));
   TRY(ensure(c, c->hash_scalars, 64));
   PHASE_BEGIN("hash_count");
-  LAUNCH(hash_init_kernel, std::min<uint32_t>(grid_for(slots, 256), kNumSMsB200 * 16), 256, 0, (HashSlot *)c->hash_slots.p, slots);
+  LAUNCH(hash_init_kernel, std::min<uint32_t>(grid_for(slots, 256), c->n_sms * 16), 256, 0, (HashSlot *)c->hash_slots.p, slots);
   CK(cudaMemsetAsync(c->hash_scalars.p, 0, 64, c->stream));
   HashTable T;
   T.slots = (HashSlot *)c->hash_slots.p;
@@ -875,7 +879,7 @@ int finish_pairs(kmc_ctx *c) {
   T.n_used = (unsigned long long *)c->hash_scalars.p; T.n_total = T.n_used + 1; T.n_ones = T.n_used + 2;
   T.limit = slots; T.flags = d_err(c);
   for (auto &a : c->ingested_pairs)
-    if (a.n) LAUNCH(hash_count_pairs_kernel, std::min<uint32_t>(grid_for(a.n, 1024), kNumSMsB200 * 8), 256, 0, a.keys, a.counts, a.n, T);
+    if (a.n) LAUNCH(hash_count_pairs_kernel, std::min<uint32_t>(grid_for(a.n, 1024), c->n_sms * 8), 256, 0, a.keys, a.counts, a.n, T);
   PHASE_END();
   uint32_t err = 0;
   TRY(read_scalars(c, nullptr, &err));
@@ -891,10 +895,10 @@ int finish_pairs(kmc_ctx *c) {
   uint64_t *dense = (uint64_t *)c->t_lo.p, *scratch = (uint64_t *)c->keys_b.p, *sorted = nullptr;
   if (d) {
     CK(cudaMemsetAsync(d_cursor(c), 0, 8, c->stream));
-    LAUNCH(hash_compact_kernel, std::min<uint32_t>(grid_for(T.mask + 1, 256), kNumSMsB200 * 16), 256, 0, T, dense, d_cursor(c));
+    LAUNCH(hash_compact_kernel, std::min<uint32_t>(grid_for(T.mask + 1, 256), c->n_sms * 16), 256, 0, T, dense, d_cursor(c));
     TRY(radix_sort<uint64_t>(c, dense, scratch, d, c->key_bits, &sorted));
     if (sorted != dense) CK(cudaMemcpyAsync(dense, sorted, d * 8, cudaMemcpyDeviceToDevice, c->stream));
-    LAUNCH(hash_lookup_kernel, std::min<uint32_t>(grid_for(d, 256), kNumSMsB200 * 16), 256, 0, T, (const uint64_t *)dense, d,
+    LAUNCH(hash_lookup_kernel, std::min<uint32_t>(grid_for(d, 256), c->n_sms * 16), 256, 0, T, (const uint64_t *)dense, d,
            (uint32_t *)c->t_cnt.p);
   }
   uint64_t rows = d;
@@ -936,7 +940,7 @@ int hash_probe(kmc_ctx *c, bool *low_cardinality) {
     const uint32_t thr = (uint32_t)std::max<uint64_t>(64, sc[1] / 50000);
     unsigned int *d_nhot = (unsigned int *)((unsigned char *)c->hash_hot.p + kHotMax * 8);
     CK(cudaMemsetAsync(d_nhot, 0, 4, c->stream));
-    LAUNCH(hash_hot_kernel, kNumSMsB200 * 8, 256, 0, T, thr, (uint64_t *)c->hash_hot.p, d_nhot);
+    LAUNCH(hash_hot_kernel, c->n_sms * 8, 256, 0, T, thr, (uint64_t *)c->hash_hot.p, d_nhot);
     unsigned int nh = 0;
     TRY(d2h_small(c, &nh, d_nhot, 4));
     c->n_hot = std::min<uint32_t>(nh, kHotMax);
@@ -963,7 +967,7 @@ int coarse_hist(kmc_ctx *c, const KeyArrays &ka, std::vector<uint64_t> &hist, ui
   PHASE_BEGIN("fast_hist");
   if (ka.from_array) {
     for (auto &a : ka.arrays) {
-      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024 * step), (uint64_t)kNumSMsB200 * 8);
+      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024 * step), (uint64_t)c->n_sms * 8);
       auto fast_hist_array = fast_hist_array_kernel<KeyT>;
       LAUNCH(fast_hist_array, grid, 256, ncoarse * 4, (const KeyT *)a.first, a.second, step, kb - cb, ncoarse, ghist);
     }
@@ -975,7 +979,7 @@ int coarse_hist(kmc_ctx *c, const KeyArrays &ka, std::vector<uint64_t> &hist, ui
       if (!sample_host) TRY(seg_wait(c, s));
       ExtractParams P = seg_params(c, s, sample_host);
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)kNumSMsB200 * 8);
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)c->n_sms * 8);
       auto fast_hist = fast_hist_kernel<KeyT, true>;
       LAUNCH(fast_hist, grid, 256, ncoarse * 4, P, tiles, step, kb - cb, ncoarse, ghist);
     }
@@ -1283,7 +1287,7 @@ int fast_feed_array(kmc_ctx *c, const void *keys, uint64_t n, bool incremental) 
   auto fast_part1_array = fast_part1_array_kernel<KeyT>;
   CK(cudaFuncSetAttribute(fast_part1_array, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PHASE_BEGIN("fast_part1");
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(n, arr_tile<KeyT>()), (uint64_t)kNumSMsB200);
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(n, arr_tile<KeyT>()), (uint64_t)c->n_sms);
   LAUNCH(fast_part1_array, grid, kFastThreads, smem, (const KeyT *)keys, n, J.pl, (KeyT *)c->fast_l1.p, d_err(c));
   PHASE_END();
   J.fed += n;
@@ -1321,28 +1325,28 @@ int fast_end(kmc_ctx *c, bool incremental, bool *used) {
       size_t fsmem = sizeof(FinishSmem<U128>);
       auto fast_finish = fast_finish_kernel<U128>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2);
+      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * 2);
       LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const U128 *)c->fast_l2.p, (uint64_t *)c->t_lo.p, (uint64_t *)c->t_hi.p,
              (uint32_t *)c->t_cnt.p, J.status, J.ticket, d_err(c), J.d_total, prof);
     } else if (key32) {
       size_t fsmem = sizeof(FinishSmem<uint32_t>);
       auto fast_finish = fast_finish_kernel<uint32_t>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB32);
+      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * KMC_FINISH_MINB32);
       LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint32_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
              (uint32_t *)c->t_cnt.p, J.status, J.ticket, d_err(c), J.d_total, prof);
     } else if (split64) {
       size_t fsmem = sizeof(FinishSmem<Split64>);
       auto fast_finish = fast_finish_kernel<Split64>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2);
+      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * 2);
       LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
              (uint32_t *)c->t_cnt.p, J.status, J.ticket, d_err(c), J.d_total, prof);
     } else {
       size_t fsmem = sizeof(FinishSmem<uint64_t>);
       auto fast_finish = fast_finish_kernel<uint64_t>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB64);
+      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * KMC_FINISH_MINB64);
       LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
              (uint32_t *)c->t_cnt.p, J.status, J.ticket, d_err(c), J.d_total, prof);
     }
@@ -1444,7 +1448,7 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
       TRY(seg_wait(c, s));
       ExtractParams P = seg_params(c, s);
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)c->n_sms);
       const uint64_t n_ct = (tiles + kFastWarps - 1) / kFastWarps;
       if (ranged) LAUNCH(fast_part1_ranged, grid, kFastThreads, smem, P, tiles, pl, bucket_ranged, (KeyT *)c->fast_l1.p, d_err(c), (uint64_t)0, n_ct);
       else LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->fast_l1.p, d_err(c), (uint64_t)0, n_ct);
@@ -1615,7 +1619,7 @@ int dist_scatter_impl(kmc_ctx *c, void *const *peer_buf, uint32_t *overflow) {
       TRY(seg_wait(c, s));
       ExtractParams P = seg_params(c, s);
       uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)kNumSMsB200);
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)c->n_sms);
       LAUNCH(fast_scatter_to_owners, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)nullptr, d_err(c), (uint64_t)0,
              (tiles + kFastWarps - 1) / kFastWarps);
     }
@@ -1725,26 +1729,26 @@ int finish_dist(kmc_ctx *c) {
       size_t fsmem = sizeof(FinishSmem<U128>);
       auto fast_finish = fast_finish_kernel<U128>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2), kFinThreads, fsmem, pl, (const U128 *)c->fast_l2.p,
+      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * 2), kFinThreads, fsmem, pl, (const U128 *)c->fast_l2.p,
              (uint64_t *)c->t_lo.p, (uint64_t *)c->t_hi.p, (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
     } else if (key32) {
       size_t fsmem = sizeof(FinishSmem<uint32_t>);
       auto fast_finish = fast_finish_kernel<uint32_t>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB32), kFinThreads, fsmem, pl,
+      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * KMC_FINISH_MINB32), kFinThreads, fsmem, pl,
              (const uint32_t *)c->fast_l2.p, (uint64_t *)c->t_lo.p, (uint64_t *)nullptr, (uint32_t *)c->t_cnt.p, status, ticket, d_err(c),
              d_total, prof);
     } else if (split64) {
       size_t fsmem = sizeof(FinishSmem<Split64>);
       auto fast_finish = fast_finish_kernel<Split64>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * 2), kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p,
+      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * 2), kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p,
              (uint64_t *)c->t_lo.p, (uint64_t *)nullptr, (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
     } else {
       size_t fsmem = sizeof(FinishSmem<uint64_t>);
       auto fast_finish = fast_finish_kernel<uint64_t>;
       CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)kNumSMsB200 * KMC_FINISH_MINB64), kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p,
+      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * KMC_FINISH_MINB64), kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p,
              (uint64_t *)c->t_lo.p, (uint64_t *)nullptr, (uint32_t *)c->t_cnt.p, status, ticket, d_err(c), d_total, prof);
     }
   }
@@ -1994,6 +1998,7 @@ int kmc_create(kmc_ctx **out, const kmc_config *cfg) {
   if (!x) return fail(c, KMC_E_NOMEM, "host allocation failed");
   x->cfg = f;
   x->device = dev;
+  x->n_sms = (uint32_t)prop.multiProcessorCount;
   x->key_bases = f.mode == KMC_MODE_CONTIGUOUS ? f.k : f.l_len + f.r_len;
   x->key_bits = 2 * x->key_bases;
   x->wide = x->key_bits > 64;
@@ -2233,7 +2238,7 @@ int kmc_table_route(kmc_ctx *c, uint32_t n_parts, uint64_t *part_begin, uint64_t
   std::vector<unsigned long long> h(n_parts, 0);
   if (rows) {
     CK(cudaMemsetAsync(state, 0, (size_t)n_parts * 8, c->stream));
-    const uint32_t grid = std::min<uint32_t>(grid_for(rows, 1024), kNumSMsB200 * 8);
+    const uint32_t grid = std::min<uint32_t>(grid_for(rows, 1024), c->n_sms * 8);
     LAUNCH(table_owner_hist_kernel, grid, 256, 0, (const uint64_t *)c->t_lo.p, rows, n_parts, state);
     TRY(d2h_small(c, h.data(), state, (size_t)n_parts * 8));
     std::vector<unsigned long long> begin(n_parts, 0);
@@ -2391,7 +2396,7 @@ int kmc_format(kmc_ctx *c, uint64_t first, uint64_t n, int expanded, size_t max_
     CK(cudaHostAlloc((void **)&c->fmt_host, cap, cudaHostAllocDefault));
     c->fmt_host_cap = cap;
   }
-  LAUNCH(fmt_write_kernel, std::min<uint32_t>(grid_for(n, 8), kNumSMsB200 * 16), 256, 0, (const uint64_t *)c->t_lo.p + first,
+  LAUNCH(fmt_write_kernel, std::min<uint32_t>(grid_for(n, 8), c->n_sms * 16), 256, 0, (const uint64_t *)c->t_lo.p + first,
          c->wide ? (const uint64_t *)c->t_hi.p + first : (const uint64_t *)nullptr, cnt, (const uint64_t *)c->fmt_off.p, n, nb, expanded,
          (char *)c->fmt_text.p);
   CK(cudaMemcpyAsync(c->fmt_host, c->fmt_text.p, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -2415,7 +2420,7 @@ int kmc_digest(kmc_ctx *c, uint64_t *digest) {
   CK(cudaSetDevice(c->device));
   CK(cudaMemsetAsync(d_digest(c), 0, 8, c->stream));
   if (c->n_distinct)
-    LAUNCH(digest_kernel, std::min<uint32_t>(grid_for(c->n_distinct, 256), kNumSMsB200 * 8), 256, 0, (const uint64_t *)c->t_lo.p,
+    LAUNCH(digest_kernel, std::min<uint32_t>(grid_for(c->n_distinct, 256), c->n_sms * 8), 256, 0, (const uint64_t *)c->t_lo.p,
            c->wide ? (const uint64_t *)c->t_hi.p : (const uint64_t *)nullptr, (const uint32_t *)c->t_cnt.p, c->n_distinct,
            d_digest(c));
   unsigned long long h = 0;
@@ -2567,7 +2572,7 @@ int kmc_gen_bases(kmc_ctx *c, uint64_t seed, uint64_t first, uint64_t n, uint8_t
   if (!c || (!d_out && n)) return KMC_E_ARG;
   if (!n) return KMC_OK;
   CK(cudaSetDevice(c->device));
-  LAUNCH(gen_bases_kernel, (uint32_t)std::min<uint64_t>(grid_for(n / 16 + 2, 256), (uint64_t)kNumSMsB200 * 16), 256, 0, seed, first, n, d_out);
+  LAUNCH(gen_bases_kernel, (uint32_t)std::min<uint64_t>(grid_for(n / 16 + 2, 256), (uint64_t)c->n_sms * 16), 256, 0, seed, first, n, d_out);
   return KMC_OK;
 }
 
@@ -2575,7 +2580,7 @@ int kmc_gen_nruns(kmc_ctx *c, uint64_t seed, uint64_t first, uint64_t n, uint8_t
   if (!c || (!d_bases && n)) return KMC_E_ARG;
   if (!n) return KMC_OK;
   CK(cudaSetDevice(c->device));
-  LAUNCH(gen_nruns_kernel, (uint32_t)std::min<uint64_t>(grid_for(n / kGenNBlock + 2, 256), (uint64_t)kNumSMsB200 * 16), 256, 0, seed, first, n, d_bases);
+  LAUNCH(gen_nruns_kernel, (uint32_t)std::min<uint64_t>(grid_for(n / kGenNBlock + 2, 256), (uint64_t)c->n_sms * 16), 256, 0, seed, first, n, d_bases);
   return KMC_OK;
 }
 
@@ -2585,7 +2590,7 @@ int kmc_gen_reads(kmc_ctx *c, uint64_t seed, const uint8_t *d_genome, uint64_t g
   if (read_len < 1 || genome_len < read_len) return fail(c, KMC_E_ARG, "kmc_gen_reads: need 1 <= read_len <= genome_len");
   if (!n_reads) return KMC_OK;
   CK(cudaSetDevice(c->device));
-  LAUNCH(gen_reads_kernel, (uint32_t)std::min<uint64_t>(grid_for(n_reads * read_len, 1024), (uint64_t)kNumSMsB200 * 16), 256, 0, seed, d_genome,
+  LAUNCH(gen_reads_kernel, (uint32_t)std::min<uint64_t>(grid_for(n_reads * read_len, 1024), (uint64_t)c->n_sms * 16), 256, 0, seed, d_genome,
          genome_len, read_len, first_read, n_reads, d_out);
   return KMC_OK;
 }

@@ -5,7 +5,6 @@
 
 namespace kmc {
 
-constexpr int kNumSMsB200 = 148;
 
 // ---- 128-bit key as two words (AoS on the device: {lo, hi}) --------------------------------------
 struct __align__(16) U128 {
