@@ -221,6 +221,16 @@ int kmc_ingest_keys(kmc_ctx *ctx, const void *d_keys, uint64_t n_keys);
 int kmc_table_route(kmc_ctx *ctx, uint32_t n_parts, uint64_t *part_begin, uint64_t *part_count, const uint64_t **d_keys,
                     const uint64_t **d_counts);
 int kmc_ingest_pairs(kmc_ctx *ctx, const uint64_t *d_keys, const uint64_t *d_counts, uint64_t n_rows);
+/* ---- multi-GPU output stage: one ascending table from the owners' tables (main.rs:87-90 on N ranks) -----
+ * After a hash-partitioned count every rank holds an ascending table of keys no other rank holds; what the
+ * reference prints is their merge.  kmc_merge_tables makes that merge this ctx's table (as after kmc_finish:
+ * kmc_read / kmc_format / kmc_digest / kmc_table_device work on it): n_runs ascending runs of rows in DEVICE
+ * memory, columns laid out like kmc_table_device's (d_key_hi may be NULL for keys of <= 64 bits), n_rows[r]
+ * rows each; the runs are not referenced after the call returns.  The runs' key sets must be pairwise disjoint
+ * (KMC_E_ARG otherwise).  The ctx must hold no input (fresh, or after kmc_reset), and no run may be this ctx's
+ * own table (merge into a second ctx).                                                                    */
+int kmc_merge_tables(kmc_ctx *ctx, uint32_t n_runs, const uint64_t *const *d_key_lo, const uint64_t *const *d_key_hi,
+                     const uint32_t *const *d_count, const uint64_t *n_rows, uint64_t *n_distinct, uint64_t *n_total);
 /* owner part of a key, host-side (the same function the device uses).                            */
 uint32_t kmc_owner_of(uint64_t key_hi, uint64_t key_lo, uint32_t n_parts);
 

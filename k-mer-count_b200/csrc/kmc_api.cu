@@ -23,6 +23,7 @@
 #include "kmc_fasta.cuh"
 #include "kmc_format.cuh"
 #include "kmc_gen.cuh"
+#include "kmc_merge.cuh"
 #include <cmath>
 
 using namespace kmc;
@@ -121,6 +122,7 @@ struct kmc_ctx {
   DevBuf hash_slots, hash_scalars, hash_hot;
   DevBuf fa_raw, fa_tiles, fa_flags;
   DevBuf fmt_len, fmt_off, fmt_text;
+  DevBuf merge_lo, merge_hi, merge_cnt; // kmc_merge_tables: the other half of the ping-pong
   char *fmt_host = nullptr;
   size_t fmt_host_cap = 0;
   uint64_t probe_distinct = 0;
@@ -2026,7 +2028,7 @@ void kmc_destroy(kmc_ctx *c) {
   if (c->fmt_host) cudaFreeHost(c->fmt_host);
   for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); if (s.ready) cudaEventDestroy(s.ready); }
   for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
-                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->fast_fdesc, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot, &c->fa_raw, &c->fa_tiles, &c->fa_flags, &c->fmt_len, &c->fmt_off, &c->fmt_text, &c->pair_rows, &c->pair_state,
+                    &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->fast_fdesc, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot, &c->fa_raw, &c->fa_tiles, &c->fa_flags, &c->fmt_len, &c->fmt_off, &c->fmt_text, &c->merge_lo, &c->merge_hi, &c->merge_cnt, &c->pair_rows, &c->pair_state,
                     &c->dist_tables, &c->route_state, &c->route_tables})
     release(*b);
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
@@ -2426,6 +2428,75 @@ int kmc_digest(kmc_ctx *c, uint64_t *digest) {
   unsigned long long h = 0;
   TRY(d2h_small(c, &h, d_digest(c), 8));
   *digest = h;
+  return KMC_OK;
+}
+
+// Multi-GPU output stage (kmc.h): merge ascending runs of rows with disjoint keys into this ctx's table.
+int kmc_merge_tables(kmc_ctx *c, uint32_t n_runs, const uint64_t *const *d_key_lo, const uint64_t *const *d_key_hi,
+                     const uint32_t *const *d_count, const uint64_t *n_rows, uint64_t *n_distinct, uint64_t *n_total) {
+  if (!c || !n_rows || (n_runs && (!d_key_lo || !d_count))) return KMC_E_ARG;
+  if (c->wide && n_runs && !d_key_hi) return fail(c, KMC_E_ARG, "kmc_merge_tables: 128-bit keys need d_key_hi");
+  if (c->n_segs || !c->ingested.empty() || !c->ingested_pairs.empty())
+    return fail(c, KMC_E_ARG, "kmc_merge_tables: the ctx holds input (call kmc_reset first)");
+  CK(cudaSetDevice(c->device));
+  const bool wide = c->wide;
+  std::vector<RunView> cur;
+  uint64_t total = 0;
+  for (uint32_t r = 0; r < n_runs; r++) {
+    if (!n_rows[r]) continue;
+    if (!d_key_lo[r] || !d_count[r] || (wide && !d_key_hi[r])) return fail(c, KMC_E_ARG, "kmc_merge_tables: run %u has null columns", r);
+    cur.push_back(RunView{d_key_lo[r], wide ? d_key_hi[r] : nullptr, d_count[r], n_rows[r]});
+    total += n_rows[r];
+  }
+  c->phases.clear(); c->klaunches.clear(); c->events_used = 0; c->launches = 0;
+  TRY(zero_scalars(c));
+  uint32_t rounds = 0;
+  for (size_t m = cur.size(); m > 1; m = (m + 1) / 2) rounds++;
+  TRY(ensure(c, c->t_lo, total * 8 + 64));
+  if (wide) TRY(ensure(c, c->t_hi, total * 8 + 64));
+  TRY(ensure(c, c->t_cnt, total * 4 + 64));
+  if (rounds > 1) {
+    TRY(ensure(c, c->merge_lo, total * 8 + 64));
+    if (wide) TRY(ensure(c, c->merge_hi, total * 8 + 64));
+    TRY(ensure(c, c->merge_cnt, total * 4 + 64));
+  }
+  PHASE_BEGIN("merge");
+  if (cur.size() == 1) { // one run: the table is a copy of it
+    LAUNCH(merge_copy_kernel, std::min<uint32_t>(grid_for(total, 256), c->n_sms * 8), 256, 0, cur[0], (uint64_t *)c->t_lo.p,
+           (uint64_t *)c->t_hi.p, (uint32_t *)c->t_cnt.p);
+  }
+  for (uint32_t round = 1; cur.size() > 1; round++) {
+    const bool to_table = ((rounds - round) & 1u) == 0; // the last round writes the table; the ones before alternate
+    uint64_t *o_lo = (uint64_t *)(to_table ? c->t_lo.p : c->merge_lo.p), *o_hi = (uint64_t *)(to_table ? c->t_hi.p : c->merge_hi.p);
+    uint32_t *o_cnt = (uint32_t *)(to_table ? c->t_cnt.p : c->merge_cnt.p);
+    std::vector<RunView> next;
+    uint64_t off = 0;
+    for (size_t i = 0; i < cur.size(); i += 2) {
+      const uint64_t n = cur[i].n + (i + 1 < cur.size() ? cur[i + 1].n : 0);
+      if (i + 1 < cur.size()) {
+        const uint32_t grid = grid_for(n, 256 * kMergeRows);
+        if (wide) LAUNCH(merge_pair_kernel<true>, grid, 256, 0, cur[i], cur[i + 1], o_lo + off, o_hi + off, o_cnt + off, d_err(c));
+        else LAUNCH(merge_pair_kernel<false>, grid, 256, 0, cur[i], cur[i + 1], o_lo + off, o_hi, o_cnt + off, d_err(c));
+      } else {
+        LAUNCH(merge_copy_kernel, std::min<uint32_t>(grid_for(n, 256), c->n_sms * 8), 256, 0, cur[i], o_lo + off, wide ? o_hi + off : o_hi, o_cnt + off);
+      }
+      next.push_back(RunView{o_lo + off, wide ? o_hi + off : nullptr, o_cnt + off, n});
+      off += n;
+    }
+    cur.swap(next);
+  }
+  if (total) LAUNCH(count_sum_kernel, std::min<uint32_t>(grid_for(total, 1024), c->n_sms * 8), 256, 0, (const uint32_t *)c->t_cnt.p, total, d_total_all(c));
+  PHASE_END();
+  uint32_t err = 0;
+  uint64_t sum = 0;
+  TRY(read_scalars(c, nullptr, &err, &sum));
+  if (err & kFlagSharedKey) return fail(c, KMC_E_ARG, "kmc_merge_tables: two runs hold the same key (owners must hold disjoint key sets)");
+  for (auto &p : c->phases) cudaEventElapsedTime(&p.ms, p.a, p.b);
+  c->n_distinct = total; c->n_total = sum;
+  c->strategy_used = KMC_STRATEGY_SORT;
+  c->finished = true;
+  if (n_distinct) *n_distinct = total;
+  if (n_total) *n_total = sum;
   return KMC_OK;
 }
 

@@ -5,6 +5,9 @@
 //                                   one per line (main.rs:87-90); exit 101 with a panic-style message on the
 //                                   inputs on which the reference panics (main.rs:44,59,23,35).
 //   kmer-count FASTA -k K [-o OUT]  ordinary canonical k-mers, "kmer<TAB>count" lines ascending by k-mer.
+//   kmer-count --gpus N ...         the same job on N GPUs of this box, the same bytes out: hands over to the
+//                                   multi-process host program (k-mer-count_b200/cli_dist.py under torchrun, one
+//                                   process per GPU; records sharded, keys routed to their owner GPU, one merged stream).
 //
 // Host side only: FASTA parsing (what bio::io::fasta::Reader does for main.rs:45,59-62), pinned staging,
 // text output.  All counting happens on the GPU behind kmc.h; there is no CPU counting path in this program.
@@ -16,6 +19,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+
+#include <unistd.h>
 
 #include "../../include/kmc.h"
 
@@ -45,9 +50,38 @@ struct Options {
 void usage() {
   fputs("usage: kmer-count [FASTA] [-k K] [-o OUT] [--mode lr-gapped|contiguous] [--canonical|--no-canonical]\n"
         "                  [--strategy auto|hash|sort|baseline] [--lr L R DMIN DMAX] [--counts] [--device N] [--stats FILE]\n"
-        "                  [--host-parse] [--parts P]\n"
+        "                  [--host-parse] [--parts P] [--gpus N]\n"
         "  no arguments: read ./sample.fasta and print the reference's output (sorted L27+R27 gapped chunks)\n",
         stderr);
+}
+
+// --gpus N (N > 1): one process per GPU.  This program is one process on one GPU; the multi-GPU job is run by the
+// Python host side over the same C ABI (cli_dist.py), launched with torchrun.  Does not return when it hands over.
+void maybe_hand_over_to_ranks(int argc, char **argv) {
+  int gpus = 1, at = -1;
+  for (int i = 1; i + 1 < argc; i++) if (!strcmp(argv[i], "--gpus")) { gpus = atoi(argv[i + 1]); at = i; }
+  if (at < 0) return;
+  if (gpus < 1) { fputs("kmer-count: --gpus needs a positive number\n", stderr); exit(2); }
+  if (gpus == 1) return;
+  char exe[4096];
+  ssize_t n = readlink("/proc/self/exe", exe, sizeof exe - 1);
+  if (n <= 0) { perror("kmer-count: readlink /proc/self/exe"); exit(3); }
+  exe[n] = 0;
+  std::string root(exe); // <root>/k-mer-count_b200/bin/kmer-count
+  for (int up = 0; up < 3; up++) { size_t p = root.rfind('/'); if (p == std::string::npos) break; root.resize(p); }
+  std::string pp = root;
+  if (const char *old = getenv("PYTHONPATH")) { pp += ":"; pp += old; }
+  setenv("PYTHONPATH", pp.c_str(), 1);
+  const std::string nproc = std::to_string(gpus), port = std::to_string(29600 + (int)(getpid() % 300));
+  std::vector<std::string> a = {"python3", "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", nproc, "--master-addr", "127.0.0.1",
+                                "--master-port", port, "-m", "kmer_count_b200.cli_dist"};
+  for (int i = 1; i < argc; i++) { if (i == at || i == at + 1) continue; a.push_back(argv[i]); }
+  std::vector<char *> av;
+  for (auto &x : a) av.push_back(const_cast<char *>(x.c_str()));
+  av.push_back(nullptr);
+  execvp(av[0], av.data());
+  perror("kmer-count: cannot start python3 -m torch.distributed.run");
+  exit(3);
 }
 
 Options parse_args(int argc, char **argv) {
@@ -68,6 +102,7 @@ Options parse_args(int argc, char **argv) {
     else if (a == "--no-canonical") { o.canonical = 0; canon_given = true; }
     else if (a == "--counts") o.expanded = false;
     else if (a == "--host-parse") o.host_parse = true;
+    else if (a == "--gpus") { need(1); ++i; } // 1: this process (larger values never get here)
     else if (a == "--parts") { need(1); o.parts = atoi(argv[++i]); if (o.parts < 1) { usage(); exit(2); } }
     else if (a == "--strategy") {
       need(1); std::string s = argv[++i];
@@ -201,6 +236,7 @@ void emit(const Options &o, kmc_ctx *ctx, uint64_t n_distinct, FILE *out) {
 } // namespace
 
 int main(int argc, char **argv) {
+  maybe_hand_over_to_ranks(argc, argv);
   Options o = parse_args(argc, argv);
   kmc_config cfg;
   memset(&cfg, 0, sizeof cfg);

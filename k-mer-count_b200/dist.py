@@ -13,7 +13,9 @@ import time
 
 import numpy as np
 
-from .host import KmerCounter
+from .host import KmcError, KmerCounter
+
+E_EMPTY, E_CAPACITY = -6, -8   # KMC_E_EMPTY, KMC_E_CAPACITY (include/kmc.h)
 
 _PROF = os.environ.get("KMC_DIST_PROF") == "1"
 
@@ -23,6 +25,13 @@ class _DevArray:
 
     def __init__(self, ptr, n_words):
         self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+class _DevArray32:
+    """The same for 32-bit words (the table's count column)."""
+
+    def __init__(self, ptr, n_words):
+        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i4", "data": (ptr, False), "version": 2}
 
 
 def _view(torch, ptr, n_words, dev):
@@ -88,6 +97,44 @@ def exchange(torch, dist, send_parts):
     return recv, recv_sizes
 
 
+def agree_status(torch, dist, dev, code):
+    """Every rank's status code (0 = fine, else a KMC_E_* value) → list, one per rank.  Called before the collectives of
+    a step that can fail on one rank only (a bad base in one shard, main.rs:23): either every rank goes on, or every rank
+    raises — nobody is left waiting in an all-to-all."""
+    mine = torch.tensor([int(code)], dtype=torch.int64, device=dev)
+    allc = torch.empty(dist.get_world_size(), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allc, mine)
+    return [int(x) for x in allc.cpu().tolist()]
+
+
+def gather_runs(torch, dist, cols, root=0):
+    """The multi-GPU output stage's transport: every rank's table columns (1-D tensors: key_lo int64, [key_hi int64,]
+    count int32, all of one length) to `root`.  → on root a list over ranks of column lists (the root's own are passed
+    through, not copied); None elsewhere.  Point-to-point send/recv — NCCL on the GPU box, gloo in the CPU tests."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = cols[0].device
+    n = torch.tensor([cols[0].numel()], dtype=torch.int64, device=dev)
+    alln = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(alln, n)
+    alln = [int(x) for x in alln.cpu().tolist()]
+    if rank != root:
+        if alln[rank]:
+            for c in cols:
+                dist.send(c.contiguous(), root)
+        return None
+    runs = []
+    for r in range(world):
+        if r == root:
+            runs.append(list(cols))
+            continue
+        got = [torch.empty(alln[r], dtype=c.dtype, device=dev) for c in cols]
+        if alln[r]:
+            for g in got:
+                dist.recv(g, r)
+        runs.append(got)
+    return runs
+
+
 def finish_combined(kc, torch, dist, world, dev, keep):
     """Low-cardinality input on several GPUs ("(key,count) pairs after local combine"): every rank counts
     its own shard, the rows of its table are grouped by owner (kmc_table_route) and exchanged — two small all-to-alls
@@ -128,6 +175,9 @@ class DistCounter:
         self._opened = []
         self._t = []
         self.path = None
+        self._empty = False   # this rank owns no key of the last job (its ctx holds no table)
+        self._kw = dict(k=k, canonical=canonical, strategy=strategy, device=device, **kw)
+        self._merger = None
         self.n_bases = 0
         self.key_bytes = 8 if self.key_bits <= 64 else 16
         self.use_peer = world > 1 and kw.get("mode", 0) == 0 and os.environ.get("KMC_DIST_EXCHANGE", "peer") == "peer"
@@ -151,6 +201,7 @@ class DistCounter:
     def reset(self):
         self.kc.reset()
         self._keep = None
+        self._empty = False
         self.n_bases = 0
 
     def submit_device(self, d_bases, d_off, n_bases, n_recs):
@@ -323,15 +374,35 @@ class DistCounter:
                 for src, n in enumerate(got):
                     self.kc.ingest_keys(mine + src * cap * self.key_bytes, n)
         else:
-            begin, count, ptr, key_bytes = self.kc.route(self.world)
+            # a shard may fail on its own (a non-ACGT byte inside a chunk, main.rs:23) or simply hold no chunk (every
+            # record of THIS shard shorter than d_min — the reference's panic of main.rs:35 is about the whole input):
+            # the ranks agree on what happened before anyone enters the all-to-all
+            words, err = self.key_bytes // 8, None
+            try:
+                begin, count, ptr, _ = self.kc.route(self.world)
+                code = 0
+            except KmcError as e:
+                begin = count = np.zeros(self.world, np.uint64)
+                ptr, code, err = 0, e.code, e
+            codes = agree_status(torch, dist, dev, code)
+            bad = [c for c in codes if c not in (0, E_EMPTY)]
+            if bad:
+                raise err if code == bad[0] else KmcError(bad[0], "raised by another rank's shard")
+            if all(c == E_EMPTY for c in codes):
+                raise err                        # no chunk in the whole input: main.rs:35
             mark()
-            words = key_bytes // 8
             span = int((begin + count).max()) * words
-            buf = torch.as_tensor(_DevArray(ptr, max(span, 1)), device=dev)
+            buf = torch.as_tensor(_DevArray(ptr, span), device=dev) if span else torch.empty(0, dtype=torch.int64, device=dev)
             parts = [buf[int(b) * words:(int(b) + int(n)) * words] for b, n in zip(begin, count)]
             recv, _ = exchange(torch, dist, parts)
             mark()
             self._keep = recv  # referenced by the ctx until finish returns
+            if code == E_EMPTY:
+                self.kc.reset()  # this shard held no chunk: the ctx counts only what the other ranks sent it
+            if recv.numel() == 0:
+                self.kc.reset()
+                self._empty = True
+                return 0, 0
             self.kc.ingest_keys(recv.data_ptr(), recv.numel() // words)
         out = self.kc.finish()
         mark()
@@ -343,8 +414,62 @@ class DistCounter:
                   f"phases={self.kc.stats().get('phases_ms')}", file=sys.stderr)
         return out
 
+    # -- output stage (main.rs:87-90 on N ranks): ONE ascending table / text stream
+    def merged(self, root=0):
+        """After finish(): the ranks' tables — disjoint key sets, each ascending — merged on `root`'s GPU into the table a
+        single GPU would have produced.  → on root a KmerCounter holding it (read / format / digest), None elsewhere.
+        Every rank calls this.  (The whole table must fit root's HBM twice; a range-partitioned count needs no merge —
+        its tables follow each other in rank order — but goes through the same call.)"""
+        if self.world == 1:
+            return self.kc
+        torch, dist = self.torch, self.dist
+        dev = torch.device("cuda", torch.cuda.current_device())
+        wide = self.key_bytes == 16
+        if self._empty or not getattr(self.kc, "n_distinct", 0):
+            cols = [torch.empty(0, dtype=torch.int64, device=dev) for _ in range(2 if wide else 1)]
+            cols.append(torch.empty(0, dtype=torch.int32, device=dev))
+        else:
+            lo, hi, cnt = self.kc.table_device()
+            n = self.kc.n_distinct
+            cols = [torch.as_tensor(_DevArray(lo, n), device=dev)]
+            if wide:
+                cols.append(torch.as_tensor(_DevArray(hi, n), device=dev))
+            cols.append(torch.as_tensor(_DevArray32(cnt, n), device=dev))
+        torch.cuda.current_stream().synchronize()
+        runs = gather_runs(torch, dist, cols, root)
+        if runs is None:
+            return None
+        torch.cuda.current_stream().synchronize()   # the received columns are read by libkmc's kernels next
+        if self._merger is None:
+            self._merger = KmerCounter(**self._kw)
+        self._merger.reset()
+        self._merger.merge_tables([(r[0].data_ptr() if r[0].numel() else 0, r[1].data_ptr() if wide and r[1].numel() else 0,
+                                    r[-1].data_ptr() if r[-1].numel() else 0, r[0].numel()) for r in runs])
+        return self._merger
+
+    def write_text(self, out, expanded, root=0, rows_per_call=1 << 22):
+        """The reference's output (main.rs:88-90; expanded: every key `count` times, else kmer<TAB>count) of the whole
+        multi-GPU job, written by `root` to the binary file object `out` (ignored on the other ranks)."""
+        kc = self.merged(root)
+        if kc is None:
+            return 0
+        written, first, step = 0, 0, rows_per_call
+        while first < kc.n_distinct:
+            n = min(step, kc.n_distinct - first)
+            try:
+                text = kc.format(first, n, expanded=expanded)
+            except KmcError as e:
+                if e.code != E_CAPACITY or n == 1:   # KMC_E_CAPACITY: huge multiplicities — fewer rows per call
+                    raise
+                step = max(1, n // 4)
+                continue
+            out.write(text)
+            written += len(text)
+            first += n
+        return written
+
     def digest(self):
-        return self.kc.digest()
+        return 0 if self._empty else self.kc.digest()
 
     def stats(self):
         return self.kc.stats()
@@ -362,4 +487,7 @@ class DistCounter:
             except Exception:
                 pass
         self._opened = []
+        if self._merger is not None:
+            self._merger.close()
+            self._merger = None
         self.kc.close()

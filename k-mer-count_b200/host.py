@@ -91,6 +91,7 @@ def load_library(path=None):
     L.kmc_table_route.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(vp), C.POINTER(vp)]
     L.kmc_ingest_pairs.argtypes = [vp, vp, vp, C.c_uint64]
     L.kmc_route_to_peers_part.argtypes = [vp, C.c_uint32, vp, C.c_uint64, vp, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.kmc_merge_tables.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, u64p, u64p]
     L.kmc_owner_begin.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     L.kmc_owner_feed.argtypes = [vp, vp, C.c_uint64]
     L.kmc_gen_bases.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
@@ -328,6 +329,23 @@ class KmerCounter:
         keys, counts = C.c_void_p(), C.c_void_p()
         self._ck(self._L.kmc_table_route(self._h, n_parts, begin.ctypes.data, count.ctypes.data, C.byref(keys), C.byref(counts)))
         return begin, count, keys.value, counts.value
+
+    # -- multi-GPU output stage
+    def merge_tables(self, runs):
+        """runs: [(d_key_lo, d_key_hi or 0, d_count, n_rows)] — ascending device tables with pairwise disjoint keys (the
+        owners' tables of a hash-partitioned count).  Their merge becomes this counter's table (main.rs:87-90 on N ranks:
+        one ascending stream).  → (n_distinct, n_total).  No run may be this counter's own table."""
+        m = len(runs)
+        lo = np.array([r[0] or 0 for r in runs], np.uint64)
+        hi = np.array([r[1] or 0 for r in runs], np.uint64)
+        cnt = np.array([r[2] or 0 for r in runs], np.uint64)
+        rows = np.array([r[3] for r in runs], np.uint64)
+        d, t = C.c_uint64(), C.c_uint64()
+        wide = self.key_bases > 32
+        self._ck(self._L.kmc_merge_tables(self._h, m, lo.ctypes.data, hi.ctypes.data if wide else None, cnt.ctypes.data,
+                                          rows.ctypes.data, C.byref(d), C.byref(t)))
+        self.n_distinct, self.n_total = d.value, t.value
+        return d.value, t.value
 
     # -- synthetic input on the device (csrc/kmc_gen.cuh; host twin: gen.py)
     def gen_bases(self, seed, first, n, d_out_ptr):

@@ -148,3 +148,42 @@ def test_finish_combined_merges_local_tables():
             assert k not in got
             got[k] = c
     assert got == dict(zip(want_k.tolist(), want_c.tolist()))
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kmer_count_b200.dist import agree_status, gather_runs
+    codes = agree_status(torch, dist, torch.device("cpu"), -5 if rank == 1 else 0)
+    n = [0, 7, 3][rank]                                   # rank 0 (the root) owns nothing: an empty run
+    cols = [torch.arange(n, dtype=torch.int64) + 100 * rank, torch.arange(n, dtype=torch.int64) + 1000 * rank,
+            torch.full((n,), rank + 1, dtype=torch.int32)]
+    runs = gather_runs(torch, dist, cols, root=0)
+    if rank == 0:
+        q.put((codes, [[c.tolist() for c in r] for r in runs]))
+    else:
+        assert runs is None
+        q.put((codes, None))
+    dist.destroy_process_group()
+
+
+def test_output_stage_transport_and_status_agreement():
+    """gather_runs brings every rank's table columns to the root (empty tables included); agree_status lets every rank
+    see that one shard failed (main.rs:23 on one rank) before any of them enters a collective."""
+    import kmer_count_b200 as K
+    K.build()
+    world, port = 3, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[0] == [0, -5, 0] for r in res)
+    runs = next(r[1] for r in res if r[1] is not None)
+    assert [len(r[0]) for r in runs] == [0, 7, 3]
+    assert runs[1][0] == list(range(100, 107)) and runs[1][1] == list(range(1000, 1007)) and runs[1][2] == [2] * 7
+    assert runs[2][0] == [200, 201, 202] and runs[2][2] == [3] * 3
