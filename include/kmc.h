@@ -179,22 +179,38 @@ int kmc_owner_begin(kmc_ctx *ctx, const uint64_t global_hist[4096], uint32_t n_o
 int kmc_owner_feed(kmc_ctx *ctx, const void *d_keys, uint64_t n_keys);
 /* ---- multi-GPU, range partition: the level-1 scatter of the counting pipeline done by the SENDERS --------
  * For high-cardinality input the hash route above costs an extra pass: owners re-scatter what they received.
- * Here the ranks agree on one plan for the whole key space and every sender's scatter kernel stores each key
- * straight into its level-1 bucket inside its owner's receive buffer (NVLink peer stores); owners run only the
- * second scatter and the per-bucket sort.  Owners hold consecutive key ranges of about equal population, so the
- * ranks' tables in rank order are the globally sorted table.  Per job, on every rank:
- *   kmc_submit* → kmc_dist_hist → [all-gather the histograms] → kmc_dist_plan → kmc_recv_buffer(need) (+ IPC
- *   exchange when a buffer moved) → kmc_dist_scatter → [all-reduce of `overflow` = rank barrier] → kmc_finish
+ * Here the ranks agree on one plan for the whole key space; every sender runs the ordinary level-1 scatter into a
+ * local staging array laid out owner by owner, and each owner's slab crosses NVLink as ONE device-to-device copy
+ * into the owner's receive buffer; owners run only the second scatter and the per-bucket sort.  Owners hold
+ * consecutive key ranges of about equal population, so the ranks' tables in rank order are the globally sorted
+ * table.  The input goes in n_chunks equal chunks: chunk c + 1 is scattered while chunk c is on the links and
+ * the owners work on chunk c - 1.  Per job, on every rank:
+ *   kmc_submit* → kmc_dist_hist → [all-gather the histograms] → kmc_dist_plan_chunks → kmc_recv_buffer(need) (+ IPC
+ *   exchange when a buffer moved) → for every chunk c: kmc_dist_scatter_part(c) [asynchronous], then
+ *   kmc_dist_scatter_wait(c) → [rank barrier: everybody's chunk c has landed] → kmc_dist_owner_part(c);
+ *   → kmc_dist_scatter_end → [all-reduce of `overflow`] → kmc_finish
  * kmc_dist_hist: upper-estimate histogram of this rank's keys over the top 12 key bits (4096 bins; sampled), and
  *   whether its input looks low-cardinality (then the hash route + hash table is the better path).
- * kmc_dist_plan: all_hist = the `world` histograms in rank order (identical on every rank, so every rank derives
- *   the same plan).  need_bytes[r] = receive-buffer size rank r must provide (kmc_recv_buffer); all zero when the
- *   job does not suit the plan (tiny, or keys sharing long prefixes) — use the hash route then.
- * kmc_dist_scatter: d_peer_buf[r] = rank r's receive buffer as mapped in this process.  *overflow != 0: a bucket
- *   exceeded its planned capacity; all ranks must then recount through the hash route (input is still resident).
+ * kmc_dist_plan_chunks: all_hist = the `world` histograms in rank order (identical on every rank, so every rank
+ *   derives the same plan).  need_bytes[r] = receive-buffer size rank r must provide (kmc_recv_buffer); all zero
+ *   when the job does not suit the plan (tiny, or keys sharing long prefixes) — use the hash route then.
+ *   kmc_dist_plan = one chunk.
+ * kmc_dist_scatter_part: d_peer_buf[r] = rank r's receive buffer as mapped in this process; chunks in order.
+ * kmc_dist_scatter_wait: returns when this rank's copies of that chunk have landed in the owners' buffers.
+ * kmc_dist_owner_part: this rank's level-2 scatter over a chunk every sender has delivered (optional: what has not
+ *   been handed over chunk by chunk is done by kmc_finish).
+ * kmc_dist_scatter_end: *overflow != 0: a bucket exceeded its planned capacity; all ranks must then recount through
+ *   the hash route (input is still resident).
+ * kmc_dist_scatter: all chunks, then kmc_dist_scatter_end (no overlap with the owners; one-call form).
  * kmc_finish afterwards counts what the senders stored in this rank's receive buffer.                         */
 int kmc_dist_hist(kmc_ctx *ctx, uint64_t hist[4096], uint32_t *low_cardinality);
 int kmc_dist_plan(kmc_ctx *ctx, uint32_t world, uint32_t rank, const uint64_t *all_hist, uint64_t *need_bytes);
+int kmc_dist_plan_chunks(kmc_ctx *ctx, uint32_t world, uint32_t rank, const uint64_t *all_hist, uint32_t n_chunks,
+                         uint64_t *need_bytes);
+int kmc_dist_scatter_part(kmc_ctx *ctx, void *const *d_peer_buf, uint32_t chunk);
+int kmc_dist_scatter_wait(kmc_ctx *ctx, uint32_t chunk);
+int kmc_dist_owner_part(kmc_ctx *ctx, uint32_t chunk);
+int kmc_dist_scatter_end(kmc_ctx *ctx, uint32_t *overflow);
 int kmc_dist_scatter(kmc_ctx *ctx, void *const *d_peer_buf, uint32_t *overflow);
 /* Library-owned device buffer for received keys (grow-only; 16 bytes per key in 128-bit mode).      */
 int kmc_recv_buffer(kmc_ctx *ctx, uint64_t n_keys, void **d_ptr);

@@ -178,6 +178,7 @@ class DistCounter:
         self._empty = False   # this rank owns no key of the last job (its ctx holds no table)
         self._kw = dict(k=k, canonical=canonical, strategy=strategy, device=device, **kw)
         self._merger = None
+        self._side = self._flag = None
         self.n_bases = 0
         self.key_bytes = 8 if self.key_bits <= 64 else 16
         self.use_peer = world > 1 and kw.get("mode", 0) == 0 and os.environ.get("KMC_DIST_EXCHANGE", "peer") == "peer"
@@ -293,33 +294,45 @@ class DistCounter:
             min_cap = int(worst * n_chunks / (c + 1) * 1.05) + 4096
         raise RuntimeError("kmc dist: a receive region overflowed twice")
 
-    def _finish_range(self):
-        """Range partition (kmc_dist_*): the senders' scatter kernels store every key straight into its level-1 bucket
-        in its owner's receive buffer; the owners run only the second scatter and the bucket sort.  None = this job does
-        not suit it (every rank comes to the same conclusion) and goes through the hash route instead."""
+    def _handover(self):
+        """Rank barrier that does not queue behind this rank's own kernels: a one-word all-reduce on a side stream."""
+        torch, dist = self.torch, self.dist
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+            self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self._flag)
+        self._side.synchronize()
+
+    def _finish_range(self, allv):
+        """Range partition (kmc_dist_*): every sender runs the level-1 scatter locally, laid out owner by owner, and each
+        owner's slab crosses NVLink as one copy; the owners run only the second scatter and the bucket sort.  The input
+        goes in chunks: chunk c + 1 is scattered while chunk c is on the links and the owners work on chunk c - 1.
+        None = this job does not suit it (every rank comes to the same conclusion) and goes through the hash route."""
         torch, dist = self.torch, self.dist
         dev = torch.device("cuda", torch.cuda.current_device())
-        hist, low = self.kc.dist_hist()
-        # one all-gather per job: the histograms every rank plans from, plus what decides the fall-backs.  It is also the
-        # point after which nobody is still reading its receive buffer from the previous job.
-        mine = np.concatenate([hist, np.array([int(low), self._map[0]], np.uint64)])
-        send = torch.from_numpy(mine.view(np.int64)).to(dev)
-        allv = torch.empty(self.world * send.numel(), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allv, send)
-        allv = allv.cpu().numpy().view(np.uint64).reshape(self.world, -1)
-        self._mark()
+        # allv: every rank's histogram | low-cardinality flag | receive-buffer bytes | shard size (finish's all-gather)
         if allv[:, 4096].any():
             return None                          # low-cardinality input somewhere: hash route + hash table
-        need = self.kc.dist_plan(self.world, self.rank, allv[:, :4096])
+        n_chunks = int(os.environ.get("KMC_DIST_CHUNKS", "6")) if int(allv[:, 4098].max()) >= (1 << 26) else 1
+        need = self.kc.dist_plan(self.world, self.rank, allv[:, :4096], n_chunks)
         if not need.all():
             return None
         if (need > allv[:, 4097]).any():         # some rank's buffer must grow; every rank sees that
             self._map_buffers(int(need[self.rank]))
         self._mark()
-        overflow = self.kc.dist_scatter(self._map[2])
+        bufs = self._map[2]
+        self.kc.dist_scatter_part(bufs, 0)
+        for c in range(n_chunks):
+            if c + 1 < n_chunks:
+                self.kc.dist_scatter_part(bufs, c + 1)
+            self.kc.dist_scatter_wait(c)         # my copies of chunk c have landed ...
+            self._handover()                     # ... and so have everybody else's
+            self.kc.dist_owner_part(c)
+        overflow = self.kc.dist_scatter_end()
         self._mark()
         flag = torch.tensor([int(overflow)], dtype=torch.int64, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)   # the hand-over point: every rank's scatter kernel is done
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
         if int(flag):
             return None
         self._mark()
@@ -342,8 +355,10 @@ class DistCounter:
         if self.use_peer:
             # one all-gather per job: every rank's sampled coarse histogram (the owners plan their counts from the sum)
             # and its cardinality probe (the combine route is taken only if every rank's shard is low-cardinality)
+            # (+ the size of its receive buffer and of its shard: what the range partition plans from).  It is also the
+            # point after which nobody is still reading its receive buffer from the previous job.
             hist, low = self.kc.dist_hist()
-            mine = np.concatenate([hist, np.array([int(low)], np.uint64)])
+            mine = np.concatenate([hist, np.array([int(low), self._map[0], self.n_bases], np.uint64)])
             send = torch.from_numpy(mine.view(np.int64)).to(dev)
             allv = torch.empty(self.world * send.numel(), dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(allv, send)
@@ -355,7 +370,7 @@ class DistCounter:
                 return finish_combined(self.kc, torch, dist, self.world, dev, self._keep)
             global_hist = allv[:, :4096].sum(axis=0)
         if self.use_range:
-            out = self._finish_range()
+            out = self._finish_range(allv)
             if out is not None:
                 self.path = "range"
                 if _PROF:

@@ -26,7 +26,9 @@ SYMBOLS = ["kmc_create", "kmc_destroy", "kmc_last_error", "kmc_strerror", "kmc_s
            "kmc_stats_json", "kmc_route_to_peers", "kmc_recv_buffer", "kmc_ipc_export", "kmc_ipc_open",
            "kmc_ipc_close", "kmc_submit_fasta", "kmc_format", "kmc_finish_part",
            "kmc_dist_hist", "kmc_dist_plan", "kmc_dist_scatter", "kmc_table_route", "kmc_ingest_pairs",
-           "kmc_gen_bases", "kmc_gen_nruns", "kmc_gen_reads", "kmc_route_to_peers_part", "kmc_owner_begin", "kmc_owner_feed"]
+           "kmc_gen_bases", "kmc_gen_nruns", "kmc_gen_reads", "kmc_route_to_peers_part", "kmc_owner_begin", "kmc_owner_feed",
+           "kmc_merge_tables", "kmc_dist_plan_chunks", "kmc_dist_scatter_part", "kmc_dist_scatter_wait", "kmc_dist_owner_part",
+           "kmc_dist_scatter_end"]
 
 
 class KmcConfig(C.Structure):
@@ -85,6 +87,11 @@ def load_library(path=None):
     L.kmc_dist_hist.argtypes = [vp, vp, C.POINTER(C.c_uint32)]
     L.kmc_dist_plan.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp]
     L.kmc_dist_scatter.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint32)]
+    L.kmc_dist_plan_chunks.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp]
+    L.kmc_dist_scatter_part.argtypes = [vp, C.POINTER(vp), C.c_uint32]
+    L.kmc_dist_scatter_wait.argtypes = [vp, C.c_uint32]
+    L.kmc_dist_owner_part.argtypes = [vp, C.c_uint32]
+    L.kmc_dist_scatter_end.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.kmc_ipc_export.argtypes = [vp, vp, C.c_char_p]
     L.kmc_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.kmc_ipc_close.argtypes = [vp, vp]
@@ -284,14 +291,34 @@ class KmerCounter:
         self._ck(self._L.kmc_dist_hist(self._h, h.ctypes.data, C.byref(low)))
         return h, bool(low.value)
 
-    def dist_plan(self, world, rank, all_hist):
+    def dist_plan(self, world, rank, all_hist, n_chunks=1):
         """all_hist: (world, 4096) uint64, the same on every rank → bytes every rank's receive buffer must have
-        (all zero: the job does not suit the range partition)."""
+        (all zero: the job does not suit the range partition).  n_chunks: the input is scattered and exchanged in that
+        many pieces (dist_scatter_part / dist_scatter_wait / dist_owner_part per piece)."""
         ah = np.ascontiguousarray(all_hist, dtype=np.uint64)
         assert ah.shape == (world, 4096)
         need = np.zeros(world, np.uint64)
-        self._ck(self._L.kmc_dist_plan(self._h, world, rank, ah.ctypes.data, need.ctypes.data))
+        self._ck(self._L.kmc_dist_plan_chunks(self._h, world, rank, ah.ctypes.data, n_chunks, need.ctypes.data))
         return need
+
+    def dist_scatter_part(self, peer_bufs, chunk):
+        """Asynchronous: level-1 scatter of input chunk `chunk`, then its slabs' copies into the owners' buffers."""
+        arr = (C.c_void_p * len(peer_bufs))(*[int(p) for p in peer_bufs])
+        self._ck(self._L.kmc_dist_scatter_part(self._h, arr, chunk))
+
+    def dist_scatter_wait(self, chunk):
+        """Block until this rank's copies of `chunk` have landed."""
+        self._ck(self._L.kmc_dist_scatter_wait(self._h, chunk))
+
+    def dist_owner_part(self, chunk):
+        """Owner side: level-2 scatter over `chunk` (every sender has delivered it), on the ctx's second stream."""
+        self._ck(self._L.kmc_dist_owner_part(self._h, chunk))
+
+    def dist_scatter_end(self):
+        """→ True if one of this rank's buckets overflowed (every rank must then take the hash route)."""
+        ov = C.c_uint32()
+        self._ck(self._L.kmc_dist_scatter_end(self._h, C.byref(ov)))
+        return bool(ov.value)
 
     def dist_scatter(self, peer_bufs):
         """Level-1 scatter of this rank's keys into the owners' receive buffers → True if a bucket overflowed."""

@@ -26,7 +26,7 @@ def _shards(bases, off, world):
         yield bases[int(off[a]):int(off[z])], (off[a:z + 1] - off[a]).astype(np.uint64)
 
 
-def _run(kmc, bases, off, k, canonical, world, strategy=2):
+def _run(kmc, bases, off, k, canonical, world, strategy=2, n_chunks=1):
     import torch
     key_bytes = 8 if k <= 32 else 16
     ctxs = [kmc.KmerCounter(k=k, canonical=canonical, strategy=strategy) for _ in range(world)]
@@ -37,14 +37,29 @@ def _run(kmc, bases, off, k, canonical, world, strategy=2):
             h, low = kc.dist_hist()
             hists.append(h); lows.append(low)
         all_hist = np.stack(hists)
-        needs = [kc.dist_plan(world, r, all_hist) for r, kc in enumerate(ctxs)]
+        needs = [kc.dist_plan(world, r, all_hist, n_chunks) for r, kc in enumerate(ctxs)]
         for nd in needs[1:]:
             assert np.array_equal(nd, needs[0])          # every rank derives the same plan
         if not needs[0].all():
             return None, lows, needs[0]
         bufs = [kc.recv_buffer(int(needs[0][r]) // key_bytes + 1) for r, kc in enumerate(ctxs)]
-        for kc in ctxs:
-            assert not kc.dist_scatter(bufs)
+        if n_chunks == 1:
+            for kc in ctxs:
+                assert not kc.dist_scatter(bufs)             # the one-call form; the owners do everything in finish()
+        else:
+            # the pipelined form, as dist.py drives it: chunk c + 1 is scattered before chunk c is handed over
+            for kc in ctxs:
+                kc.dist_scatter_part(bufs, 0)
+            for c in range(n_chunks):
+                for kc in ctxs:
+                    if c + 1 < n_chunks:
+                        kc.dist_scatter_part(bufs, c + 1)
+                for kc in ctxs:
+                    kc.dist_scatter_wait(c)                  # every "rank"'s chunk c has landed: the hand-over
+                for kc in ctxs[: world - 1]:                 # (the last owner leaves its chunks to finish())
+                    kc.dist_owner_part(c)
+            for kc in ctxs:
+                assert not kc.dist_scatter_end()
         torch.cuda.synchronize()
         his, los, cnts, totals, ranges = [], [], [], 0, []
         for kc in ctxs:
@@ -76,6 +91,21 @@ def test_range_partition_emulated(kmc, orc, k, canonical, world, n):
     assert got is not None
     assert_tables_equal(got, want)                       # rank order = key order: the concatenation is sorted
     assert max(per_rank) < 1.06 * want.n_total / world + 65536, per_rank   # equal population
+
+
+@pytest.mark.parametrize("k,world,n,n_chunks", [(21, 4, 14_000_000, 3), (31, 2, 8_000_000, 6), (63, 3, 9_000_000, 2), (21, 8, 20_000_000, 4)])
+def test_range_partition_chunked_emulated(kmc, orc, k, world, n, n_chunks):
+    """The exchange in chunks (scatter chunk c + 1 while chunk c is copied and chunk c - 1 is taken up by its owners)
+    leaves the same tables."""
+    rng = np.random.default_rng(7 * k + world)
+    bases = ACGT[rng.integers(0, 4, n)]
+    for s in rng.integers(0, n - 200, n // 20000):
+        bases[s:s + int(rng.integers(1, 90))] = ord("N")
+    off = np.unique(np.append(np.arange(0, n, 1500), n)).astype(np.uint64)
+    want = orc.contiguous_mt(bases, off, k, True)
+    got, lows, per_rank = _run(kmc, bases, off, k, True, world, n_chunks=n_chunks)
+    assert got is not None
+    assert_tables_equal(got, want)
 
 
 def test_range_partition_declines(kmc):
