@@ -97,6 +97,11 @@ def main(argv=None):
     import kmer_count_b200 as K
     from kmer_count_b200.dist import DistCounter, agree_status
     o = parse_args(sys.argv[1:] if argv is None else argv)
+    # stdout carries the program's output and nothing else (main.rs:88-90): whatever libraries print there (NCCL's version
+    # banner) goes to stderr, the text to the saved descriptor
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -105,10 +110,17 @@ def main(argv=None):
     K.build()
 
     def leave(status):
+        # under torchrun a non-zero exit of any rank becomes the launcher's own status 1: the program's status (101 when
+        # the reference would have panicked) goes through the file the C++ launcher named, and the ranks leave with 0
+        path = os.environ.get("KMC_CLI_STATUS")
+        if path and rank == 0:
+            with open(path, "w") as f:
+                f.write(str(status))
         if world > 1:
             dist.destroy_process_group()
         sys.stdout.flush()
-        os._exit(status)
+        sys.stderr.flush()
+        os._exit(0 if path else status)
 
     try:
         text = np.fromfile(o["fasta"], dtype=np.uint8)
@@ -145,12 +157,10 @@ def main(argv=None):
         leave(101)
     out = None
     if rank == 0:   # opened after the count: the reference prints nothing when it panics
-        out = open(o["out"], "wb") if o["out"] else sys.stdout.buffer
+        out = open(o["out"], "wb") if o["out"] else os.fdopen(out_fd, "wb")
     dc.write_text(out, expanded=o["mode"] == 1 and o["expanded"])
     if rank == 0:
-        out.flush()
-        if o["out"]:
-            out.close()
+        out.close()
     dc.close()
     leave(0)
 

@@ -79,6 +79,7 @@ struct DistPlan {
   bool valid = false, scattered = false, owner_ready = false;
   uint32_t world = 0, rank = 0, b1 = 0, n_all = 0; // n_all = 2^b1 level-1 buckets over the whole key space
   uint32_t n_chunks = 1, chunks_sent = 0, chunks_owned = 0;
+  uint32_t fine_cap = 0;                           // capacity of a fine bucket's element buffer in fast_finish for this plan
   std::vector<uint32_t> own_lo;                    // [world+1] first level-1 bucket of every owner
   // sender view: capacity of MY region of bucket b (per chunk) and its offset inside my slab at b's owner; per owner:
   // where my slab starts inside a chunk of its array, the slab's length, the length of one chunk of its array, and
@@ -1542,7 +1543,7 @@ int dist_hist_impl(kmc_ctx *c, uint64_t *hist_out, uint32_t *low_cardinality) {
 template <typename KeyT>
 int dist_plan_impl(kmc_ctx *c, uint32_t world, uint32_t rank, const uint64_t *all_hist, uint32_t n_chunks, uint64_t *need_bytes) {
   constexpr bool kWide = sizeof(KeyT) == 16;
-  const int kTarget = kWide ? 3200 : kFineTarget64; // <= kFineTarget: fits whichever element width the owners end up with
+  int kTarget = kWide ? 3200 : kFineTarget;
   const uint32_t kb = c->key_bits, cb = coarse_bits(c), ncoarse = 1u << cb;
   DistPlan &D = c->dist;
   D.valid = false; D.scattered = false;
@@ -1556,7 +1557,20 @@ int dist_plan_impl(kmc_ctx *c, uint32_t world, uint32_t rank, const uint64_t *al
   // at least 64 level-1 buckets per owner, so that owners can be balanced to a few percent
   uint32_t b1_min = 6;
   while ((1u << (b1_min - 6)) < world) b1_min++;
-  if (!plan_shape(G, kb, 0, ncoarse, false, kTarget, shape, b1_min, getenv("KMC_NO_SPLIT64") ? 0u : split64_min_e(kb, n_est, kWide))) return KMC_OK;
+  const uint32_t min_e = getenv("KMC_NO_SPLIT64") ? 0u : split64_min_e(kb, n_est, kWide);
+  if (!plan_shape(G, kb, 0, ncoarse, false, kTarget, shape, b1_min, min_e)) return KMC_OK;
+  D.fine_cap = kWide ? 4096 : kFineCap;
+  if (!kWide && (kFineCap64 != kFineCap || kFineTarget64 != kFineTarget)) {
+    // buckets that leave more than 32 key bits are sorted as 64-bit elements, whose bucket shape is smaller: plan again
+    // (as fast_begin does; every rank sees the same global histogram, so every rank decides the same)
+    bool wide_elems = false;
+    for (uint32_t b = 0; b < shape.n_l1; b++) if (kb - shape.b1 - shape.l1e[b] > 32) wide_elems = true;
+    if (wide_elems) {
+      kTarget = kFineTarget64;
+      D.fine_cap = kFineCap64;
+      if (!plan_shape(G, kb, 0, ncoarse, false, kTarget, shape, b1_min, min_e)) return KMC_OK;
+    }
+  }
   const uint32_t b1 = shape.b1, n_all = 1u << b1, cshift = cb - b1;
   if (n_all < world) return KMC_OK;
   // owners: consecutive level-1 buckets, about equal population
@@ -1628,9 +1642,9 @@ struct StreamSwap {   // helpers launch on c->stream: run them on another stream
 template <typename KeyT>
 int dist_owner_begin(kmc_ctx *c) {
   constexpr bool kWide = sizeof(KeyT) == 16;
-  constexpr int kCap = kWide ? 4096 : kFineCap64; // <= kFineCap
   DistPlan &D = c->dist;
   DistOwner &O = D.owner;
+  const int kCap = (int)D.fine_cap;
   const uint32_t kb = c->key_bits, cb = coarse_bits(c), b1 = D.b1, cshift = cb - b1, world = D.world, C = D.n_chunks;
   const uint32_t my_lo = D.own_lo[D.rank], my_n = D.own_lo[D.rank + 1] - my_lo, n_xc = my_n * world, n_x = n_xc * C, n_cb = my_n << cshift;
   if (!c->recv_keys.p || c->recv_keys.cap < kDistHeader + (D.l1_keys + 2 * kMaxTile) * sizeof(KeyT))

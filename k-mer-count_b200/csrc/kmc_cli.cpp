@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 
+#include <sys/wait.h>
 #include <unistd.h>
 
 #include "../../include/kmc.h"
@@ -56,7 +57,7 @@ void usage() {
 }
 
 // --gpus N (N > 1): one process per GPU.  This program is one process on one GPU; the multi-GPU job is run by the
-// Python host side over the same C ABI (cli_dist.py), launched with torchrun.  Does not return when it hands over.
+// Python host side over the same C ABI (cli_dist.py), launched with torchrun as a child.  Does not return when it hands over.
 void maybe_hand_over_to_ranks(int argc, char **argv) {
   int gpus = 1, at = -1;
   for (int i = 1; i + 1 < argc; i++) if (!strcmp(argv[i], "--gpus")) { gpus = atoi(argv[i + 1]); at = i; }
@@ -79,9 +80,24 @@ void maybe_hand_over_to_ranks(int argc, char **argv) {
   std::vector<char *> av;
   for (auto &x : a) av.push_back(const_cast<char *>(x.c_str()));
   av.push_back(nullptr);
-  execvp(av[0], av.data());
-  perror("kmer-count: cannot start python3 -m torch.distributed.run");
-  exit(3);
+  // torchrun turns any failing rank into its own exit status 1, so the ranks report the program's status — 101 when
+  // the reference would have panicked — through a file and leave with 0
+  char status_path[] = "/tmp/kmer-count-status-XXXXXX";
+  int sfd = mkstemp(status_path);
+  if (sfd >= 0) { close(sfd); setenv("KMC_CLI_STATUS", status_path, 1); }
+  pid_t pid = fork();
+  if (pid == 0) {
+    execvp(av[0], av.data());
+    perror("kmer-count: cannot start python3 -m torch.distributed.run");
+    _exit(3);
+  }
+  int st = 0, code = 3;
+  if (pid > 0 && waitpid(pid, &st, 0) == pid) code = WIFEXITED(st) ? WEXITSTATUS(st) : 3;
+  if (sfd >= 0) {
+    if (FILE *f = fopen(status_path, "r")) { int v = -1; if (fscanf(f, "%d", &v) == 1 && v >= 0) code = v; fclose(f); }
+    unlink(status_path);
+  }
+  exit(code);
 }
 
 Options parse_args(int argc, char **argv) {

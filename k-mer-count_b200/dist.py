@@ -1,10 +1,12 @@
 """Multi-GPU host logic: one process per GPU, reads sharded across ranks, every key sent to the GPU that owns
 it.  Two partitions of the key space:
-  * hash (default): owner = hash prefix; the routing kernel stores keys into per-source regions of the owner's buffer
-    over NVLink (or they are exchanged with an NCCL all-to-all), and the owner counts what it received;
-  * range (KMC_DIST_PARTITION=range): owners hold consecutive key ranges of equal population, chosen from the
-    all-gathered coarse histograms; the senders' scatter kernels store keys straight into their level-1 bucket inside
-    the owner's buffer, so the exchange IS the first pass of the count and the ranks' tables are globally sorted.
+  * range (default for contiguous mode): owners hold consecutive key ranges of equal population, chosen from the
+    all-gathered coarse histograms; every sender runs the counting pipeline's level-1 scatter locally, laid out owner
+    by owner, the slabs cross NVLink as bulk copies while the next chunk is scattered, and the owners run only the
+    level-2 scatter and the bucket sort — the exchange costs no extra pass and the ranks' tables are globally sorted;
+  * hash (KMC_DIST_PARTITION=hash; lr-gapped mode; what the range partition declines): owner = hash prefix; the routing
+    kernel stores keys into per-source regions of the owner's buffer over NVLink (or they are exchanged with an NCCL
+    all-to-all), and the owner counts what it received;
 `torch.distributed` carries only histograms, counts and the rank barrier (NCCL on the GPU box; gloo in the CPU tests of
 the routing arithmetic); everything either side of it is libkmc through its C ABI."""
 import os
@@ -182,11 +184,11 @@ class DistCounter:
         self.n_bases = 0
         self.key_bytes = 8 if self.key_bits <= 64 else 16
         self.use_peer = world > 1 and kw.get("mode", 0) == 0 and os.environ.get("KMC_DIST_EXCHANGE", "peer") == "peer"
-        # KMC_DIST_PARTITION=range: owners hold key ranges and the senders do the level-1 scatter (see _finish_range).
-        # Measured on B200 x2 it is as fast as the hash route (26.1 vs 26.0 ms/step): the owners skip their level-1
-        # scatter (-4.6 ms), but the senders' NVLink stores now come in runs of ~250 B instead of ~16 KB and reach
-        # 360 instead of 535 GB/s (+3.5 ms), and with more GPUs the runs only get shorter.  Default: hash.
-        self.use_range = self.use_peer and strategy in (0, 2) and os.environ.get("KMC_DIST_PARTITION", "hash") == "range"
+        # Range partition (default for contiguous mode; KMC_DIST_PARTITION=hash switches it off): owners hold key ranges, the
+        # senders do the level-1 scatter locally and the slabs cross NVLink as bulk copies (see _finish_range).  Measured on
+        # B200 x2, cfg2 per GPU: 18.8 ms/step against 24.0 through the hash route (owners re-scatter what they received)
+        # and 15.96 on one GPU.  Jobs it declines (small, low-cardinality, keys sharing long prefixes) take the hash route.
+        self.use_range = self.use_peer and strategy in (0, 2) and os.environ.get("KMC_DIST_PARTITION", "range") == "range"
         # KMC_DIST_COMBINE=1 (opt-in until it has been measured on a multi-GPU box): when every rank's input is
         # low-cardinality — the hash strategy's case — count locally and exchange table rows (finish_combined)
         self.use_combine = (world > 1 and kw.get("mode", 0) == 0 and self.key_bytes == 8 and strategy in (0, 1)
@@ -314,7 +316,7 @@ class DistCounter:
         # allv: every rank's histogram | low-cardinality flag | receive-buffer bytes | shard size (finish's all-gather)
         if allv[:, 4096].any():
             return None                          # low-cardinality input somewhere: hash route + hash table
-        n_chunks = int(os.environ.get("KMC_DIST_CHUNKS", "6")) if int(allv[:, 4098].max()) >= (1 << 26) else 1
+        n_chunks = int(os.environ.get("KMC_RANGE_CHUNKS", "8")) if int(allv[:, 4098].max()) >= int(os.environ.get("KMC_RANGE_CHUNK_MIN", 1 << 26)) else 1
         need = self.kc.dist_plan(self.world, self.rank, allv[:, :4096], n_chunks)
         if not need.all():
             return None

@@ -48,14 +48,18 @@ def main():
     K.build()
     n = int(a.bases)
     cases = [
-        dict(name="hash-peer k21", k=21, seed=21, n=n),
-        dict(name="hash-peer k31", k=31, seed=31, n=n),
-        dict(name="hash-peer k63 ragged+N", k=63, seed=63, n=n, ragged=True),
-        dict(name="range k31", k=31, seed=32, n=n, env={"KMC_DIST_PARTITION": "range"}),
+        dict(name="range k21", k=21, seed=21, n=n),
+        dict(name="range k31", k=31, seed=32, n=n),
+        dict(name="range k63 ragged+N", k=63, seed=63, n=n, ragged=True),
+        dict(name="range k31, 4 chunks", k=31, seed=33, n=n, env={"KMC_RANGE_CHUNKS": "4", "KMC_RANGE_CHUNK_MIN": "1"}),
+        dict(name="hash-peer k21", k=21, seed=21, n=n, env={"KMC_DIST_PARTITION": "hash"}),
+        dict(name="hash-peer k31", k=31, seed=31, n=n, env={"KMC_DIST_PARTITION": "hash"}),
+        dict(name="hash-peer k63 ragged+N", k=63, seed=63, n=n, ragged=True, env={"KMC_DIST_PARTITION": "hash"}),
         dict(name="nccl-route k21", k=21, seed=22, n=n // 4, strategy=2, env={"KMC_DIST_EXCHANGE": "nccl"}),
         dict(name="combine k31 low-cardinality", k=31, seed=51, n=n, genome=300_000),
         dict(name="lr-gapped 27+27", mode=1, seed=71, n=60_000),
-        dict(name="skewed shard (region overflow)", k=21, seed=81, n=n // 2, skew=True),
+        dict(name="skewed shard (region overflow)", k=21, seed=81, n=n // 2, skew=True, env={"KMC_DIST_PARTITION": "hash"}),
+        dict(name="skewed shard, default route", k=21, seed=82, n=n // 2, skew=True),
     ]
     failed = 0
     for case in cases:
