@@ -154,6 +154,12 @@ struct kmc_ctx {
   bool range_on = false;
   uint32_t range_lo = 0, range_n = 0;
   std::vector<uint64_t> part_hist; // raw (sampled) counts per coarse bin
+  // ... and, for contiguous input, ALL keys scattered once by their top bits (kmc_finish_part, first call): every part is
+  // then counted from its slice of this array instead of extracting the whole input again
+  bool kept_valid = false, kept_tried = false;
+  uint32_t kept_b1 = 0;
+  std::vector<uint64_t> kept_start, kept_count; // per top-bits bucket: key index in kept_keys, keys
+  DevBuf kept_keys, kept_tables, kept_state;
   uint32_t part_hist_step = 0;     // sampling step of part_hist; 0 = not computed yet
 
   // multi-GPU range partition (kmc_dist_*): plan shared by all ranks, this rank's views of it
@@ -374,6 +380,7 @@ int new_segment(kmc_ctx *c, Segment **out) {
   s.bases = nullptr; s.rec_off = nullptr; s.n_bases = s.n_recs = 0;
   s.off_shift = 0; s.host_alias = nullptr; s.wait_ready = false;
   c->part_hist_step = 0; // new input: the partial-count histogram is stale
+  c->kept_valid = false; c->kept_tried = false;
   *out = &s;
   return KMC_OK;
 }
@@ -1486,6 +1493,80 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
   return fast_end<KeyT>(c, incremental, used);
 }
 
+// ---- partial counts of one input (kmc_finish_part): all keys scattered ONCE by their top bits --------------------------
+// A job too large to be counted in one go (1e10 bases at k=31: level-1 + level-2 arrays + table exceed HBM) is counted
+// in key ranges.  Extracting the whole input again for every range cost 47 ms x 8 of 634 ms at that size; instead the
+// first call runs the level-1 scatter kernel once over everything, 2^b1 buckets by key prefix (74 GB of keys fit beside
+// the 10 GB of bases), and part p is then counted from the buckets of its range through the key-array front end.
+template <typename KeyT>
+int kept_scatter(kmc_ctx *c) {
+  const uint32_t kb = c->key_bits, cb = coarse_bits(c), ncoarse = 1u << cb;
+  const uint32_t b1 = std::min<uint32_t>(cb, (uint32_t)env_int("KMC_KEPT_BITS", 8)), n_l1 = 1u << b1, cshift = cb - b1;
+  c->kept_valid = false;
+  c->kept_start.assign(n_l1 + 1, 0); c->kept_count.assign(n_l1, 0);
+  std::vector<uint64_t> cap(n_l1, 0);
+  uint64_t total = 0;
+  for (uint32_t b = 0; b < n_l1; b++) {
+    double nb = 0;
+    for (uint32_t ci = b << cshift; ci < ((b + 1) << cshift) && ci < ncoarse; ci++) {
+      double est = (double)c->part_hist[ci] * c->part_hist_step;
+      if (c->part_hist_step > 1) est += 5.0 * std::sqrt(est * c->part_hist_step) + c->part_hist_step;
+      nb += est;
+    }
+    cap[b] = ((uint64_t)(nb * 1.02) + 8192 + 15) & ~15ull;
+    c->kept_start[b] = total;
+    total += cap[b];
+  }
+  c->kept_start[n_l1] = total;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t need = (total + 2 * kMaxTile) * sizeof(KeyT);
+  // room for the array AND for one part's own buffers afterwards, or the old way (extract per part) is the only way
+  if (need > c->kept_keys.cap && need + need / 2 > free_b + c->kept_keys.cap) return KMC_OK;
+  TRY(ensure(c, c->kept_keys, need));
+  auto al16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+  const size_t o_s = 0, o_c = al16((size_t)(n_l1 + 1) * 8), tab_bytes = o_c + al16((size_t)n_l1 * 8);
+  std::vector<unsigned char> host(tab_bytes, 0);
+  memcpy(host.data() + o_s, c->kept_start.data(), (size_t)(n_l1 + 1) * 8);
+  memcpy(host.data() + o_c, cap.data(), (size_t)n_l1 * 8);
+  TRY(ensure(c, c->kept_tables, tab_bytes));
+  TRY(ensure(c, c->kept_state, (size_t)kMaxL1 * 8 + 64));
+  TRY(zero_scalars(c));
+  CK(cudaMemsetAsync(c->kept_state.p, 0, (size_t)kMaxL1 * 8, c->stream));
+  TRY(h2d_small(c, c->kept_tables.p, host.data(), tab_bytes));
+  FastPlan pl{};
+  pl.kb = kb; pl.b1 = b1; pl.n_l1 = n_l1; pl.l1_base = 0; pl.l1_trash = total;
+  pl.l1_start = (const uint64_t *)((unsigned char *)c->kept_tables.p + o_s);
+  pl.l1_cap = (const uint64_t *)((unsigned char *)c->kept_tables.p + o_c);
+  pl.l1_cursor = (unsigned long long *)c->kept_state.p;
+  PHASE_BEGIN("kept_scatter");
+  {
+    size_t smem = L1Smem<KeyT>::bytes(part1_stage<KeyT>(), n_l1);
+    auto fast_part1 = fast_part1_kernel<KeyT, true, PrefixBucket>;
+    CK(cudaFuncSetAttribute(fast_part1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const PrefixBucket bucket = make_prefix_bucket<false>(kb, b1);
+    for (size_t i = 0; i < c->n_segs; i++) {
+      Segment &s = c->segs[i];
+      if (!s.n_bases) continue;
+      TRY(seg_wait(c, s));
+      ExtractParams P = seg_params(c, s);
+      const uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>()), n_ct = (tiles + kFastWarps - 1) / kFastWarps;
+      LAUNCH(fast_part1, (uint32_t)std::min<uint64_t>(n_ct, (uint64_t)c->n_sms), kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->kept_keys.p,
+             d_err(c), (uint64_t)0, n_ct);
+    }
+  }
+  PHASE_END();
+  std::vector<unsigned long long> cur(n_l1);
+  uint32_t err = 0;
+  TRY(d2h_small(c, cur.data(), pl.l1_cursor, (size_t)n_l1 * 8));
+  TRY(read_scalars(c, nullptr, &err));
+  if (err & kFlagOverflow) { TRY(zero_scalars(c)); return KMC_OK; } // skewed beyond the estimate: the old way
+  for (uint32_t b = 0; b < n_l1; b++) c->kept_count[b] = cur[b];
+  c->kept_b1 = b1;
+  c->kept_valid = true;
+  return KMC_OK;
+}
+
 // ---- multi-GPU: range partition, the level-1 scatter done by the SENDERS, the exchange by the copy engines --
 // Every rank holds a shard of the reads.  Instead of routing keys to owners by hash and letting every owner run the
 // level-1 scatter over what it received (an extra pass over all keys), the ranks agree on ONE plan for the whole key
@@ -1504,8 +1585,17 @@ int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
 //   [ cursor table: (chunk, bucket, sender) -> keys stored, u64, kDistHeader bytes ][ level-1 array ]
 // level-1 array of owner o: for chunk c, for sender s, for bucket b of o: a region of cap(s, b) keys — so the slab
 // (c, s) is contiguous, and is what sender s copies in one piece.
-constexpr size_t kDistHeader = (size_t)kMaxL1 * 16 * 8;
 constexpr uint32_t kDistMaxWorld = 16, kDistMaxChunks = 16;
+constexpr size_t kDistHeader = (size_t)kMaxL1 * kDistMaxWorld * kDistMaxChunks * 8; // 2 MB: any owner may hold most buckets
+
+// sum of a u64 array (the keys an owner received = the sum of its cursor table)
+__global__ void __launch_bounds__(256) sum_u64_kernel(const unsigned long long *__restrict__ v, uint64_t n, unsigned long long *__restrict__ total) {
+  unsigned long long s = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) s += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
+}
 
 __global__ void dist_publish_kernel(const unsigned long long *__restrict__ cursor, const uint64_t *__restrict__ cap,
                                     const uint32_t *__restrict__ own_lo, const uint64_t *__restrict__ peer_header,
@@ -1927,12 +2017,10 @@ int finish_dist(kmc_ctx *c) {
     // keys I own = what the senders' cursor table says
     uint64_t N = 0;
     const size_t n_x = (size_t)O.n_xc * D.n_chunks;
-    std::vector<unsigned long long> cur(n_x);
-    for (size_t o = 0; o < n_x; o += 4096) { // mailbox-sized pieces
-      size_t m = std::min<size_t>(4096, n_x - o);
-      TRY(d2h_small(c, cur.data() + o, header + o, m * 8));
-    }
-    for (unsigned long long v : cur) N += v;
+    CK(cudaMemsetAsync(d_total_all(c), 0, 8, c->stream));
+    LAUNCH(sum_u64_kernel, std::min<uint32_t>(grid_for(n_x, 256), 64), 256, 0, header, (uint64_t)n_x, d_total_all(c));
+    c->launches--;
+    TRY(d2h_small(c, &N, d_total_all(c), 8));
     c->n_total = N; c->n_distinct = d;
   }
   c->strategy_used = KMC_STRATEGY_SORT;
@@ -2191,7 +2279,7 @@ void kmc_destroy(kmc_ctx *c) {
   for (auto &s : c->segs) { release(s.own_bases); release(s.own_off); release(s.brk); if (s.ready) cudaEventDestroy(s.ready); }
   for (DevBuf *b : {&c->keys_a, &c->keys_b, &c->block_hist, &c->offsets, &c->sums, &c->scalars, &c->route_keys, &c->gap_l,
                     &c->gap_r, &c->gap_f, &c->t_lo, &c->t_hi, &c->t_cnt, &c->fast_l1, &c->fast_l2, &c->fast_state, &c->fast_tables, &c->fast_fdesc, &c->recv_keys, &c->hash_slots, &c->hash_scalars, &c->hash_hot, &c->fa_raw, &c->fa_tiles, &c->fa_flags, &c->fmt_len, &c->fmt_off, &c->fmt_text, &c->merge_lo, &c->merge_hi, &c->merge_cnt, &c->pair_rows, &c->pair_state,
-                    &c->dist_tables, &c->dist_stage, &c->dist_cursors, &c->route_state, &c->route_tables})
+                    &c->kept_keys, &c->kept_tables, &c->kept_state, &c->dist_tables, &c->dist_stage, &c->dist_cursors, &c->route_state, &c->route_tables})
     release(*b);
   for (auto ev : c->event_pool) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -2224,6 +2312,7 @@ int kmc_reset(kmc_ctx *c) {
   c->ingested_pairs.clear();
   c->finished = false; c->n_total = c->n_distinct = 0;
   c->range_on = false; c->part_hist_step = 0;
+  c->kept_valid = false; c->kept_tried = false;
   dist_abandon(c);
   c->phases.clear(); c->klaunches.clear(); c->events_used = 0;
   c->launches_total += c->launches; c->launches = 0; c->h2d_bytes = 0;
@@ -2497,6 +2586,44 @@ int kmc_finish_part(kmc_ctx *c, uint32_t part, uint32_t n_parts, uint64_t *n_dis
       TRY(c->wide ? coarse_hist<U128>(c, ka, c->part_hist, &step) : coarse_hist<uint64_t>(c, ka, c->part_hist, &step));
       c->part_hist_step = step;
     }
+  }
+  // contiguous input: scatter all keys once (first call), then every part is a slice of that array
+  if (!c->kept_tried && c->cfg.mode == KMC_MODE_CONTIGUOUS && c->cfg.strategy != KMC_STRATEGY_SORT_BASELINE &&
+      c->total_bases >= (uint64_t)env_int("KMC_KEPT_MIN_BASES", 1 << 22)) {
+    c->kept_tried = true;
+    TRY(c->wide ? kept_scatter<U128>(c) : kept_scatter<uint64_t>(c));
+  }
+  if (c->kept_valid) {
+    // part p = top-bits buckets [B(p), B(p+1)), B(p) = the first bucket with at least p/n_parts of the keys before it
+    const uint32_t n_l1 = 1u << c->kept_b1;
+    if (n_parts > n_l1) return fail(c, KMC_E_ARG, "kmc_finish_part: at most %u parts for this input", n_l1);
+    unsigned __int128 all = 0;
+    for (uint64_t v : c->kept_count) all += v;
+    auto bound = [&](uint32_t p) -> uint32_t {
+      if (p == 0) return 0;
+      if (p >= n_parts) return n_l1;
+      const unsigned __int128 want = (all * p + n_parts - 1) / n_parts;
+      unsigned __int128 before = 0;
+      uint32_t idx = 0;
+      while (idx < n_l1 && before < want) before += c->kept_count[idx++];
+      return idx;
+    };
+    const uint32_t lo = bound(part), hi = bound(part + 1);
+    const size_t kw = c->wide ? 16 : 8;
+    c->ingested.clear();
+    for (uint32_t b = lo; b < hi; b++)
+      if (c->kept_count[b]) c->ingested.emplace_back((const unsigned char *)c->kept_keys.p + c->kept_start[b] * kw, c->kept_count[b]);
+    int rc;
+    if (c->ingested.empty()) { // a range without keys: the empty table
+      c->n_total = c->n_distinct = 0; c->finished = true;
+      if (n_distinct) *n_distinct = 0;
+      if (n_total) *n_total = 0;
+      rc = KMC_OK;
+    } else {
+      rc = finish_common(c, n_distinct, n_total);
+    }
+    c->ingested.clear();
+    return rc;
   }
   // part p = coarse bins [B(p), B(p+1)), B(p) = the first bin with at least p/n_parts of the keys before it
   unsigned __int128 total = 0;

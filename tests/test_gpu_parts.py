@@ -75,6 +75,9 @@ def test_parts_partitioned_path(kmc, orc, k, canonical, n, n_parts):
     assert dig == want.digest()
     for st in stats:
         assert st["strategy_used"] == 2 and st["fast_fallbacks"] == 0, st
+    # all keys were scattered once, by the first part; the other parts did not extract again
+    if n >= 1 << 22:   # (smaller inputs are extracted again per part: not worth the array)
+        assert "kept_scatter" in stats[0]["phases_ms"] and all("kept_scatter" not in st["phases_ms"] for st in stats[1:]), stats
     # the ranges are cut for equal population
     assert max(totals) < 1.25 * want.n_total / n_parts + 4096, totals
 

@@ -42,8 +42,11 @@ def main():
     torch.cuda.set_device(0)
     os.environ.setdefault("KMC_KERNEL_TIMING", "1")
     K.build()
+    from kmer_count_b200 import gen
+    kc = K.KmerCounter(k=wl["k"], canonical=wl["canonical"], strategy=args.strategy, device=0)
+    kc.set_stream(torch.cuda.current_stream().cuda_stream)
     t0 = time.perf_counter()
-    bases, off = bench.synth(torch, n, wl["rec_len"], 3, dev, n_runs=(args.workload == "cfg4"))
+    bases, off = bench.device_input(torch, np, gen, kc, args.workload, wl, 0, n, dev)   # the bench's generator bytes
     torch.cuda.synchronize()
     t_synth = time.perf_counter() - t0
     n_recs = off.numel() - 1
@@ -53,8 +56,6 @@ def main():
     out = {"workload": args.workload + ": " + wl["desc"].split(",")[0], "k": wl["k"], "canonical": wl["canonical"],
            "bases": n, "records": n_recs, "synth_seconds": round(t_synth, 2), "hbm_total_gb": round(total_mem / 1e9, 1),
            "runs": []}
-    kc = K.KmerCounter(k=wl["k"], canonical=wl["canonical"], strategy=args.strategy, device=0)
-    kc.set_stream(torch.cuda.current_stream().cuda_stream)
     kc.submit_device(bases.data_ptr(), off.data_ptr(), n, n_recs)
     for n_parts in [p for p in (args.parts, args.parts2) if p]:
         dig, tot, dist_, ascending = 0, 0, 0, True

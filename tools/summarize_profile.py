@@ -18,7 +18,11 @@ cols = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "launch__registers_per_thread", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_requests_srcunit_tex_op_write.sum"]
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_requests_srcunit_tex_op_write.sum",
+        # the hash strategy's counters (north_star: atomic throughput, L2 hit rate)
+        "lts__t_sector_hit_rate.pct", "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum",
+        "lts__t_sectors_srcunit_tex_op_read.sum", "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum",
+        "l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 os.makedirs("profiles", exist_ok=True)
 traffic_path = "profiles/traffic.json"
 traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
