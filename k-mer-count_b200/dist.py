@@ -309,14 +309,16 @@ class DistCounter:
     def _finish_range(self, allv):
         """Range partition (kmc_dist_*): every sender runs the level-1 scatter locally, laid out owner by owner, and each
         owner's slab crosses NVLink as one copy; the owners run only the second scatter and the bucket sort.  The input
-        goes in chunks: chunk c + 1 is scattered while chunk c is on the links and the owners work on chunk c - 1.
+        goes in chunks: chunk c + 1 is scattered while chunk c is on the links and the owners work on chunk c - 1
+        (8 chunks at 2 GPUs, where the SMs are the bound and short fill/drain phases matter; 4 at more, where the links
+        are: measured 27.5 ms/step with 4 chunks against 29.3 with 8 and 29.7 with 12 at 8 GPUs).
         None = this job does not suit it (every rank comes to the same conclusion) and goes through the hash route."""
         torch, dist = self.torch, self.dist
         dev = torch.device("cuda", torch.cuda.current_device())
         # allv: every rank's histogram | low-cardinality flag | receive-buffer bytes | shard size (finish's all-gather)
         if allv[:, 4096].any():
             return None                          # low-cardinality input somewhere: hash route + hash table
-        n_chunks = int(os.environ.get("KMC_RANGE_CHUNKS", "8")) if int(allv[:, 4098].max()) >= int(os.environ.get("KMC_RANGE_CHUNK_MIN", 1 << 26)) else 1
+        n_chunks = int(os.environ.get("KMC_RANGE_CHUNKS", "8" if self.world <= 2 else "4")) if int(allv[:, 4098].max()) >= int(os.environ.get("KMC_RANGE_CHUNK_MIN", 1 << 26)) else 1
         need = self.kc.dist_plan(self.world, self.rank, allv[:, :4096], n_chunks)
         if not need.all():
             return None
