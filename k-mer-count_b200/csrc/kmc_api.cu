@@ -2637,7 +2637,12 @@ int kmc_finish_part(kmc_ctx *c, uint32_t part, uint32_t n_parts, uint64_t *n_dis
       if (n_total) *n_total = 0;
       rc = KMC_OK;
     } else {
+      // the part's keys share their top bits: plan as for a key range (level-1 bits may go below the coarse prefix —
+      // a dense range of canonical k-mers needs them), from the whole input's histogram
+      const uint32_t sh = coarse_bits(c) - c->kept_b1;
+      c->range_on = true; c->range_lo = lo << sh; c->range_n = (hi - lo) << sh;
       rc = finish_common(c, n_distinct, n_total);
+      c->range_on = false;
     }
     c->ingested.clear();
     return rc;
