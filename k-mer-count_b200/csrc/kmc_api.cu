@@ -84,12 +84,13 @@ struct DistPlan {
   // sender view: capacity of MY region of bucket b (per chunk) and its offset inside my slab at b's owner; per owner:
   // where my slab starts inside a chunk of its array, the slab's length, the length of one chunk of its array, and
   // where the slab sits in my staging array
-  std::vector<uint64_t> s_cap, s_in;               // [n_all]
-  std::vector<uint64_t> slab_pre, slab_len, chunk_len, stage_off; // [world]
-  uint64_t stage_len = 0;                          // keys of one staging half (the slabs of all other owners)
+  std::vector<double> cum_frac;                    // [n_chunks+1] chunk c = the input's CTA tiles [cum_frac[c], cum_frac[c+1]) (first and last chunk are half-size: short fill and drain)
+  std::vector<uint64_t> s_cap, s_in;               // [n_chunks x n_all]
+  std::vector<uint64_t> slab_pre, slab_len, chunk_off, stage_off; // [n_chunks x world]; chunk_off = start of chunk c in that owner's array
+  uint64_t stage_len = 0;                          // keys of one staging half (the largest chunk's slabs for all other owners)
   std::vector<uint8_t> l1e;                        // [n_all]
   std::vector<uint64_t> fine_hist;                 // [ncoarse] global upper estimate (fine-bucket capacities)
-  std::vector<uint64_t> x_cap, x_off;              // [my level-1 buckets x world] owner view: capacity / offset within a chunk of every sender's region
+  std::vector<uint64_t> x_cap, x_off;              // [n_chunks x my level-1 buckets x world] owner view: capacity / offset in my array of every sender's region
   uint64_t l1_keys = 0;                            // keys my level-1 array must hold (all chunks)
   DistOwner owner;
   cudaEvent_t ev_ready = nullptr, ev_scattered[16] = {}, ev_copied[16] = {};
@@ -1685,36 +1686,53 @@ int dist_plan_impl(kmc_ctx *c, uint32_t world, uint32_t rank, const uint64_t *al
   }
   for (uint32_t o = 0; o < world; o++) // the owner's cursor table must hold (chunk, bucket, sender)
     if ((uint64_t)n_chunks * (D.own_lo[o + 1] - D.own_lo[o]) * world > kDistHeader / 8) return KMC_OK;
-  // region (chunk, sender, bucket): capacity from that sender's own histogram, the same in every chunk (chunks are
-  // equal slices of the sender's input)
-  D.s_cap.assign(n_all, 0); D.s_in.assign(n_all, 0);
-  D.slab_pre.assign(world, 0); D.slab_len.assign(world, 0); D.chunk_len.assign(world, 0); D.stage_off.assign(world, 0);
+  // chunks: equal slices of every sender's input, except that the first and the last are half as long — the exchange is
+  // a chain (scatter chunk 0, then one copy after the other, then the level-2 scatter of the last chunk), and its two
+  // ends are the part nothing overlaps
+  D.cum_frac.assign(n_chunks + 1, 0.0);
+  {
+    const double unit = n_chunks > 2 ? 1.0 / (n_chunks - 1) : 1.0 / n_chunks;
+    for (uint32_t ch = 0; ch < n_chunks; ch++)
+      D.cum_frac[ch + 1] = D.cum_frac[ch] + ((n_chunks > 2 && (ch == 0 || ch + 1 == n_chunks)) ? 0.5 * unit : unit);
+    D.cum_frac[n_chunks] = 1.0;
+  }
+  // region (chunk, sender, bucket): capacity from that sender's own histogram and the chunk's share of its input
+  D.s_cap.assign((size_t)n_chunks * n_all, 0); D.s_in.assign((size_t)n_chunks * n_all, 0);
+  D.slab_pre.assign((size_t)n_chunks * world, 0); D.slab_len.assign((size_t)n_chunks * world, 0);
+  D.chunk_off.assign((size_t)n_chunks * world, 0); D.stage_off.assign((size_t)n_chunks * world, 0);
   D.x_cap.clear(); D.x_off.clear();
   const uint64_t slack = 2 * kMaxTile;
-  uint64_t stage = 0;
+  std::vector<uint64_t> stage(n_chunks, 0);
   for (uint32_t o = 0; o < world; o++) {
     uint64_t off = 0;
     const uint32_t my_n = D.own_lo[o + 1] - D.own_lo[o];
-    if (o == rank) { D.x_cap.assign((size_t)my_n * world, 0); D.x_off.assign((size_t)my_n * world, 0); }
-    for (uint32_t s = 0; s < world; s++) {
-      const uint64_t slab0 = off;
-      for (uint32_t b = D.own_lo[o]; b < D.own_lo[o + 1]; b++) {
-        uint64_t nb = 0;
-        for (uint32_t ci = b << cshift; ci < ((b + 1) << cshift); ci++) nb += all_hist[(size_t)s * 4096 + ci];
-        const uint64_t cap1 = n_chunks > 1 ? (((uint64_t)((double)nb / n_chunks * 1.04) + 2048 + 15) & ~15ull)
-                                           : (((uint64_t)((double)nb * 1.03) + 4096 + 15) & ~15ull);
-        if (s == rank) { D.s_in[b] = off - slab0; D.s_cap[b] = cap1; }
-        if (o == rank) { D.x_cap[(size_t)(b - D.own_lo[o]) * world + s] = cap1; D.x_off[(size_t)(b - D.own_lo[o]) * world + s] = off; }
-        off += cap1;
+    if (o == rank) { D.x_cap.assign((size_t)n_chunks * my_n * world, 0); D.x_off.assign((size_t)n_chunks * my_n * world, 0); }
+    for (uint32_t ch = 0; ch < n_chunks; ch++) {
+      const double frac = D.cum_frac[ch + 1] - D.cum_frac[ch];
+      D.chunk_off[(size_t)ch * world + o] = off;
+      for (uint32_t s = 0; s < world; s++) {
+        const uint64_t slab0 = off;
+        for (uint32_t b = D.own_lo[o]; b < D.own_lo[o + 1]; b++) {
+          uint64_t nb = 0;
+          for (uint32_t ci = b << cshift; ci < ((b + 1) << cshift); ci++) nb += all_hist[(size_t)s * 4096 + ci];
+          const uint64_t cap1 = n_chunks > 1 ? (((uint64_t)((double)nb * frac * 1.04) + 2048 + 15) & ~15ull)
+                                             : (((uint64_t)((double)nb * 1.03) + 4096 + 15) & ~15ull);
+          if (s == rank) { D.s_in[(size_t)ch * n_all + b] = off - slab0; D.s_cap[(size_t)ch * n_all + b] = cap1; }
+          if (o == rank) {
+            const size_t x = ((size_t)ch * my_n + (b - D.own_lo[o])) * world + s;
+            D.x_cap[x] = cap1; D.x_off[x] = off;
+          }
+          off += cap1;
+        }
+        if (s == rank) { D.slab_pre[(size_t)ch * world + o] = slab0; D.slab_len[(size_t)ch * world + o] = off - slab0; }
       }
-      if (s == rank) { D.slab_pre[o] = slab0; D.slab_len[o] = off - slab0; }
+      if (o != rank) { D.stage_off[(size_t)ch * world + o] = stage[ch]; stage[ch] += D.slab_len[(size_t)ch * world + o]; }
     }
-    D.chunk_len[o] = off;
-    need_bytes[o] = kDistHeader + (off * n_chunks + slack) * sizeof(KeyT);
-    if (o == rank) D.l1_keys = off * n_chunks;
-    if (o != rank) { D.stage_off[o] = stage; stage += D.slab_len[o]; }
+    need_bytes[o] = kDistHeader + (off + slack) * sizeof(KeyT);
+    if (o == rank) D.l1_keys = off;
   }
-  D.stage_len = stage;
+  D.stage_len = 0;
+  for (uint64_t v : stage) D.stage_len = std::max(D.stage_len, v);
   D.world = world; D.rank = rank; D.b1 = b1; D.n_all = n_all; D.n_chunks = n_chunks;
   D.l1e = shape.l1e;
   D.fine_hist = G;
@@ -1770,8 +1788,8 @@ int dist_owner_begin(kmc_ctx *c) {
     for (uint32_t ch = 0; ch < C; ch++)
       for (uint32_t s = 0; s < world; s++) {
         const uint32_t x = ch * n_xc + rb * world + s;
-        const uint64_t cap1 = D.x_cap[(size_t)rb * world + s];
-        xs[x] = (uint64_t)ch * D.chunk_len[D.rank] + D.x_off[(size_t)rb * world + s];
+        const uint64_t cap1 = D.x_cap[((size_t)ch * my_n + rb) * world + s];
+        xs[x] = D.x_off[((size_t)ch * my_n + rb) * world + s];
         xc[x] = cap1; xf[x] = fb; xe[x] = (uint8_t)e;
         tiles2 += (cap1 + p2_tile<KeyT>() - 1) / p2_tile<KeyT>();
         t_max = std::max<uint64_t>(t_max, (cap1 + p2_tile<KeyT>() - 1) / p2_tile<KeyT>());
@@ -1836,7 +1854,7 @@ int dist_scatter_part_impl(kmc_ctx *c, void *const *peer_buf, uint32_t chunk) {
   if (chunk != D.chunks_sent || chunk >= C) return fail(c, KMC_E_ARG, "kmc_dist_scatter_part: chunks go in order, 0..%u", C - 1);
   auto al16 = [](size_t x) { return (x + 15) & ~size_t(15); };
   // sender tables: per chunk l1_start (absolute address / key size) | l1_cap | own_lo | peer header pointers
-  const size_t o_s = 0, o_c = o_s + al16((size_t)C * (n_all + 1) * 8), o_own = o_c + al16((size_t)n_all * 8),
+  const size_t o_s = 0, o_c = o_s + al16((size_t)C * (n_all + 1) * 8), o_own = o_c + al16((size_t)C * n_all * 8),
                o_ph = o_own + al16((size_t)(world + 1) * 4), tab_bytes = o_ph + al16((size_t)world * 8);
   if (chunk == 0) {
     TRY(zero_scalars(c));
@@ -1851,12 +1869,14 @@ int dist_scatter_part_impl(kmc_ctx *c, void *const *peer_buf, uint32_t chunk) {
     uint64_t *ph = (uint64_t *)(host.data() + o_ph);
     for (uint32_t ch = 0; ch < C; ch++)
       for (uint32_t o = 0; o < world; o++) {
+        const size_t co = (size_t)ch * world + o;
         const uint64_t base = o == D.rank
-            ? ((uint64_t)(uintptr_t)c->recv_keys.p + kDistHeader) / sizeof(KeyT) + (uint64_t)ch * D.chunk_len[o] + D.slab_pre[o]
-            : (uint64_t)(uintptr_t)c->dist_stage.p / sizeof(KeyT) + (uint64_t)(ch & 1) * D.stage_len + D.stage_off[o];
-        for (uint32_t b = D.own_lo[o]; b < D.own_lo[o + 1]; b++) l1s[(size_t)ch * (n_all + 1) + b] = base + D.s_in[b];
+            ? ((uint64_t)(uintptr_t)c->recv_keys.p + kDistHeader) / sizeof(KeyT) + D.slab_pre[co]
+            : (uint64_t)(uintptr_t)c->dist_stage.p / sizeof(KeyT) + (uint64_t)(ch & 1) * D.stage_len + D.stage_off[co];
+        for (uint32_t b = D.own_lo[o]; b < D.own_lo[o + 1]; b++) l1s[(size_t)ch * (n_all + 1) + b] = base + D.s_in[(size_t)ch * n_all + b];
       }
-    for (uint32_t b = 0; b < n_all; b++) l1c[b] = D.s_cap[b];
+    for (uint32_t ch = 0; ch < C; ch++)
+      for (uint32_t b = 0; b < n_all; b++) l1c[(size_t)ch * n_all + b] = D.s_cap[(size_t)ch * n_all + b];
     for (uint32_t o = 0; o < world; o++) ph[o] = (uint64_t)(uintptr_t)peer_buf[o];
     for (uint32_t o = 0; o <= world; o++) own[o] = D.own_lo[o];
     CK(cudaMemsetAsync(c->dist_cursors.p, 0, (size_t)C * kMaxL1 * 8, c->stream));
@@ -1871,7 +1891,7 @@ int dist_scatter_part_impl(kmc_ctx *c, void *const *peer_buf, uint32_t chunk) {
   pl.kb = kb; pl.b1 = D.b1; pl.n_l1 = n_all; pl.n_fine = 0; pl.l1_base = 0;
   pl.l1_trash = ((uint64_t)(uintptr_t)c->route_keys.p + sizeof(KeyT) - 1) / sizeof(KeyT);
   pl.l1_start = (const uint64_t *)(tb + o_s) + (size_t)chunk * (n_all + 1);
-  pl.l1_cap = (const uint64_t *)(tb + o_c);
+  pl.l1_cap = (const uint64_t *)(tb + o_c) + (size_t)chunk * n_all;
   pl.l1_cursor = (unsigned long long *)c->dist_cursors.p + (size_t)chunk * kMaxL1;
   // the staging half this chunk scatters into was copied out two chunks ago
   if (chunk >= 2) CK(cudaStreamWaitEvent(c->stream, D.ev_copied[chunk - 2], 0));
@@ -1879,7 +1899,7 @@ int dist_scatter_part_impl(kmc_ctx *c, void *const *peer_buf, uint32_t chunk) {
   uint64_t all_ct = 0;
   for (size_t i = 0; i < c->n_segs; i++)
     if (c->segs[i].n_bases) all_ct += (num_warp_tiles(c->segs[i].n_bases, win_lanes<KeyT>()) + kFastWarps - 1) / kFastWarps;
-  const uint64_t g0 = all_ct * chunk / C, g1 = all_ct * (chunk + 1) / C;
+  const uint64_t g0 = (uint64_t)((double)all_ct * D.cum_frac[chunk]), g1 = chunk + 1 == C ? all_ct : (uint64_t)((double)all_ct * D.cum_frac[chunk + 1]);
   PHASE_BEGIN("route");
   {
     size_t smem = L1Smem<KeyT>::bytes(part1_stage<KeyT>(), n_all);
@@ -1915,10 +1935,11 @@ int dist_scatter_part_impl(kmc_ctx *c, void *const *peer_buf, uint32_t chunk) {
   }
   for (uint32_t d = 1; d < world; d++) {
     const uint32_t o = (D.rank + d) % world;
-    if (!D.slab_len[o]) continue;
+    const size_t co = (size_t)chunk * world + o;
+    if (!D.slab_len[co]) continue;
     const int l = (int)((d - 1) % (uint32_t)n_lanes);
-    KeyT *dst = (KeyT *)((unsigned char *)peer_buf[o] + kDistHeader) + (size_t)chunk * D.chunk_len[o] + D.slab_pre[o];
-    CK(cudaMemcpyAsync(dst, stage + D.stage_off[o], D.slab_len[o] * sizeof(KeyT), cudaMemcpyDeviceToDevice, l ? c->peer_lane[l] : c->peer_stream));
+    KeyT *dst = (KeyT *)((unsigned char *)peer_buf[o] + kDistHeader) + D.slab_pre[co];
+    CK(cudaMemcpyAsync(dst, stage + D.stage_off[co], D.slab_len[co] * sizeof(KeyT), cudaMemcpyDeviceToDevice, l ? c->peer_lane[l] : c->peer_stream));
   }
   for (int l = 1; l < n_lanes; l++) {
     CK(cudaEventRecord(c->peer_lane_ev[l], c->peer_lane[l]));

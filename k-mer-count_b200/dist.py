@@ -318,7 +318,7 @@ class DistCounter:
         # allv: every rank's histogram | low-cardinality flag | receive-buffer bytes | shard size (finish's all-gather)
         if allv[:, 4096].any():
             return None                          # low-cardinality input somewhere: hash route + hash table
-        n_chunks = int(os.environ.get("KMC_RANGE_CHUNKS", "8" if self.world <= 2 else "4")) if int(allv[:, 4098].max()) >= int(os.environ.get("KMC_RANGE_CHUNK_MIN", 1 << 26)) else 1
+        n_chunks = int(os.environ.get("KMC_RANGE_CHUNKS", "8" if self.world <= 2 else "5")) if int(allv[:, 4098].max()) >= int(os.environ.get("KMC_RANGE_CHUNK_MIN", 1 << 26)) else 1
         need = self.kc.dist_plan(self.world, self.rank, allv[:, :4096], n_chunks)
         if not need.all():
             return None
