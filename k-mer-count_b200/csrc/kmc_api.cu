@@ -20,6 +20,7 @@
 #include "kmc_sort.cuh"
 #include "kmc_fast.cuh"
 #include "kmc_hash.cuh"
+#include "kmc_hash128.cuh"
 #include "kmc_fasta.cuh"
 #include "kmc_format.cuh"
 #include "kmc_gen.cuh"
@@ -886,6 +887,125 @@ int finish_hash(kmc_ctx *c, uint32_t log2_slots, uint64_t limit, bool *used) {
   c->n_total = n_total; c->n_distinct = rows;
   c->strategy_used = KMC_STRATEGY_HASH;
   *used = true;
+  return KMC_OK;
+}
+
+// ---- hash strategy, keys of more than 64 bits (kmc_hash128.cuh) --------------------------------------------------
+// The same steps as hash_run / finish_hash / hash_probe for 64-bit keys, without the hot-key counters.
+int hash128_run(kmc_ctx *c, const KeyArrays &ka, uint32_t log2_slots, uint64_t limit, uint32_t step, bool *ok, HashTable128 *out,
+                bool throttle = true) {
+  *ok = false;
+  const uint64_t max_warps = std::max<uint64_t>(64, (1ull << log2_slots) / 4 / 992);
+  const uint32_t max_ctas = throttle ? (uint32_t)std::min<uint64_t>((uint64_t)c->n_sms * 8, std::max<uint64_t>(8, max_warps / 8))
+                                     : (uint32_t)c->n_sms * 8;
+  const uint64_t slots = 1ull << log2_slots;
+  TRY(ensure(c, c->hash_slots, slots * sizeof(HashSlot128)));
+  TRY(ensure(c, c->hash_scalars, 64));
+  LAUNCH(hash128_init_kernel, std::min<uint32_t>(grid_for(slots, 256), c->n_sms * 16), 256, 0, (HashSlot128 *)c->hash_slots.p, slots);
+  CK(cudaMemsetAsync(c->hash_scalars.p, 0, 64, c->stream));
+  HashTable128 T;
+  T.slots = (HashSlot128 *)c->hash_slots.p;
+  T.mask = slots - 1; T.shift = 64 - log2_slots;
+  T.n_used = (unsigned long long *)c->hash_scalars.p; T.n_total = T.n_used + 1; T.n_ones = T.n_used + 2;
+  T.limit = limit; T.flags = d_err(c);
+  if (ka.from_array) {
+    for (auto &a : ka.arrays) {
+      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024ull * step), (uint64_t)max_ctas);
+      LAUNCH(hash128_count_array_kernel, grid, 256, 0, (const U128 *)a.first, a.second, step, T);
+    }
+  } else {
+    for (size_t i = 0; i < c->n_segs; i++) {
+      Segment &s = c->segs[i];
+      if (!s.n_bases) continue;
+      const bool sample_host = step > 1 && s.host_alias && s.wait_ready;
+      if (!sample_host) TRY(seg_wait(c, s));
+      ExtractParams P = seg_params(c, s, sample_host);
+      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<U128>());
+      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)max_ctas);
+      auto hash128_count = hash128_count_kernel<true>;
+      LAUNCH(hash128_count, grid, 256, 0, P, tiles, step, T);
+    }
+  }
+  uint32_t err = 0;
+  TRY(read_scalars(c, nullptr, &err));
+  if (err & kFlagHashFull) {
+    CK(cudaMemsetAsync(d_err(c), 0, 4, c->stream)); // a full table is not an error: the caller picks another route
+    return KMC_OK;
+  }
+  *ok = true;
+  if (out) *out = T;
+  return KMC_OK;
+}
+
+int finish_hash128(kmc_ctx *c, uint32_t log2_slots, uint64_t limit, bool *used) {
+  *used = false;
+  KeyArrays ka;
+  TRY(key_sources<U128>(c, &ka));
+  HashTable128 T;
+  bool ok = false;
+  PHASE_BEGIN("hash_count");
+  TRY(hash128_run(c, ka, log2_slots, limit, 1, &ok, &T, /*throttle=*/c->probe_distinct == 0));
+  PHASE_END();
+  if (!ok) { c->hash_aborts++; return KMC_OK; }
+  unsigned long long sc[3];
+  TRY(d2h_small(c, sc, c->hash_scalars.p, sizeof sc));
+  const uint64_t d = sc[0], n_total = sc[1], n_ones = sc[2];
+  if (n_ones > 0xFFFFFFFFull) return fail(c, KMC_E_COUNT_OVERFLOW, "a k-mer occurs more than 2^32-1 times");
+  PHASE_BEGIN("hash_sort");
+  // distinct keys → dense array → sorted → the table's columns; the key arrays of key_sources() are no longer needed
+  TRY(ensure(c, c->keys_a, (d + 2) * sizeof(U128)));
+  TRY(ensure(c, c->keys_b, (d + 2) * sizeof(U128)));
+  TRY(ensure(c, c->t_lo, (d + 2) * 8));
+  TRY(ensure(c, c->t_hi, (d + 2) * 8));
+  TRY(ensure(c, c->t_cnt, (d + 2) * 4));
+  if (d) {
+    U128 *dense = (U128 *)c->keys_a.p, *sorted = nullptr;
+    CK(cudaMemsetAsync(d_cursor(c), 0, 8, c->stream));
+    LAUNCH(hash128_compact_kernel, std::min<uint32_t>(grid_for(T.mask + 1, 256), c->n_sms * 16), 256, 0, T, dense, d_cursor(c));
+    TRY(radix_sort<U128>(c, dense, (U128 *)c->keys_b.p, d, c->key_bits, &sorted));
+    LAUNCH(hash128_lookup_kernel, std::min<uint32_t>(grid_for(d, 256), c->n_sms * 16), 256, 0, T, (const U128 *)sorted, d,
+           (uint64_t *)c->t_lo.p, (uint64_t *)c->t_hi.p, (uint32_t *)c->t_cnt.p);
+  }
+  uint64_t rows = d;
+  if (n_ones) { // the all-ones key (128 key bits: k = 64, non-canonical poly-T) sorts last
+    uint64_t k1 = kHashEmpty;
+    uint32_t c1 = (uint32_t)n_ones;
+    CK(cudaMemcpyAsync((uint64_t *)c->t_lo.p + d, &k1, 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync((uint64_t *)c->t_hi.p + d, &k1, 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync((uint32_t *)c->t_cnt.p + d, &c1, 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    rows++;
+  }
+  PHASE_END();
+  c->n_total = n_total; c->n_distinct = rows;
+  c->strategy_used = KMC_STRATEGY_HASH;
+  *used = true;
+  return KMC_OK;
+}
+
+// cardinality probe for wide keys: the same insert kernel on a 1-in-step sample into a 2^22-slot table with a fill limit
+int hash128_probe(kmc_ctx *c, bool *low_cardinality) {
+  *low_cardinality = false;
+  c->probe_distinct = 0;
+  c->n_hot = 0;
+  KeyArrays ka;
+  ka.from_array = !c->ingested.empty();
+  if (c->cfg.mode == KMC_MODE_LR_GAPPED) return KMC_OK; // keys would have to be materialised first: skip the probe
+  if (ka.from_array) for (auto &e : c->ingested) if (e.second) { ka.arrays.emplace_back(e.first, e.second); ka.n += e.second; }
+  const uint64_t n_in = ka.from_array ? ka.n : c->total_bases;
+  if (n_in < (1u << 18)) return KMC_OK;
+  uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
+  bool ok = false;
+  HashTable128 T;
+  PHASE_BEGIN("hash_probe");
+  TRY(hash128_run(c, ka, 22, 1ull << 20, step, &ok, &T));
+  if (ok) {
+    unsigned long long sc[3];
+    TRY(d2h_small(c, sc, c->hash_scalars.p, sizeof sc));
+    c->probe_distinct = sc[0];
+  }
+  PHASE_END();
+  *low_cardinality = ok;
   return KMC_OK;
 }
 
@@ -2163,6 +2283,32 @@ int finish_impl(kmc_ctx *c) {
           if (used) return KMC_OK;
           if (lg < 25) {
             TRY(finish_hash(c, 25, 1ull << 24, &used));
+            if (used) return KMC_OK;
+          }
+        }
+      }
+    }
+    if constexpr (sizeof(KeyT) == 16) {
+      if (strat == KMC_STRATEGY_HASH) {
+        // forced: size the table for the worst case (every key distinct), at most 2^31 slots of 32 bytes
+        uint64_t n_in = 0;
+        for (auto &e : c->ingested) n_in += e.second;
+        if (c->ingested.empty()) n_in = c->cfg.mode == KMC_MODE_LR_GAPPED ? c->total_bases * (c->cfg.d_max - c->cfg.d_min + 1) : c->total_bases;
+        c->probe_distinct = 0;
+        uint32_t lg = 20;
+        while (lg < 31 && (1ull << lg) < 2 * n_in) lg++;
+        TRY(finish_hash128(c, lg, (1ull << lg) / 10 * 7, &used));
+        if (used) return KMC_OK;
+      } else if (strat == KMC_STRATEGY_AUTO) {
+        bool low = false;
+        TRY(hash128_probe(c, &low));
+        if (low) { // a table sized from the sample, as for 64-bit keys; once more with a big one if it fills
+          uint32_t lg = 20;
+          while (lg < 24 && (1ull << lg) < 4 * c->probe_distinct) lg++;
+          TRY(finish_hash128(c, lg, (1ull << lg) / 2, &used));
+          if (used) return KMC_OK;
+          if (lg < 24) {
+            TRY(finish_hash128(c, 24, 1ull << 23, &used));
             if (used) return KMC_OK;
           }
         }
