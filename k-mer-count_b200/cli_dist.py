@@ -135,7 +135,7 @@ def main(argv=None):
     code = 0
     try:
         if len(piece):
-            dc.kc.submit_fasta(piece)
+            dc.submit_fasta(piece)
     except K.KmcError as e:
         code = e.code
     codes = agree_status(torch, dist, dev, code) if world > 1 else [code]

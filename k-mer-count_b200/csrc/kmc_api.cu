@@ -2497,6 +2497,7 @@ int kmc_reset(kmc_ctx *c) {
   c->finished = false; c->n_total = c->n_distinct = 0;
   c->range_on = false; c->part_hist_step = 0;
   c->kept_valid = false; c->kept_tried = false;
+  if (c->kept_keys.cap > ((size_t)1 << 30)) release(c->kept_keys); // the one work buffer as large as the input's keys: not kept across jobs
   dist_abandon(c);
   c->phases.clear(); c->klaunches.clear(); c->events_used = 0;
   c->launches_total += c->launches; c->launches = 0; c->h2d_bytes = 0;

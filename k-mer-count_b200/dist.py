@@ -215,6 +215,12 @@ class DistCounter:
         self.n_bases += len(bases)
         self.kc.submit_host(bases, rec_off)
 
+    def submit_fasta(self, text):
+        """Raw FASTA text of this rank's shard (parsed on the device) → (n_bases, n_recs)."""
+        nb, nr = self.kc.submit_fasta(text)
+        self.n_bases += nb
+        return nb, nr
+
     # -- receive buffers: one per rank, mapped by every peer with CUDA IPC; remapped only when one has to grow
     def _map_buffers(self, my_bytes):
         """Every rank calls this together (the decision to call it must be the same on all ranks)."""
