@@ -54,15 +54,6 @@ constexpr int kHistSampleMax = 16;       // fast_hist looks at every step-th til
 #ifndef KMC_ALIGNED_ROWS
 #define KMC_ALIGNED_ROWS 1
 #endif
-#ifndef KMC_P2_PSEARCH
-#define KMC_P2_PSEARCH 1   // fast_part2 finds its level-1 bucket with all threads at once
-#endif
-#ifndef KMC_LB_SLEEP
-#define KMC_LB_SLEEP 0      // look-back: nanoseconds to sleep between polls of a predecessor that has not published yet
-#endif
-#ifndef KMC_L1_NO_TMA
-#define KMC_L1_NO_TMA 0
-#endif
 #ifndef KMC_PART1_PREFETCH
 #define KMC_PART1_PREFETCH 1  // fast_part1: request the next tile's bases before writing the current tile out
 #endif                        // (measured on B200, profiles/r02_ab_prepared_variants.jsonl: 5.67 -> 5.28 ms at 1e9 bases)
@@ -362,11 +353,7 @@ __device__ __forceinline__ void scatter_tile_l1(const FastPlan &pl, L1Smem<KeyT>
         if (dst & 1ull) { *d = *src; d++; src++; n--; } // head key up to the 16-byte boundary
         if (n & 1u) { d[n - 1] = src[n - 1]; n--; }      // odd tail key
       }
-#if KMC_L1_NO_TMA // debugging aid: the same runs by plain stores
-      for (uint32_t i = 0; i < n; i++) d[i] = src[i];
-#else
       if (n) bulk_store_s2g(d, src, n * (uint32_t)sizeof(KeyT));
-#endif
     }
   }
   bulk_commit();
@@ -612,7 +599,6 @@ __device__ __forceinline__ unsigned long long lookback_resolve(unsigned long lon
       uint32_t spins = 0;
       while (((v = ld_status(&status[idx])) >> 62) == 0) {
         if (++spins > (1u << 24)) { atomicOr(flags, kFlagSpin); v = kIncl; break; }
-        if (KMC_LB_SLEEP) __nanosleep(KMC_LB_SLEEP);
       }
     }
     uint32_t incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
@@ -658,16 +644,13 @@ static_assert(fin_kpt<uint32_t>() <= 32 && fin_kpt<uint32_t>() * kFinWarps <= kF
 #ifndef KMC_FINISH_DEFER
 #define KMC_FINISH_DEFER 1
 #endif
-#ifndef KMC_FINISH_DEFER64
-#define KMC_FINISH_DEFER64 0 // the same for 64-bit level-2 elements (needs a KMC_FINE_CAP64 small enough for two buffers)
-#endif
 #ifndef KMC_FINISH_DEFER_SPLIT
 #define KMC_FINISH_DEFER_SPLIT 1
 #endif
 template <typename L2T> __host__ __device__ constexpr int fin_bufs() {
   using ST = typename FinTraits<L2T>::Smem;
   if (FinTraits<L2T>::kSplit) return KMC_FINISH_DEFER_SPLIT ? 2 : 1;
-  return ((KMC_FINISH_DEFER && sizeof(ST) == 4) || (KMC_FINISH_DEFER64 && sizeof(ST) == 8)) ? 2 : 1;
+  return (KMC_FINISH_DEFER && sizeof(ST) == 4) ? 2 : 1; // whole 64-bit elements: two 44 KB buffers + the rest leave one CTA per SM
 }
 
 template <typename L2T>
