@@ -793,1463 +793,9 @@ int key_sources(kmc_ctx *c, KeyArrays *ka) {
   return KMC_OK;
 }
 
-// ---- hash strategy (kmc_hash.cuh), 64-bit keys ---------------------------------------------------------------
-// step > 1: cardinality probe on a sample (table stays, nothing else is produced); *ok = table did not fill.
-int hash_run(kmc_ctx *c, const KeyArrays &ka, uint32_t log2_slots, uint64_t limit, uint32_t step, bool *ok, HashTable *out,
-             uint32_t n_hot = 0, bool throttle = true) {
-  *ok = false;
-  TRY(ensure(c, c->hash_hot, kHotMax * 8 + 64));
-  const uint64_t *hot = (const uint64_t *)c->hash_hot.p;
-  // the fill limit is only checked between tiles: keep the keys in flight (one tile per resident warp) well below
-  // the table size, or a high-cardinality input would swamp the table before anybody notices
-  // (the real run's table is sized from the probe, so only the probe itself — step > 1 or forced — is throttled)
-  const uint64_t max_warps = std::max<uint64_t>(64, (1ull << log2_slots) / 4 / 992);
-  const uint32_t max_ctas = throttle ? (uint32_t)std::min<uint64_t>((uint64_t)c->n_sms * 8, std::max<uint64_t>(8, max_warps / 8))
-                                     : (uint32_t)c->n_sms * 8;
-  const uint64_t slots = 1ull << log2_slots;
-  TRY(ensure(c, c->hash_slots, slots * sizeof(HashSlot)));
-  TRY(ensure(c, c->hash_scalars, 64));
-  LAUNCH(hash_init_kernel, std::min<uint32_t>(grid_for(slots, 256), c->n_sms * 16), 256, 0, (HashSlot *)c->hash_slots.p, slots);
-  CK(cudaMemsetAsync(c->hash_scalars.p, 0, 64, c->stream));
-  HashTable T;
-  T.slots = (HashSlot *)c->hash_slots.p;
-  T.mask = slots - 1; T.shift = 64 - log2_slots;
-  T.n_used = (unsigned long long *)c->hash_scalars.p; T.n_total = T.n_used + 1; T.n_ones = T.n_used + 2;
-  T.limit = limit; T.flags = d_err(c);
-  if (ka.from_array) {
-    for (auto &a : ka.arrays) {
-      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024ull * step), (uint64_t)max_ctas);
-      LAUNCH(hash_count_array_kernel, grid, 256, 0, (const uint64_t *)a.first, a.second, step, T, hot, n_hot);
-    }
-  } else {
-    for (size_t i = 0; i < c->n_segs; i++) {
-      Segment &s = c->segs[i];
-      if (!s.n_bases) continue;
-      const bool sample_host = step > 1 && s.host_alias && s.wait_ready;
-      if (!sample_host) TRY(seg_wait(c, s));
-      ExtractParams P = seg_params(c, s, sample_host);
-      uint64_t tiles = num_warp_tiles(s.n_bases, 31);
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)max_ctas);
-      auto hash_count = hash_count_kernel<true>;
-      LAUNCH(hash_count, grid, 256, 0, P, tiles, step, T, hot, n_hot);
-    }
-  }
-  uint32_t err = 0;
-  TRY(read_scalars(c, nullptr, &err));
-  if (err & kFlagHashFull) {
-    CK(cudaMemsetAsync(d_err(c), 0, 4, c->stream)); // a full table is not an error: the caller picks another route
-    return KMC_OK;
-  }
-  *ok = true;
-  if (out) *out = T;
-  return KMC_OK;
-}
-
-int finish_hash(kmc_ctx *c, uint32_t log2_slots, uint64_t limit, bool *used) {
-  *used = false;
-  KeyArrays ka;
-  TRY(key_sources<uint64_t>(c, &ka));
-  HashTable T;
-  bool ok = false;
-  PHASE_BEGIN("hash_count");
-  TRY(hash_run(c, ka, log2_slots, limit, 1, &ok, &T, c->n_hot, /*throttle=*/c->probe_distinct == 0));
-  PHASE_END();
-  if (!ok) { c->hash_aborts++; return KMC_OK; }
-  unsigned long long sc[3];
-  TRY(d2h_small(c, sc, c->hash_scalars.p, sizeof sc));
-  const uint64_t d = sc[0], n_total = sc[1], n_ones = sc[2];
-  if (n_ones > 0xFFFFFFFFull) return fail(c, KMC_E_COUNT_OVERFLOW, "a k-mer occurs more than 2^32-1 times");
-  PHASE_BEGIN("hash_sort");
-  // distinct keys → dense array → sorted; the key arrays of key_sources() are no longer needed
-  uint64_t *dense = nullptr, *scratch = nullptr, *sorted = nullptr;
-  TRY(ensure(c, c->t_lo, (d + 2) * 8));
-  TRY(ensure(c, c->keys_b, (d + 2) * 8));
-  TRY(ensure(c, c->t_cnt, (d + 2) * 4));
-  dense = (uint64_t *)c->t_lo.p; scratch = (uint64_t *)c->keys_b.p;
-  if (d) {
-    CK(cudaMemsetAsync(d_cursor(c), 0, 8, c->stream));
-    LAUNCH(hash_compact_kernel, std::min<uint32_t>(grid_for(T.mask + 1, 256), c->n_sms * 16), 256, 0, T, dense, d_cursor(c));
-    TRY(radix_sort<uint64_t>(c, dense, scratch, d, c->key_bits, &sorted));
-    if (sorted != dense) CK(cudaMemcpyAsync(dense, sorted, d * 8, cudaMemcpyDeviceToDevice, c->stream));
-    LAUNCH(hash_lookup_kernel, std::min<uint32_t>(grid_for(d, 256), c->n_sms * 16), 256, 0, T, (const uint64_t *)dense, d,
-           (uint32_t *)c->t_cnt.p);
-  }
-  uint64_t rows = d;
-  if (n_ones) { // the all-ones key (k = 32) sorts last
-    uint64_t k1 = kHashEmpty;
-    uint32_t c1 = (uint32_t)n_ones;
-    CK(cudaMemcpyAsync(dense + d, &k1, 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync((uint32_t *)c->t_cnt.p + d, &c1, 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    rows++;
-  }
-  PHASE_END();
-  c->n_total = n_total; c->n_distinct = rows;
-  c->strategy_used = KMC_STRATEGY_HASH;
-  *used = true;
-  return KMC_OK;
-}
-
-// ---- hash strategy, keys of more than 64 bits (kmc_hash128.cuh) --------------------------------------------------
-// The same steps as hash_run / finish_hash / hash_probe for 64-bit keys, without the hot-key counters.
-int hash128_run(kmc_ctx *c, const KeyArrays &ka, uint32_t log2_slots, uint64_t limit, uint32_t step, bool *ok, HashTable128 *out,
-                bool throttle = true) {
-  *ok = false;
-  const uint64_t max_warps = std::max<uint64_t>(64, (1ull << log2_slots) / 4 / 992);
-  const uint32_t max_ctas = throttle ? (uint32_t)std::min<uint64_t>((uint64_t)c->n_sms * 8, std::max<uint64_t>(8, max_warps / 8))
-                                     : (uint32_t)c->n_sms * 8;
-  const uint64_t slots = 1ull << log2_slots;
-  TRY(ensure(c, c->hash_slots, slots * sizeof(HashSlot128)));
-  TRY(ensure(c, c->hash_scalars, 64));
-  LAUNCH(hash128_init_kernel, std::min<uint32_t>(grid_for(slots, 256), c->n_sms * 16), 256, 0, (HashSlot128 *)c->hash_slots.p, slots);
-  CK(cudaMemsetAsync(c->hash_scalars.p, 0, 64, c->stream));
-  HashTable128 T;
-  T.slots = (HashSlot128 *)c->hash_slots.p;
-  T.mask = slots - 1; T.shift = 64 - log2_slots;
-  T.n_used = (unsigned long long *)c->hash_scalars.p; T.n_total = T.n_used + 1; T.n_ones = T.n_used + 2;
-  T.limit = limit; T.flags = d_err(c);
-  if (ka.from_array) {
-    for (auto &a : ka.arrays) {
-      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024ull * step), (uint64_t)max_ctas);
-      LAUNCH(hash128_count_array_kernel, grid, 256, 0, (const U128 *)a.first, a.second, step, T);
-    }
-  } else {
-    for (size_t i = 0; i < c->n_segs; i++) {
-      Segment &s = c->segs[i];
-      if (!s.n_bases) continue;
-      const bool sample_host = step > 1 && s.host_alias && s.wait_ready;
-      if (!sample_host) TRY(seg_wait(c, s));
-      ExtractParams P = seg_params(c, s, sample_host);
-      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<U128>());
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)max_ctas);
-      auto hash128_count = hash128_count_kernel<true>;
-      LAUNCH(hash128_count, grid, 256, 0, P, tiles, step, T);
-    }
-  }
-  uint32_t err = 0;
-  TRY(read_scalars(c, nullptr, &err));
-  if (err & kFlagHashFull) {
-    CK(cudaMemsetAsync(d_err(c), 0, 4, c->stream)); // a full table is not an error: the caller picks another route
-    return KMC_OK;
-  }
-  *ok = true;
-  if (out) *out = T;
-  return KMC_OK;
-}
-
-int finish_hash128(kmc_ctx *c, uint32_t log2_slots, uint64_t limit, bool *used) {
-  *used = false;
-  KeyArrays ka;
-  TRY(key_sources<U128>(c, &ka));
-  HashTable128 T;
-  bool ok = false;
-  PHASE_BEGIN("hash_count");
-  TRY(hash128_run(c, ka, log2_slots, limit, 1, &ok, &T, /*throttle=*/c->probe_distinct == 0));
-  PHASE_END();
-  if (!ok) { c->hash_aborts++; return KMC_OK; }
-  unsigned long long sc[3];
-  TRY(d2h_small(c, sc, c->hash_scalars.p, sizeof sc));
-  const uint64_t d = sc[0], n_total = sc[1], n_ones = sc[2];
-  if (n_ones > 0xFFFFFFFFull) return fail(c, KMC_E_COUNT_OVERFLOW, "a k-mer occurs more than 2^32-1 times");
-  PHASE_BEGIN("hash_sort");
-  // distinct keys → dense array → sorted → the table's columns; the key arrays of key_sources() are no longer needed
-  TRY(ensure(c, c->keys_a, (d + 2) * sizeof(U128)));
-  TRY(ensure(c, c->keys_b, (d + 2) * sizeof(U128)));
-  TRY(ensure(c, c->t_lo, (d + 2) * 8));
-  TRY(ensure(c, c->t_hi, (d + 2) * 8));
-  TRY(ensure(c, c->t_cnt, (d + 2) * 4));
-  if (d) {
-    U128 *dense = (U128 *)c->keys_a.p, *sorted = nullptr;
-    CK(cudaMemsetAsync(d_cursor(c), 0, 8, c->stream));
-    LAUNCH(hash128_compact_kernel, std::min<uint32_t>(grid_for(T.mask + 1, 256), c->n_sms * 16), 256, 0, T, dense, d_cursor(c));
-    TRY(radix_sort<U128>(c, dense, (U128 *)c->keys_b.p, d, c->key_bits, &sorted));
-    LAUNCH(hash128_lookup_kernel, std::min<uint32_t>(grid_for(d, 256), c->n_sms * 16), 256, 0, T, (const U128 *)sorted, d,
-           (uint64_t *)c->t_lo.p, (uint64_t *)c->t_hi.p, (uint32_t *)c->t_cnt.p);
-  }
-  uint64_t rows = d;
-  if (n_ones) { // the all-ones key (128 key bits: k = 64, non-canonical poly-T) sorts last
-    uint64_t k1 = kHashEmpty;
-    uint32_t c1 = (uint32_t)n_ones;
-    CK(cudaMemcpyAsync((uint64_t *)c->t_lo.p + d, &k1, 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync((uint64_t *)c->t_hi.p + d, &k1, 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync((uint32_t *)c->t_cnt.p + d, &c1, 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    rows++;
-  }
-  PHASE_END();
-  c->n_total = n_total; c->n_distinct = rows;
-  c->strategy_used = KMC_STRATEGY_HASH;
-  *used = true;
-  return KMC_OK;
-}
-
-// cardinality probe for wide keys: the same insert kernel on a 1-in-step sample into a 2^22-slot table with a fill limit
-int hash128_probe(kmc_ctx *c, bool *low_cardinality) {
-  *low_cardinality = false;
-  c->probe_distinct = 0;
-  c->n_hot = 0;
-  KeyArrays ka;
-  ka.from_array = !c->ingested.empty();
-  if (c->cfg.mode == KMC_MODE_LR_GAPPED) return KMC_OK; // keys would have to be materialised first: skip the probe
-  if (ka.from_array) for (auto &e : c->ingested) if (e.second) { ka.arrays.emplace_back(e.first, e.second); ka.n += e.second; }
-  const uint64_t n_in = ka.from_array ? ka.n : c->total_bases;
-  if (n_in < (1u << 18)) return KMC_OK;
-  uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
-  bool ok = false;
-  HashTable128 T;
-  PHASE_BEGIN("hash_probe");
-  TRY(hash128_run(c, ka, 22, 1ull << 20, step, &ok, &T));
-  if (ok) {
-    unsigned long long sc[3];
-    TRY(d2h_small(c, sc, c->hash_scalars.p, sizeof sc));
-    c->probe_distinct = sc[0];
-  }
-  PHASE_END();
-  *low_cardinality = ok;
-  return KMC_OK;
-}
-
-// (key, count) rows handed over with kmc_ingest_pairs: merge them through the hash table (equal keys add up), then
-// the same compaction / sort / look-up as finish_hash.  Kept apart from finish_hash on purpose: that one is the measured
-// single-GPU path.
-int finish_pairs(kmc_ctx *c) {
-  uint64_t rows_in = 0;
-  for (auto &a : c->ingested_pairs) rows_in += a.n;
-  uint32_t lg = 10;
-  while (lg < 33 && (1ull << lg) < 2 * rows_in + 2) lg++; // load factor <= 1/2 even if every row is a distinct key
-  const uint64_t slots = 1ull << lg;
-  TRY(ensure(c, c->hash_slots, slots * sizeof(HashSlot)));
-  TRY(ensure(c, c->hash_scalars, 64));
-  PHASE_BEGIN("hash_count");
-  LAUNCH(hash_init_kernel, std::min<uint32_t>(grid_for(slots, 256), c->n_sms * 16), 256, 0, (HashSlot *)c->hash_slots.p, slots);
-  CK(cudaMemsetAsync(c->hash_scalars.p, 0, 64, c->stream));
-  HashTable T;
-  T.slots = (HashSlot *)c->hash_slots.p;
-  T.mask = slots - 1; T.shift = 64 - lg;
-  T.n_used = (unsigned long long *)c->hash_scalars.p; T.n_total = T.n_used + 1; T.n_ones = T.n_used + 2;
-  T.limit = slots; T.flags = d_err(c);
-  for (auto &a : c->ingested_pairs)
-    if (a.n) LAUNCH(hash_count_pairs_kernel, std::min<uint32_t>(grid_for(a.n, 1024), c->n_sms * 8), 256, 0, a.keys, a.counts, a.n, T);
-  PHASE_END();
-  uint32_t err = 0;
-  TRY(read_scalars(c, nullptr, &err));
-  if (err & kFlagHashFull) return fail(c, KMC_E_CAPACITY, "kmc_finish: the merge table filled up (internal sizing error)");
-  unsigned long long sc[3];
-  TRY(d2h_small(c, sc, c->hash_scalars.p, sizeof sc));
-  const uint64_t d = sc[0], n_total = sc[1], n_ones = sc[2];
-  if (n_ones > 0xFFFFFFFFull) return fail(c, KMC_E_COUNT_OVERFLOW, "a k-mer occurs more than 2^32-1 times");
-  PHASE_BEGIN("hash_sort");
-  TRY(ensure(c, c->t_lo, (d + 2) * 8));
-  TRY(ensure(c, c->keys_b, (d + 2) * 8));
-  TRY(ensure(c, c->t_cnt, (d + 2) * 4));
-  uint64_t *dense = (uint64_t *)c->t_lo.p, *scratch = (uint64_t *)c->keys_b.p, *sorted = nullptr;
-  if (d) {
-    CK(cudaMemsetAsync(d_cursor(c), 0, 8, c->stream));
-    LAUNCH(hash_compact_kernel, std::min<uint32_t>(grid_for(T.mask + 1, 256), c->n_sms * 16), 256, 0, T, dense, d_cursor(c));
-    TRY(radix_sort<uint64_t>(c, dense, scratch, d, c->key_bits, &sorted));
-    if (sorted != dense) CK(cudaMemcpyAsync(dense, sorted, d * 8, cudaMemcpyDeviceToDevice, c->stream));
-    LAUNCH(hash_lookup_kernel, std::min<uint32_t>(grid_for(d, 256), c->n_sms * 16), 256, 0, T, (const uint64_t *)dense, d,
-           (uint32_t *)c->t_cnt.p);
-  }
-  uint64_t rows = d;
-  if (n_ones) { // the all-ones key (k = 32) sorts last
-    uint64_t k1 = kHashEmpty;
-    uint32_t c1 = (uint32_t)n_ones;
-    CK(cudaMemcpyAsync(dense + d, &k1, 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync((uint32_t *)c->t_cnt.p + d, &c1, 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    rows++;
-  }
-  PHASE_END();
-  c->n_total = n_total; c->n_distinct = rows;
-  c->strategy_used = KMC_STRATEGY_HASH;
-  return KMC_OK;
-}
-
-// AUTO: is the number of distinct keys small enough for an L2-resident table?  Insert a sample into a small table.
-int hash_probe(kmc_ctx *c, bool *low_cardinality) {
-  *low_cardinality = false;
-  c->probe_distinct = 0;
-  KeyArrays ka;
-  ka.from_array = !c->ingested.empty();
-  if (c->cfg.mode == KMC_MODE_LR_GAPPED) return KMC_OK; // keys would have to be materialised first: skip the probe
-  if (ka.from_array) for (auto &e : c->ingested) if (e.second) { ka.arrays.emplace_back(e.first, e.second); ka.n += e.second; }
-  const uint64_t n_in = ka.from_array ? ka.n : c->total_bases;
-  if (n_in < (1u << 18)) return KMC_OK;
-  uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
-  if (!ka.from_array) for (size_t i = 0; i < c->n_segs; i++) if (c->segs[i].wait_ready && c->segs[i].host_alias && step > 1) { step = std::min<uint32_t>(64, step * 4); break; }
-  bool ok = false;
-  HashTable T;
-  c->n_hot = 0;
-  PHASE_BEGIN("hash_probe");
-  TRY(hash_run(c, ka, 23, 1ull << 21, step, &ok, &T));
-  if (ok) {
-    // keys that make up more than 1/50000 of the sampled occurrences get private shared-memory counters later
-    unsigned long long sc[3];
-    TRY(d2h_small(c, sc, c->hash_scalars.p, sizeof sc));
-    const uint32_t thr = (uint32_t)std::max<uint64_t>(64, sc[1] / 50000);
-    unsigned int *d_nhot = (unsigned int *)((unsigned char *)c->hash_hot.p + kHotMax * 8);
-    CK(cudaMemsetAsync(d_nhot, 0, 4, c->stream));
-    LAUNCH(hash_hot_kernel, c->n_sms * 8, 256, 0, T, thr, (uint64_t *)c->hash_hot.p, d_nhot);
-    unsigned int nh = 0;
-    TRY(d2h_small(c, &nh, d_nhot, 4));
-    c->n_hot = std::min<uint32_t>(nh, kHotMax);
-    c->probe_distinct = sc[0];
-  }
-  PHASE_END();
-  *low_cardinality = ok;
-  return KMC_OK;
-}
-
-// Sampled histogram of the top coarse_bits() key bits of the job's keys (raw counts; *step_out = sampling step).
-// Uses the head of c->fast_state.
-template <typename KeyT>
-int coarse_hist(kmc_ctx *c, const KeyArrays &ka, std::vector<uint64_t> &hist, uint32_t *step_out) {
-  const uint32_t kb = c->key_bits, cb = coarse_bits(c), ncoarse = 1u << cb;
-  TRY(ensure(c, c->fast_state, 4096 * 8 + 64));
-  CK(cudaMemsetAsync(c->fast_state.p, 0, 4096 * 8, c->stream));
-  unsigned long long *ghist = (unsigned long long *)c->fast_state.p;
-  // sample so that ~64M keys are looked at (all of them for small inputs)
-  const uint64_t n_in = ka.from_array ? ka.n : c->total_bases;
-  uint32_t step = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kHistSampleMax, n_in >> 26));
-  // chunks still on their way are sampled straight from pinned host memory: read 4x less of it over the bus
-  if (!ka.from_array) for (size_t i = 0; i < c->n_segs; i++) if (c->segs[i].wait_ready && c->segs[i].host_alias && step > 1) { step = std::min<uint32_t>(64, step * 4); break; }
-  PHASE_BEGIN("fast_hist");
-  if (ka.from_array) {
-    for (auto &a : ka.arrays) {
-      uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(a.second, 1024 * step), (uint64_t)c->n_sms * 8);
-      auto fast_hist_array = fast_hist_array_kernel<KeyT>;
-      LAUNCH(fast_hist_array, grid, 256, ncoarse * 4, (const KeyT *)a.first, a.second, step, kb - cb, ncoarse, ghist);
-    }
-  } else {
-    for (size_t i = 0; i < c->n_segs; i++) {
-      Segment &s = c->segs[i];
-      if (!s.n_bases) continue;
-      const bool sample_host = step > 1 && s.host_alias && s.wait_ready;
-      if (!sample_host) TRY(seg_wait(c, s));
-      ExtractParams P = seg_params(c, s, sample_host);
-      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles / step + 8) / 8, (uint64_t)c->n_sms * 8);
-      auto fast_hist = fast_hist_kernel<KeyT, true>;
-      LAUNCH(fast_hist, grid, 256, ncoarse * 4, P, tiles, step, kb - cb, ncoarse, ghist);
-    }
-  }
-  PHASE_END();
-  hist.assign(ncoarse, 0);
-  TRY(d2h_small(c, hist.data(), ghist, ncoarse * 8));
-  *step_out = step;
-  return KMC_OK;
-}
-
-// lr-gapped keys are never materialised as a whole in a partial count: exact histogram straight from the L/R-mers
-template <typename KeyT>
-int coarse_hist_gapped(kmc_ctx *c, std::vector<uint64_t> &hist) {
-  const uint32_t kb = c->key_bits, cb = coarse_bits(c), ncoarse = 1u << cb;
-  TRY(ensure(c, c->fast_state, 4096 * 8 + 64));
-  CK(cudaMemsetAsync(c->fast_state.p, 0, 4096 * 8, c->stream));
-  uint64_t mx = 1;
-  for (size_t i = 0; i < c->n_segs; i++) mx = std::max<uint64_t>(mx, c->segs[i].n_bases);
-  TRY(ensure(c, c->gap_l, mx * 8));
-  TRY(ensure(c, c->gap_r, mx * 8));
-  TRY(ensure(c, c->gap_f, mx));
-  PHASE_BEGIN("fast_hist");
-  for (size_t i = 0; i < c->n_segs; i++) {
-    Segment &s = c->segs[i];
-    if (!s.n_bases) continue;
-    TRY(seg_wait(c, s));
-    GapParams P = gap_params(c, s);
-    uint32_t g = grid_for(s.n_bases, 256);
-    LAUNCH(gap_mers_kernel, g, 256, 0, P, (uint64_t *)c->gap_l.p, (uint64_t *)c->gap_r.p, (uint8_t *)c->gap_f.p);
-    auto gap_hist = gap_hist_kernel<KeyT>;
-    LAUNCH(gap_hist, g, 256, ncoarse * 4, P, (const uint64_t *)c->gap_l.p, (const uint64_t *)c->gap_r.p, kb - cb, ncoarse,
-           (unsigned long long *)c->fast_state.p);
-  }
-  PHASE_END();
-  hist.assign(ncoarse, 0);
-  TRY(d2h_small(c, hist.data(), c->fast_state.p, ncoarse * 8));
-  return KMC_OK;
-}
-
-// Shape of the two-level partition for an (upper-estimate) coarse histogram: how finely every coarse bin is split
-// (2^e[ci] fine buckets of <= target keys), the level-1 width b1, and per level-1 bucket the number of key bits
-// (below the b1 prefix) that select its fine bucket.  Level 1 = the top b1 key bits.  Only the level-1 buckets that
-// meet the coarse range [c_lo, c_hi) exist, numbered from l1_base (all 2^b1 of them unless this is a partial count —
-// which may therefore use more level-1 bits: what is bounded is the number of buckets the scatter kernel ranks in
-// shared memory, kMaxL1).  false: the input does not suit the partitioned path.
-// Capacity of the fine buckets of a coarse bin whose fine buckets expect `avg` keys each: 10 % + 6 sigma of slack,
-// a multiple of kFineAlign (bucket starts are sums of capacities: fast_finish's loads then start on a 128 B line).
-inline uint32_t fine_cap_for(double avg, uint32_t cap_max) {
-  uint32_t cp = (uint32_t)(avg * 1.10 + 6.0 * std::sqrt(avg) + 64.0);
-  return std::min<uint32_t>((cp + (kFineAlign - 1)) & ~(uint32_t)(kFineAlign - 1), cap_max);
-}
-// development knobs (tools/ab.py): KMC_FINE_TARGET_RT = keys aimed at per 64-bit-key fine bucket, KMC_B1 = level-1 bits
-inline int env_int(const char *name, int dflt) {
-  const char *v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
-}
-
-// 64-bit keys whose fine buckets leave more than 32 key bits are sorted fastest as Split64 (kmc_fast.cuh), which needs
-// every bucket to leave at most 32 + kFinishBits bits.  Sparse coarse bins (canonical k-mers thin out towards the top
-// of the key space) would be split less than that: the number of extra splits that brings them within reach, or 0
-// when the input is too small for it to pay (buckets of a few hundred keys).
-inline uint32_t split64_min_e(uint32_t kb, uint64_t n_est, bool wide) {
-  const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb);
-  if (wide || kb <= cb + 32 + (uint32_t)kFinishBits) return 0;
-  const uint32_t me = kb - cb - (32 + (uint32_t)kFinishBits);
-  if (me > 12 || (n_est >> (cb + me)) < 512) return 0;
-  return me;
-}
-
-struct PlanShape {
-  uint32_t b1 = 0, l1_base = 0, n_l1 = 0;
-  std::vector<uint32_t> e;   // [ncoarse]
-  std::vector<uint8_t> l1e;  // [n_l1]
-  uint64_t n_fine = 0;
-};
-// min_e: split every coarse bin at least 2^min_e ways (split64_min_e: keeps sparse bins within Split64's reach)
-bool plan_shape(const std::vector<uint64_t> &hist, uint32_t kb, uint32_t c_lo, uint32_t c_hi, bool ranged, int target,
-                PlanShape &P, uint32_t b1_min = 0, uint32_t min_e = 0) {
-  const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb), ncoarse = 1u << cb;
-  P.e.assign(ncoarse, 0);
-  for (uint32_t ci = 0; ci < ncoarse; ci++) {
-    uint32_t ee = hist[ci] ? min_e : 0;
-    while (((hist[ci] + ((1ull << ee) - 1)) >> ee) > (uint64_t)target) ee++;
-    if (ee > kb - cb) return false; // cannot split far enough: too many keys share a prefix (duplicates)
-    P.e[ci] = ee;
-  }
-  uint32_t b1_lo = cb > 6 ? cb - 6 : 0, b1_hi = ranged ? cb : std::min<uint32_t>(cb, 10);
-  uint64_t nf_guess = 0;
-  for (uint32_t ci = c_lo; ci < c_hi; ci++) nf_guess += 1ull << P.e[ci];
-  uint32_t b1 = (uint32_t)std::lround(std::log2(std::sqrt((double)nf_guess) * (double)ncoarse / (double)(c_hi - c_lo)));
-  b1 = std::max(std::max(b1_lo, std::min(b1_min, b1_hi)), std::min(b1, b1_hi));
-  if (const int forced = env_int("KMC_B1", 0); forced > 0) b1 = std::max(b1_lo, std::min<uint32_t>((uint32_t)forced, b1_hi));
-  auto l1_span = [&](uint32_t bits, uint32_t *base) { // level-1 buckets met by the coarse range at `bits` level-1 bits
-    *base = c_lo >> (cb - bits);
-    return ((c_hi - 1) >> (cb - bits)) + 1 - *base;
-  };
-  uint32_t l1_base = 0, n_l1 = 0;
-  while (b1 > b1_lo && l1_span(b1, &l1_base) > (uint32_t)kMaxL1) b1--;
-  for (;; b1++) {
-    if (b1 > b1_hi) return false;
-    n_l1 = l1_span(b1, &l1_base);
-    if (n_l1 > (uint32_t)kMaxL1) return false; // too many keys for two levels of this size
-    P.l1e.assign(n_l1, 0);
-    uint32_t mx = 0;
-    for (uint32_t rb = 0; rb < n_l1; rb++) {
-      const uint32_t b = l1_base + rb;
-      uint32_t em = 0;
-      for (uint32_t ci = b << (cb - b1); ci < ((b + 1) << (cb - b1)); ci++) em = std::max(em, P.e[ci]);
-      P.l1e[rb] = (uint8_t)(cb - b1 + em);
-      mx = std::max<uint32_t>(mx, P.l1e[rb]);
-    }
-    if ((1ull << mx) <= (uint64_t)kMaxFinePerL1) break;
-  }
-  P.b1 = b1; P.l1_base = l1_base; P.n_l1 = n_l1;
-  P.n_fine = 0;
-  for (uint32_t b = 0; b < n_l1; b++) P.n_fine += 1ull << P.l1e[b];
-  return P.n_fine <= (1ull << 28);
-}
-
-// level-2 scatter of the keys in [l1_done, l1_cursor) of every level-1 bucket (all of them if done == nullptr);
-// t_max = tiles per bucket the grid provides (a CTA takes several if there are more); nb_max = most fine buckets
-// under one level-1 bucket (sizes the shared memory).
-template <typename KeyT, typename L2T>
-int launch_part2_as(kmc_ctx *c, const FastPlan &pl, const KeyT *l1, uint32_t nb_max, uint64_t t_max, unsigned long long *done, bool flush) {
-  const size_t smem = PartSmem<KeyT>::bytes(p2_tile<KeyT>(), nb_max);
-  auto fast_part2 = fast_part2_kernel<KeyT, L2T>;
-  CK(cudaFuncSetAttribute(fast_part2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const dim3 grid((uint32_t)std::min<uint64_t>(std::max<uint64_t>(t_max, 1), 1u << 20), pl.n_l1);
-  LAUNCH(fast_part2, grid, kFastThreads, smem, pl, l1, (L2T *)c->fast_l2.p, d_err(c), (const unsigned long long *)done, flush ? 1u : 0u, nb_max);
-  if (done) {
-    LAUNCH(l2_done_kernel, grid_for(pl.n_l1, 256), 256, 0, pl, done, (uint32_t)p2_tile<KeyT>(), flush ? 1u : 0u, grid.x);
-    c->launches--; // plumbing
-  }
-  return KMC_OK;
-}
-template <typename KeyT>
-int launch_part2(kmc_ctx *c, const FastPlan &pl, const KeyT *l1, bool key32, uint32_t nb_max, uint64_t t_max, unsigned long long *done = nullptr,
-                 bool flush = true) {
-  if constexpr (sizeof(KeyT) == 16) return launch_part2_as<U128, U128>(c, pl, l1, nb_max, t_max, done, flush);
-  else if (key32) return launch_part2_as<uint64_t, uint32_t>(c, pl, l1, nb_max, t_max, done, flush);
-  else return launch_part2_as<uint64_t, uint64_t>(c, pl, l1, nb_max, t_max, done, flush);
-}
-
-constexpr uint64_t kFastMinKeys = 1u << 18, kFastMinKeysGapped = 1u << 23;
-
-struct FastJob {   // one partitioned count in progress: the plan, and what the later stages need of it
-  bool active = false;
-  FastPlan pl{};
-  bool key32 = false, split64 = false, ranged = false;
-  uint32_t nb_max = 1, c_lo = 0, c_hi = 0;
-  uint64_t t_max = 1, n_fine = 0, fed = 0;
-  unsigned int *ticket = nullptr;
-  unsigned long long *d_total = nullptr, *status = nullptr, *l1_done = nullptr;
-};
-FastJob &job_of(kmc_ctx *c) {
-  if (!c->job_box) c->job_box = new FastJob();
-  return *static_cast<FastJob *>(c->job_box);
-}
-
-// ---- partitioned fast path (kmc_fast.cuh) --------------------------------------------------------------------
-// Three stages, so that keys can be fed while they arrive (chunks of a pinned submit; chunks routed by the other ranks):
-//   fast_begin  plan from an upper-estimate coarse histogram, buffers, tables            → *ok
-//   fast_feed_* level-1 scatter of a segment / a key array (+ the level-2 scatter of what has come in so far)
-//   fast_end    (rest of the) level-2 scatter, bucket sort, totals                      → *used
-// *ok / *used = false: the input does not suit the path (tiny, duplicate-heavy, or a bucket overflowed); nothing is left
-// behind and the caller counts with the baseline path.
-// relax = 1: aim at half-full buckets (retry after an overflow: input whose keys come in many copies spreads
-// less evenly than the plan's Poisson slack assumes).
-template <typename KeyT>
-int fast_begin(kmc_ctx *c, std::vector<uint64_t> &hist, uint64_t n_est, int relax, bool *ok) {
-  constexpr bool kWide = sizeof(KeyT) == 16;
-  int kCap = kWide ? 4096 : kFineCap;
-  int kTarget = (kWide ? 3200 : std::min(env_int("KMC_FINE_TARGET_RT", kFineTarget), kFineTarget)) >> relax;
-  *ok = false;
-  FastJob &J = job_of(c);
-  J.active = false;
-  const uint32_t kb = c->key_bits;
-  const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb);
-  const uint32_t ncoarse = 1u << cb;
-  const bool ranged = c->range_on;
-  const uint32_t c_lo = ranged ? c->range_lo : 0u, c_hi = ranged ? c->range_lo + c->range_n : ncoarse;
-  // fast_state layout: ghist[4096] u64 | ticket u32 (+pad) | d_total u64 | l1_cursor[kMaxL1] u64 | l1_done[kMaxL1] u64 | fine_cursor[nf] u32 | status[nf] u64
-  const size_t off_ticket = 4096 * 8, off_dtotal = off_ticket + 8, off_l1cur = off_dtotal + 8, off_l1done = off_l1cur + kMaxL1 * 8,
-               off_fine = off_l1done + kMaxL1 * 8;
-  // ---- plan
-  PlanShape shape;
-  const uint32_t min_e = getenv("KMC_NO_SPLIT64") ? 0u : split64_min_e(kb, n_est, kWide);
-  if (!plan_shape(hist, kb, c_lo, c_hi, ranged, kTarget, shape, 0, min_e)) return KMC_OK;
-  if (!kWide && (kFineCap64 != kFineCap || kFineTarget64 != kFineTarget)) {
-    // buckets that leave more than 32 key bits are sorted as 64-bit elements, whose bucket shape is smaller: plan again
-    bool wide_elems = false;
-    for (uint32_t b = 0; b < shape.n_l1; b++) if (kb - shape.b1 - shape.l1e[b] > 32) wide_elems = true;
-    if (wide_elems) {
-      kCap = kFineCap64;
-      kTarget = std::min(kTarget, kFineTarget64 >> relax);
-      if (!plan_shape(hist, kb, c_lo, c_hi, ranged, kTarget, shape, 0, min_e)) return KMC_OK;
-    }
-  }
-  const uint32_t b1 = shape.b1, l1_base = shape.l1_base, n_l1 = shape.n_l1;
-  const std::vector<uint8_t> &l1e = shape.l1e;
-  const uint64_t n_fine = shape.n_fine;
-  // Host tables (a few tens of KB): per level-1 bucket l1_start | l1_cap | l1_tile0 | l1_fine0 | l1_e, and per coarse
-  // bin the first fine bucket, its level-2 start and the capacity of its fine buckets.  The per-fine-bucket
-  // descriptors (n_fine x 32 B, megabytes) are expanded from these on the device (plan_expand_kernel): filling and
-  // uploading them from the host cost ~1.2 ms of idle GPU per job.
-  auto al16 = [](size_t x) { return (x + 15) & ~size_t(15); };
-  const uint32_t cshift = cb - b1, n_cb = n_l1 << cshift; // coarse bins under the existing level-1 buckets
-  const size_t o_l1s = 0, o_cap = o_l1s + al16((size_t)(n_l1 + 1) * 8),
-               o_t0 = o_cap + al16((size_t)n_l1 * 8), o_f0 = o_t0 + al16((size_t)(n_l1 + 1) * 4),
-               o_e = o_f0 + al16((size_t)(n_l1 + 1) * 4), o_cs = o_e + al16(n_l1), o_cf = o_cs + al16((size_t)n_cb * 8),
-               o_cc = o_cf + al16((size_t)n_cb * 4), tab_bytes = o_cc + al16((size_t)n_cb * 2);
-  c->fast_host.assign(tab_bytes, 0);
-  uint64_t *cstart = (uint64_t *)(c->fast_host.data() + o_cs);
-  uint32_t *cfine0 = (uint32_t *)(c->fast_host.data() + o_cf);
-  uint16_t *ccap = (uint16_t *)(c->fast_host.data() + o_cc);
-  uint64_t *l1s = (uint64_t *)(c->fast_host.data() + o_l1s), *l1cap = (uint64_t *)(c->fast_host.data() + o_cap);
-  uint32_t *t0 = (uint32_t *)(c->fast_host.data() + o_t0), *f0 = (uint32_t *)(c->fast_host.data() + o_f0);
-  uint8_t *l1ep = c->fast_host.data() + o_e;
-  uint64_t l1_keys = 0, l2_keys = 0, tiles2 = 0, t_max = 1;
-  uint32_t fb = 0, nb_max = 1;
-  bool key32 = !kWide; // every bucket leaves <= 32 key bits: level 2 stores 32-bit suffixes
-  bool split64 = !kWide && !getenv("KMC_NO_SPLIT64"); // ... at most 32 + kFinishBits: sorted as 32-bit suffixes + sub-bin ids (Split64)
-  for (uint32_t b = 0; b < n_l1; b++) {
-    if (kb - b1 - l1e[b] > 32) key32 = false;
-    if (kb - b1 - l1e[b] > 32 + (uint32_t)kFinishBits) split64 = false;
-  }
-  if (key32) split64 = false;
-  for (uint32_t b = 0; b < n_l1; b++) { // b: index among the existing level-1 buckets; b_abs: its key prefix
-    const uint32_t b_abs = l1_base + b;
-    uint64_t nb = 0;
-    const uint32_t sub_bits = l1e[b] - (cb - b1); // fine buckets per coarse bin of this level-1 bucket = 2^sub_bits
-    f0[b] = fb;
-    for (uint32_t ci = b_abs << (cb - b1); ci < ((b_abs + 1) << (cb - b1)); ci++) {
-      nb += hist[ci];
-      double avg = (double)hist[ci] / (double)(1ull << sub_bits);
-      const uint32_t cp = relax ? (uint32_t)kCap : fine_cap_for(avg, kCap);
-      const uint32_t ci_rel = ci - (l1_base << cshift);
-      cstart[ci_rel] = l2_keys; cfine0[ci_rel] = fb; ccap[ci_rel] = (uint16_t)cp;
-      l2_keys += (uint64_t)cp << sub_bits;
-      fb += 1u << sub_bits;
-    }
-    uint64_t cap1 = ((uint64_t)((double)nb * 1.03) + 8192 + 15) & ~15ull;
-    l1s[b] = l1_keys; l1cap[b] = cap1; t0[b] = (uint32_t)tiles2; l1ep[b] = l1e[b];
-    l1_keys += cap1;
-    tiles2 += (cap1 + p2_tile<KeyT>() - 1) / p2_tile<KeyT>();
-    t_max = std::max<uint64_t>(t_max, (cap1 + p2_tile<KeyT>() - 1) / p2_tile<KeyT>());
-    nb_max = std::max<uint32_t>(nb_max, 1u << l1e[b]);
-  }
-  l1s[n_l1] = l1_keys; t0[n_l1] = (uint32_t)tiles2; f0[n_l1] = fb;
-  if (tiles2 > 0x7FFFFFFFull) return KMC_OK;
-  HOST_MARK("planned");
-
-  // ---- buffers (each array ends with a trash area of one tile + slack for runs that spill over a bucket end)
-  const uint64_t slack = 2 * kMaxTile;
-  TRY(ensure(c, c->fast_tables, tab_bytes));
-  TRY(ensure(c, c->fast_fdesc, n_fine * sizeof(FineDesc)));
-  TRY(ensure(c, c->fast_l1, (l1_keys + slack) * sizeof(KeyT)));
-  // the level-1 array and the table's key column trade places after every job (64-bit keys): size both, or the
-  // smaller one would be freed and reallocated on alternate jobs
-  if (!kWide) TRY(ensure(c, c->t_lo, (l1_keys + slack) * sizeof(KeyT)));
-  TRY(ensure(c, c->fast_l2, (l2_keys + 2 * slack) * sizeof(KeyT)));
-  if (kWide) { TRY(ensure(c, c->t_lo, l1_keys * 8)); TRY(ensure(c, c->t_hi, l1_keys * 8)); }
-  TRY(ensure(c, c->t_cnt, l1_keys * 4));
-  const size_t off_status = (off_fine + n_fine * 4 + 15) & ~size_t(15);
-  if (off_status + n_fine * 8 + 64 > c->fast_state.cap) {
-    TRY(ensure(c, c->fast_state, off_status + n_fine * 8 + 64));
-  }
-  HOST_MARK("buffers");
-  CK(cudaMemsetAsync(c->fast_state.p, 0, off_status + n_fine * 8, c->stream));
-  TRY(h2d_small(c, c->fast_tables.p, c->fast_host.data(), tab_bytes));
-  HOST_MARK("uploaded");
-  unsigned char *st = (unsigned char *)c->fast_state.p, *tb = (unsigned char *)c->fast_tables.p;
-  FastPlan &pl = J.pl;
-  pl = FastPlan{};
-  pl.kb = kb; pl.b1 = b1; pl.n_l1 = n_l1; pl.n_fine = (uint32_t)n_fine; pl.l1_base = l1_base;
-  pl.l1_trash = l1_keys; pl.l2_trash = l2_keys + slack;
-  pl.fdesc = (const FineDesc *)c->fast_fdesc.p;
-  pl.l1_start = (const uint64_t *)(tb + o_l1s); pl.l1_cap = (const uint64_t *)(tb + o_cap);
-  pl.l1_tile0 = (const uint32_t *)(tb + o_t0); pl.l1_fine0 = (const uint32_t *)(tb + o_f0); pl.l1_e = (const uint8_t *)(tb + o_e);
-  pl.l1_cursor = (unsigned long long *)(st + off_l1cur); pl.fine_cursor = (uint32_t *)(st + off_fine);
-  J.ticket = (unsigned int *)(st + off_ticket);
-  J.d_total = (unsigned long long *)(st + off_dtotal);
-  J.status = (unsigned long long *)(st + off_status);
-  J.l1_done = (unsigned long long *)(st + off_l1done);
-  LAUNCH(plan_expand_kernel, n_cb, 128, 0, (FineDesc *)c->fast_fdesc.p, (const uint64_t *)(tb + o_cs), (const uint32_t *)(tb + o_cf),
-         (const uint16_t *)(tb + o_cc), pl.l1_fine0, pl.l1_e, cshift, l1_base, kb, b1, (uint32_t)kWide);
-  c->launches--; // plumbing
-
-
-  J.key32 = key32; J.split64 = split64; J.ranged = ranged; J.nb_max = nb_max; J.c_lo = c_lo; J.c_hi = c_hi;
-  J.t_max = t_max; J.n_fine = n_fine; J.fed = 0;
-  J.active = true;
-  c->fast_variant = kWide ? "u128" : key32 ? "u32" : split64 ? "split64" : "u64";
-  *ok = true;
-  return KMC_OK;
-}
-
-// level-1 scatter of a key array; incremental: follow it with the level-2 scatter of the whole tiles that have come in
-template <typename KeyT>
-int fast_feed_array(kmc_ctx *c, const void *keys, uint64_t n, bool incremental) {
-  FastJob &J = job_of(c);
-  if (!n) return KMC_OK;
-  const size_t smem = L1Smem<KeyT>::bytes(arr_tile<KeyT>(), J.pl.n_l1);
-  auto fast_part1_array = fast_part1_array_kernel<KeyT>;
-  CK(cudaFuncSetAttribute(fast_part1_array, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PHASE_BEGIN("fast_part1");
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(grid_for(n, arr_tile<KeyT>()), (uint64_t)c->n_sms);
-  LAUNCH(fast_part1_array, grid, kFastThreads, smem, (const KeyT *)keys, n, J.pl, (KeyT *)c->fast_l1.p, d_err(c));
-  PHASE_END();
-  J.fed += n;
-  if (incremental) {
-    PHASE_BEGIN("fast_part2");
-    const uint64_t t_arr = (uint64_t)((double)n / J.pl.n_l1 / p2_tile<KeyT>() * 1.25) + 2;
-    TRY(launch_part2<KeyT>(c, J.pl, (const KeyT *)c->fast_l1.p, J.key32, J.nb_max, std::min(t_arr, J.t_max), J.l1_done, false));
-    PHASE_END();
-  }
-  return KMC_OK;
-}
-
-template <typename KeyT>
-int fast_end(kmc_ctx *c, bool incremental, bool *used) {
-  constexpr bool kWide = sizeof(KeyT) == 16;
-  FastJob &J = job_of(c);
-  *used = false;
-  J.active = false;
-  const FastPlan &pl = J.pl;
-  const bool key32 = J.key32, split64 = J.split64;
-  const uint64_t n_fine = J.n_fine;
-  const uint32_t n_l1 = pl.n_l1;
-  // ---- level 2 (all of it, or what the incremental rounds have left)
-  PHASE_BEGIN("fast_part2");
-  TRY(launch_part2<KeyT>(c, pl, (const KeyT *)c->fast_l1.p, key32, J.nb_max, J.t_max, incremental ? J.l1_done : nullptr, true));
-  PHASE_END();
-  // ---- finish: the level-1 array is dead after part2 and (64-bit keys) becomes the table's key column
-  PHASE_BEGIN("fast_finish");
-  {
-    unsigned long long *prof = nullptr;
-    static const bool want_prof = getenv("KMC_FINISH_PROF") && getenv("KMC_FINISH_PROF")[0] == '1';
-    if (want_prof) { prof = (unsigned long long *)c->fast_state.p; CK(cudaMemsetAsync(prof, 0, 16 * 8, c->stream)); } // the histogram is dead by now
-    uint32_t grid;
-    if constexpr (kWide) {
-      size_t fsmem = sizeof(FinishSmem<U128>);
-      auto fast_finish = fast_finish_kernel<U128>;
-      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * 2);
-      LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const U128 *)c->fast_l2.p, (uint64_t *)c->t_lo.p, (uint64_t *)c->t_hi.p,
-             (uint32_t *)c->t_cnt.p, J.status, J.ticket, d_err(c), J.d_total, prof);
-    } else if (key32) {
-      size_t fsmem = sizeof(FinishSmem<uint32_t>);
-      auto fast_finish = fast_finish_kernel<uint32_t>;
-      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * KMC_FINISH_MINB32);
-      LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint32_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
-             (uint32_t *)c->t_cnt.p, J.status, J.ticket, d_err(c), J.d_total, prof);
-    } else if (split64) {
-      size_t fsmem = sizeof(FinishSmem<Split64>);
-      auto fast_finish = fast_finish_kernel<Split64>;
-      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * 2);
-      LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
-             (uint32_t *)c->t_cnt.p, J.status, J.ticket, d_err(c), J.d_total, prof);
-    } else {
-      size_t fsmem = sizeof(FinishSmem<uint64_t>);
-      auto fast_finish = fast_finish_kernel<uint64_t>;
-      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      grid = (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * KMC_FINISH_MINB64);
-      LAUNCH(fast_finish, grid, kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p, (uint64_t *)c->fast_l1.p, (uint64_t *)nullptr,
-             (uint32_t *)c->t_cnt.p, J.status, J.ticket, d_err(c), J.d_total, prof);
-    }
-    if (want_prof) {
-      unsigned long long h[16];
-      CK(cudaMemcpyAsync(h, prof, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      unsigned long long tot = 0;
-      for (int i = 0; i < 10; i++) tot += h[i];
-      fprintf(stderr, "[kmc] fast_finish cycles per phase (thread 0, summed over %u CTAs), %% of total:", grid);
-      for (int i = 0; i < 11; i++) fprintf(stderr, " p%d=%.1f%%", i, 100.0 * (double)h[i] / (double)std::max<unsigned long long>(1, tot));
-      fprintf(stderr, "  total=%.0f cycles/CTA\n", (double)tot / grid);
-    }
-  }
-  PHASE_END();
-  uint64_t d = 0;
-  uint32_t err = 0;
-  std::vector<unsigned long long> cur(n_l1);
-  TRY(d2h_small(c, &d, J.d_total, 8));
-  TRY(d2h_small(c, cur.data(), pl.l1_cursor, (size_t)n_l1 * 8));
-  TRY(read_scalars(c, nullptr, &err));
-  if (err & kFlagSpin) return fail(c, KMC_E_CUDA, "fast_finish: look-back did not make progress");
-  if (err & kFlagOverflow) {
-    c->fast_fallbacks++;
-    TRY(zero_scalars(c));
-    return KMC_OK; // recount with the data-independent path
-  }
-
-  uint64_t N = 0;
-  for (unsigned long long v : cur) N += v;
-  if (!kWide) std::swap(c->t_lo, c->fast_l1);
-  c->n_total = N; c->n_distinct = d;
-  c->strategy_used = KMC_STRATEGY_SORT;
-  *used = true;
-  return KMC_OK;
-}
-
-template <typename KeyT>
-int finish_fast(kmc_ctx *c, bool *used, int relax = 0) {
-  *used = false;
-  const uint32_t kb = c->key_bits;
-  const uint32_t cb = std::min<uint32_t>(kCoarseBitsMax, kb);
-  const uint32_t ncoarse = 1u << cb;
-  KeyArrays ka;
-  TRY(key_sources<KeyT>(c, &ka));
-  TRY(ensure(c, c->fast_state, 4096 * 8 + 64));
-  std::vector<uint64_t> hist;
-  uint32_t step = 1;
-  if (c->range_on && c->part_hist_step) { hist = c->part_hist; step = c->part_hist_step; } // partial count: computed once per input
-  else TRY(coarse_hist<KeyT>(c, ka, hist, &step));
-  // a partial count sees only the coarse bins of its key range
-  const bool ranged = c->range_on;
-  const uint32_t c_lo = ranged ? c->range_lo : 0u, c_hi = ranged ? c->range_lo + c->range_n : ncoarse;
-  if (ranged) for (uint32_t ci = 0; ci < ncoarse; ci++) if (ci < c_lo || ci >= c_hi) hist[ci] = 0;
-  if (c_hi <= c_lo) return KMC_OK; // empty range: the generic path returns the empty table
-  // the histogram is a 1-in-step sample: scale it to an upper estimate (+5 sigma of the sampling noise)
-  uint64_t n_est = 0;
-  for (uint64_t &v : hist) {
-    double est = (double)v * step;
-    if (step > 1) est += 5.0 * std::sqrt(est * step) + step;
-    v = (uint64_t)est;
-    n_est += v;
-  }
-  // small job: the generic path is as fast (a few passes over a few MB) and does not care what the keys look like.
-  // lr-gapped keys come in groups of up to d_max - d_min + 1 that share their L-mer, 2 * l_len bits; when the input is
-  // repetitive as well (the reference's own fixture: 3.55 M keys, 54-bit prefixes shared by the thousand) no prefix
-  // partition can separate them, so such jobs take the generic path up to a larger size.
-  if (n_est < (c->cfg.mode == KMC_MODE_LR_GAPPED ? kFastMinKeysGapped : kFastMinKeys)) return KMC_OK;
-  HOST_MARK("hist_read");
-  bool ok = false;
-  TRY(fast_begin<KeyT>(c, hist, n_est, relax, &ok));
-  if (!ok) return KMC_OK;
-  FastJob &J = job_of(c);
-  const FastPlan &pl = J.pl;
-  const uint32_t b1 = pl.b1, l1_base = pl.l1_base, n_l1 = pl.n_l1;
-
-  // ---- level 1
-  bool incremental = false;
-  if (ka.from_array) {
-    for (auto &a : ka.arrays) TRY(fast_feed_array<KeyT>(c, a.first, a.second, false));
-  } else {
-    PHASE_BEGIN("fast_part1");
-    size_t smem = L1Smem<KeyT>::bytes(part1_stage<KeyT>(), n_l1);
-    auto fast_part1 = fast_part1_kernel<KeyT, true, PrefixBucket>;
-    auto fast_part1_ranged = fast_part1_kernel<KeyT, true, PrefixBucketT<true>>;
-    if (ranged) CK(cudaFuncSetAttribute(fast_part1_ranged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else CK(cudaFuncSetAttribute(fast_part1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const PrefixBucket bucket = make_prefix_bucket<false>(kb, b1);
-    const PrefixBucketT<true> bucket_ranged = make_prefix_bucket<true>(kb, b1, l1_base, kb - cb, c_lo, c_hi - c_lo);
-    // A large pinned submit arrives in chunks (submit_chunked): the level-2 scatter then follows every chunk's level-1
-    // scatter for the keys that have come in so far (whole tiles only; fast_end takes the rest), so that when
-    // the last chunk has landed only its own share of the two scatters and the bucket sort remain.
-    size_t n_live = 0, i_last = 0;
-    for (size_t i = 0; i < c->n_segs; i++) if (c->segs[i].n_bases) { n_live++; i_last = i; }
-    incremental = n_live >= 4;
-    for (size_t i = 0; i < c->n_segs; i++) {
-      Segment &s = c->segs[i];
-      if (!s.n_bases) continue;
-      TRY(seg_wait(c, s));
-      ExtractParams P = seg_params(c, s);
-      uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>());
-      uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + kFastWarps - 1) / kFastWarps, (uint64_t)c->n_sms);
-      const uint64_t n_ct = (tiles + kFastWarps - 1) / kFastWarps;
-      if (ranged) LAUNCH(fast_part1_ranged, grid, kFastThreads, smem, P, tiles, pl, bucket_ranged, (KeyT *)c->fast_l1.p, d_err(c), (uint64_t)0, n_ct);
-      else LAUNCH(fast_part1, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->fast_l1.p, d_err(c), (uint64_t)0, n_ct);
-      if (incremental && i != i_last) {
-        PHASE_END();
-        PHASE_BEGIN("fast_part2");
-        const uint64_t t_seg = (uint64_t)((double)s.n_bases / n_l1 / p2_tile<KeyT>() * 1.25) + 2;
-        TRY(launch_part2<KeyT>(c, pl, (const KeyT *)c->fast_l1.p, J.key32, J.nb_max, std::min(t_seg, J.t_max), J.l1_done, false));
-        PHASE_END();
-        PHASE_BEGIN("fast_part1");
-      }
-    }
-    PHASE_END();
-  }
-  return fast_end<KeyT>(c, incremental, used);
-}
-
-// ---- partial counts of one input (kmc_finish_part): all keys scattered ONCE by their top bits --------------------------
-// A job too large to be counted in one go (1e10 bases at k=31: level-1 + level-2 arrays + table exceed HBM) is counted
-// in key ranges.  Extracting the whole input again for every range cost 47 ms x 8 of 634 ms at that size; instead the
-// first call runs the level-1 scatter kernel once over everything, 2^b1 buckets by key prefix (74 GB of keys fit beside
-// the 10 GB of bases), and part p is then counted from the buckets of its range through the key-array front end.
-template <typename KeyT>
-int kept_scatter(kmc_ctx *c) {
-  const uint32_t kb = c->key_bits, cb = coarse_bits(c), ncoarse = 1u << cb;
-  const uint32_t b1 = std::min<uint32_t>(cb, (uint32_t)env_int("KMC_KEPT_BITS", 8)), n_l1 = 1u << b1, cshift = cb - b1;
-  c->kept_valid = false;
-  c->kept_start.assign(n_l1 + 1, 0); c->kept_count.assign(n_l1, 0);
-  std::vector<uint64_t> cap(n_l1, 0);
-  uint64_t total = 0;
-  for (uint32_t b = 0; b < n_l1; b++) {
-    double nb = 0;
-    for (uint32_t ci = b << cshift; ci < ((b + 1) << cshift) && ci < ncoarse; ci++) {
-      double est = (double)c->part_hist[ci] * c->part_hist_step;
-      if (c->part_hist_step > 1) est += 5.0 * std::sqrt(est * c->part_hist_step) + c->part_hist_step;
-      nb += est;
-    }
-    cap[b] = ((uint64_t)(nb * 1.02) + 8192 + 15) & ~15ull;
-    c->kept_start[b] = total;
-    total += cap[b];
-  }
-  c->kept_start[n_l1] = total;
-  size_t free_b = 0, total_b = 0;
-  CK(cudaMemGetInfo(&free_b, &total_b));
-  const size_t need = (total + 2 * kMaxTile) * sizeof(KeyT);
-  // room for the array AND for one part's own buffers afterwards, or the old way (extract per part) is the only way
-  if (need > c->kept_keys.cap && need + need / 2 > free_b + c->kept_keys.cap) return KMC_OK;
-  TRY(ensure(c, c->kept_keys, need));
-  auto al16 = [](size_t x) { return (x + 15) & ~size_t(15); };
-  const size_t o_s = 0, o_c = al16((size_t)(n_l1 + 1) * 8), tab_bytes = o_c + al16((size_t)n_l1 * 8);
-  std::vector<unsigned char> host(tab_bytes, 0);
-  memcpy(host.data() + o_s, c->kept_start.data(), (size_t)(n_l1 + 1) * 8);
-  memcpy(host.data() + o_c, cap.data(), (size_t)n_l1 * 8);
-  TRY(ensure(c, c->kept_tables, tab_bytes));
-  TRY(ensure(c, c->kept_state, (size_t)kMaxL1 * 8 + 64));
-  TRY(zero_scalars(c));
-  CK(cudaMemsetAsync(c->kept_state.p, 0, (size_t)kMaxL1 * 8, c->stream));
-  TRY(h2d_small(c, c->kept_tables.p, host.data(), tab_bytes));
-  FastPlan pl{};
-  pl.kb = kb; pl.b1 = b1; pl.n_l1 = n_l1; pl.l1_base = 0; pl.l1_trash = total;
-  pl.l1_start = (const uint64_t *)((unsigned char *)c->kept_tables.p + o_s);
-  pl.l1_cap = (const uint64_t *)((unsigned char *)c->kept_tables.p + o_c);
-  pl.l1_cursor = (unsigned long long *)c->kept_state.p;
-  PHASE_BEGIN("kept_scatter");
-  {
-    size_t smem = L1Smem<KeyT>::bytes(part1_stage<KeyT>(), n_l1);
-    auto fast_part1 = fast_part1_kernel<KeyT, true, PrefixBucket>;
-    CK(cudaFuncSetAttribute(fast_part1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const PrefixBucket bucket = make_prefix_bucket<false>(kb, b1);
-    for (size_t i = 0; i < c->n_segs; i++) {
-      Segment &s = c->segs[i];
-      if (!s.n_bases) continue;
-      TRY(seg_wait(c, s));
-      ExtractParams P = seg_params(c, s);
-      const uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>()), n_ct = (tiles + kFastWarps - 1) / kFastWarps;
-      LAUNCH(fast_part1, (uint32_t)std::min<uint64_t>(n_ct, (uint64_t)c->n_sms), kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)c->kept_keys.p,
-             d_err(c), (uint64_t)0, n_ct);
-    }
-  }
-  PHASE_END();
-  std::vector<unsigned long long> cur(n_l1);
-  uint32_t err = 0;
-  TRY(d2h_small(c, cur.data(), pl.l1_cursor, (size_t)n_l1 * 8));
-  TRY(read_scalars(c, nullptr, &err));
-  if (err & kFlagOverflow) { TRY(zero_scalars(c)); return KMC_OK; } // skewed beyond the estimate: the old way
-  for (uint32_t b = 0; b < n_l1; b++) c->kept_count[b] = cur[b];
-  c->kept_b1 = b1;
-  c->kept_valid = true;
-  return KMC_OK;
-}
-
-// ---- multi-GPU: range partition, the level-1 scatter done by the SENDERS, the exchange by the copy engines --
-// Every rank holds a shard of the reads.  Instead of routing keys to owners by hash and letting every owner run the
-// level-1 scatter over what it received (an extra pass over all keys), the ranks agree on ONE plan for the whole key
-// space — from the all-gathered coarse histograms, so every rank computes the same plan by itself — whose level-1
-// buckets are dealt to the owners in consecutive, equally populated runs.  A sender's level-1 scatter is then the same
-// kernel, at the same speed, as on one GPU: it writes into a LOCAL staging array laid out owner by owner, and each
-// owner's slab of it crosses NVLink as one large device-to-device copy (the buckets this rank owns itself are
-// scattered straight into its own receive buffer).  (The first form of this path stored every bucket run — ~250 B —
-// into peer memory from the scatter kernel: 14.5 ms per 1e9 bases at 2 GPUs against 4.5 for the local scatter.)
-// The input is cut into chunks: while chunk c + 1 is being scattered, chunk c is on the links and the owners run the
-// level-2 scatter over chunk c - 1 on a second stream, so the exchange costs no SM time and hides behind the count.
-// The owner runs fast_part2 + fast_finish only, and its table is the key range it owns: the ranks' tables, in rank
-// order, are the globally sorted table.
-//
-// Receive buffer of an owner (kmc_recv_buffer, mapped by the peers with CUDA IPC):
-//   [ cursor table: (chunk, bucket, sender) -> keys stored, u64, kDistHeader bytes ][ level-1 array ]
-// level-1 array of owner o: for chunk c, for sender s, for bucket b of o: a region of cap(s, b) keys — so the slab
-// (c, s) is contiguous, and is what sender s copies in one piece.
-constexpr uint32_t kDistMaxWorld = 16, kDistMaxChunks = 16;
-constexpr size_t kDistHeader = (size_t)kMaxL1 * kDistMaxWorld * kDistMaxChunks * 8; // 2 MB: any owner may hold most buckets
-
-// sum of a u64 array (the keys an owner received = the sum of its cursor table)
-__global__ void __launch_bounds__(256) sum_u64_kernel(const unsigned long long *__restrict__ v, uint64_t n, unsigned long long *__restrict__ total) {
-  unsigned long long s = 0;
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) s += v[i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
-}
-
-__global__ void dist_publish_kernel(const unsigned long long *__restrict__ cursor, const uint64_t *__restrict__ cap,
-                                    const uint32_t *__restrict__ own_lo, const uint64_t *__restrict__ peer_header,
-                                    uint32_t n_all, uint32_t world, uint32_t rank, uint32_t chunk) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n_all) return;
-  uint32_t o = 0;
-  while (o + 1 < world && own_lo[o + 1] <= b) o++;
-  unsigned long long v = cursor[b];
-  if (v > cap[b]) v = cap[b]; // overflow was flagged by the scatter; the job is recounted
-  const uint32_t my_n = own_lo[o + 1] - own_lo[o];
-  unsigned long long *dst = reinterpret_cast<unsigned long long *>(peer_header[o]) + ((size_t)chunk * my_n + (b - own_lo[o])) * world + rank;
-  *dst = v;
-}
-
-template <typename KeyT>
-int dist_hist_impl(kmc_ctx *c, uint64_t *hist_out, uint32_t *low_cardinality) {
-  const uint32_t ncoarse = 1u << coarse_bits(c);
-  TRY(zero_scalars(c));
-  bool low = c->cfg.strategy == KMC_STRATEGY_HASH;
-  if (c->cfg.strategy == KMC_STRATEGY_AUTO && sizeof(KeyT) == 8) TRY(hash_probe(c, &low));
-  KeyArrays ka;
-  std::vector<uint64_t> hist;
-  uint32_t step = 1;
-  TRY(coarse_hist<KeyT>(c, ka, hist, &step));
-  for (uint32_t i = 0; i < 4096; i++) {
-    double est = i < ncoarse ? (double)hist[i] * step : 0.0;
-    if (step > 1 && i < ncoarse) est += 5.0 * std::sqrt(est * step) + step; // upper estimate, as in finish_fast
-    hist_out[i] = (uint64_t)est;
-  }
-  if (low_cardinality) *low_cardinality = low ? 1u : 0u;
-  return KMC_OK;
-}
-
-template <typename KeyT>
-int dist_plan_impl(kmc_ctx *c, uint32_t world, uint32_t rank, const uint64_t *all_hist, uint32_t n_chunks, uint64_t *need_bytes) {
-  constexpr bool kWide = sizeof(KeyT) == 16;
-  int kTarget = kWide ? 3200 : kFineTarget;
-  const uint32_t kb = c->key_bits, cb = coarse_bits(c), ncoarse = 1u << cb;
-  DistPlan &D = c->dist;
-  D.valid = false; D.scattered = false;
-  for (uint32_t o = 0; o < world; o++) need_bytes[o] = 0;
-  std::vector<uint64_t> G(ncoarse, 0);
-  uint64_t n_est = 0;
-  for (uint32_t s = 0; s < world; s++)
-    for (uint32_t ci = 0; ci < ncoarse; ci++) { G[ci] += all_hist[(size_t)s * 4096 + ci]; n_est += all_hist[(size_t)s * 4096 + ci]; }
-  if (n_est < ((uint64_t)world << 20)) return KMC_OK; // small job: not worth a plan
-  PlanShape shape;
-  // at least 64 level-1 buckets per owner, so that owners can be balanced to a few percent
-  uint32_t b1_min = 6;
-  while ((1u << (b1_min - 6)) < world) b1_min++;
-  const uint32_t min_e = getenv("KMC_NO_SPLIT64") ? 0u : split64_min_e(kb, n_est, kWide);
-  if (!plan_shape(G, kb, 0, ncoarse, false, kTarget, shape, b1_min, min_e)) return KMC_OK;
-  D.fine_cap = kWide ? 4096 : kFineCap;
-  if (!kWide && (kFineCap64 != kFineCap || kFineTarget64 != kFineTarget)) {
-    // buckets that leave more than 32 key bits are sorted as 64-bit elements, whose bucket shape is smaller: plan again
-    // (as fast_begin does; every rank sees the same global histogram, so every rank decides the same)
-    bool wide_elems = false;
-    for (uint32_t b = 0; b < shape.n_l1; b++) if (kb - shape.b1 - shape.l1e[b] > 32) wide_elems = true;
-    if (wide_elems) {
-      kTarget = kFineTarget64;
-      D.fine_cap = kFineCap64;
-      if (!plan_shape(G, kb, 0, ncoarse, false, kTarget, shape, b1_min, min_e)) return KMC_OK;
-    }
-  }
-  const uint32_t b1 = shape.b1, n_all = 1u << b1, cshift = cb - b1;
-  if (n_all < world) return KMC_OK;
-  // owners: consecutive level-1 buckets, about equal population
-  std::vector<uint64_t> pop(n_all, 0);
-  unsigned __int128 total = 0;
-  for (uint32_t b = 0; b < n_all; b++) {
-    for (uint32_t ci = b << cshift; ci < ((b + 1) << cshift); ci++) pop[b] += G[ci];
-    total += pop[b];
-  }
-  D.own_lo.assign(world + 1, 0);
-  {
-    unsigned __int128 before = 0;
-    uint32_t b = 0;
-    for (uint32_t o = 1; o < world; o++) {
-      const unsigned __int128 want = (total * o + world - 1) / world;
-      while (b < n_all && before < want) before += pop[b++];
-      D.own_lo[o] = b;
-    }
-    D.own_lo[world] = n_all;
-  }
-  for (uint32_t o = 0; o < world; o++) // the owner's cursor table must hold (chunk, bucket, sender)
-    if ((uint64_t)n_chunks * (D.own_lo[o + 1] - D.own_lo[o]) * world > kDistHeader / 8) return KMC_OK;
-  // chunks: equal slices of every sender's input, except that the first and the last are half as long — the exchange is
-  // a chain (scatter chunk 0, then one copy after the other, then the level-2 scatter of the last chunk), and its two
-  // ends are the part nothing overlaps
-  D.cum_frac.assign(n_chunks + 1, 0.0);
-  {
-    const double unit = n_chunks > 2 ? 1.0 / (n_chunks - 1) : 1.0 / n_chunks;
-    for (uint32_t ch = 0; ch < n_chunks; ch++)
-      D.cum_frac[ch + 1] = D.cum_frac[ch] + ((n_chunks > 2 && (ch == 0 || ch + 1 == n_chunks)) ? 0.5 * unit : unit);
-    D.cum_frac[n_chunks] = 1.0;
-  }
-  // region (chunk, sender, bucket): capacity from that sender's own histogram and the chunk's share of its input
-  D.s_cap.assign((size_t)n_chunks * n_all, 0); D.s_in.assign((size_t)n_chunks * n_all, 0);
-  D.slab_pre.assign((size_t)n_chunks * world, 0); D.slab_len.assign((size_t)n_chunks * world, 0);
-  D.chunk_off.assign((size_t)n_chunks * world, 0); D.stage_off.assign((size_t)n_chunks * world, 0);
-  D.x_cap.clear(); D.x_off.clear();
-  const uint64_t slack = 2 * kMaxTile;
-  std::vector<uint64_t> stage(n_chunks, 0);
-  for (uint32_t o = 0; o < world; o++) {
-    uint64_t off = 0;
-    const uint32_t my_n = D.own_lo[o + 1] - D.own_lo[o];
-    if (o == rank) { D.x_cap.assign((size_t)n_chunks * my_n * world, 0); D.x_off.assign((size_t)n_chunks * my_n * world, 0); }
-    for (uint32_t ch = 0; ch < n_chunks; ch++) {
-      const double frac = D.cum_frac[ch + 1] - D.cum_frac[ch];
-      D.chunk_off[(size_t)ch * world + o] = off;
-      for (uint32_t s = 0; s < world; s++) {
-        const uint64_t slab0 = off;
-        for (uint32_t b = D.own_lo[o]; b < D.own_lo[o + 1]; b++) {
-          uint64_t nb = 0;
-          for (uint32_t ci = b << cshift; ci < ((b + 1) << cshift); ci++) nb += all_hist[(size_t)s * 4096 + ci];
-          const uint64_t cap1 = n_chunks > 1 ? (((uint64_t)((double)nb * frac * 1.04) + 2048 + 15) & ~15ull)
-                                             : (((uint64_t)((double)nb * 1.03) + 4096 + 15) & ~15ull);
-          if (s == rank) { D.s_in[(size_t)ch * n_all + b] = off - slab0; D.s_cap[(size_t)ch * n_all + b] = cap1; }
-          if (o == rank) {
-            const size_t x = ((size_t)ch * my_n + (b - D.own_lo[o])) * world + s;
-            D.x_cap[x] = cap1; D.x_off[x] = off;
-          }
-          off += cap1;
-        }
-        if (s == rank) { D.slab_pre[(size_t)ch * world + o] = slab0; D.slab_len[(size_t)ch * world + o] = off - slab0; }
-      }
-      if (o != rank) { D.stage_off[(size_t)ch * world + o] = stage[ch]; stage[ch] += D.slab_len[(size_t)ch * world + o]; }
-    }
-    need_bytes[o] = kDistHeader + (off + slack) * sizeof(KeyT);
-    if (o == rank) D.l1_keys = off;
-  }
-  D.stage_len = 0;
-  for (uint64_t v : stage) D.stage_len = std::max(D.stage_len, v);
-  D.world = world; D.rank = rank; D.b1 = b1; D.n_all = n_all; D.n_chunks = n_chunks;
-  D.l1e = shape.l1e;
-  D.fine_hist = G;
-  D.owner_ready = false; D.chunks_sent = 0; D.chunks_owned = 0;
-  D.valid = true;
-  return KMC_OK;
-}
-
-struct StreamSwap {   // helpers launch on c->stream: run them on another stream of the ctx for a while
-  kmc_ctx *c; cudaStream_t saved;
-  StreamSwap(kmc_ctx *c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
-  ~StreamSwap() { c->stream = saved; }
-};
-
-// The owner's plan over what the senders will leave in the receive buffer: one pseudo-bucket per (chunk, bucket,
-// sender) region, all regions of a bucket feeding the same fine buckets.  Tables, buffers, descriptors; no key is touched.
-template <typename KeyT>
-int dist_owner_begin(kmc_ctx *c) {
-  constexpr bool kWide = sizeof(KeyT) == 16;
-  DistPlan &D = c->dist;
-  DistOwner &O = D.owner;
-  const int kCap = (int)D.fine_cap;
-  const uint32_t kb = c->key_bits, cb = coarse_bits(c), b1 = D.b1, cshift = cb - b1, world = D.world, C = D.n_chunks;
-  const uint32_t my_lo = D.own_lo[D.rank], my_n = D.own_lo[D.rank + 1] - my_lo, n_xc = my_n * world, n_x = n_xc * C, n_cb = my_n << cshift;
-  if (!c->recv_keys.p || c->recv_keys.cap < kDistHeader + (D.l1_keys + 2 * kMaxTile) * sizeof(KeyT))
-    return fail(c, KMC_E_ARG, "kmc_dist_scatter: the receive buffer is smaller than kmc_dist_plan asked for");
-  auto al16 = [](size_t x) { return (x + 15) & ~size_t(15); };
-  // owner tables: per pseudo-bucket x = (chunk, bucket, sender): start | cap | tile0 | fine0 | e;  per bucket: fine0 | e;
-  // per coarse bin: start | fine0 | cap
-  const size_t o_xs = 0, o_xc = o_xs + al16((size_t)(n_x + 1) * 8), o_xt = o_xc + al16((size_t)n_x * 8),
-               o_xf = o_xt + al16((size_t)(n_x + 1) * 4), o_xe = o_xf + al16((size_t)(n_x + 1) * 4), o_rf = o_xe + al16(n_x),
-               o_re = o_rf + al16((size_t)(my_n + 1) * 4), o_cs = o_re + al16(my_n), o_cf = o_cs + al16((size_t)n_cb * 8),
-               o_cc = o_cf + al16((size_t)n_cb * 4), tab_bytes = o_cc + al16((size_t)n_cb * 2);
-  c->fast_host.assign(tab_bytes, 0);
-  unsigned char *hb = c->fast_host.data();
-  uint64_t *xs = (uint64_t *)(hb + o_xs), *xc = (uint64_t *)(hb + o_xc);
-  uint32_t *xf = (uint32_t *)(hb + o_xf), *rf = (uint32_t *)(hb + o_rf);
-  uint8_t *xe = hb + o_xe, *re = hb + o_re;
-  uint64_t *cstart = (uint64_t *)(hb + o_cs);
-  uint32_t *cfine0 = (uint32_t *)(hb + o_cf);
-  uint16_t *ccap = (uint16_t *)(hb + o_cc);
-  uint64_t l2_keys = 0, tiles2 = 0, t_max = 1;
-  uint32_t fb = 0, nb_max = 1;
-  bool key32 = !kWide, split64 = !kWide && !getenv("KMC_NO_SPLIT64");
-  for (uint32_t rb = 0; rb < my_n; rb++) {
-    if (kb - b1 - D.l1e[my_lo + rb] > 32) key32 = false;
-    if (kb - b1 - D.l1e[my_lo + rb] > 32 + (uint32_t)kFinishBits) split64 = false;
-  }
-  if (key32) split64 = false;
-  for (uint32_t rb = 0; rb < my_n; rb++) {
-    const uint32_t b = my_lo + rb, e = D.l1e[b], sub_bits = e - cshift;
-    rf[rb] = fb; re[rb] = (uint8_t)e;
-    for (uint32_t ch = 0; ch < C; ch++)
-      for (uint32_t s = 0; s < world; s++) {
-        const uint32_t x = ch * n_xc + rb * world + s;
-        const uint64_t cap1 = D.x_cap[((size_t)ch * my_n + rb) * world + s];
-        xs[x] = D.x_off[((size_t)ch * my_n + rb) * world + s];
-        xc[x] = cap1; xf[x] = fb; xe[x] = (uint8_t)e;
-        tiles2 += (cap1 + p2_tile<KeyT>() - 1) / p2_tile<KeyT>();
-        t_max = std::max<uint64_t>(t_max, (cap1 + p2_tile<KeyT>() - 1) / p2_tile<KeyT>());
-      }
-    nb_max = std::max<uint32_t>(nb_max, 1u << e);
-    for (uint32_t ci = b << cshift; ci < ((b + 1) << cshift); ci++) {
-      double avg = (double)D.fine_hist[ci] / (double)(1ull << sub_bits);
-      const uint32_t cp = fine_cap_for(avg, kCap);
-      const uint32_t ci_rel = ci - (my_lo << cshift);
-      cstart[ci_rel] = l2_keys; cfine0[ci_rel] = fb; ccap[ci_rel] = (uint16_t)cp;
-      l2_keys += (uint64_t)cp << sub_bits;
-      fb += 1u << sub_bits;
-    }
-  }
-  const uint64_t l1_keys = D.l1_keys;
-  xs[n_x] = l1_keys; xf[n_x] = fb; rf[my_n] = fb;
-  const uint64_t n_fine = fb;
-  if (tiles2 > 0x7FFFFFFFull || n_fine == 0) return fail(c, KMC_E_CAPACITY, "kmc_dist_scatter: range-partition plan too large");
-  const uint64_t slack = 2 * kMaxTile;
-  const size_t off_ticket = 4096 * 8, off_dtotal = off_ticket + 8, off_l1cur = off_dtotal + 8, off_fine = off_l1cur + kMaxL1 * 8;
-  const size_t off_status = (off_fine + n_fine * 4 + 15) & ~size_t(15);
-  TRY(ensure(c, c->fast_tables, tab_bytes));
-  TRY(ensure(c, c->fast_fdesc, n_fine * sizeof(FineDesc)));
-  TRY(ensure(c, c->fast_l2, (l2_keys + 2 * slack) * sizeof(KeyT)));
-  TRY(ensure(c, c->t_lo, l1_keys * 8 + 64));
-  if (kWide) TRY(ensure(c, c->t_hi, l1_keys * 8 + 64));
-  TRY(ensure(c, c->t_cnt, l1_keys * 4 + 64));
-  TRY(ensure(c, c->fast_state, off_status + n_fine * 8 + 64));
-  CK(cudaMemsetAsync(c->fast_state.p, 0, off_status + n_fine * 8, c->stream));
-  TRY(h2d_small(c, c->fast_tables.p, c->fast_host.data(), tab_bytes));
-  unsigned char *st = (unsigned char *)c->fast_state.p, *tb = (unsigned char *)c->fast_tables.p;
-  FastPlan &pl = O.pl;
-  pl = FastPlan{};
-  pl.kb = kb; pl.b1 = b1; pl.n_l1 = n_x; pl.n_fine = (uint32_t)n_fine; pl.l1_base = my_lo;
-  pl.l1_trash = l1_keys; pl.l2_trash = l2_keys + slack;
-  pl.fdesc = (const FineDesc *)c->fast_fdesc.p;
-  pl.l1_start = (const uint64_t *)(tb + o_xs); pl.l1_cap = (const uint64_t *)(tb + o_xc);
-  pl.l1_tile0 = (const uint32_t *)(tb + o_xt); pl.l1_fine0 = (const uint32_t *)(tb + o_xf); pl.l1_e = tb + o_xe;
-  pl.l1_cursor = (unsigned long long *)c->recv_keys.p; pl.fine_cursor = (uint32_t *)(st + off_fine);
-  O.ticket = (unsigned int *)(st + off_ticket);
-  O.d_total = (unsigned long long *)(st + off_dtotal);
-  O.status = (unsigned long long *)(st + off_status);
-  O.key32 = key32; O.split64 = split64; O.nb_max = nb_max; O.t_max = t_max; O.n_fine = n_fine; O.n_xc = n_xc;
-  LAUNCH(plan_expand_kernel, n_cb, 128, 0, (FineDesc *)c->fast_fdesc.p, (const uint64_t *)(tb + o_cs), (const uint32_t *)(tb + o_cf),
-         (const uint16_t *)(tb + o_cc), (const uint32_t *)(tb + o_rf), (const uint8_t *)(tb + o_re), cshift, my_lo, kb, b1, (uint32_t)kWide);
-  c->launches--;
-  if (!c->owner_stream) CK(cudaStreamCreateWithFlags(&c->owner_stream, cudaStreamNonBlocking));
-  if (!D.ev_ready) CK(cudaEventCreateWithFlags(&D.ev_ready, cudaEventDisableTiming));
-  CK(cudaEventRecord(D.ev_ready, c->stream));
-  CK(cudaStreamWaitEvent(c->owner_stream, D.ev_ready, 0));
-  c->fast_variant = kWide ? "u128" : key32 ? "u32" : split64 ? "split64" : "u64";
-  D.owner_ready = true;
-  return KMC_OK;
-}
-
-// sender: level-1 scatter of input chunk `chunk` into the staging array (own buckets: into the own receive buffer), then
-// — on the peer stream, so that the next chunk's scatter runs meanwhile — one copy per owner and the chunk's cursors.
-template <typename KeyT>
-int dist_scatter_part_impl(kmc_ctx *c, void *const *peer_buf, uint32_t chunk) {
-  DistPlan &D = c->dist;
-  const uint32_t n_all = D.n_all, world = D.world, kb = c->key_bits, C = D.n_chunks;
-  if (chunk != D.chunks_sent || chunk >= C) return fail(c, KMC_E_ARG, "kmc_dist_scatter_part: chunks go in order, 0..%u", C - 1);
-  auto al16 = [](size_t x) { return (x + 15) & ~size_t(15); };
-  // sender tables: per chunk l1_start (absolute address / key size) | l1_cap | own_lo | peer header pointers
-  const size_t o_s = 0, o_c = o_s + al16((size_t)C * (n_all + 1) * 8), o_own = o_c + al16((size_t)C * n_all * 8),
-               o_ph = o_own + al16((size_t)(world + 1) * 4), tab_bytes = o_ph + al16((size_t)world * 8);
-  if (chunk == 0) {
-    TRY(zero_scalars(c));
-    TRY(dist_owner_begin<KeyT>(c)); // buffers first: nothing below may be freed under a running kernel
-    TRY(ensure(c, c->dist_stage, (2 * D.stage_len + 64) * sizeof(KeyT)));
-    TRY(ensure(c, c->dist_tables, tab_bytes));
-    TRY(ensure(c, c->route_keys, (size_t)2 * kMaxTile * sizeof(KeyT) + 256)); // trash area for runs that do not fit
-    TRY(ensure(c, c->dist_cursors, (size_t)kDistMaxChunks * kMaxL1 * 8));
-    std::vector<unsigned char> host(tab_bytes, 0);
-    uint64_t *l1s = (uint64_t *)(host.data() + o_s), *l1c = (uint64_t *)(host.data() + o_c);
-    uint32_t *own = (uint32_t *)(host.data() + o_own);
-    uint64_t *ph = (uint64_t *)(host.data() + o_ph);
-    for (uint32_t ch = 0; ch < C; ch++)
-      for (uint32_t o = 0; o < world; o++) {
-        const size_t co = (size_t)ch * world + o;
-        const uint64_t base = o == D.rank
-            ? ((uint64_t)(uintptr_t)c->recv_keys.p + kDistHeader) / sizeof(KeyT) + D.slab_pre[co]
-            : (uint64_t)(uintptr_t)c->dist_stage.p / sizeof(KeyT) + (uint64_t)(ch & 1) * D.stage_len + D.stage_off[co];
-        for (uint32_t b = D.own_lo[o]; b < D.own_lo[o + 1]; b++) l1s[(size_t)ch * (n_all + 1) + b] = base + D.s_in[(size_t)ch * n_all + b];
-      }
-    for (uint32_t ch = 0; ch < C; ch++)
-      for (uint32_t b = 0; b < n_all; b++) l1c[(size_t)ch * n_all + b] = D.s_cap[(size_t)ch * n_all + b];
-    for (uint32_t o = 0; o < world; o++) ph[o] = (uint64_t)(uintptr_t)peer_buf[o];
-    for (uint32_t o = 0; o <= world; o++) own[o] = D.own_lo[o];
-    CK(cudaMemsetAsync(c->dist_cursors.p, 0, (size_t)C * kMaxL1 * 8, c->stream));
-    TRY(h2d_small(c, c->dist_tables.p, host.data(), tab_bytes));
-    if (!c->peer_stream) CK(cudaStreamCreateWithFlags(&c->peer_stream, cudaStreamNonBlocking));
-    for (uint32_t ch = 0; ch < C; ch++)
-      for (cudaEvent_t *e : {&D.ev_scattered[ch], &D.ev_copied[ch]})
-        if (!*e) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-  }
-  unsigned char *tb = (unsigned char *)c->dist_tables.p;
-  FastPlan pl{};
-  pl.kb = kb; pl.b1 = D.b1; pl.n_l1 = n_all; pl.n_fine = 0; pl.l1_base = 0;
-  pl.l1_trash = ((uint64_t)(uintptr_t)c->route_keys.p + sizeof(KeyT) - 1) / sizeof(KeyT);
-  pl.l1_start = (const uint64_t *)(tb + o_s) + (size_t)chunk * (n_all + 1);
-  pl.l1_cap = (const uint64_t *)(tb + o_c) + (size_t)chunk * n_all;
-  pl.l1_cursor = (unsigned long long *)c->dist_cursors.p + (size_t)chunk * kMaxL1;
-  // the staging half this chunk scatters into was copied out two chunks ago
-  if (chunk >= 2) CK(cudaStreamWaitEvent(c->stream, D.ev_copied[chunk - 2], 0));
-  // this chunk's share of the CTA tiles of all segments, in segment order
-  uint64_t all_ct = 0;
-  for (size_t i = 0; i < c->n_segs; i++)
-    if (c->segs[i].n_bases) all_ct += (num_warp_tiles(c->segs[i].n_bases, win_lanes<KeyT>()) + kFastWarps - 1) / kFastWarps;
-  const uint64_t g0 = (uint64_t)((double)all_ct * D.cum_frac[chunk]), g1 = chunk + 1 == C ? all_ct : (uint64_t)((double)all_ct * D.cum_frac[chunk + 1]);
-  PHASE_BEGIN("route");
-  {
-    size_t smem = L1Smem<KeyT>::bytes(part1_stage<KeyT>(), n_all);
-    auto fast_scatter_to_owners = fast_part1_kernel<KeyT, true, PrefixBucket>;
-    CK(cudaFuncSetAttribute(fast_scatter_to_owners, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const PrefixBucket bucket = make_prefix_bucket<false>(kb, D.b1);
-    uint64_t seg0 = 0;
-    for (size_t i = 0; i < c->n_segs; i++) {
-      Segment &s = c->segs[i];
-      if (!s.n_bases) continue;
-      const uint64_t tiles = num_warp_tiles(s.n_bases, win_lanes<KeyT>()), n_ct = (tiles + kFastWarps - 1) / kFastWarps;
-      const uint64_t lo = std::max(g0, seg0), hi = std::min(g1, seg0 + n_ct);
-      seg0 += n_ct;
-      if (hi <= lo) continue;
-      TRY(seg_wait(c, s));
-      ExtractParams P = seg_params(c, s);
-      uint32_t grid = (uint32_t)std::min<uint64_t>(hi - lo, (uint64_t)c->n_sms);
-      LAUNCH(fast_scatter_to_owners, grid, kFastThreads, smem, P, tiles, pl, bucket, (KeyT *)nullptr, d_err(c), lo - (seg0 - n_ct), hi - (seg0 - n_ct));
-    }
-  }
-  PHASE_END();
-  CK(cudaEventRecord(D.ev_scattered[chunk], c->stream));
-  CK(cudaStreamWaitEvent(c->peer_stream, D.ev_scattered[chunk], 0));
-  const KeyT *stage = (const KeyT *)c->dist_stage.p + (size_t)(chunk & 1) * D.stage_len;
-  // the slabs leave staggered, so that at any moment every rank writes to a different peer.  KMC_PEER_STREAMS > 1 puts
-  // them on several streams at once (the first then waits for the others); measured at 8 GPUs it does not help — 28.9
-  // ms/step with 4 streams against 27.5 with one: the links, not a copy engine, are the bound (~480 GB/s leave a GPU)
-  static const int n_lanes = std::max(1, std::min(env_int("KMC_PEER_STREAMS", 1), 8));
-  for (int l = 1; l < n_lanes; l++) {
-    if (!c->peer_lane[l]) CK(cudaStreamCreateWithFlags(&c->peer_lane[l], cudaStreamNonBlocking));
-    if (!c->peer_lane_ev[l]) CK(cudaEventCreateWithFlags(&c->peer_lane_ev[l], cudaEventDisableTiming));
-    CK(cudaStreamWaitEvent(c->peer_lane[l], D.ev_scattered[chunk], 0));
-  }
-  for (uint32_t d = 1; d < world; d++) {
-    const uint32_t o = (D.rank + d) % world;
-    const size_t co = (size_t)chunk * world + o;
-    if (!D.slab_len[co]) continue;
-    const int l = (int)((d - 1) % (uint32_t)n_lanes);
-    KeyT *dst = (KeyT *)((unsigned char *)peer_buf[o] + kDistHeader) + D.slab_pre[co];
-    CK(cudaMemcpyAsync(dst, stage + D.stage_off[co], D.slab_len[co] * sizeof(KeyT), cudaMemcpyDeviceToDevice, l ? c->peer_lane[l] : c->peer_stream));
-  }
-  for (int l = 1; l < n_lanes; l++) {
-    CK(cudaEventRecord(c->peer_lane_ev[l], c->peer_lane[l]));
-    CK(cudaStreamWaitEvent(c->peer_stream, c->peer_lane_ev[l], 0));
-  }
-  {
-    StreamSwap sw(c, c->peer_stream);
-    const bool kt = c->ktiming;
-    c->ktiming = false; // per-kernel event pairs belong to the compute stream
-    LAUNCH(dist_publish_kernel, grid_for(n_all, 256), 256, 0, pl.l1_cursor, pl.l1_cap, (const uint32_t *)(tb + o_own),
-           (const uint64_t *)(tb + o_ph), n_all, world, D.rank, chunk);
-    c->launches--;
-    c->ktiming = kt;
-  }
-  CK(cudaEventRecord(D.ev_copied[chunk], c->peer_stream));
-  D.chunks_sent = chunk + 1;
-  return KMC_OK;
-}
-
-// owner: level-2 scatter over the regions of one chunk (every sender's copy of it has landed: the caller's hand-over)
-template <typename KeyT>
-int dist_owner_part_impl(kmc_ctx *c, uint32_t chunk) {
-  DistPlan &D = c->dist;
-  DistOwner &O = D.owner;
-  if (!D.owner_ready) return fail(c, KMC_E_ARG, "kmc_dist_owner_part before kmc_dist_scatter_part");
-  if (chunk != D.chunks_owned || chunk >= D.n_chunks) return fail(c, KMC_E_ARG, "kmc_dist_owner_part: chunks go in order");
-  StreamSwap sw(c, c->owner_stream);
-  FastPlan pl = O.pl;
-  const size_t x0 = (size_t)chunk * O.n_xc;
-  pl.n_l1 = O.n_xc;
-  pl.l1_start += x0; pl.l1_cap += x0; pl.l1_tile0 += x0; pl.l1_fine0 += x0; pl.l1_e += x0; pl.l1_cursor += x0;
-  const KeyT *l1 = (const KeyT *)((unsigned char *)c->recv_keys.p + kDistHeader);
-  const bool kt = c->ktiming;
-  c->ktiming = false;
-  PHASE_BEGIN("fast_part2");
-  int rc = launch_part2<KeyT>(c, pl, l1, O.key32, O.nb_max, O.t_max);
-  c->ktiming = kt;
-  if (rc) return rc;
-  PHASE_END();
-  D.chunks_owned = chunk + 1;
-  return KMC_OK;
-}
-
-// sender: everything this rank had to store has landed; did it fit?
-int dist_scatter_end_impl(kmc_ctx *c, uint32_t *overflow) {
-  DistPlan &D = c->dist;
-  if (D.chunks_sent != D.n_chunks) return fail(c, KMC_E_ARG, "kmc_dist_scatter_end: %u of %u chunks scattered", D.chunks_sent, D.n_chunks);
-  CK(cudaStreamSynchronize(c->peer_stream));
-  uint32_t err = 0;
-  TRY(read_scalars(c, nullptr, &err));
-  *overflow = (err & kFlagOverflow) ? 1u : 0u;
-  if (*overflow) {
-    if (c->owner_stream) CK(cudaStreamSynchronize(c->owner_stream));
-  if (c->peer_stream) CK(cudaStreamSynchronize(c->peer_stream));
-    TRY(zero_scalars(c));
-  }
-  D.scattered = !*overflow;
-  return KMC_OK;
-}
-
-// the owner's last part: (the level-2 scatter of chunks not handed over one by one, then) the bucket sort
-template <typename KeyT>
-int finish_dist(kmc_ctx *c) {
-  constexpr bool kWide = sizeof(KeyT) == 16;
-  DistPlan &D = c->dist;
-  DistOwner &O = D.owner;
-  while (D.chunks_owned < D.n_chunks) TRY(dist_owner_part_impl<KeyT>(c, D.chunks_owned));
-  const FastPlan &pl = O.pl;
-  const uint64_t n_fine = O.n_fine;
-  unsigned long long *header = (unsigned long long *)c->recv_keys.p;
-  {
-    StreamSwap sw(c, c->owner_stream);
-    PHASE_BEGIN("fast_finish");
-    unsigned long long *prof = nullptr;
-    if constexpr (kWide) {
-      size_t fsmem = sizeof(FinishSmem<U128>);
-      auto fast_finish = fast_finish_kernel<U128>;
-      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * 2), kFinThreads, fsmem, pl, (const U128 *)c->fast_l2.p,
-             (uint64_t *)c->t_lo.p, (uint64_t *)c->t_hi.p, (uint32_t *)c->t_cnt.p, O.status, O.ticket, d_err(c), O.d_total, prof);
-    } else if (O.key32) {
-      size_t fsmem = sizeof(FinishSmem<uint32_t>);
-      auto fast_finish = fast_finish_kernel<uint32_t>;
-      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * KMC_FINISH_MINB32), kFinThreads, fsmem, pl,
-             (const uint32_t *)c->fast_l2.p, (uint64_t *)c->t_lo.p, (uint64_t *)nullptr, (uint32_t *)c->t_cnt.p, O.status, O.ticket, d_err(c),
-             O.d_total, prof);
-    } else if (O.split64) {
-      size_t fsmem = sizeof(FinishSmem<Split64>);
-      auto fast_finish = fast_finish_kernel<Split64>;
-      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * 2), kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p,
-             (uint64_t *)c->t_lo.p, (uint64_t *)nullptr, (uint32_t *)c->t_cnt.p, O.status, O.ticket, d_err(c), O.d_total, prof);
-    } else {
-      size_t fsmem = sizeof(FinishSmem<uint64_t>);
-      auto fast_finish = fast_finish_kernel<uint64_t>;
-      CK(cudaFuncSetAttribute(fast_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      LAUNCH(fast_finish, (uint32_t)std::min<uint64_t>(n_fine, (uint64_t)c->n_sms * KMC_FINISH_MINB64), kFinThreads, fsmem, pl, (const uint64_t *)c->fast_l2.p,
-             (uint64_t *)c->t_lo.p, (uint64_t *)nullptr, (uint32_t *)c->t_cnt.p, O.status, O.ticket, d_err(c), O.d_total, prof);
-    }
-    PHASE_END();
-    uint64_t d = 0;
-    uint32_t err = 0;
-    TRY(d2h_small(c, &d, O.d_total, 8));
-    TRY(read_scalars(c, nullptr, &err));
-    if (err & kFlagSpin) return fail(c, KMC_E_CUDA, "fast_finish: look-back did not make progress");
-    if (err & kFlagOverflow) {
-      c->fast_fallbacks++;
-      TRY(zero_scalars(c));
-      return fail(c, KMC_E_CAPACITY, "range-partitioned count: a fine bucket overflowed (recount through kmc_route_to_peers)");
-    }
-    // keys I own = what the senders' cursor table says
-    uint64_t N = 0;
-    const size_t n_x = (size_t)O.n_xc * D.n_chunks;
-    CK(cudaMemsetAsync(d_total_all(c), 0, 8, c->stream));
-    LAUNCH(sum_u64_kernel, std::min<uint32_t>(grid_for(n_x, 256), 64), 256, 0, header, (uint64_t)n_x, d_total_all(c));
-    c->launches--;
-    TRY(d2h_small(c, &N, d_total_all(c), 8));
-    c->n_total = N; c->n_distinct = d;
-  }
-  c->strategy_used = KMC_STRATEGY_SORT;
-  D.scattered = false; D.owner_ready = false;
-  return KMC_OK;
-}
-
-
-// ---- streaming owner (multi-GPU): count what the other ranks route here WHILE they are still routing ------
-// The routing pass is cut into chunks (kmc_route_to_peers_part); after every chunk the ranks agree on the counts and
-// each owner feeds the keys that have just arrived to its partitioned count — level-1 scatter and the whole tiles of
-// the level-2 scatter — on a second stream, beside the routing kernel of the next chunk (which leaves it some SMs).
-// kmc_finish then only has the rest of the level-2 scatter and the bucket sort left.
-
-template <typename KeyT>
-int owner_begin_impl(kmc_ctx *c, const uint64_t *global_hist, uint32_t n_owners, uint32_t *streaming) {
-  *streaming = 0;
-  const uint32_t ncoarse = 1u << coarse_bits(c);
-  // this owner's share of every coarse bin: the owner function is a hash, so 1 / n_owners of it, Poisson-distributed
-  std::vector<uint64_t> hist(ncoarse);
-  uint64_t n_est = 0;
-  for (uint32_t ci = 0; ci < ncoarse; ci++) {
-    const double m = (double)global_hist[ci] / n_owners;
-    hist[ci] = (uint64_t)(m * 1.02 + 6.0 * std::sqrt(m) + 64.0);
-    n_est += hist[ci];
-  }
-  if (n_est < (1u << 22)) return KMC_OK; // small job: not worth the choreography
-  if (!c->owner_stream) CK(cudaStreamCreateWithFlags(&c->owner_stream, cudaStreamNonBlocking));
-  CK(cudaStreamSynchronize(c->stream)); // buffers the plan touches may still be read by the previous job's tail
-  StreamSwap sw(c, c->owner_stream);
-  TRY(zero_scalars(c));
-  bool ok = false;
-  TRY(fast_begin<KeyT>(c, hist, n_est, 0, &ok));
-  if (!ok) return KMC_OK;
-  c->owner_on = true;
-  c->owner_fed.clear();
-  *streaming = 1;
-  return KMC_OK;
-}
-
-template <typename KeyT>
-int owner_feed_impl(kmc_ctx *c, const void *d_keys, uint64_t n) {
-  if (!n) return KMC_OK;
-  c->owner_fed.emplace_back(d_keys, n);
-  StreamSwap sw(c, c->owner_stream);
-  return fast_feed_array<KeyT>(c, d_keys, n, true);
-}
-
-template <typename KeyT>
-int finish_impl(kmc_ctx *c);
-
-template <typename KeyT>
-int owner_finish(kmc_ctx *c) {
-  bool used = false;
-  {
-    StreamSwap sw(c, c->owner_stream);
-    TRY(fast_end<KeyT>(c, true, &used));
-  }
-  c->owner_on = false;
-  if (used) return KMC_OK;
-  // the count did not suit the partitioned path (a bucket overflowed): recount what was fed, any way that works
-  CK(cudaStreamSynchronize(c->owner_stream));
-  c->ingested.clear();
-  for (auto &e : c->owner_fed) {
-    if (!c->ingested.empty() && (const char *)c->ingested.back().first + c->ingested.back().second * sizeof(KeyT) == (const char *)e.first)
-      c->ingested.back().second += e.second;       // chunks of one region are adjacent
-    else c->ingested.push_back(e);
-  }
-  c->owner_fed.clear();
-  TRY(zero_scalars(c));
-  return finish_impl<KeyT>(c);
-}
+#include "kmc_api_hash.cuh"   // hash strategies, cardinality probe
+#include "kmc_api_fast.cuh"   // partitioned path, kept key array
+#include "kmc_api_dist.cuh"   // range partition, streaming owner
 
 template <typename KeyT>
 int finish_impl(kmc_ctx *c) {
