@@ -67,3 +67,25 @@ def test_header_is_plain_c():
                 ["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", hdr]):
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_sass_data_movement_is_what_design_md_says(kmc):
+    """The shipped library's SASS (no GPU needed to read it): the level-1 scatter / routing kernels hand their bucket runs to
+    the TMA unit (UBLKCP, `cp.async.bulk` shared -> global), the extraction front ends load 128 bits per lane
+    (LDG.E.NA.128), the wide hash table claims slots with a 16-byte CAS, and nothing uses tensor cores — k-mer counting is
+    not a contraction (profiles/r02_sass_opcodes.txt)."""
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", kmc.lib_path()], capture_output=True, text=True).stdout
+    per, cur = {}, None
+    for ln in sass.splitlines():
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            cur = m.group(1)
+            per[cur] = ""
+        elif cur:
+            per[cur] += ln + "\n"
+    scatter = [k for k in per if "fast_part1" in k]
+    assert len(scatter) >= 6 and all("UBLKCP" in per[k] for k in scatter), [k for k in scatter if "UBLKCP" not in per[k]]
+    assert any("LDG.E.NA.128" in per[k] for k in scatter)
+    assert any("ATOMG.E.CAS.128" in v for k, v in per.items() if "hash128" in k)
+    assert not re.search(r"\b(HMMA|IMMA|UTCMMA|UTCHMMA|WGMMA)\b", sass)
